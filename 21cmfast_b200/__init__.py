@@ -1,0 +1,18 @@
+"""21cmfast_b200 -- B200-native (sm_100a) implementation of 21cmFAST's 3-D grid hot path.
+
+InitialConditions -> PerturbedField -> IonizedBox behind the reference's own C entry points
+(``ComputeInitialConditions`` / ``ComputePerturbedField`` / ``ComputeIonizedBox``).  The product
+is the C-ABI shared library ``csrc/lib21cmfast_b200.so`` (hand-written CUDA + C host glue, see
+``include/py21cmfast_b200.h``); this package is the thin Python mirror of the reference's
+wrapper/driver layer for that path.  The directory name starts with a digit, so import it with
+``importlib.import_module("21cmfast_b200")``.
+"""
+from .drivers import (brightness_temperature, compute_initial_conditions,  # noqa: F401
+                      compute_ionization_field, perturb_field, run_coeval)
+from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  # noqa: F401
+                     MatterOptions, SimulationOptions)
+from .outputs import (BrightnessTemp, InitialConditions, IonizedBox,  # noqa: F401
+                      PerturbedField)
+from ._lib import Backend, BackendError, get_backend  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,261 @@
+/*
+ * oracle/shims/fftw_shim.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Stand-in for libfftw3f so that the reference's own sources (dft.c:18-72) compile and run here.
+ * Semantics restated from the FFTW3 manual ("Multi-Dimensional DFTs of Real Data"):
+ *   r2c: Y[k0,k1,k2] = sum_n X[n] exp(-2 pi i (k.n/N)), k2 = 0..n2/2, in-place, real rows padded
+ *        to 2*(n2/2+1) floats; c2r is the unnormalised inverse (c2r(r2c(X)) = N X).
+ * Back-ends (env ORACLE_FFT = "own" | "mkl", default "mkl" when libtorch_cpu.so can be dlopen'ed
+ * from ORACLE_TORCH_LIB, else "own"):
+ *   own : float mixed-radix (2,3,4,5, generic) decimation-in-time, row-column over the 3 axes.
+ *   mkl : Intel MKL DFTI (DftiCreateDescriptor_s_md ...) found inside torch's libtorch_cpu.so; the
+ *         interface constants are declared by hand (no mkl_dfti.h in the image) and the back-end
+ *         is cross-checked against `own` and numpy in tests/test_oracle_shims.py.
+ * ORACLE_FFT_THREADS (default 1) mirrors the reference, whose FFT calls never enable FFTW
+ * threading (dft.c:82-85).
+ */
+#include "fftw3.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef float _Complex cpx;
+
+struct oracle_fftwf_plan_s {
+    int n0, n1, n2, inverse;
+    void *data;
+};
+
+/* ----------------------------------------------------------- own 1-D FFT */
+typedef struct {
+    int n, nf, fac[64];
+    cpx *tw; /* exp(-2 pi i k / n) */
+} fft1d_t;
+
+static void fft1d_init(fft1d_t *p, int n) {
+    int m = n, k = 0;
+    p->n = n;
+    while (m % 4 == 0) { p->fac[k++] = 4; m /= 4; }
+    while (m % 2 == 0) { p->fac[k++] = 2; m /= 2; }
+    for (int f = 3; f * f <= m; f += 2)
+        while (m % f == 0) { p->fac[k++] = f; m /= f; }
+    if (m > 1) p->fac[k++] = m;
+    p->nf = k;
+    p->tw = (cpx *)malloc(sizeof(cpx) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        double ph = -2.0 * M_PI * i / n;
+        p->tw[i] = (float)cos(ph) + (float)sin(ph) * I;
+    }
+}
+
+/* recursive DIT: out[0..n) = DFT of in[0], in[stride], ...; tws = twiddle stride for this level */
+static void fft1d_rec(const fft1d_t *p, cpx *out, const cpx *in, int n, int stride, int level,
+                      int sign, cpx *scratch) {
+    if (n == 1) { out[0] = in[0]; return; }
+    const int r = p->fac[level], m = n / r;
+    for (int q = 0; q < r; q++)
+        fft1d_rec(p, out + q * m, in + q * stride, m, stride * r, level + 1, sign, scratch);
+    const int tws = p->n / n;
+    for (int k = 0; k < m; k++) {
+        cpx t[r];
+        for (int q = 0; q < r; q++) {
+            cpx w = p->tw[(size_t)(q * k * tws) % p->n];
+            if (sign > 0) w = conjf(w);
+            t[q] = out[q * m + k] * w;
+        }
+        if (r == 2) {
+            out[k] = t[0] + t[1];
+            out[k + m] = t[0] - t[1];
+        } else if (r == 4) {
+            cpx a = t[0] + t[2], b = t[0] - t[2], c = t[1] + t[3], d = (t[1] - t[3]) * (sign > 0 ? I : -I);
+            out[k] = a + c; out[k + m] = b + d; out[k + 2 * m] = a - c; out[k + 3 * m] = b - d;
+        } else {
+            for (int j = 0; j < r; j++) {
+                cpx acc = 0;
+                for (int q = 0; q < r; q++) {
+                    cpx w = p->tw[(size_t)((long)q * j * (p->n / r)) % p->n];
+                    if (sign > 0) w = conjf(w);
+                    acc += t[q] * w;
+                }
+                scratch[j] = acc;
+            }
+            for (int j = 0; j < r; j++) out[k + j * m] = scratch[j];
+        }
+    }
+}
+static void fft1d_exec(const fft1d_t *p, cpx *out, const cpx *in, int sign) {
+    cpx scratch[p->n > 64 ? 64 : p->n + 1];
+    cpx *big = NULL;
+    int maxf = 1;
+    for (int i = 0; i < p->nf; i++) if (p->fac[i] > maxf) maxf = p->fac[i];
+    if (maxf > 64) big = (cpx *)malloc(sizeof(cpx) * maxf);
+    fft1d_rec(p, out, in, p->n, 1, 0, sign, big ? big : scratch);
+    free(big);
+}
+
+static int fft_threads(void) {
+    const char *e = getenv("ORACLE_FFT_THREADS");
+    int t = e ? atoi(e) : 1;
+    return t > 0 ? t : 1;
+}
+
+static void own_execute(const struct oracle_fftwf_plan_s *pl) {
+    const int n0 = pl->n0, n1 = pl->n1, n2 = pl->n2, nc = n2 / 2 + 1;
+    cpx *c = (cpx *)pl->data;
+    float *r = (float *)pl->data;
+    fft1d_t p0, p1, p2;
+    fft1d_init(&p0, n0); fft1d_init(&p1, n1); fft1d_init(&p2, n2);
+    const int nt = fft_threads();
+    const int sign = pl->inverse ? +1 : -1;
+#pragma omp parallel num_threads(nt)
+    {
+        int nmax = n0 > n1 ? n0 : n1; if (n2 > nmax) nmax = n2;
+        cpx *a = (cpx *)malloc(sizeof(cpx) * nmax), *b = (cpx *)malloc(sizeof(cpx) * nmax);
+        if (!pl->inverse) {
+#pragma omp for collapse(2)
+            for (int i = 0; i < n0; i++)
+                for (int j = 0; j < n1; j++) {
+                    float *row = r + ((size_t)i * n1 + j) * 2 * nc;
+                    for (int k = 0; k < n2; k++) a[k] = row[k];
+                    fft1d_exec(&p2, b, a, sign);
+                    memcpy(row, b, sizeof(cpx) * nc);
+                }
+        }
+        /* axis 1 */
+#pragma omp for collapse(2)
+        for (int i = 0; i < n0; i++)
+            for (int k = 0; k < nc; k++) {
+                cpx *base = c + (size_t)i * n1 * nc + k;
+                for (int j = 0; j < n1; j++) a[j] = base[(size_t)j * nc];
+                fft1d_exec(&p1, b, a, sign);
+                for (int j = 0; j < n1; j++) base[(size_t)j * nc] = b[j];
+            }
+        /* axis 0 */
+#pragma omp for collapse(2)
+        for (int j = 0; j < n1; j++)
+            for (int k = 0; k < nc; k++) {
+                cpx *base = c + (size_t)j * nc + k;
+                for (int i = 0; i < n0; i++) a[i] = base[(size_t)i * n1 * nc];
+                fft1d_exec(&p0, b, a, sign);
+                for (int i = 0; i < n0; i++) base[(size_t)i * n1 * nc] = b[i];
+            }
+        if (pl->inverse) {
+#pragma omp for collapse(2)
+            for (int i = 0; i < n0; i++)
+                for (int j = 0; j < n1; j++) {
+                    cpx *row = c + ((size_t)i * n1 + j) * nc;
+                    for (int k = 0; k < nc; k++) a[k] = row[k];
+                    a[0] = crealf(a[0]);
+                    if (n2 % 2 == 0) a[n2 / 2] = crealf(a[n2 / 2]);
+                    for (int k = nc; k < n2; k++) a[k] = conjf(row[n2 - k]);
+                    fft1d_exec(&p2, b, a, sign);
+                    float *rr = (float *)row;
+                    for (int k = 0; k < n2; k++) rr[k] = crealf(b[k]);
+                }
+        }
+        free(a); free(b);
+    }
+    free(p0.tw); free(p1.tw); free(p2.tw);
+}
+
+/* ---------------------------------------------------------- MKL back-end */
+typedef long (*dfti_create_md_t)(void **, int, long, long *);
+typedef long (*dfti_set_t)(void *, int, ...);
+typedef long (*dfti_commit_t)(void *);
+typedef long (*dfti_compute_t)(void *, void *, ...);
+typedef long (*dfti_free_t)(void **);
+static struct {
+    int tried, ok;
+    dfti_create_md_t create;
+    dfti_set_t set;
+    dfti_commit_t commit;
+    dfti_compute_t fwd, bwd;
+    dfti_free_t free_;
+} mkl;
+enum { DFTI_PLACEMENT = 11, DFTI_INPUT_STRIDES = 12, DFTI_OUTPUT_STRIDES = 13,
+       DFTI_CONJUGATE_EVEN_STORAGE = 10, DFTI_PACKED_FORMAT = 21, DFTI_THREAD_LIMIT = 27,
+       DFTI_REAL = 33, DFTI_COMPLEX_COMPLEX = 39, DFTI_INPLACE = 43, DFTI_CCE_FORMAT = 57 };
+
+static int mkl_load(void) {
+    if (mkl.tried) return mkl.ok;
+    mkl.tried = 1;
+    const char *sel = getenv("ORACLE_FFT");
+    if (sel && strcmp(sel, "own") == 0) return 0;
+    const char *path = getenv("ORACLE_TORCH_LIB");
+    void *h = dlopen(path ? path : "libtorch_cpu.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return 0;
+    mkl.create = (dfti_create_md_t)dlsym(h, "DftiCreateDescriptor_s_md");
+    mkl.set = (dfti_set_t)dlsym(h, "DftiSetValue");
+    mkl.commit = (dfti_commit_t)dlsym(h, "DftiCommitDescriptor");
+    mkl.fwd = (dfti_compute_t)dlsym(h, "DftiComputeForward");
+    mkl.bwd = (dfti_compute_t)dlsym(h, "DftiComputeBackward");
+    mkl.free_ = (dfti_free_t)dlsym(h, "DftiFreeDescriptor");
+    mkl.ok = mkl.create && mkl.set && mkl.commit && mkl.fwd && mkl.bwd && mkl.free_;
+    return mkl.ok;
+}
+
+static int mkl_execute(const struct oracle_fftwf_plan_s *pl) {
+    void *d = NULL;
+    long len[3] = {pl->n0, pl->n1, pl->n2};
+    long nc = pl->n2 / 2 + 1;
+    long rs[4] = {0, (long)pl->n1 * 2 * nc, 2 * nc, 1};
+    long cs[4] = {0, (long)pl->n1 * nc, nc, 1};
+    if (mkl.create(&d, DFTI_REAL, 3, len) != 0) return -1;
+    long st = 0;
+    st |= mkl.set(d, DFTI_PLACEMENT, DFTI_INPLACE);
+    st |= mkl.set(d, DFTI_CONJUGATE_EVEN_STORAGE, DFTI_COMPLEX_COMPLEX);
+    st |= mkl.set(d, DFTI_PACKED_FORMAT, DFTI_CCE_FORMAT);
+    st |= mkl.set(d, DFTI_THREAD_LIMIT, (long)fft_threads());
+    if (!pl->inverse) {
+        st |= mkl.set(d, DFTI_INPUT_STRIDES, rs);
+        st |= mkl.set(d, DFTI_OUTPUT_STRIDES, cs);
+    } else {
+        st |= mkl.set(d, DFTI_INPUT_STRIDES, cs);
+        st |= mkl.set(d, DFTI_OUTPUT_STRIDES, rs);
+    }
+    st |= mkl.commit(d);
+    if (st == 0) st = pl->inverse ? mkl.bwd(d, pl->data) : mkl.fwd(d, pl->data);
+    mkl.free_(&d);
+    return st == 0 ? 0 : -1;
+}
+
+/* ------------------------------------------------------------- FFTW API */
+void *fftwf_malloc(size_t n) {
+    void *p = NULL;
+    if (posix_memalign(&p, 64, n ? n : 64) != 0) return NULL;
+    return p;
+}
+void fftwf_free(void *p) { free(p); }
+static fftwf_plan mkplan(int n0, int n1, int n2, void *data, int inverse) {
+    fftwf_plan p = (fftwf_plan)malloc(sizeof(*p));
+    p->n0 = n0; p->n1 = n1; p->n2 = n2; p->data = data; p->inverse = inverse;
+    return p;
+}
+fftwf_plan fftwf_plan_dft_r2c_3d(int n0, int n1, int n2, float *in, fftwf_complex *out, unsigned f) {
+    (void)f;
+    if ((void *)in != (void *)out) { fprintf(stderr, "oracle fftw shim: in-place only\n"); abort(); }
+    return mkplan(n0, n1, n2, in, 0);
+}
+fftwf_plan fftwf_plan_dft_c2r_3d(int n0, int n1, int n2, fftwf_complex *in, float *out, unsigned f) {
+    (void)f;
+    if ((void *)in != (void *)out) { fprintf(stderr, "oracle fftw shim: in-place only\n"); abort(); }
+    return mkplan(n0, n1, n2, in, 1);
+}
+void fftwf_execute(const fftwf_plan p) {
+    if (mkl_load() && mkl_execute(p) == 0) return;
+    own_execute(p);
+}
+void fftwf_destroy_plan(fftwf_plan p) { free(p); }
+void fftwf_cleanup(void) {}
+void fftwf_cleanup_threads(void) {}
+void fftwf_forget_wisdom(void) {}
+int fftwf_init_threads(void) { return 1; }
+void fftwf_plan_with_nthreads(int n) { (void)n; }
+int fftwf_import_wisdom_from_filename(const char *fn) { (void)fn; return 0; }
+int fftwf_export_wisdom_to_filename(const char *fn) { (void)fn; return 1; }
+/* which back-end will run (1 = mkl, 0 = own); exported for the harness / bench labels */
+int oracle_fft_backend_is_mkl(void) { return mkl_load(); }
