@@ -40,7 +40,7 @@ class Backend:
                 "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
                 "There is no CPU fallback.")
         self.path = path
-        self.lib = lib = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+        self.lib = lib = C.CDLL(str(path), mode=C.RTLD_LOCAL)
         P = C.POINTER
         lib.ComputeInitialConditions.argtypes = [C.c_ulonglong, P(_abi.InitialConditionsStruct)]
         lib.ComputePerturbedField.argtypes = [C.c_float, P(_abi.InitialConditionsStruct),

@@ -1,0 +1,566 @@
+/* fft.cu -- batched shared-memory Stockham FFTs and the 3-D r2c / c2r drivers (see fft.h). */
+#include "fft.h"
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+/* ------------------------------------------------------------------ complex helpers */
+DEV float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+/* multiply by -i*sign... : rot(a, s) = a * (s * i), s = +1 or -1 */
+DEV float2 crot(float2 a, int s) { return s > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+/* ------------------------------------------------------------------ small DFTs
+ * sign = -1 forward (exp(-i...)), +1 inverse. */
+DEV void bfly2(float2 *v) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+}
+DEV void bfly4(float2 *v, int sign) {
+    float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+    float2 c = cadd(v[1], v[3]), d = crot(csub(v[1], v[3]), sign);
+    v[0] = cadd(a, c);
+    v[1] = cadd(b, d);
+    v[2] = csub(a, c);
+    v[3] = csub(b, d);
+}
+DEV void bfly8(float2 *v, int sign) {
+    const float h = 0.70710678118654752440f;
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    bfly4(e, sign);
+    bfly4(o, sign);
+    /* W8^k * o[k], W8 = exp(sign * 2 pi i / 8) */
+    float2 t1 = make_float2(h * (o[1].x - sign * o[1].y), h * (o[1].y + sign * o[1].x));
+    float2 t2 = crot(o[2], sign);
+    float2 t3 = make_float2(h * (-o[3].x - sign * o[3].y), h * (-o[3].y + sign * o[3].x));
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], t1);   v[5] = csub(e[1], t1);
+    v[2] = cadd(e[2], t2);   v[6] = csub(e[2], t2);
+    v[3] = cadd(e[3], t3);   v[7] = csub(e[3], t3);
+}
+DEV void bfly3(float2 *v, int sign) {
+    const float s3 = 0.86602540378443864676f;
+    float2 t1 = cadd(v[1], v[2]);
+    float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+    float2 d = csub(v[1], v[2]);
+    float2 t3 = crot(make_float2(s3 * d.x, s3 * d.y), sign); /* sign*i*s3*(b-c) */
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(t2, t3);
+    v[2] = csub(t2, t3);
+}
+/* generic odd radix by direct summation; cs/sn hold cos/sin(2 pi m / R) */
+template <int R> DEV void bfly_generic(float2 *v, int sign, const float *cs, const float *sn) {
+    float2 out[R];
+#pragma unroll
+    for (int p = 0; p < R; p++) {
+        float2 acc = v[0];
+#pragma unroll
+        for (int q = 1; q < R; q++) {
+            int m = (p * q) % R;
+            float2 w = make_float2(cs[m], sign * sn[m]);
+            acc = cadd(acc, cmul(v[q], w));
+        }
+        out[p] = acc;
+    }
+#pragma unroll
+    for (int p = 0; p < R; p++) v[p] = out[p];
+}
+#ifndef B200_EMU
+__device__ const float c5_cs[5] = {1.f, 0.30901699437494742410f, -0.80901699437494742410f,
+                                   -0.80901699437494742410f, 0.30901699437494742410f};
+__device__ const float c5_sn[5] = {0.f, 0.95105651629515357212f, 0.58778525229247312917f,
+                                   -0.58778525229247312917f, -0.95105651629515357212f};
+__device__ const float c7_cs[7] = {1.f, 0.62348980185873353053f, -0.22252093395631440429f,
+                                   -0.90096886790241912624f, -0.90096886790241912624f,
+                                   -0.22252093395631440429f, 0.62348980185873353053f};
+__device__ const float c7_sn[7] = {0.f, 0.78183148246802980871f, 0.97492791218182360702f,
+                                   0.43388373911755812048f, -0.43388373911755812048f,
+                                   -0.97492791218182360702f, -0.78183148246802980871f};
+#else
+static const float c5_cs[5] = {1.f, 0.30901699437494742410f, -0.80901699437494742410f,
+                               -0.80901699437494742410f, 0.30901699437494742410f};
+static const float c5_sn[5] = {0.f, 0.95105651629515357212f, 0.58778525229247312917f,
+                               -0.58778525229247312917f, -0.95105651629515357212f};
+static const float c7_cs[7] = {1.f, 0.62348980185873353053f, -0.22252093395631440429f,
+                               -0.90096886790241912624f, -0.90096886790241912624f,
+                               -0.22252093395631440429f, 0.62348980185873353053f};
+static const float c7_sn[7] = {0.f, 0.78183148246802980871f, 0.97492791218182360702f,
+                               0.43388373911755812048f, -0.43388373911755812048f,
+                               -0.97492791218182360702f, -0.78183148246802980871f};
+#endif
+
+template <int R> DEV void small_dft(float2 *v, int sign);
+template <> DEV void small_dft<2>(float2 *v, int) { bfly2(v); }
+template <> DEV void small_dft<3>(float2 *v, int sign) { bfly3(v, sign); }
+template <> DEV void small_dft<4>(float2 *v, int sign) { bfly4(v, sign); }
+template <> DEV void small_dft<5>(float2 *v, int sign) { bfly_generic<5>(v, sign, c5_cs, c5_sn); }
+template <> DEV void small_dft<7>(float2 *v, int sign) { bfly_generic<7>(v, sign, c7_cs, c7_sn); }
+template <> DEV void small_dft<8>(float2 *v, int sign) { bfly8(v, sign); }
+
+/* ------------------------------------------------------------------ one Stockham stage
+ * Tile layout in shared memory: element i of line c lives at [i * Tp + c] (Tp = T + 1 pad).
+ * Work item w -> (line c = w % T, butterfly j = w / T) so that a warp touches consecutive
+ * addresses.  Ns = product of the radices already applied. */
+template <int R>
+DEV void stockham_stage(const float2 *src, float2 *dst, int n, int Ns, int T, int Tp,
+                        const float2 *__restrict__ tw, int sign) {
+    const int nb = n / R;
+    const int tws = n / (Ns * R);
+    for (int w = threadIdx.x; w < nb * T; w += blockDim.x) {
+        const int c = w % T, j = w / T;
+        const int k = j % Ns;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) v[q] = src[(j + q * nb) * Tp + c];
+        if (Ns > 1) {
+            const int t1 = k * tws;
+#pragma unroll
+            for (int q = 1; q < R; q++) {
+                float2 t = ldg(&tw[q * t1]);
+                if (sign > 0) t.y = -t.y;
+                v[q] = cmul(v[q], t);
+            }
+        }
+        small_dft<R>(v, sign);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; q++) dst[(j0 + q * Ns) * Tp + c] = v[q];
+    }
+}
+
+/* generic prime radix (11..31) with local arrays: rare sizes only */
+DEV void stockham_stage_any(int R, const float2 *src, float2 *dst, int n, int Ns, int T, int Tp,
+                            const float2 *__restrict__ tw, int sign) {
+    const int nb = n / R;
+    const int tws = n / (Ns * R);
+    const int rstep = n / R;
+    for (int w = threadIdx.x; w < nb * T; w += blockDim.x) {
+        const int c = w % T, j = w / T;
+        const int k = j % Ns;
+        float2 v[32];
+        for (int q = 0; q < R; q++) {
+            float2 a = src[(j + q * nb) * Tp + c];
+            if (q > 0 && Ns > 1) {
+                float2 t = ldg(&tw[q * k * tws]);
+                if (sign > 0) t.y = -t.y;
+                a = cmul(a, t);
+            }
+            v[q] = a;
+        }
+        const int j0 = (j - k) * R + k;
+        for (int p = 0; p < R; p++) {
+            float2 acc = v[0];
+            for (int q = 1; q < R; q++) {
+                float2 t = ldg(&tw[((p * q) % R) * rstep]);
+                if (sign > 0) t.y = -t.y;
+                acc = cadd(acc, cmul(v[q], t));
+            }
+            dst[(j0 + p * Ns) * Tp + c] = acc;
+        }
+    }
+}
+
+/* all stages; returns the buffer holding the result */
+DEV float2 *fft_tile(float2 *A, float2 *B, int n, int T, int Tp, const FftFactors &f,
+                     const float2 *__restrict__ tw, int sign) {
+    float2 *src = A, *dst = B;
+    int Ns = 1;
+    for (int s = 0; s < f.nf; s++) {
+        const int R = f.r[s];
+        switch (R) {
+            case 8: stockham_stage<8>(src, dst, n, Ns, T, Tp, tw, sign); break;
+            case 4: stockham_stage<4>(src, dst, n, Ns, T, Tp, tw, sign); break;
+            case 2: stockham_stage<2>(src, dst, n, Ns, T, Tp, tw, sign); break;
+            case 3: stockham_stage<3>(src, dst, n, Ns, T, Tp, tw, sign); break;
+            case 5: stockham_stage<5>(src, dst, n, Ns, T, Tp, tw, sign); break;
+            case 7: stockham_stage<7>(src, dst, n, Ns, T, Tp, tw, sign); break;
+            default: stockham_stage_any(R, src, dst, n, Ns, T, Tp, tw, sign); break;
+        }
+        __syncthreads();
+        Ns *= R;
+        float2 *t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+/* ------------------------------------------------------------------ strided-axis kernel */
+struct StridedArgs {
+    int n;                 /* line length */
+    long long line_stride; /* complex elements between consecutive points of a line */
+    int ncols;             /* lines per group (adjacent lines are 1 element apart) */
+    long long group_stride;
+    int T, Tp, sign;
+    float scale;
+    FftFactors f;
+    const float2 *tw;
+    /* KMUL geometry: the line axis is x; column m of a group is (y, kz) = (m / nzc, m % nzc) */
+    int kmul, filter_type, nx, ny, nz, nzc;
+    float R;
+    double R_param, r_const, dkx, dky, dkz;
+    int op, axis_a, axis_b;
+    double op_factor;
+};
+
+/* index_to_k (indexing.h:116-120): double wavenumber of a grid index */
+DEV double kd_of_index(int n, int dim, double dk) {
+    const double buf = (n <= dim / 2) ? n : (n - dim);
+    return buf * dk;
+}
+
+__global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restrict__ src,
+                                                          float2 *__restrict__ dst,
+                                                          StridedArgs a) {
+    DYN_SMEM(float2, smem);
+    float2 *A = smem, *B = smem + (size_t)a.n * a.Tp;
+    const int col0 = blockIdx.x * a.T;
+    const long long gbase = (long long)blockIdx.y * a.group_stride;
+    for (int w = threadIdx.x; w < a.n * a.T; w += blockDim.x) {
+        const int c = w % a.T, i = w / a.T;
+        const int col = col0 + c;
+        float2 v = make_float2(0.f, 0.f);
+        if (col < a.ncols) {
+            v = src[gbase + (long long)i * a.line_stride + col];
+            if (a.op != KOP_NONE) {
+                const int iy = col / a.nzc, iz = col - iy * a.nzc;
+                if (i == 0 && iy == 0 && iz == 0) {
+                    v = make_float2(0.f, 0.f);
+                } else if (a.op == KOP_VELOCITY_F) {
+                    /* float wavenumbers straight from index_to_k's double value */
+                    const float kv[3] = {(float)kd_of_index(i, a.nx, a.dkx), (float)kd_of_index(iy, a.ny, a.dky),
+                                         (float)kd_of_index(iz, a.nz, a.dkz)};
+                    const float ksq = kmag_sq_f(kv[0], kv[1], kv[2]);
+                    const double g = a.op_factor * (double)kv[a.axis_a] / (double)ksq;
+                    /* (re + i im) * (i g) */
+                    v = make_float2((float)(-(double)v.y * g), (float)((double)v.x * g));
+                } else {
+                    const double kv[3] = {kd_of_index(i, a.nx, a.dkx), kd_of_index(iy, a.ny, a.dky),
+                                          kd_of_index(iz, a.nz, a.dkz)};
+                    const double ksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+                    if (a.op == KOP_GRADIENT_D) {
+                        const double g = kv[a.axis_a] / ksq;
+                        v = make_float2((float)(-(double)v.y * g), (float)((double)v.x * g));
+                    } else {
+                        const double g = -kv[a.axis_a] * kv[a.axis_b] / ksq;
+                        v = make_float2((float)((double)v.x * g), (float)((double)v.y * g));
+                    }
+                }
+            }
+            if (a.kmul == KMUL_FILTER) {
+                const int iy = col / a.nzc, iz = col - iy * a.nzc;
+                const float kx = kf_of_index(i, a.nx, a.dkx);
+                const float ky = kf_of_index(iy, a.ny, a.dky);
+                const float kz = (float)((double)iz * a.dkz);
+                const double W = window_value(a.filter_type, kmag_sq_f(kx, ky, kz), a.R,
+                                              a.R_param, a.r_const);
+                v.x = (float)((double)v.x * W);
+                v.y = (float)((double)v.y * W);
+            }
+        }
+        A[i * a.Tp + c] = v;
+    }
+    __syncthreads();
+    const float2 *res = fft_tile(A, B, a.n, a.T, a.Tp, a.f, a.tw, a.sign);
+    for (int w = threadIdx.x; w < a.n * a.T; w += blockDim.x) {
+        const int c = w % a.T, i = w / a.T;
+        const int col = col0 + c;
+        if (col < a.ncols) {
+            float2 v = res[i * a.Tp + c];
+            if (a.scale != 1.f) { v.x *= a.scale; v.y *= a.scale; }
+            dst[gbase + (long long)i * a.line_stride + col] = v;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ z-axis kernels */
+struct ZArgs {
+    int n, nzc, nrows, L, Tp;
+    FftFactors f;
+    const float2 *tw;
+    float scale;
+    int clip;
+    float clip_lo, clip_hi;
+    float *minmax_partial;      /* [2 * gridDim.x] or null */
+    long long real_row_stride;  /* floats between rows of the real side */
+    float premul;
+};
+
+/* complex rows -> real rows (inverse).  Builds the full Hermitian line in shared memory. */
+__global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict__ src,
+                                                        float *__restrict__ dst, ZArgs a) {
+    DYN_SMEM(float2, smem);
+    float2 *A = smem, *B = smem + (size_t)a.n * a.Tp;
+    const long long row0 = (long long)blockIdx.x * a.L;
+    const int n = a.n, nzc = a.nzc;
+    for (int w = threadIdx.x; w < a.L * nzc; w += blockDim.x) {
+        const int k = w % nzc, l = w / nzc;
+        const long long row = row0 + l;
+        float2 v = make_float2(0.f, 0.f);
+        if (row < a.nrows) v = src[row * nzc + k];
+        if (k == 0 || 2 * k == n) v.y = 0.f;
+        A[k * a.Tp + l] = v;
+        if (k > 0 && 2 * k < n) A[(n - k) * a.Tp + l] = make_float2(v.x, -v.y);
+    }
+    __syncthreads();
+    const float2 *res = fft_tile(A, B, n, a.L, a.Tp, a.f, a.tw, +1);
+    float lmin = 3.0e38f, lmax = -3.0e38f;
+    for (int w = threadIdx.x; w < a.L * n; w += blockDim.x) {
+        const int z = w % n, l = w / n;
+        const long long row = row0 + l;
+        if (row < a.nrows) {
+            float val = res[z * a.Tp + l].x * a.scale;
+            lmin = fminf(lmin, val);
+            lmax = fmaxf(lmax, val);
+            if (a.clip) val = fmaxf(fminf(val, a.clip_hi), a.clip_lo);
+            dst[row * a.real_row_stride + z] = val;
+        }
+    }
+    if (a.minmax_partial) {
+        /* block reduction through shared memory (reuse A: all reads of res are done) */
+        __syncthreads();
+        float *red = reinterpret_cast<float *>(smem);
+        red[threadIdx.x] = lmin;
+        red[blockDim.x + threadIdx.x] = lmax;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) {
+                red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + s]);
+                red[blockDim.x + threadIdx.x] =
+                    fmaxf(red[blockDim.x + threadIdx.x], red[blockDim.x + threadIdx.x + s]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.minmax_partial[2 * blockIdx.x] = red[0];
+            a.minmax_partial[2 * blockIdx.x + 1] = red[blockDim.x];
+        }
+    }
+}
+
+/* real rows -> complex rows (forward) */
+__global__ void __launch_bounds__(256) fft_r2c_z_kernel(const float *__restrict__ src,
+                                                        float2 *__restrict__ dst, ZArgs a) {
+    DYN_SMEM(float2, smem);
+    float2 *A = smem, *B = smem + (size_t)a.n * a.Tp;
+    const long long row0 = (long long)blockIdx.x * a.L;
+    const int n = a.n, nzc = a.nzc;
+    for (int w = threadIdx.x; w < a.L * n; w += blockDim.x) {
+        const int z = w % n, l = w / n;
+        const long long row = row0 + l;
+        float val = 0.f;
+        if (row < a.nrows) {
+            val = src[row * a.real_row_stride + z];
+            if (a.premul != 1.f || a.clip) {
+                /* prepare_box_for_filtering (IonisationBox.c:343-346): double product, clamp */
+                double cc = (double)val * (double)a.premul;
+                if (a.clip) cc = fmax(fmin(cc, (double)a.clip_hi), (double)a.clip_lo);
+                val = (float)cc;
+            }
+        }
+        A[z * a.Tp + l] = make_float2(val, 0.f);
+    }
+    __syncthreads();
+    const float2 *res = fft_tile(A, B, n, a.L, a.Tp, a.f, a.tw, -1);
+    for (int w = threadIdx.x; w < a.L * nzc; w += blockDim.x) {
+        const int k = w % nzc, l = w / nzc;
+        const long long row = row0 + l;
+        if (row < a.nrows) {
+            float2 v = res[k * a.Tp + l];
+            if (a.scale != 1.f) { v.x *= a.scale; v.y *= a.scale; }
+            dst[row * nzc + k] = v;
+        }
+    }
+}
+
+/* min/max partials -> 2 floats */
+__global__ void minmax_finish_kernel(const float *__restrict__ partial, int nblocks,
+                                     float *__restrict__ out) {
+    DYN_SMEM(float, red);
+    float lmin = 3.0e38f, lmax = -3.0e38f;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+        lmin = fminf(lmin, partial[2 * i]);
+        lmax = fmaxf(lmax, partial[2 * i + 1]);
+    }
+    red[threadIdx.x] = lmin;
+    red[blockDim.x + threadIdx.x] = lmax;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + s]);
+            red[blockDim.x + threadIdx.x] =
+                fmaxf(red[blockDim.x + threadIdx.x], red[blockDim.x + threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = red[0];
+        out[1] = red[blockDim.x];
+    }
+}
+
+/* ------------------------------------------------------------------ plans */
+static bool factorize(int n, FftFactors &f) {
+    f.nf = 0;
+    int e = 0;
+    while (n % 2 == 0) { n /= 2; e++; }
+    int n8 = e / 3, rem = e % 3;
+    int n4 = 0, n2 = 0;
+    if (rem == 1) { if (n8 >= 1) { n8--; n4 = 2; } else n2 = 1; }
+    else if (rem == 2) n4 = 1;
+    for (int i = 0; i < n8; i++) f.r[f.nf++] = 8;
+    for (int i = 0; i < n4; i++) f.r[f.nf++] = 4;
+    for (int i = 0; i < n2; i++) f.r[f.nf++] = 2;
+    for (int p = 3; p <= 31; p += 2)
+        while (n % p == 0) {
+            if (f.nf >= FFT_MAX_FACTORS) return false;
+            f.r[f.nf++] = p;
+            n /= p;
+        }
+    return n == 1;
+}
+
+static std::map<int, Fft1D> g_plans1d;
+static std::map<std::tuple<int, int, int>, Fft3D *> g_plans3d;
+static DevBuf<float> g_minmax_partial;
+
+static Fft1D &plan1d(int n) {
+    auto it = g_plans1d.find(n);
+    if (it != g_plans1d.end()) return it->second;
+    Fft1D p;
+    p.n = n;
+    if (!factorize(n, p.f))
+        b200_throw(B200_ValueError, "FFT length %d has a prime factor > 31 (unsupported)", n);
+    std::vector<float2> tw(n);
+    for (int k = 0; k < n; k++) {
+        double ph = -2.0 * M_PI * (double)k / (double)n;
+        tw[k] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+    p.tw = (float2 *)dev_alloc(sizeof(float2) * n);
+    h2d(p.tw, tw.data(), sizeof(float2) * n);
+    dev_sync();
+    g_stats.h2d -= (long long)sizeof(float2) * n; /* plan tables are not per-call traffic */
+    return g_plans1d.emplace(n, p).first->second;
+}
+
+Fft3D *fft_plan(int nx, int ny, int nz) {
+    auto key = std::make_tuple(nx, ny, nz);
+    auto it = g_plans3d.find(key);
+    if (it != g_plans3d.end()) return it->second;
+    Fft3D *p = new Fft3D();
+    p->nx = nx; p->ny = ny; p->nz = nz; p->nzc = nz / 2 + 1;
+    p->px = plan1d(nx); p->py = plan1d(ny); p->pz = plan1d(nz);
+    g_plans3d[key] = p;
+    return p;
+}
+
+void fft_plans_drop() {
+    for (auto &kv : g_plans3d) delete kv.second;
+    g_plans3d.clear();
+    for (auto &kv : g_plans1d) dev_free(kv.second.tw);
+    g_plans1d.clear();
+    g_minmax_partial.release();
+}
+
+/* tile width: as many lines per CTA as fit ~72 KB (3 CTAs/SM), else 110 KB, else 220 KB */
+static int pick_tile(int n, int maxT) {
+    const size_t budgets[3] = {72 * 1024, 110 * 1024, 220 * 1024};
+    for (int b = 0; b < 3; b++)
+        for (int T = maxT; T >= 1; T >>= 1) {
+            size_t bytes = 2 * (size_t)n * (T + 1) * sizeof(float2);
+            if (bytes <= budgets[b] && (T >= 4 || b == 2 || T == maxT)) return T;
+        }
+    b200_throw(B200_ValueError, "FFT length %d does not fit in shared memory", n);
+}
+static size_t tile_smem(int n, int T) {
+    size_t b = 2 * (size_t)n * (T + 1) * sizeof(float2);
+    return b < 2048 ? 2048 : b;
+}
+
+#ifndef B200_EMU
+template <typename K> static void allow_smem(K kernel, size_t bytes) {
+    static std::map<const void *, size_t> done;
+    size_t &cur = done[(const void *)kernel];
+    if (bytes > cur && bytes > 48 * 1024) {
+        CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)bytes));
+        cur = bytes;
+    }
+}
+#else
+template <typename K> static void allow_smem(K, size_t) {}
+#endif
+
+static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long long line_stride,
+                        int ncols, long long group_stride, int ngroups, int sign, float scale,
+                        const KMul *km, const Fft3D *p3) {
+    StridedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = p1.n; a.line_stride = line_stride; a.ncols = ncols; a.group_stride = group_stride;
+    a.T = pick_tile(p1.n, 8); a.Tp = a.T + 1; a.sign = sign; a.scale = scale;
+    a.f = p1.f; a.tw = p1.tw;
+    a.kmul = KMUL_NONE;
+    a.op = KOP_NONE;
+    if (km && km->active()) {
+        a.kmul = km->kind; a.filter_type = km->filter_type;
+        a.nx = p3->nx; a.ny = p3->ny; a.nz = p3->nz; a.nzc = p3->nzc;
+        a.R = km->R; a.R_param = km->R_param; a.r_const = km->r_const;
+        a.dkx = km->dk[0]; a.dky = km->dk[1]; a.dkz = km->dk[2];
+        a.op = km->op; a.axis_a = km->axis_a; a.axis_b = km->axis_b; a.op_factor = km->op_factor;
+    }
+    size_t smem = tile_smem(a.n, a.T);
+    allow_smem(fft_strided_kernel, smem);
+    dim3 grid((ncols + a.T - 1) / a.T, ngroups, 1);
+    B200_LAUNCH(fft_strided_kernel, grid, 256, smem, src, dst, a);
+}
+
+void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZEpilogue &epi) {
+    const int nx = p->nx, ny = p->ny, nzc = p->nzc;
+    /* x: lines over (y,kz) flattened, stride ny*nzc; filter rides on the load */
+    run_strided(p->px, src, work, (long long)ny * nzc, ny * nzc, 0, 1, +1, 1.f, &km, p);
+    /* y: for each x, lines over kz, stride nzc */
+    run_strided(p->py, work, work, nzc, nzc, (long long)ny * nzc, nx, +1, 1.f, nullptr, p);
+    /* z: contiguous rows, complex -> real */
+    ZArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = p->nz; a.nzc = nzc; a.nrows = nx * ny;
+    a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
+    a.f = p->pz.f; a.tw = p->pz.tw;
+    a.scale = epi.scale; a.clip = epi.clip; a.clip_lo = epi.clip_lo; a.clip_hi = epi.clip_hi;
+    float *dst = epi.dst ? epi.dst : reinterpret_cast<float *>(work);
+    a.real_row_stride = epi.dst ? epi.dst_row_stride : 2LL * nzc;
+    const int nblocks = (a.nrows + a.L - 1) / a.L;
+    if (epi.minmax) {
+        g_minmax_partial.ensure(2 * (size_t)nblocks);
+        a.minmax_partial = g_minmax_partial;
+    }
+    size_t smem = tile_smem(a.n, a.L);
+    allow_smem(fft_c2r_z_kernel, smem);
+    B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, work, dst, a);
+    if (epi.minmax)
+        B200_LAUNCH(minmax_finish_kernel, dim3(1), 256, 2 * 256 * sizeof(float),
+                    (const float *)g_minmax_partial, nblocks, epi.minmax);
+}
+
+void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {
+    const int nx = p->nx, ny = p->ny, nzc = p->nzc;
+    ZArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = p->nz; a.nzc = nzc; a.nrows = nx * ny;
+    a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
+    a.f = p->pz.f; a.tw = p->pz.tw;
+    a.scale = 1.f; a.premul = pro.premul; a.clip = pro.clip;
+    a.clip_lo = pro.clip_lo; a.clip_hi = pro.clip_hi;
+    const float *src = pro.src ? pro.src : reinterpret_cast<const float *>(box);
+    a.real_row_stride = pro.src ? pro.src_row_stride : 2LL * nzc;
+    const int nblocks = (a.nrows + a.L - 1) / a.L;
+    size_t smem = tile_smem(a.n, a.L);
+    allow_smem(fft_r2c_z_kernel, smem);
+    B200_LAUNCH(fft_r2c_z_kernel, dim3(nblocks), 256, smem, src, box, a);
+    run_strided(p->py, box, box, nzc, nzc, (long long)ny * nzc, nx, -1, 1.f, nullptr, p);
+    run_strided(p->px, box, box, (long long)ny * nzc, ny * nzc, 0, 1, -1, pro.post_scale, nullptr, p);
+}

@@ -1,0 +1,145 @@
+/*
+ * fft.h -- the library's own 3-D real<->complex FFT (replaces dft_r2c_cube / dft_c2r_cube,
+ * reference dft.c:18-72, and carries filter_box, filtering.c:308-394, in its load stage).
+ *
+ * Layout: FFTW's in-place convention, which the reference uses everywhere
+ * (indexing.h:84-98): complex box [nx][ny][nzc] (nzc = nz/2+1) aliasing the padded real box
+ * [nx][ny][2*nzc].  Transforms are unnormalised in both directions, like FFTW.
+ *
+ * Algorithm: three passes of batched 1-D Stockham autosort FFTs held entirely in shared memory
+ * (mixed radix 8/4/2/3/5/7 + generic small primes), one pass per axis:
+ *   x, y axes : strided lines; a CTA owns a tile of T adjacent lines so that every global
+ *               row access is T*8 contiguous bytes
+ *   z axis    : contiguous lines; the real<->complex conversion, scaling, clipping and the
+ *               global min/max reduction ride along in the load/store stages.
+ */
+#pragma once
+#include "rt.h"
+
+#define FFT_MAX_FACTORS 16
+struct FftFactors {
+    int nf;
+    int r[FFT_MAX_FACTORS];
+};
+
+struct Fft1D {
+    int n = 0;
+    FftFactors f;
+    float2 *tw = nullptr; /* device, n entries: exp(-2 pi i k / n) */
+};
+
+struct Fft3D {
+    int nx, ny, nz, nzc;
+    Fft1D px, py, pz;
+    size_t n_real() const { return (size_t)nx * ny * nz; }
+    size_t n_cplx() const { return (size_t)nx * ny * nzc; }
+    size_t n_padded() const { return (size_t)nx * ny * 2 * nzc; }
+};
+
+/* k-space multipliers applied while the x-pass of a c2r transform loads its lines.  A
+   derivative operator (if any) is applied first and rounded to float, then the window (if any),
+   which reproduces the reference's separate passes over the complex float box. */
+enum { KMUL_NONE = 0, KMUL_FILTER = 1 };
+enum {
+    KOP_NONE = 0,
+    KOP_VELOCITY_F = 1, /* delta_k * (c * i k_a / k^2), k in float  (PerturbedField.c:320-350) */
+    KOP_GRADIENT_D = 2, /* delta_k * (i k_a / k^2), k in double, DC -> 0 (InitialConditions.c:240-267) */
+    KOP_LAPLACIAN_D = 3 /* delta_k * (-k_a k_b / k^2), DC -> 0          (InitialConditions.c:269-297) */
+};
+struct KMul {
+    int kind = KMUL_NONE;      /* window on/off */
+    int filter_type = 0;       /* 0 real-space top-hat, 1 sharp-k, 2 gaussian, 3 exp-mfp, 4 shell */
+    float R = 0.f;             /* filter_box takes float R (filtering.c:308) */
+    double R_param = 0.;       /* mfp (type 3) or inner radius (type 4) */
+    double r_const = 0.;       /* exp(-R/R_param) for type 3 */
+    double dk[3] = {0, 0, 0};  /* 2 pi / box length per axis (filtering.c:310-314) */
+    int op = KOP_NONE;         /* derivative operator */
+    int axis_a = 0, axis_b = 0;
+    double op_factor = 1.;     /* c in KOP_VELOCITY_F */
+    bool active() const { return kind != KMUL_NONE || op != KOP_NONE; }
+};
+
+/* what the last (z) pass of a c2r transform does with each real value */
+struct ZEpilogue {
+    float scale = 1.f;          /* multiply (e.g. 1/VOLUME) */
+    int clip = 0;               /* clamp to [clip_lo, clip_hi] after min/max were taken */
+    float clip_lo = 0.f, clip_hi = 0.f;
+    float *minmax = nullptr;    /* device float[2]: global min / max of the unclipped values */
+    float *dst = nullptr;       /* optional separate real destination (else in place, padded) */
+    long long dst_row_stride = 0; /* floats between consecutive (x,y) rows of dst */
+};
+
+/* what the first (z) pass of an r2c transform does while loading real rows */
+struct ZPrologue {
+    const float *src = nullptr;   /* real source (else in place, padded) */
+    long long src_row_stride = 0; /* floats between consecutive rows of src */
+    float premul = 1.f;           /* value * premul, then clamp if clip */
+    int clip = 0;
+    float clip_lo = 0.f, clip_hi = 0.f;
+    float post_scale = 1.f;       /* applied to the complex output of the whole 3-D transform */
+};
+
+Fft3D *fft_plan(int nx, int ny, int nz);
+
+/* forward: real (padded or pro.src) -> complex in `box` */
+void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro);
+/* inverse: complex `src` -> real in `work` (src may equal work); optional k-space multiplier */
+void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZEpilogue &epi);
+
+/* Restatement of the reference's window functions (filtering.c:18-117) with the arithmetic
+   types of the -Ofast x86-64 build of filter_box (filtering.c:331-381): |k|^2 is accumulated in
+   float, kR = (float)(sqrt((double)k2) * (double)R), the window is evaluated in double and the
+   complex float mode is multiplied in double and rounded once. */
+HD double window_value(int type, float kmag_sq, float R, double R_param, double r_const) {
+    if (type == 0) {  /* real-space top-hat: 3 (sin x - x cos x) / x^3, Taylor below 1e-4 */
+        float kRf = (float)(sqrt((double)kmag_sq) * (double)R);
+        double x = (double)kRf;
+        double x2 = x * x;
+        if (x < 1e-4) return 1.0 - x2 * 0.1;
+        double s, c;
+        sincos(x, &s, &c);
+        return (3.0 / (x2 * x)) * (s - x * c);
+    } else if (type == 1) {  /* sharp-k: zero above kR = (9 pi / 2)^(1/3) */
+        float kRf = (float)(sqrt((double)kmag_sq) * (double)R);
+        return ((double)kRf * 0.413566994 > 1.0) ? 0.0 : 1.0;
+    } else if (type == 2) {  /* gaussian: the reference passes (kR)^2 held in a float */
+        float kR2 = kmag_sq * (R * R); /* -Ofast hoists R*R (float) out of the loop */
+        return exp(-0.643 * 0.643 * (double)kR2 / 2.);
+    } else if (type == 3) {  /* exponentially attenuated top-hat (Davies & Furlanetto) */
+        double k = sqrt((double)kmag_sq);
+        double kR = k * (double)R, ratio = R_param / (double)R;
+        if (kR < 1e-4) {
+            double r2 = ratio * ratio, r3 = r2 * ratio;
+            double ts_0 = 6 * r3 - r_const * (6 * r3 + 6 * r2 + 3 * ratio);
+            return ts_0 + (r_const * (2 * r2 + 0.5 * ratio) - 2 * ts_0 * r2) * kR * kR;
+        }
+        double r2 = ratio * ratio, s, c;
+        sincos(kR, &s, &c);
+        double f = (kR * kR * r2 + 2 * ratio + 1) * ratio * c;
+        f += (kR * kR * (r2 - r2 * ratio) + ratio + 1) * s / kR;
+        f *= r_const;
+        f -= 2 * r2;
+        double den = kR * ratio * kR * ratio + 1;
+        f *= -3 * ratio / (den * den);
+        return f;
+    } else if (type == 4) {  /* spherical shell between R_param (inner) and R (outer) */
+        double k = sqrt((double)kmag_sq);
+        double ko = k * (double)R, ki = k * R_param;
+        if (ko < 1e-4) {
+            double q = R_param / (double)R;
+            return 1. - ko * ko / 10 * (q * q * q * q * q - 1) / (q * q * q - 1);
+        }
+        return 3.0 / (ko * ko * ko - ki * ki * ki) * (sin(ko) - cos(ko) * ko - sin(ki) + cos(ki) * ki);
+    }
+    return 1.0;
+}
+
+/* float wavenumber of grid index n on an axis of `dim` cells: the reference computes
+   (float)(n_signed * delta_k) with delta_k a double (filtering.c:338-352). */
+HD float kf_of_index(int n, int dim, double dk) {
+    int ns = (n > dim / 2) ? n - dim : n;
+    return (float)((double)ns * dk);
+}
+DEV float kmag_sq_f(float kx, float ky, float kz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
+}

@@ -1,0 +1,509 @@
+/*
+ * ionize.cu -- ComputeIonizedBox: excursion-set ionisation field (reference IonisationBox.c).
+ *
+ * Scope: SOURCE_MODEL in {CONST-ION-EFF, E-INTEGRAL}, USE_TS_FLUCT off,
+ * RECOMB_MODEL none, no mini-halos, centre-cell flagging.  Other branches return ValueError.
+ *
+ * Data flow per call (all grids stay in HBM; the k-space density is transformed once and stays
+ * resident across the whole radius ladder):
+ *
+ *   density (host) --H2D--> r2c with clip / (1/N) fused          [prepare_box_for_filtering]
+ *   for R from largest to smallest:
+ *     c2r with W(kR) multiplied on load, clip + global min/max in the epilogue
+ *                                                   [copy_filter_transform + clip_and_get_extrema]
+ *     2 floats D2H -> host builds the 400-point f_coll(delta) table -> 1.6 KB H2D
+ *                                                   [setup_integration_tables]
+ *     sweep 1: table lookup per cell, deterministic double sum  [calculate_fcoll_grid]
+ *     sweep 2: lookup again (float-rounded like the stored grid), mean fix, barrier test,
+ *              flags / z_reion / partial ionisation             [find_ionised_regions]
+ *   temperatures of ionised cells, D2H of the outputs           [set_ionized_temperatures]
+ *
+ * The f_coll grid is never materialised except for the radius whose values the reference
+ * leaves in `unnormalised_nion`: sweep 2 recomputes the lookup instead of re-reading 4N bytes.
+ */
+#include "fft.h"
+#include "host_physics.h"
+
+#include <vector>
+
+#define HII_ROUND_ERR (1e-5)
+
+struct IonConsts {
+    double redshift, stored_redshift, prev_redshift, growth_factor;
+    bool mass_dep_zeta;
+    int hii_filter;
+    ScalingConstants sc;
+    double T_re, ion_eff_factor, ion_eff_factor_gl;
+    double TK_nofluct, adia_TK_term;
+    double M_min, lnMmin, lnMmax_gl, sigma_minmass, pixel_length;
+};
+struct RadiusSpec {
+    double R, M_max_R, ln_M_max_R, sigma_maxmass;
+    int R_index;
+};
+
+static void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
+    /* IonisationBox.c:125-227 (photon-conservation and recombination terms are out of scope) */
+    c->redshift = redshift;
+    c->prev_redshift = prev_redshift;
+    c->stored_redshift = redshift;
+    set_scaling_constants(redshift, &c->sc);
+    c->growth_factor = dicke(redshift);
+    c->mass_dep_zeta = matter_options_global->SOURCE_MODEL != SRC_CONST_ION_EFF;
+    c->hii_filter = astro_options_global->HII_FILTER;
+    c->T_re = astro_params_global->T_RE;
+    if (c->mass_dep_zeta)
+        c->ion_eff_factor_gl = c->sc.pop2_ion * c->sc.fstar_10 * c->sc.fesc_10;
+    else
+        c->ion_eff_factor_gl = astro_params_global->HII_EFF_FACTOR;
+    c->ion_eff_factor = c->ion_eff_factor_gl;
+    c->M_min = minimum_source_mass(redshift, false);
+    c->lnMmin = log(c->M_min);
+    c->lnMmax_gl = log(pc::M_MAX_INTEGRAL);
+    c->sigma_minmass = sigma_z0(c->M_min);
+    c->TK_nofluct = T_RECFAST(redshift);
+    c->adia_TK_term = cT_approx(redshift);
+    c->pixel_length = simulation_options_global->BOX_LEN / (double)simulation_options_global->HII_DIM;
+}
+
+static std::vector<RadiusSpec> setup_radii(const IonConsts &c) { /* IonisationBox.c:964-1006 */
+    const AstroParams *ap = astro_params_global;
+    const double maximum_radius = fmin(ap->R_BUBBLE_MAX, pc::l_factor * simulation_options_global->BOX_LEN);
+    const double minimum_radius = fmax(ap->R_BUBBLE_MIN, pc::l_factor * c.pixel_length);
+    int n_radii = (int)(log(maximum_radius / minimum_radius) / log(ap->DELTA_R_HII_FACTOR) + 1);
+    std::vector<RadiusSpec> r;
+    for (int i = 0; i < n_radii; i++) {
+        RadiusSpec s;
+        s.R_index = i;
+        s.R = minimum_radius * pow(ap->DELTA_R_HII_FACTOR, i);
+        if (s.R > maximum_radius - pc::FRACT_FLOAT_ERR) {
+            s.R = maximum_radius;
+            n_radii = i + 1;
+        }
+        s.M_max_R = RtoM(s.R);
+        s.ln_M_max_R = log(s.M_max_R);
+        s.sigma_maxmass = sigma_z0(s.M_max_R);
+        r.push_back(s);
+    }
+    return r;
+}
+
+/* ------------------------------------------------------------------ device side */
+struct DevTable {
+    double x_min, x_width;
+    int log_valued;
+    float y[N_DENS_INTERP];
+};
+
+/* EvaluateRGTable1D_f (interpolation.c:123-131) on a table staged in shared memory */
+DEV double table_eval(double x, double x_min, double x_width, const float *y) {
+    const int idx = (int)floor((x - x_min) / x_width);
+    const double table_val = x_min + x_width * (float)idx;
+    const double t = (x - table_val) / x_width;
+    return (double)y[idx] * (1 - t) + (double)y[idx + 1] * t;
+}
+DEV double fcoll_of_delta(float dens, const DevTable *hdr, const float *y) {
+    const double v = table_eval((double)dens, hdr->x_min, hdr->x_width, y);
+    return hdr->log_valued ? exp(v) : v;
+}
+
+struct SweepArgs {
+    int nx, ny, nz, nzc;
+    const float *filtered;   /* padded real rows, already clipped to [-1, 1e6] */
+    const DevTable *table;
+    double *partial;         /* [gridDim.x] block sums */
+    float *nion_out;         /* unnormalised_nion[0] or null */
+};
+
+/* sweep 1: f_coll per cell + block partial sums (calculate_fcoll_grid, IonisationBox.c:773-962) */
+__global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
+    DYN_SMEM(float, ytab);
+    __shared__ double red[256];
+    for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) ytab[i] = a.table->y[i];
+    __syncthreads();
+    const long long nrows = (long long)a.nx * a.ny;
+    const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
+    double acc = 0.;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const float *src = a.filtered + row * 2 * a.nzc;
+        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
+            const float d = fmaxf(src[z], dens_floor);
+            const double fc = fcoll_of_delta(d, a.table, ytab);
+            acc += fc;
+            if (a.nion_out) a.nion_out[row * a.nz + z] = (float)fc;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
+}
+
+/* fixed-order finish so the grid mean is bit-reproducible run to run */
+__global__ void sum_finish_kernel(const double *partial, int n, double *out) {
+    __shared__ double red[256];
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+struct CritArgs {
+    int nx, ny, nz, nzc;
+    const float *filtered;
+    const DevTable *table;
+    const double *fcoll_total;
+    const float *density;    /* unfiltered perturbed density, unpadded */
+    const float *prev_zre;   /* previous box z_reion or null (= all -1) */
+    float *xH, *z_reion, *Tk;
+    double n_cells, mean_f_coll, f_limit, ion_eff_factor;
+    int mass_dep_zeta, last_radius, R_index;
+    double redshift, TK_nofluct, adia_TK_term, T_re;
+};
+
+DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { /* thermochem.c:58-63 */
+    if (res_xH <= 0.) return T_re;
+    if (res_xH >= 1) return T_HI;
+    return T_HI * res_xH + T_re * (1. - res_xH);
+}
+
+/* sweep 2: find_ionised_regions (IonisationBox.c:1008-1201), centre-cell method */
+__global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
+    DYN_SMEM(float, ytab);
+    for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) ytab[i] = a.table->y[i];
+    __syncthreads();
+    /* grid mean with the reference's floor (IonisationBox.c:1566-1576), then the mean fix */
+    double grid_mean = *a.fcoll_total / a.n_cells;
+    if (a.mass_dep_zeta) {
+        if (grid_mean <= a.f_limit) grid_mean = a.f_limit;
+    } else {
+        if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
+    }
+    const double mean_fix = a.mean_f_coll / grid_mean;
+    const long long nrows = (long long)a.nx * a.ny;
+    const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const float *src = a.filtered + row * 2 * a.nzc;
+        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
+            const long long idx = row * a.nz + z;
+            const float d = fmaxf(src[z], dens_floor);
+            /* the reference reads f_coll back from the float grid it stored in sweep 1 */
+            double curr_fcoll = (double)(float)fcoll_of_delta(d, a.table, ytab);
+            curr_fcoll = mean_fix * curr_fcoll;
+            if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
+            if (curr_fcoll * a.ion_eff_factor > 1.0) {
+                const float pz = a.prev_zre ? a.prev_zre[idx] : -1.f;
+                a.z_reion[idx] = (pz < 0) ? (float)a.redshift : pz;
+                a.xH[idx] = 0.f;
+            } else if (a.R_index == 0 && (a.xH[idx] > pc::TINY)) {
+                double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
+                if (a.Tk) {
+                    const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
+                    a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
+                }
+                if (res_xH < 0) res_xH = 0;
+                else if (res_xH > 1) res_xH = 1;
+                a.xH[idx] = (float)res_xH;
+            }
+        }
+    }
+}
+
+DEV float fully_ionized_temperature(float z_re, float z, float delta, float T_re) { /* thermochem.c:31-56 */
+    float result, delta_re;
+    if (fabs(z - z_re) < 1e-4)
+        result = 1;
+    else {
+        delta_re = delta * (1. + z) / (1. + z_re);
+        if (delta_re <= -1) delta_re = -1. + 9e-8;
+        if (delta <= -1) delta = -1. + 9e-8;
+        result = pow((1. + delta) / (1. + delta_re), 1.1333);
+        result *= pow((1. + z) / (1. + z_re), 3.4);
+        result *= expf(pow((1. + z) / 7.1, 2.5) - pow((1. + z_re) / 7.1, 2.5));
+    }
+    result *= pow((double)T_re, 1.7);
+    result += pow(1e4 * ((1. + z) / 4.), 1.7) * (1 + delta);
+    result = pow((double)result, 0.5882);
+    return result;
+}
+
+struct TempArgs {
+    long long n;
+    const float *xH, *z_reion, *density;
+    float *Tk;
+    int *nonfinite;
+    double stored_redshift, T_re, TK_nofluct, adia_TK_term;
+};
+/* set_ionized_temperatures (IonisationBox.c:1203-1256) */
+__global__ void __launch_bounds__(256) ionized_temperature_kernel(TempArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float tk = a.Tk[i];
+        if ((a.z_reion[i] > 0) && (a.xH[i] < pc::TINY)) {
+            tk = fully_ionized_temperature(a.z_reion[i], (float)a.stored_redshift, a.density[i], (float)a.T_re);
+            const float thistk = a.TK_nofluct * (1 + a.adia_TK_term * a.density[i]);
+            if (tk < thistk) tk = thistk;
+            a.Tk[i] = tk;
+        }
+        if (!isfinite(tk)) *a.nonfinite = 1;
+    }
+}
+
+struct FillArgs {
+    long long n;
+    float *p;
+    float v;
+};
+__global__ void fill_kernel(FillArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x)
+        a.p[i] = a.v;
+}
+
+struct NeutralArgs {
+    long long n;
+    const float *density;
+    float *xH, *Tk;
+    float xH_val;
+    double TK_nofluct, adia_TK_term;
+};
+/* set_fully_neutral_box (IonisationBox.c:531-565), no-Ts branch */
+__global__ void neutral_box_kernel(NeutralArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        a.xH[i] = a.xH_val;
+        if (a.Tk) a.Tk[i] = a.TK_nofluct * (1.0 + a.adia_TK_term * a.density[i]);
+    }
+}
+
+/* ------------------------------------------------------------------ orchestration */
+static int grid_for(long long n_items, int per_block) {
+    long long want = (n_items + per_block - 1) / per_block;
+    long long cap = (long long)dev_num_sms() * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+struct IonDeviceIO {
+    const float *density;   /* device, N */
+    const float *prev_zre;  /* device or null */
+    float *xH, *z_reion, *Tk, *nion; /* device, N each; Tk / nion may be null */
+};
+
+static void ionize_core(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box) {
+    const SimulationOptions *so = simulation_options_global;
+    const AstroOptions *ao = astro_options_global;
+    const MatterOptions *mo = matter_options_global;
+    if (mo->SOURCE_MODEL != SRC_CONST_ION_EFF && mo->SOURCE_MODEL != SRC_E_INTEGRAL)
+        b200_throw(B200_ValueError, "SOURCE_MODEL=%d: only CONST-ION-EFF and E-INTEGRAL are in scope", mo->SOURCE_MODEL);
+    if (ao->USE_TS_FLUCT || ao->RECOMB_MODEL != 0 || ao->USE_MINI_HALOS || ao->IONISE_ENTIRE_SPHERE ||
+        ao->PHOTON_CONS_TYPE != 0)
+        b200_throw(B200_ValueError, "USE_TS_FLUCT / RECOMB_MODEL / USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / "
+                                    "photon conservation are outside the scoped IonizeBox path");
+    if (mo->SOURCE_MODEL == SRC_E_INTEGRAL && mo->USE_INTERPOLATION_TABLES != 2)
+        b200_throw(B200_ValueError, "E-INTEGRAL needs USE_INTERPOLATION_TABLES='hmf-interpolation' in this build");
+    if (mo->SOURCE_MODEL == SRC_CONST_ION_EFF && mo->USE_INTERPOLATION_TABLES != 2)
+        b200_throw(B200_ValueError, "CONST-ION-EFF needs USE_INTERPOLATION_TABLES='hmf-interpolation' in this build");
+
+    const double redshift = redshift_f, prev_redshift = prev_redshift_f;
+    IonConsts c;
+    set_ionbox_constants(redshift, prev_redshift, &c);
+    const int nx = so->HII_DIM, ny = so->HII_DIM, nz = hii_d_para();
+    const long long N = (long long)nx * ny * nz;
+    Fft3D *plan = fft_plan(nx, ny, nz);
+
+    { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
+
+    std::vector<RadiusSpec> radii = setup_radii(c);
+    const int n_radii = (int)radii.size();
+
+    /* box-level scalars (IonisationBox.c:1431-1455) */
+    double Mturn_avg;
+    if (c.mass_dep_zeta) {
+        Mturn_avg = astro_params_global->M_TURN;
+        box->log10_Mturnover_ave = log10(Mturn_avg);
+    } else {
+        Mturn_avg = c.M_min;
+        box->log10_Mturnover_ave = log10(c.M_min);
+    }
+    box->log10_Mturnover_MINI_ave = 0.0;
+    const int method = ao->INTEGRATION_METHOD_ATOMIC;
+    if (method == INTEG_GL) initialise_GL(c.lnMmin, c.lnMmax_gl);
+
+    /* set_mean_fcoll (IonisationBox.c:468-529) */
+    double f_limit = 0.;
+    if (c.mass_dep_zeta) {
+        box->mean_f_coll = Nion_General(redshift, c.lnMmin, c.lnMmax_gl, Mturn_avg, &c.sc);
+        f_limit = Nion_General(so->Z_HEAT_MAX, c.lnMmin, c.lnMmax_gl, Mturn_avg, &c.sc);
+    } else {
+        box->mean_f_coll = Fcoll_General(redshift, c.lnMmin, c.lnMmax_gl);
+        f_limit = Fcoll_General(so->Z_HEAT_MAX, c.lnMmin, c.lnMmax_gl);
+    }
+    box->mean_f_coll_MINI = 0.;
+    if (!std::isfinite(box->mean_f_coll) || box->mean_f_coll < 0)
+        b200_throw(B200_InfinityorNaNError, "Mean collapse fraction is invalid");
+
+    const double exp_global_hii = box->mean_f_coll * c.ion_eff_factor_gl;
+    if (exp_global_hii < HII_ROUND_ERR) {
+        NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term};
+        B200_LAUNCH(neutral_box_kernel, grid_for(N, 1024), 256, 0, na);
+        return;
+    }
+
+    DevBuf<float2> k_unfiltered(plan->n_cplx()), work(plan->n_cplx());
+    DevBuf<float> d_minmax(2);
+    DevBuf<DevTable> d_table(1);
+    const int sweep_blocks = grid_for((long long)nx * ny, 1);
+    DevBuf<double> d_partial(sweep_blocks), d_total(1);
+    DevBuf<int> d_flag(1);
+    dev_zero(d_flag, sizeof(int));
+
+    /* prepare_box_for_filtering (IonisationBox.c:323-360) */
+    ZPrologue pro;
+    pro.src = io.density; pro.src_row_stride = nz; pro.premul = 1.f;
+    pro.clip = 1; pro.clip_lo = -1.f; pro.clip_hi = 1e6f;
+    pro.post_scale = 1.f / (float)N;
+    fft_r2c(plan, k_unfiltered, pro);
+
+    /* the radius whose f_coll the reference leaves in unnormalised_nion (last one processed) */
+    int last_Rct = -1;
+    for (int R_ct = n_radii; R_ct--;) {
+        if (c.M_min > RtoM(radii[R_ct].R)) break;
+        last_Rct = R_ct;
+    }
+
+    const double dk0 = 2.0 * M_PI / so->BOX_LEN;
+    const double dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
+    FcollTable htab;
+    DevTable stage;
+    for (int R_ct = n_radii; R_ct--;) {
+        const RadiusSpec &rs = radii[R_ct];
+        if (c.M_min > RtoM(rs.R)) break;
+
+        KMul km;
+        if (rs.R_index > 0) {
+            km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R;
+            km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
+        }
+        ZEpilogue epi;
+        epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f; epi.minmax = d_minmax;
+        fft_c2r(plan, k_unfiltered, work, km, epi);
+
+        float mm[2];
+        d2h(mm, d_minmax, sizeof(mm));
+        g_stats.d2h -= (long long)sizeof(mm); /* control scalars, not payload */
+        const double min_density = (double)mm[0] - 0.001, max_density = (double)mm[1] + 0.001;
+
+        if (c.mass_dep_zeta) {
+            if (method == INTEG_GL) initialise_GL(c.lnMmin, rs.ln_M_max_R);
+            build_nion_table(&htab, c.redshift, min_density, max_density, c.M_min, rs.M_max_R, &c.sc, method, so->N_THREADS);
+        } else {
+            build_fgtrm_table(&htab, min_density, max_density, c.growth_factor, c.sigma_minmass, rs.sigma_maxmass);
+        }
+        stage.x_min = htab.x_min; stage.x_width = htab.x_width; stage.log_valued = htab.log_valued;
+        memcpy(stage.y, htab.y, sizeof(stage.y));
+        h2d(d_table, &stage, sizeof(DevTable));
+        g_stats.h2d -= (long long)sizeof(DevTable);
+
+        SweepArgs sa = {nx, ny, nz, plan->nzc, reinterpret_cast<const float *>(work.p), d_table, d_partial,
+                        (R_ct == last_Rct) ? io.nion : nullptr};
+        B200_LAUNCH(fcoll_sum_kernel, sweep_blocks, 256, N_DENS_INTERP * sizeof(float), sa);
+        B200_LAUNCH(sum_finish_kernel, 1, 256, 0, (const double *)d_partial, sweep_blocks, (double *)d_total);
+
+        CritArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.nx = nx; ca.ny = ny; ca.nz = nz; ca.nzc = plan->nzc;
+        ca.filtered = reinterpret_cast<const float *>(work.p);
+        ca.table = d_table; ca.fcoll_total = d_total; ca.density = io.density; ca.prev_zre = io.prev_zre;
+        ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
+        ca.n_cells = (double)N; ca.mean_f_coll = box->mean_f_coll; ca.f_limit = f_limit;
+        ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
+        ca.R_index = rs.R_index; ca.redshift = c.redshift;
+        ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
+        B200_LAUNCH(ionise_kernel, sweep_blocks, 256, N_DENS_INTERP * sizeof(float), ca);
+    }
+
+    if (io.Tk) {
+        TempArgs ta = {N, io.xH, io.z_reion, io.density, io.Tk, d_flag, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term};
+        B200_LAUNCH(ionized_temperature_kernel, grid_for(N, 1024), 256, 0, ta);
+        int flag = 0;
+        d2h(&flag, d_flag, sizeof(int));
+        g_stats.d2h -= (long long)sizeof(int);
+        if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
+    }
+}
+
+static void reset_stats() { g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0; }
+
+extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedField *perturbed_field,
+                                 PerturbedField *previous_perturbed_field, IonizedBox *previous_ionize_box,
+                                 TsBox *spin_temp, HaloBox *halos, InitialConditions *ini_boxes, IonizedBox *box) {
+    (void)previous_perturbed_field; (void)spin_temp; (void)halos; (void)ini_boxes;
+    try {
+        require_params(true);
+        rt_init();
+        reset_stats();
+        DevTimer timer;
+        timer.start();
+        const SimulationOptions *so = simulation_options_global;
+        const long long N = (long long)so->HII_DIM * so->HII_DIM * hii_d_para();
+        if (!perturbed_field || !perturbed_field->density || !box || !box->neutral_fraction || !box->z_reion)
+            b200_throw(B200_ValueError, "ComputeIonizedBox: required arrays are NULL");
+
+        /* first snapshot: the reference writes z_reion = -1 into the *previous* box
+           (setup_first_z_prevbox, IonisationBox.c:365-386) */
+        const bool first = prev_redshift < 1;
+        if (first && previous_ionize_box && previous_ionize_box->z_reion)
+            for (long long i = 0; i < N; i++) previous_ionize_box->z_reion[i] = -1.0f;
+
+        DevBuf<float> d_density(N), d_xH(N), d_zre(N), d_prev, d_Tk, d_nion;
+        h2d(d_density, perturbed_field->density, N * sizeof(float));
+        h2d(d_xH, box->neutral_fraction, N * sizeof(float));
+        const bool want_Tk = !matter_options_global->MINIMIZE_MEMORY && box->kinetic_temperature;
+        if (want_Tk) { d_Tk.alloc(N); h2d(d_Tk, box->kinetic_temperature, N * sizeof(float)); }
+        if (box->unnormalised_nion) d_nion.alloc(N);
+        if (!first && previous_ionize_box && previous_ionize_box->z_reion) {
+            d_prev.alloc(N);
+            h2d(d_prev, previous_ionize_box->z_reion, N * sizeof(float));
+        }
+        IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p};
+        ionize_core(redshift, prev_redshift, io, box);
+
+        d2h(box->neutral_fraction, d_xH, N * sizeof(float));
+        d2h(box->z_reion, d_zre, N * sizeof(float));
+        if (want_Tk) d2h(box->kinetic_temperature, d_Tk, N * sizeof(float));
+        if (d_nion.p) d2h(box->unnormalised_nion, d_nion, N * sizeof(float));
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
+            fprintf(stderr, "[21cmfast_b200] ComputeIonizedBox: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+/* Device-resident variant (bench.py `value` leg): d_* structs hold DEVICE pointers. */
+extern "C" int b200_ComputeIonizedBox_device(float redshift, float prev_redshift, PerturbedField *d_pf, IonizedBox *d_box) {
+    try {
+        require_params(true);
+        rt_init();
+        reset_stats();
+        DevTimer timer;
+        timer.start();
+        IonDeviceIO io = {d_pf->density, nullptr, d_box->neutral_fraction, d_box->z_reion, d_box->kinetic_temperature,
+                          d_box->unnormalised_nion};
+        ionize_core(redshift, prev_redshift, io, d_box);
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ComputeIonizedBox_device: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}

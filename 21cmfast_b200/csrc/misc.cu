@@ -1,0 +1,98 @@
+/*
+ * misc.cu -- test_filter (filtering.c:397-445) and ComputeBrightnessTemp
+ * (BrightnessTemperatureBox.c:22-105, the no-spin-temperature branch).
+ */
+#include "fft.h"
+#include "host_physics.h"
+
+struct Cast64Args {
+    long long n;
+    const float *src;
+    double *dst;
+};
+__global__ void float_to_double_kernel(Cast64Args a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x)
+        a.dst[i] = (double)a.src[i];
+}
+
+/* r2c, divide by N, one filter_box, c2r: the reference's known-answer hook for its filter tests */
+extern "C" int test_filter(float *input_box, double R, double R_param, double R_star, int filter_flag,
+                           double *result) {
+    (void)R_star;
+    try {
+        require_params(false);
+        rt_init();
+        g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0;
+        if (filter_flag < 0 || filter_flag > 4)
+            b200_throw(B200_ValueError, "filter type %d is outside the scoped path (0-4 supported)", filter_flag);
+        const SimulationOptions *so = simulation_options_global;
+        const int nx = so->HII_DIM, ny = so->HII_DIM, nz = (int)(so->NON_CUBIC_FACTOR * so->HII_DIM);
+        const long long N = (long long)nx * ny * nz;
+        Fft3D *plan = fft_plan(nx, ny, nz);
+        DevBuf<float> d_in(N), d_out(N);
+        DevBuf<double> d_res(N);
+        DevBuf<float2> kbox(plan->n_cplx()), work(plan->n_cplx());
+        h2d(d_in, input_box, N * sizeof(float));
+        ZPrologue pro;
+        pro.src = d_in; pro.src_row_stride = nz;
+        pro.post_scale = (float)(1.0 / (double)N);
+        fft_r2c(plan, kbox, pro);
+        KMul km;
+        km.kind = KMUL_FILTER; km.filter_type = filter_flag; km.R = (float)R; km.R_param = (float)R_param;
+        if (filter_flag == 3) km.r_const = exp(-(double)(float)R / (double)(float)R_param);
+        km.dk[0] = 2.0 * M_PI / so->BOX_LEN; km.dk[1] = km.dk[0];
+        km.dk[2] = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
+        ZEpilogue epi;
+        epi.dst = d_out; epi.dst_row_stride = nz;
+        fft_c2r(plan, kbox, work, km, epi);
+        Cast64Args ca = {N, d_out, d_res};
+        B200_LAUNCH(float_to_double_kernel, dev_num_sms() * 4, 256, 0, ca);
+        d2h(result, d_res, N * sizeof(double));
+    } catch (B200Error &e) {
+        if (getenv("B200_VERBOSE") || e.code == B200_CUDAError) fprintf(stderr, "[21cmfast_b200] test_filter: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+struct TbArgs {
+    long long n;
+    const float *density, *xH;
+    float *tb;
+    float const_factor;
+};
+__global__ void brightness_kernel(TbArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x)
+        a.tb[i] = a.const_factor * a.xH[i] * (1 + a.density[i]);
+}
+
+extern "C" int ComputeBrightnessTemp(float redshift, TsBox *spin_temp, IonizedBox *ionized_box,
+                                     PerturbedField *perturb_field, BrightnessTemp *box) {
+    (void)spin_temp;
+    try {
+        require_params(true);
+        rt_init();
+        g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0;
+        if (astro_options_global->USE_TS_FLUCT)
+            b200_throw(B200_ValueError, "USE_TS_FLUCT is outside the scoped path");
+        const SimulationOptions *so = simulation_options_global;
+        const CosmoParams *cp = cosmo_params_global;
+        const long long N = (long long)so->HII_DIM * so->HII_DIM * hii_d_para();
+        const float const_factor =
+            27 * (cp->OMb * cp->hlittle * cp->hlittle / 0.023) *
+            sqrt((0.15 / (cp->OMm) / (cp->hlittle) / (cp->hlittle)) * (1. + redshift) / 10.0);
+        DevBuf<float> d_d(N), d_x(N), d_t(N);
+        h2d(d_d, perturb_field->density, N * sizeof(float));
+        h2d(d_x, ionized_box->neutral_fraction, N * sizeof(float));
+        TbArgs a = {N, d_d, d_x, d_t, const_factor};
+        B200_LAUNCH(brightness_kernel, dev_num_sms() * 4, 256, 0, a);
+        d2h(box->brightness_temp, d_t, N * sizeof(float));
+    } catch (B200Error &e) {
+        if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
+            fprintf(stderr, "[21cmfast_b200] ComputeBrightnessTemp: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}

@@ -1,0 +1,370 @@
+/*
+ * perturb.cu -- ComputePerturbedField: move the initial-condition mass with ZA / 2LPT, deposit it
+ * with cloud-in-cell onto the low-resolution grid, clip, and derive the velocity field
+ * (reference PerturbedField.c:24-496 and move_grid_masses, map_mass.c:23-60,146-208).
+ *
+ * Scope: PERTURB_ON_HIGH_RES = False (the default).  LINEAR, ZELDOVICH and 2LPT algorithms.
+ *
+ * Deposit design: the reference adds 8 weighted contributions per hi-res particle into a double
+ * grid with `omp atomic` (order, hence rounding, varies run to run).  Here every contribution is
+ * converted to 2^-40 fixed point and accumulated in unsigned 64-bit integers: integer addition is
+ * associative, so the deposit is bit-reproducible, and its quantisation (4.5e-13 per
+ * contribution) is far below the float the sum is finally rounded to.  Each CTA owns a brick of
+ * hi-res particles, accumulates into a shared-memory tile of the low-res grid (brick + halo) with
+ * shared-memory atomics and flushes the tile once; contributions that land outside the tile go
+ * straight to global atomics, so correctness never depends on the displacement size.
+ */
+#include "fft.h"
+#include "host_physics.h"
+
+#include <vector>
+
+#define FIXED_SCALE 1099511627776.0 /* 2^40 */
+
+/* ------------------------------------------------------------------ device-resident IC cache */
+struct IcsCache {
+    bool valid = false;
+    const void *host[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long sig[7] = {0, 0, 0, 0, 0, 0, 0};
+    int dim = 0, hii = 0, dpara = 0, hpara = 0;
+    DevBuf<float> hires, v[3], v2[3];
+};
+static IcsCache g_ics;
+void ics_cache_drop() {
+    g_ics.valid = false;
+    g_ics.hires.release();
+    for (int a = 0; a < 3; a++) { g_ics.v[a].release(); g_ics.v2[a].release(); }
+}
+/* cheap content signature: 4096 evenly spaced words + length (guards against a reused pointer) */
+static unsigned long long sample_signature(const float *p, size_t n) {
+    if (!p) return 0;
+    unsigned long long h = 1469598103934665603ULL ^ n;
+    const size_t step = n / 4096 ? n / 4096 : 1;
+    for (size_t i = 0; i < n; i += step) {
+        unsigned int w;
+        memcpy(&w, p + i, 4);
+        h = (h ^ w) * 1099511628211ULL;
+    }
+    return h;
+}
+
+/* ------------------------------------------------------------------ kernels */
+struct MoveArgs {
+    int dn[3];   /* hi-res (particle) grid */
+    int vn[3];   /* velocity grid */
+    int on[3];   /* output grid */
+    const float *dens;
+    const float *v[3];
+    const float *v2[3];  /* null for Zel'dovich */
+    unsigned long long *acc;  /* output accumulator, fixed point */
+    double ratio_vel, ratio_out;
+    double vdf[3], vdf2[3];
+    double init_growth;
+    int brick[3];   /* hi-res particles per CTA along each axis */
+    int tile0[3];   /* low-res cells covered by a brick (without halo) */
+    int halo;
+    int tiles[3];   /* bricks per axis */
+};
+
+DEV int wrap_index(int i, int n) {
+    while (i >= n) i -= n;
+    while (i < 0) i += n;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) move_cic_kernel(MoveArgs a) {
+    DYN_SMEM(unsigned long long, tile);
+    const int tx = a.tile0[0] + 2 * a.halo, ty = a.tile0[1] + 2 * a.halo, tz = a.tile0[2] + 2 * a.halo;
+    const int tcells = tx * ty * tz;
+    for (int i = threadIdx.x; i < tcells; i += blockDim.x) tile[i] = 0ULL;
+    __syncthreads();
+    /* brick coordinates */
+    const int bz = blockIdx.x % a.tiles[2];
+    const int by = (blockIdx.x / a.tiles[2]) % a.tiles[1];
+    const int bx = blockIdx.x / (a.tiles[2] * a.tiles[1]);
+    const int i0 = bx * a.brick[0], j0 = by * a.brick[1], k0 = bz * a.brick[2];
+    /* low-res origin of the tile: cell containing the brick origin, minus the halo */
+    const int ox = (int)floor(i0 * a.ratio_out) - a.halo;
+    const int oy = (int)floor(j0 * a.ratio_out) - a.halo;
+    const int oz = (int)floor(k0 * a.ratio_out) - a.halo;
+    const int np = a.brick[0] * a.brick[1] * a.brick[2];
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        const int k = k0 + p % a.brick[2];
+        const int j = j0 + (p / a.brick[2]) % a.brick[1];
+        const int i = i0 + p / (a.brick[2] * a.brick[1]);
+        if (i >= a.dn[0] || j >= a.dn[1] || k >= a.dn[2]) continue;
+        /* nearest velocity cell (resample_index + wrap_coord, indexing.h:110-114) */
+        const int vi = wrap_index((int)(i * a.ratio_vel + 0.5), a.vn[0]);
+        const int vj = wrap_index((int)(j * a.ratio_vel + 0.5), a.vn[1]);
+        const int vk = wrap_index((int)(k * a.ratio_vel + 0.5), a.vn[2]);
+        const long long vidx = (long long)vk + (long long)a.vn[2] * ((long long)vj + (long long)a.vn[1] * vi);
+        double pos[3] = {(double)i, (double)j, (double)k};
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            pos[ax] += (double)a.v[ax][vidx] * a.vdf[ax];
+            if (a.v2[0]) pos[ax] -= (double)a.v2[ax][vidx] * a.vdf2[ax];
+            pos[ax] *= a.ratio_out;
+        }
+        const long long didx = (long long)k + (long long)a.dn[2] * ((long long)j + (long long)a.dn[1] * i);
+        const double mass = 1.0 + (double)a.dens[didx] * a.init_growth;
+        int ip[3];
+        double d[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            ip[ax] = (int)floor(pos[ax]);
+            d[ax] = pos[ax] - ip[ax];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int cx = c & 1, cy = (c >> 1) & 1, cz = (c >> 2) & 1;
+            const double w = (cx ? d[0] : 1. - d[0]) * (cy ? d[1] : 1. - d[1]) * (cz ? d[2] : 1. - d[2]);
+            const long long q = llrint(mass * w * FIXED_SCALE);
+            const int gx = ip[0] + cx, gy = ip[1] + cy, gz = ip[2] + cz;
+            const int lx = gx - ox, ly = gy - oy, lz = gz - oz;
+            if (lx >= 0 && lx < tx && ly >= 0 && ly < ty && lz >= 0 && lz < tz) {
+                atomic_add_u64(&tile[(lx * ty + ly) * tz + lz], (unsigned long long)q);
+            } else {
+                const int wx = wrap_index(gx, a.on[0]), wy = wrap_index(gy, a.on[1]), wz = wrap_index(gz, a.on[2]);
+                atomic_add_u64(&a.acc[(long long)wz + (long long)a.on[2] * ((long long)wy + (long long)a.on[1] * wx)],
+                               (unsigned long long)q);
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tcells; t += blockDim.x) {
+        const unsigned long long q = tile[t];
+        if (q == 0ULL) continue;
+        const int lz = t % tz, ly = (t / tz) % ty, lx = t / (tz * ty);
+        const int wx = wrap_index(ox + lx, a.on[0]), wy = wrap_index(oy + ly, a.on[1]), wz = wrap_index(oz + lz, a.on[2]);
+        atomic_add_u64(&a.acc[(long long)wz + (long long)a.on[2] * ((long long)wy + (long long)a.on[1] * wx)], q);
+    }
+}
+
+struct AccToDeltaArgs {
+    long long nrows;
+    int nz, nzc;
+    const unsigned long long *acc;
+    float *padded;
+    double mass_factor;
+};
+/* double -> float copy into the FFT layout (PerturbedField.c:115-128) + normalise_delta_grid (:180-210) */
+__global__ void acc_to_delta_kernel(AccToDeltaArgs a) {
+    for (long long row = blockIdx.x; row < a.nrows; row += gridDim.x)
+        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
+            const double m = (double)(long long)a.acc[row * a.nz + z] * (1.0 / FIXED_SCALE);
+            float v = (float)m;
+            v = (float)((double)v * a.mass_factor);
+            v = v - 1.0f;
+            a.padded[row * 2 * a.nzc + z] = v;
+        }
+}
+
+struct LinearArgs {
+    long long nrows;
+    int nz, nzc;
+    const float *dens;
+    float *padded;
+    double growth;
+};
+/* PERTURB_ALGORITHM = LINEAR (PerturbedField.c:66-82) */
+__global__ void linear_density_kernel(LinearArgs a) {
+    for (long long row = blockIdx.x; row < a.nrows; row += gridDim.x)
+        for (int z = threadIdx.x; z < a.nz; z += blockDim.x)
+            a.padded[row * 2 * a.nzc + z] = (float)(a.growth * (double)a.dens[row * a.nz + z]);
+}
+
+/* ------------------------------------------------------------------ orchestration */
+struct PerturbDeviceIO {
+    const float *hires_density; /* device, DIM^3 (2LPT / ZA) */
+    const float *lowres_density; /* device, HII^3 (LINEAR only) */
+    const float *v[3], *v2[3];   /* device low-res velocity boxes */
+    float *density, *vel[3];     /* device outputs (vel[a] may be null) */
+};
+
+static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
+    const SimulationOptions *so = simulation_options_global;
+    const MatterOptions *mo = matter_options_global;
+    if (mo->PERTURB_ON_HIGH_RES)
+        b200_throw(B200_ValueError, "PERTURB_ON_HIGH_RES=True is outside the scoped path");
+    const double redshift = redshift_f;
+    const int hn[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
+    const int dn[3] = {so->DIM, so->DIM, d_para()};
+    const long long N = (long long)hn[0] * hn[1] * hn[2];
+    const long long M = (long long)dn[0] * dn[1] * dn[2];
+    Fft3D *plan = fft_plan(hn[0], hn[1], hn[2]);
+    DevBuf<float2> kbox(plan->n_cplx()), work(plan->n_cplx());
+    float *padded = reinterpret_cast<float *>(kbox.p);
+    const int row_blocks = (int)((long long)hn[0] * hn[1] < 4096 ? (long long)hn[0] * hn[1] : 4096);
+
+    const double growth = dicke(redshift);
+    if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR) {
+        LinearArgs la = {(long long)hn[0] * hn[1], hn[2], plan->nzc, io.lowres_density, padded, growth};
+        B200_LAUNCH(linear_density_kernel, row_blocks, 256, 0, la);
+    } else {
+        /* move_grid_masses, map_mass.c:146-208 */
+        MoveArgs a;
+        memset(&a, 0, sizeof(a));
+        const double boxlen = so->BOX_LEN, boxlen_z = boxlen * so->NON_CUBIC_FACTOR;
+        const double box_size[3] = {boxlen, boxlen, boxlen_z};
+        const double init_growth = dicke(so->INITIAL_REDSHIFT);
+        const double d2 = -(3.0 / 7.0) * growth * growth, d2i = -(3.0 / 7.0) * init_growth * init_growth;
+        for (int ax = 0; ax < 3; ax++) {
+            a.dn[ax] = dn[ax]; a.vn[ax] = hn[ax]; a.on[ax] = hn[ax];
+            a.v[ax] = io.v[ax];
+            a.v2[ax] = (mo->PERTURB_ALGORITHM == PERTURB_2LPT) ? io.v2[ax] : nullptr;
+            a.vdf[ax] = (growth - init_growth) / box_size[ax] * dn[ax];
+            a.vdf2[ax] = (d2 - d2i) / box_size[ax] * dn[ax];
+        }
+        a.dens = io.hires_density;
+        a.ratio_vel = (double)hn[0] / (double)dn[0];
+        a.ratio_out = (double)hn[0] / (double)dn[0];
+        a.init_growth = init_growth;
+        DevBuf<unsigned long long> acc(N);
+        dev_zero(acc, N * sizeof(unsigned long long));
+        a.acc = acc;
+        /* bricks of ~8 low-res cells per axis (fewer if the grid is small), halo of 4 cells */
+        a.halo = 4;
+        for (int ax = 0; ax < 3; ax++) {
+            int cells = hn[ax] < 8 ? hn[ax] : 8;
+            a.brick[ax] = (int)ceil(cells / a.ratio_out);
+            if (a.brick[ax] > dn[ax]) a.brick[ax] = dn[ax];
+            a.tiles[ax] = (dn[ax] + a.brick[ax] - 1) / a.brick[ax];
+            a.tile0[ax] = (int)ceil(a.brick[ax] * a.ratio_out) + 1;
+        }
+        const size_t smem = sizeof(unsigned long long) * (size_t)(a.tile0[0] + 2 * a.halo) *
+                            (a.tile0[1] + 2 * a.halo) * (a.tile0[2] + 2 * a.halo);
+#ifndef B200_EMU
+        if (smem > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(move_cic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        B200_LAUNCH(move_cic_kernel, a.tiles[0] * a.tiles[1] * a.tiles[2], 256, smem, a);
+        AccToDeltaArgs ca = {(long long)hn[0] * hn[1], hn[2], plan->nzc, acc, padded, (double)N / (double)M};
+        B200_LAUNCH(acc_to_delta_kernel, row_blocks, 256, 0, ca);
+        /* acc returns to the pool at scope exit; reuse is stream-ordered (single stream) */
+    }
+
+    /* smooth_and_clip_density, PerturbedField.c:212-282 */
+    ZPrologue pro;
+    fft_r2c(plan, kbox, pro);
+    KMul km;
+    const double dk0 = 2.0 * M_PI / so->BOX_LEN, dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
+    km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
+    if (mo->SMOOTH_EVOLVED_DENSITY_FIELD) {
+        /* the smoothed k-space box is also what the velocities are derived from, so smooth in
+           place first (window only, no transform) */
+        b200_throw(B200_ValueError, "SMOOTH_EVOLVED_DENSITY_FIELD is outside the scoped path");
+    }
+    ZEpilogue epi;
+    epi.scale = 1.f / (float)N;
+    epi.clip = 1; epi.clip_lo = (float)(-1.0 + pc::FRACT_FLOAT_ERR); epi.clip_hi = 3.0e38f;
+    epi.dst = io.density; epi.dst_row_stride = hn[2];
+    fft_c2r(plan, kbox, work, KMul(), epi);
+
+    /* compute_perturbed_velocities, PerturbedField.c:284-387 */
+    if (so->HII_DIM > 1) {
+        const double dDdt_over_D = ddickedt(redshift) / dicke(redshift);
+        for (int ax = 0; ax < 3; ax++) {
+            if (!io.vel[ax]) continue;
+            KMul kv = km;
+            kv.op = KOP_VELOCITY_F; kv.axis_a = ax; kv.op_factor = dDdt_over_D / (double)N;
+            ZEpilogue ev;
+            ev.dst = io.vel[ax]; ev.dst_row_stride = hn[2];
+            fft_c2r(plan, kbox, work, kv, ev);
+        }
+    }
+}
+
+static void reset_stats() { g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0; }
+
+extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, PerturbedField *pf) {
+    try {
+        require_params(false);
+        rt_init();
+        reset_stats();
+        DevTimer timer;
+        timer.start();
+        const SimulationOptions *so = simulation_options_global;
+        const MatterOptions *mo = matter_options_global;
+        if (!boxes || !pf || !pf->density) b200_throw(B200_ValueError, "ComputePerturbedField: NULL struct/array");
+        const long long N = (long long)so->HII_DIM * so->HII_DIM * hii_d_para();
+        const long long M = (long long)so->DIM * so->DIM * d_para();
+        const bool linear = mo->PERTURB_ALGORITHM == PERTURB_LINEAR;
+        const bool lpt2 = mo->PERTURB_ALGORITHM == PERTURB_2LPT;
+        const float *hv[7] = {linear ? boxes->lowres_density : boxes->hires_density,
+                              boxes->lowres_vx, boxes->lowres_vy, boxes->lowres_vz,
+                              boxes->lowres_vx_2LPT, boxes->lowres_vy_2LPT, boxes->lowres_vz_2LPT};
+        const size_t hn[7] = {(size_t)(linear ? N : M), (size_t)N, (size_t)N, (size_t)N, (size_t)N, (size_t)N, (size_t)N};
+        const int nuse = linear ? 1 : (lpt2 ? 7 : 4);
+        for (int i = 0; i < nuse; i++)
+            if (!hv[i]) b200_throw(B200_ValueError, "ComputePerturbedField: a required IC array is NULL");
+        /* keep the initial conditions resident between calls (perturb_field is called once per
+           redshift on the same ICs); B200_ICS_CACHE=0 forces a fresh upload every call */
+        const char *ce = getenv("B200_ICS_CACHE");
+        const bool use_cache = !(ce && ce[0] == '0');
+        bool hit = use_cache && g_ics.valid && g_ics.dim == so->DIM && g_ics.hii == so->HII_DIM;
+        unsigned long long sig[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < nuse; i++) {
+            sig[i] = sample_signature(hv[i], hn[i]);
+            if (hit && (g_ics.host[i] != hv[i] || g_ics.sig[i] != sig[i])) hit = false;
+        }
+        if (!hit) {
+            ics_cache_drop();
+            g_ics.hires.alloc(hn[0]);
+            h2d(g_ics.hires, hv[0], hn[0] * sizeof(float));
+            for (int a = 0; a < 3 && nuse > 1; a++) {
+                g_ics.v[a].alloc(N);
+                h2d(g_ics.v[a], hv[1 + a], N * sizeof(float));
+                if (lpt2) { g_ics.v2[a].alloc(N); h2d(g_ics.v2[a], hv[4 + a], N * sizeof(float)); }
+            }
+            for (int i = 0; i < 7; i++) { g_ics.host[i] = i < nuse ? hv[i] : nullptr; g_ics.sig[i] = sig[i]; }
+            g_ics.dim = so->DIM; g_ics.hii = so->HII_DIM; g_ics.valid = true;
+        }
+        DevBuf<float> d_density(N), d_v[3];
+        float *host_v[3] = {mo->KEEP_3D_VELOCITIES ? pf->velocity_x : nullptr,
+                            mo->KEEP_3D_VELOCITIES ? pf->velocity_y : nullptr, pf->velocity_z};
+        PerturbDeviceIO io;
+        memset(&io, 0, sizeof(io));
+        io.hires_density = g_ics.hires; io.lowres_density = g_ics.hires;
+        for (int a = 0; a < 3; a++) {
+            io.v[a] = g_ics.v[a].p; io.v2[a] = g_ics.v2[a].p;
+            if (host_v[a]) { d_v[a].alloc(N); io.vel[a] = d_v[a]; }
+        }
+        io.density = d_density;
+        perturb_core(redshift, io);
+        d2h(pf->density, d_density, N * sizeof(float));
+        for (int a = 0; a < 3; a++)
+            if (host_v[a]) d2h(host_v[a], d_v[a], N * sizeof(float));
+        if (!use_cache) ics_cache_drop();
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
+            fprintf(stderr, "[21cmfast_b200] ComputePerturbedField: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+extern "C" int b200_ComputePerturbedField_device(float redshift, InitialConditions *d_boxes, PerturbedField *d_pf) {
+    try {
+        require_params(false);
+        rt_init();
+        reset_stats();
+        DevTimer timer;
+        timer.start();
+        PerturbDeviceIO io;
+        memset(&io, 0, sizeof(io));
+        io.hires_density = d_boxes->hires_density; io.lowres_density = d_boxes->lowres_density;
+        io.v[0] = d_boxes->lowres_vx; io.v[1] = d_boxes->lowres_vy; io.v[2] = d_boxes->lowres_vz;
+        io.v2[0] = d_boxes->lowres_vx_2LPT; io.v2[1] = d_boxes->lowres_vy_2LPT; io.v2[2] = d_boxes->lowres_vz_2LPT;
+        io.density = d_pf->density;
+        io.vel[0] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_x : nullptr;
+        io.vel[1] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_y : nullptr;
+        io.vel[2] = d_pf->velocity_z;
+        perturb_core(redshift, io);
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ComputePerturbedField_device: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}

@@ -1,0 +1,161 @@
+/* rt.cu -- stream, error plumbing, pooled device allocations, copy accounting. */
+#include "rt.h"
+
+#include <cstdarg>
+#include <map>
+#include <vector>
+
+CallStats g_stats = {0, 0, 0, 0.0};
+
+void b200_throw(int code, const char *fmt, ...) {
+    B200Error e;
+    e.code = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(e.msg, sizeof(e.msg), fmt, ap);
+    va_end(ap);
+    if (getenv("B200_VERBOSE")) fprintf(stderr, "[21cmfast_b200] error %d: %s\n", code, e.msg);
+    throw e;
+}
+
+/* Freed buffers are kept and handed back for the next request of the same size: a Compute* call
+   allocates the same few multi-GB work boxes every time, and cudaMalloc/cudaFree of those costs
+   milliseconds and synchronises the device. */
+static std::multimap<size_t, void *> g_free_pool;
+static std::map<void *, size_t> g_live;
+
+#ifndef B200_EMU
+cudaStream_t g_stream = nullptr;
+static int g_device = -1;
+static int g_sms = 0;
+
+void rt_init() {
+    if (g_stream) return;
+    if (g_device < 0) {
+        int dev = 0;
+        const char *lr = getenv("B200_DEVICE");
+        if (lr) dev = atoi(lr);
+        g_device = dev;
+    }
+    CUDA_CHECK(cudaSetDevice(g_device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, g_device));
+    g_sms = prop.multiProcessorCount;
+}
+int dev_num_sms() { rt_init(); return g_sms; }
+
+extern "C" int b200_set_device(int device) {
+    try {
+        if (g_stream && device != g_device) {
+            b200_release_device_cache();
+            cudaStreamDestroy(g_stream);
+            g_stream = nullptr;
+        }
+        g_device = device;
+        rt_init();
+    } catch (B200Error &e) { return e.code; }
+    return 0;
+}
+
+void *dev_alloc(size_t bytes) {
+    rt_init();
+    auto it = g_free_pool.find(bytes);
+    void *p = nullptr;
+    if (it != g_free_pool.end()) {
+        p = it->second;
+        g_free_pool.erase(it);
+    } else {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { /* retry once after dropping the pool */
+            cudaGetLastError();
+            for (auto &kv : g_free_pool) cudaFree(kv.second);
+            g_free_pool.clear();
+            CUDA_CHECK(cudaMalloc(&p, bytes));
+        }
+    }
+    g_live[p] = bytes;
+    return p;
+}
+void dev_free(void *p) {
+    auto it = g_live.find(p);
+    if (it == g_live.end()) return;
+    g_free_pool.insert({it->second, p});
+    g_live.erase(it);
+}
+static void pool_drop() {
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    for (auto &kv : g_free_pool) cudaFree(kv.second);
+    g_free_pool.clear();
+}
+void dev_zero(void *p, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, g_stream)); }
+void h2d(void *dst, const void *src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+    g_stats.h2d += (long long)bytes;
+}
+void d2h(void *dst, const void *src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    g_stats.d2h += (long long)bytes;
+}
+void d2d(void *dst, const void *src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
+}
+void dev_sync() { CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+
+void DevTimer::start() {
+    rt_init();
+    if (!a) {
+        cudaEvent_t ea, eb;
+        CUDA_CHECK(cudaEventCreate(&ea));
+        CUDA_CHECK(cudaEventCreate(&eb));
+        a = ea; b = eb;
+    }
+    CUDA_CHECK(cudaEventRecord((cudaEvent_t)a, g_stream));
+}
+double DevTimer::stop_ms() {
+    CUDA_CHECK(cudaEventRecord((cudaEvent_t)b, g_stream));
+    CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return ms;
+}
+#else
+/* ---------------------------------------------------------------- emulation */
+thread_local uint3e blockIdx = {0, 0, 0};
+thread_local uint3e gridDim = {1, 1, 1};
+thread_local unsigned char *b200_emu_smem = nullptr;
+int dev_num_sms() { return 4; }
+extern "C" int b200_set_device(int) { return 0; }
+void *dev_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (posix_memalign(&p, 256, bytes ? bytes : 256)) b200_throw(B200_MemoryAllocError, "malloc");
+    return p;
+}
+void dev_free(void *p) { free(p); }
+static void pool_drop() {}
+void dev_zero(void *p, size_t bytes) { memset(p, 0, bytes); }
+void h2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_stats.h2d += bytes; }
+void d2h(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_stats.d2h += bytes; }
+void d2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void dev_sync() {}
+void DevTimer::start() { t0 = omp_get_wtime(); }
+double DevTimer::stop_ms() { return (omp_get_wtime() - t0) * 1e3; }
+#endif
+
+void ics_cache_drop();  /* perturb.cu */
+void fft_plans_drop();  /* fft.cu */
+
+extern "C" void b200_release_device_cache(void) {
+    ics_cache_drop();
+    fft_plans_drop();
+    pool_drop();
+}
+
+extern "C" void b200_last_call_stats(long long *launches, long long *h2d_b, long long *d2h_b,
+                                     double *ms) {
+    if (launches) *launches = g_stats.launches;
+    if (h2d_b) *h2d_b = g_stats.h2d;
+    if (d2h_b) *d2h_b = g_stats.d2h;
+    if (ms) *ms = g_stats.ms;
+}

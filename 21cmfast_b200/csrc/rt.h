@@ -1,0 +1,178 @@
+/*
+ * rt.h -- thin runtime layer shared by every translation unit of lib21cmfast_b200.so.
+ *
+ * Product build (nvcc, sm_100a): CUDA runtime, one library-owned stream, launch counting,
+ * error -> status-code mapping.
+ *
+ * B200_EMU build (g++ only, used by tests/emu to check kernel *index logic* on a machine
+ * without a GPU): the same kernel sources are compiled with the CUDA execution model mapped to
+ * one logical thread per block (every kernel here is written as block-stride loops separated by
+ * __syncthreads(), so this is exact) and blocks spread over OpenMP threads.  The emulation
+ * library is test infrastructure: it is built into tests/_emu/, never into the package, and
+ * Backend() never loads it.
+ */
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/py21cmfast_b200.h"
+
+/* status codes: exceptions.h:12-21 of the reference, plus 10 for CUDA failures */
+enum {
+    B200_OK = 0, B200_IOError = 1, B200_GSLError = 2, B200_ValueError = 3,
+    B200_PhotonConsError = 4, B200_TableGenerationError = 5, B200_TableEvaluationError = 6,
+    B200_InfinityorNaNError = 7, B200_MassDepZetaError = 8, B200_MemoryAllocError = 9,
+    B200_CUDAError = 10
+};
+
+struct B200Error {
+    int code;
+    char msg[256];
+};
+[[noreturn]] void b200_throw(int code, const char *fmt, ...);
+
+struct CallStats {
+    long long launches, h2d, d2h;
+    double ms;
+};
+extern CallStats g_stats;
+
+#ifndef B200_EMU
+/* ------------------------------------------------------------------ real CUDA */
+#include <cuda_runtime.h>
+
+extern cudaStream_t g_stream;
+void rt_init();
+
+#define CUDA_CHECK(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            b200_throw(_e == cudaErrorMemoryAllocation ? B200_MemoryAllocError               \
+                                                       : B200_CUDAError,                     \
+                       "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define B200_LAUNCH(kernel, grid, block, smem, ...)                  \
+    do {                                                             \
+        kernel<<<(grid), (block), (smem), g_stream>>>(__VA_ARGS__);  \
+        g_stats.launches++;                                          \
+        CUDA_CHECK(cudaGetLastError());                              \
+    } while (0)
+
+#define DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _dyn_smem[]; \
+    type *name = reinterpret_cast<type *>(_dyn_smem)
+
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+template <typename T> DEV T ldg(const T *p) { return __ldg(p); }
+DEV void atomic_add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+DEV void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
+
+#else
+/* ------------------------------------------------------------------ host emulation */
+#include <omp.h>
+struct uint3e { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct float2 { float x, y; };
+struct double2 { double x, y; };
+static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r; }
+extern thread_local uint3e blockIdx;
+extern thread_local uint3e gridDim;
+extern thread_local unsigned char *b200_emu_smem;
+static const uint3e threadIdx = {0, 0, 0};
+static const uint3e blockDim = {1, 1, 1};
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static thread_local
+#define __syncthreads() ((void)0)
+using std::isfinite;
+#define HD inline
+#define DEV inline
+typedef int cudaStream_t;
+static inline void rt_init() {}
+template <typename T> inline T ldg(const T *p) { return *p; }
+inline void atomic_add_u64(unsigned long long *p, unsigned long long v) {
+#pragma omp atomic
+    *p += v;
+}
+inline void atomic_add_f64(double *p, double v) {
+#pragma omp atomic
+    *p += v;
+}
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline void sincospi(double x, double *s, double *c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
+
+#define DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(b200_emu_smem)
+
+#define B200_LAUNCH(kernel, grid, block, smem, ...)                                         \
+    do {                                                                                    \
+        dim3 _g = dim3(grid);                                                                    \
+        long long _nb = (long long)_g.x * _g.y * _g.z;                                      \
+        g_stats.launches++;                                                                 \
+        _Pragma("omp parallel")                                                             \
+        {                                                                                   \
+            unsigned char *_sm = (unsigned char *)malloc((size_t)(smem) + 64);              \
+            b200_emu_smem = _sm;                                                            \
+            gridDim.x = _g.x; gridDim.y = _g.y; gridDim.z = _g.z;                           \
+            _Pragma("omp for schedule(dynamic, 1)")                                         \
+            for (long long _b = 0; _b < _nb; _b++) {                                        \
+                blockIdx.x = (unsigned)(_b % _g.x);                                         \
+                blockIdx.y = (unsigned)((_b / _g.x) % _g.y);                                \
+                blockIdx.z = (unsigned)(_b / ((long long)_g.x * _g.y));                     \
+                kernel(__VA_ARGS__);                                                        \
+            }                                                                               \
+            free(_sm);                                                                      \
+        }                                                                                   \
+    } while (0)
+#endif
+
+/* ------------------------------------------------------------------ memory helpers */
+void *dev_alloc(size_t bytes);
+void dev_free(void *p);
+void dev_zero(void *p, size_t bytes);
+void h2d(void *dst, const void *src, size_t bytes);
+void d2h(void *dst, const void *src, size_t bytes);
+void d2d(void *dst, const void *src, size_t bytes);
+void dev_sync();
+int dev_num_sms();
+
+/* RAII device buffer */
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        if (count) p = (T *)dev_alloc(count * sizeof(T));
+        n = count;
+    }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+    void release() { if (p) dev_free(p); p = nullptr; n = 0; }
+    operator T *() const { return p; }
+};
+
+/* device timer (CUDA events on g_stream; wall clock in emulation) */
+struct DevTimer {
+    void *a = nullptr, *b = nullptr;
+    double t0 = 0;
+    void start();
+    double stop_ms();
+};

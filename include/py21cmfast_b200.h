@@ -1,0 +1,282 @@
+/*
+ * py21cmfast_b200.h -- C ABI of lib21cmfast_b200.so (B200 / sm_100a implementation of the
+ * 21cmFAST 3-D grid hot path).
+ *
+ * Every entry point below replaces the function of the same name in the reference's cffi
+ * extension `py21cmfast.c_21cmfast`; names, argument order, struct layouts and the integer
+ * status convention are the reference's, so a cffi/ctypes binding written for the reference
+ * binds this library unchanged (INTEGRATION.md shows the binding).  Citations are
+ * reference file:line under /root/reference/src/py21cmfast/src/.
+ *
+ * Conventions:
+ *   - all array pointers are HOST memory owned by the caller (numpy); the library copies
+ *     host->device, runs hand-written CUDA kernels and copies results back before returning;
+ *   - real boxes are unpadded C-order [x][y][z] float32 (indexing.h:84-86);
+ *   - parameters are read at call time through the global pointers set by
+ *     Broadcast_struct_global_all (InputParameters.c:11-54); the library never owns them;
+ *   - return 0 on success, else a code of exceptions.h:12-21 (10 = CUDA runtime failure);
+ *   - not re-entrant (global parameter pointers, static tables), like the reference.
+ */
+#ifndef PY21CMFAST_B200_H
+#define PY21CMFAST_B200_H
+
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- input structs: _inputparams_wrapper.h:11-182 (field order and types are ABI) ---------- */
+typedef struct CosmoParams {
+    float hlittle, OMm, OMl, OMb, POWER_INDEX;
+    float OMn, OMk, OMr, OMtot, Y_He, wl;
+} CosmoParams;
+
+typedef struct SimulationOptions {
+    int HII_DIM;
+    int DIM;
+    float BOX_LEN;
+    float NON_CUBIC_FACTOR;
+    int N_THREADS;
+    double Z_HEAT_MAX;
+    double ZPRIME_STEP_FACTOR;
+    float SAMPLER_MIN_MASS;
+    double SAMPLER_BUFFER_FACTOR;
+    int N_COND_INTERP;
+    int N_PROB_INTERP;
+    double MIN_LOGPROB;
+    double HALOMASS_CORRECTION;
+    double PARKINSON_G0;
+    double PARKINSON_y1;
+    double PARKINSON_y2;
+    float INITIAL_REDSHIFT;
+    double DELTA_R_FACTOR;
+    double DENSITY_SMOOTH_RADIUS;
+    double DEXM_OPTIMIZE_MINMASS;
+    double DEXM_R_OVERLAP;
+    double CORR_STAR;
+    double CORR_SFR;
+    double CORR_LX;
+    double MIN_XE_FOR_FCOLL_IN_TAUX;
+} SimulationOptions;
+
+typedef struct MatterOptions {
+    bool USE_FFTW_WISDOM;
+    int HMF;
+    int V_CB_MODEL;
+    int POWER_SPECTRUM;
+    int USE_INTERPOLATION_TABLES;
+    bool PERTURB_ON_HIGH_RES;
+    int PERTURB_ALGORITHM;
+    bool MINIMIZE_MEMORY;
+    bool KEEP_3D_VELOCITIES;
+    bool DEXM_OPTIMIZE;
+    int FILTER;
+    int HALO_FILTER;
+    bool SMOOTH_EVOLVED_DENSITY_FIELD;
+    int SOURCE_MODEL;
+    int SAMPLE_METHOD;
+} MatterOptions;
+
+typedef struct AstroParams {
+    float HII_EFF_FACTOR;
+    float F_STAR10;
+    float ALPHA_STAR;
+    float ALPHA_STAR_MINI;
+    float SIGMA_STAR;
+    double UPPER_STELLAR_TURNOVER_MASS;
+    double UPPER_STELLAR_TURNOVER_INDEX;
+    float F_STAR7_MINI;
+    float t_STAR;
+    double SIGMA_SFR_INDEX;
+    double SIGMA_SFR_LIM;
+    double L_X;
+    double L_X_MINI;
+    double SIGMA_LX;
+    float F_ESC10;
+    float ALPHA_ESC;
+    float F_ESC7_MINI;
+    float T_RE;
+    float M_TURN;
+    float R_BUBBLE_MAX;
+    float ION_Tvir_MIN;
+    double F_H2_SHIELD;
+    float NU_X_THRESH;
+    float X_RAY_SPEC_INDEX;
+    float X_RAY_Tvir_MIN;
+    double A_LW;
+    double BETA_LW;
+    double A_VCB;
+    double BETA_VCB;
+    double V_CB_AVG_DEBUG;
+    double POP2_ION;
+    double POP3_ION;
+    double PHOTONCONS_CALIBRATION_END;
+    double CLUMPING_FACTOR;
+    double ALPHA_UVB;
+    float R_MAX_TS;
+    int N_STEP_TS;
+    double DELTA_R_HII_FACTOR;
+    float R_BUBBLE_MIN;
+    double MAX_DVDR;
+    double NU_X_MAX;
+    double NU_X_BAND_MAX;
+} AstroParams;
+
+typedef struct AstroOptions {
+    bool USE_MINI_HALOS;
+    bool USE_X_RAY_HEATING;
+    bool USE_CMB_HEATING;
+    bool USE_LYA_HEATING;
+    int RECOMB_MODEL;
+    bool USE_TS_FLUCT;
+    bool M_MIN_in_Mass;
+    bool USE_EXP_FILTER;
+    bool CELL_RECOMB;
+    bool LYA_MULTIPLE_SCATTERING;
+    bool USE_ADIABATIC_FLUCTUATIONS;
+    int PHOTON_CONS_TYPE;
+    bool USE_UPPER_STELLAR_TURNOVER;
+    bool HALO_SCALING_RELATIONS_MEDIAN;
+    int HII_FILTER;
+    int HEAT_FILTER;
+    bool IONISE_ENTIRE_SPHERE;
+    int INTEGRATION_METHOD_ATOMIC;
+    int INTEGRATION_METHOD_MINI;
+} AstroOptions;
+
+typedef struct Table1D {
+    int size;
+    double *x_values;
+    double *y_values;
+} Table1D;
+
+typedef struct CosmoTables {
+    Table1D *transfer_density;
+    Table1D *transfer_vcb;
+    double ps_norm;
+    bool USE_SIGMA_8;
+    double V_CB_AVG;
+} CosmoTables;
+
+typedef struct ConfigSettings {
+    double HALO_CATALOG_MEM_FACTOR;
+    bool EXTRA_HALOBOX_FIELDS;
+    char *external_table_path;
+    char *wisdoms_path;
+} ConfigSettings;
+
+/* ---- output structs: _outputstructs_wrapper.h:6-105 -------------------------------------- */
+typedef struct InitialConditions {
+    float *lowres_density, *lowres_vx, *lowres_vy, *lowres_vz;
+    float *lowres_vx_2LPT, *lowres_vy_2LPT, *lowres_vz_2LPT;
+    float *hires_density, *hires_vx, *hires_vy, *hires_vz;
+    float *hires_vx_2LPT, *hires_vy_2LPT, *hires_vz_2LPT;
+    float *lowres_vcb;
+} InitialConditions;
+
+typedef struct PerturbedField {
+    float *density, *velocity_x, *velocity_y, *velocity_z;
+} PerturbedField;
+
+typedef struct HaloBox {
+    float *halo_mass, *halo_stars, *halo_stars_mini, *count;
+    float *n_ion, *halo_sfr, *halo_xray, *halo_sfr_mini, *whalo_sfr;
+    double log10_Mcrit_ACG_ave;
+    double log10_Mcrit_MCG_ave;
+} HaloBox;
+
+typedef struct TsBox {
+    float *spin_temperature, *xray_ionised_fraction, *kinetic_temp_neutral, *J_21_LW;
+    double Q_HI;
+} TsBox;
+
+typedef struct IonizedBox {
+    double mean_f_coll;
+    double mean_f_coll_MINI;
+    double log10_Mturnover_ave;
+    double log10_Mturnover_MINI_ave;
+    float *neutral_fraction;
+    float *ionisation_rate_G12;
+    float *mean_free_path;
+    float *z_reion;
+    float *cumulative_recombinations;
+    float *kinetic_temperature;
+    float *unnormalised_nion;
+    float *unnormalised_nion_mini;
+} IonizedBox;
+
+typedef struct BrightnessTemp {
+    float *brightness_temp;
+    float *tau_21;
+} BrightnessTemp;
+
+/* ---- global parameter pointers: _inputparams_wrapper.h:195-202, InputParameters.c:80-89 --- */
+extern SimulationOptions *simulation_options_global;
+extern MatterOptions *matter_options_global;
+extern CosmoParams *cosmo_params_global;
+extern AstroParams *astro_params_global;
+extern AstroOptions *astro_options_global;
+extern CosmoTables *cosmo_tables_global;
+extern ConfigSettings config_settings;
+
+/* ---- hot-path compute functions: _functionprototypes_wrapper.h:6-9,23-26,28-29 ----------- */
+int ComputeInitialConditions(unsigned long long int random_seed, InitialConditions *boxes);
+int ComputePerturbedField(float redshift, InitialConditions *boxes, PerturbedField *perturbed_field);
+int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedField *perturbed_field,
+                      PerturbedField *previous_perturbed_field, IonizedBox *previous_ionize_box,
+                      TsBox *spin_temp, HaloBox *halos, InitialConditions *ini_boxes,
+                      IonizedBox *box);
+int ComputeBrightnessTemp(float redshift, TsBox *spin_temp, IonizedBox *ionized_box,
+                          PerturbedField *perturb_field, BrightnessTemp *box);
+/* filter known-answer hook used by the reference's tests (_functionprototypes_wrapper.h:130-131) */
+int test_filter(float *input_box, double R, double R_param, double R_star, int filter_flag,
+                double *result);
+
+/* ---- initialisation / teardown: _functionprototypes_wrapper.h:67-87 ----------------------- */
+void Broadcast_struct_global_all(SimulationOptions *simulation_options,
+                                 MatterOptions *matter_options, CosmoParams *cosmo_params,
+                                 AstroParams *astro_params, AstroOptions *astro_options,
+                                 CosmoTables *cosmo_tables);
+void Broadcast_struct_global_noastro(SimulationOptions *simulation_options,
+                                     MatterOptions *matter_options, CosmoParams *cosmo_params);
+void Free_cosmo_tables_global(void);
+void init_ps(void);
+void free_ps(void);
+void initialiseSigmaMInterpTable(float M_Min, float M_Max);
+void freeSigmaMInterpTable(void);
+int init_heat(void);
+void destruct_heat(void);
+void init_MHR(void);          /* no-op: recombinations are outside the scoped path */
+void free_MHR(void);
+int CreateFFTWWisdoms(void);  /* no-op: the FFT is the library's own sm_100a kernels */
+
+/* ---- scalar cosmology helpers the Python layer and tests call directly (:136-150) -------- */
+double dicke(double z);
+double sigma_z0(double M);
+double dsigmasqdm_z0(double M);
+double power_in_k(double k);
+double get_delta_crit(int HMF, double sigma, double growthf);
+double atomic_cooling_threshold(float z);
+double minimum_source_mass(double redshift, bool xray);
+
+/* ---- B200-specific additions (not in the reference; optional for a drop-in) --------------- */
+/* Device selection for one-process-per-GPU launches (default: device 0 / CUDA_VISIBLE_DEVICES). */
+int b200_set_device(int device);
+/* Drop every cached device buffer (initial conditions kept resident between calls, FFT plans). */
+void b200_release_device_cache(void);
+/* Counters for the last Compute* call: kernels launched, H2D and D2H bytes, device milliseconds
+   (CUDA events on the library's stream). Any pointer may be NULL. */
+void b200_last_call_stats(long long *kernel_launches, long long *h2d_bytes, long long *d2h_bytes,
+                          double *device_ms);
+/* Device-resident variants used by bench.py's `value` leg (inputs already in HBM): identical
+   computation, but the structs hold DEVICE pointers and no host<->device copies are made. */
+int b200_ComputePerturbedField_device(float redshift, InitialConditions *d_boxes,
+                                      PerturbedField *d_perturbed_field);
+int b200_ComputeIonizedBox_device(float redshift, float prev_redshift,
+                                  PerturbedField *d_perturbed_field, IonizedBox *d_box);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PY21CMFAST_B200_H */

@@ -138,7 +138,7 @@ def emit(n, out):
 if __name__ == "__main__":
     path = sys.argv[1]
     with open(path, "w") as f:
-        f.write("/* Generated by oracle/tools/gen_gk_tables.py (mpmath, 60 digits). Do not edit. */\n")
+        f.write("/* Generated by tools/gen_gk_tables.py (mpmath, 60 digits). Do not edit. */\n")
         f.write("/* Gauss-Kronrod abscissae/weights in QUADPACK layout (positive half, descending). */\n\n")
         for n in (7, 10, 15, 20, 25, 30):
             emit(n, f)
