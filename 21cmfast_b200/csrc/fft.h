@@ -122,11 +122,13 @@ HD double window_value(int type, float kmag_sq, float R, double R_param, double 
         double den = kR * ratio * kR * ratio + 1;
         f *= -3 * ratio / (den * den);
         return f;
-    } else if (type == 4) {  /* spherical shell between R_param (inner) and R (outer) */
+    } else if (type == 4) {
+        /* spherical shell.  filter_box calls spherical_shell_filter(k, R, R_param) whose
+           parameters are (k, R_inner, R_outer) (filtering.c:106-117,376): R is the inner radius */
         double k = sqrt((double)kmag_sq);
-        double ko = k * (double)R, ki = k * R_param;
+        double ki = k * (double)R, ko = k * R_param;
         if (ko < 1e-4) {
-            double q = R_param / (double)R;
+            double q = (double)R / R_param;
             return 1. - ko * ko / 10 * (q * q * q * q * q - 1) / (q * q * q - 1);
         }
         return 3.0 / (ko * ko * ko - ki * ki * ki) * (sin(ko) - cos(ko) * ko - sin(ki) + cos(ki) * ki);

@@ -694,6 +694,54 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
     if (err_code) b200_throw(err_code, "conditional Nion table generation failed");
 }
 
+/* ------------------------------------------------------------------ IonizeBox host constants */
+void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
+    /* IonisationBox.c:125-227 (photon-conservation and recombination terms are out of scope) */
+    c->redshift = redshift;
+    c->prev_redshift = prev_redshift;
+    c->stored_redshift = redshift;
+    set_scaling_constants(redshift, &c->sc);
+    c->growth_factor = dicke(redshift);
+    c->mass_dep_zeta = matter_options_global->SOURCE_MODEL != SRC_CONST_ION_EFF;
+    c->hii_filter = astro_options_global->HII_FILTER;
+    c->T_re = astro_params_global->T_RE;
+    if (c->mass_dep_zeta)
+        c->ion_eff_factor_gl = c->sc.pop2_ion * c->sc.fstar_10 * c->sc.fesc_10;
+    else
+        c->ion_eff_factor_gl = astro_params_global->HII_EFF_FACTOR;
+    c->ion_eff_factor = c->ion_eff_factor_gl;
+    c->M_min = minimum_source_mass(redshift, false);
+    c->lnMmin = log(c->M_min);
+    c->lnMmax_gl = log(pc::M_MAX_INTEGRAL);
+    c->sigma_minmass = sigma_z0(c->M_min);
+    c->TK_nofluct = T_RECFAST(redshift);
+    c->adia_TK_term = cT_approx(redshift);
+    c->pixel_length = simulation_options_global->BOX_LEN / (double)simulation_options_global->HII_DIM;
+}
+
+std::vector<RadiusSpec> setup_radii(const IonConsts &c) { /* IonisationBox.c:964-1006 */
+    const AstroParams *ap = astro_params_global;
+    const double maximum_radius = fmin(ap->R_BUBBLE_MAX, pc::l_factor * simulation_options_global->BOX_LEN);
+    const double minimum_radius = fmax(ap->R_BUBBLE_MIN, pc::l_factor * c.pixel_length);
+    int n_radii = (int)(log(maximum_radius / minimum_radius) / log(ap->DELTA_R_HII_FACTOR) + 1);
+    std::vector<RadiusSpec> r;
+    for (int i = 0; i < n_radii; i++) {
+        RadiusSpec s;
+        s.R_index = i;
+        s.R = minimum_radius * pow(ap->DELTA_R_HII_FACTOR, i);
+        if (s.R > maximum_radius - pc::FRACT_FLOAT_ERR) {
+            s.R = maximum_radius;
+            n_radii = i + 1;
+        }
+        s.M_max_R = RtoM(s.R);
+        s.ln_M_max_R = log(s.M_max_R);
+        s.sigma_maxmass = sigma_z0(s.M_max_R);
+        r.push_back(s);
+    }
+    return r;
+}
+
+
 /* ------------------------------------------------------------------ RECFAST boundary values
  * heating_helper_progs.c:94-197: z, x_e, -, T_k columns, 501 rows from z=500 down to 0. */
 static hostnum::CubicSpline g_T_spline, g_x_spline;

@@ -69,6 +69,26 @@ double xion_RECFAST(float z);
 float cT_approx(float z);
 bool heat_ready();
 
+/* IonisationBox.c:125-227 / :964-1006 host constants (kept in the g++-compiled unit: under nvcc's
+   host pass, math calls on float arguments silently bind to float overloads) */
+#include <vector>
+struct IonConsts {
+    double redshift, stored_redshift, prev_redshift, growth_factor;
+    bool mass_dep_zeta;
+    int hii_filter;
+    ScalingConstants sc;
+    double T_re, ion_eff_factor, ion_eff_factor_gl;
+    double TK_nofluct, adia_TK_term;
+    double M_min, lnMmin, lnMmax_gl, sigma_minmass, pixel_length;
+};
+struct RadiusSpec {
+    double R, M_max_R, ln_M_max_R, sigma_maxmass;
+    int R_index;
+};
+
+void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c);
+std::vector<RadiusSpec> setup_radii(const IonConsts &c);
+
 /* per-radius 400-point table of f_coll(delta) (interp_tables.c:226-250 / :291-408) */
 #define N_DENS_INTERP 400
 struct FcollTable {

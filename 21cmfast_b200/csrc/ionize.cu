@@ -28,66 +28,6 @@
 
 #define HII_ROUND_ERR (1e-5)
 
-struct IonConsts {
-    double redshift, stored_redshift, prev_redshift, growth_factor;
-    bool mass_dep_zeta;
-    int hii_filter;
-    ScalingConstants sc;
-    double T_re, ion_eff_factor, ion_eff_factor_gl;
-    double TK_nofluct, adia_TK_term;
-    double M_min, lnMmin, lnMmax_gl, sigma_minmass, pixel_length;
-};
-struct RadiusSpec {
-    double R, M_max_R, ln_M_max_R, sigma_maxmass;
-    int R_index;
-};
-
-static void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
-    /* IonisationBox.c:125-227 (photon-conservation and recombination terms are out of scope) */
-    c->redshift = redshift;
-    c->prev_redshift = prev_redshift;
-    c->stored_redshift = redshift;
-    set_scaling_constants(redshift, &c->sc);
-    c->growth_factor = dicke(redshift);
-    c->mass_dep_zeta = matter_options_global->SOURCE_MODEL != SRC_CONST_ION_EFF;
-    c->hii_filter = astro_options_global->HII_FILTER;
-    c->T_re = astro_params_global->T_RE;
-    if (c->mass_dep_zeta)
-        c->ion_eff_factor_gl = c->sc.pop2_ion * c->sc.fstar_10 * c->sc.fesc_10;
-    else
-        c->ion_eff_factor_gl = astro_params_global->HII_EFF_FACTOR;
-    c->ion_eff_factor = c->ion_eff_factor_gl;
-    c->M_min = minimum_source_mass(redshift, false);
-    c->lnMmin = log(c->M_min);
-    c->lnMmax_gl = log(pc::M_MAX_INTEGRAL);
-    c->sigma_minmass = sigma_z0(c->M_min);
-    c->TK_nofluct = T_RECFAST(redshift);
-    c->adia_TK_term = cT_approx(redshift);
-    c->pixel_length = simulation_options_global->BOX_LEN / (double)simulation_options_global->HII_DIM;
-}
-
-static std::vector<RadiusSpec> setup_radii(const IonConsts &c) { /* IonisationBox.c:964-1006 */
-    const AstroParams *ap = astro_params_global;
-    const double maximum_radius = fmin(ap->R_BUBBLE_MAX, pc::l_factor * simulation_options_global->BOX_LEN);
-    const double minimum_radius = fmax(ap->R_BUBBLE_MIN, pc::l_factor * c.pixel_length);
-    int n_radii = (int)(log(maximum_radius / minimum_radius) / log(ap->DELTA_R_HII_FACTOR) + 1);
-    std::vector<RadiusSpec> r;
-    for (int i = 0; i < n_radii; i++) {
-        RadiusSpec s;
-        s.R_index = i;
-        s.R = minimum_radius * pow(ap->DELTA_R_HII_FACTOR, i);
-        if (s.R > maximum_radius - pc::FRACT_FLOAT_ERR) {
-            s.R = maximum_radius;
-            n_radii = i + 1;
-        }
-        s.M_max_R = RtoM(s.R);
-        s.ln_M_max_R = log(s.M_max_R);
-        s.sigma_maxmass = sigma_z0(s.M_max_R);
-        r.push_back(s);
-    }
-    return r;
-}
-
 /* ------------------------------------------------------------------ device side */
 struct DevTable {
     double x_min, x_width;
@@ -503,6 +443,36 @@ extern "C" int b200_ComputeIonizedBox_device(float redshift, float prev_redshift
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
         fprintf(stderr, "[21cmfast_b200] b200_ComputeIonizedBox_device: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+/* Host-only part of ComputeIonizedBox (no device work): lets the CPU test tier check the host
+   scalar chain of the shipped library against the golden fixtures.
+   out = [mean_f_coll, f_limit, M_min, sigma_minmass, TK_nofluct, growth, ion_eff_factor, n_radii,
+          R_0, sigma_max_0, R_1, sigma_max_1, ...] truncated to n entries. */
+extern "C" int b200_ionize_host_scalars(float redshift, double *out, int n) {
+    try {
+        require_params(true);
+        IonConsts c;
+        set_ionbox_constants(redshift, -1.0, &c);
+        std::vector<RadiusSpec> radii = setup_radii(c);
+        double mean_f_coll, f_limit;
+        if (c.mass_dep_zeta) {
+            mean_f_coll = Nion_General(redshift, c.lnMmin, c.lnMmax_gl, astro_params_global->M_TURN, &c.sc);
+            f_limit = Nion_General(simulation_options_global->Z_HEAT_MAX, c.lnMmin, c.lnMmax_gl,
+                                   astro_params_global->M_TURN, &c.sc);
+        } else {
+            mean_f_coll = Fcoll_General(redshift, c.lnMmin, c.lnMmax_gl);
+            f_limit = Fcoll_General(simulation_options_global->Z_HEAT_MAX, c.lnMmin, c.lnMmax_gl);
+        }
+        std::vector<double> v = {mean_f_coll, f_limit, c.M_min, c.sigma_minmass, c.TK_nofluct,
+                                 c.growth_factor, c.ion_eff_factor, (double)radii.size()};
+        for (const RadiusSpec &r : radii) { v.push_back(r.R); v.push_back(r.sigma_maxmass); }
+        for (int i = 0; i < n; i++) out[i] = i < (int)v.size() ? v[i] : 0.0;
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ionize_host_scalars: %s\n", e.msg);
         return e.code;
     }
     return 0;

@@ -120,8 +120,60 @@ double DevTimer::stop_ms() {
     CUDA_CHECK(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b));
     return ms;
 }
+
+/* ---- per-kernel event timing ------------------------------------------------------------ */
+#include <string>
+int g_profile = 0;
+struct ProfPair { std::string name; cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof_pairs;
+static std::map<std::string, std::pair<long long, double>> g_prof_acc;
+int prof_begin(const char *name) {
+    ProfPair p;
+    p.name = name;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1;
+    cudaEventRecord(p.a, g_stream);
+    g_prof_pairs.push_back(p);
+    return (int)g_prof_pairs.size() - 1;
+}
+void prof_end(int slot) { cudaEventRecord(g_prof_pairs[slot].b, g_stream); }
+static void prof_collect() {
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    for (auto &p : g_prof_pairs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            auto &acc = g_prof_acc[p.name];
+            acc.first++;
+            acc.second += ms;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_pairs.clear();
+}
+extern "C" void b200_profile_enable(int on) {
+    prof_collect();
+    if (on) g_prof_acc.clear();
+    g_profile = on;
+}
+/* writes "name count total_ms\n" lines; returns the number of bytes needed */
+extern "C" int b200_profile_report(char *buf, int buflen) {
+    prof_collect();
+    std::string out;
+    char line[256];
+    for (auto &kv : g_prof_acc) {
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && buflen > 0) {
+        strncpy(buf, out.c_str(), buflen - 1);
+        buf[buflen - 1] = 0;
+    }
+    return (int)out.size() + 1;
+}
 #else
 /* ---------------------------------------------------------------- emulation */
+extern "C" void b200_profile_enable(int) {}
+extern "C" int b200_profile_report(char *buf, int buflen) { if (buf && buflen > 0) buf[0] = 0; return 1; }
 thread_local uint3e blockIdx = {0, 0, 0};
 thread_local uint3e gridDim = {1, 1, 1};
 thread_local unsigned char *b200_emu_smem = nullptr;

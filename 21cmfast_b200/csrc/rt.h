@@ -56,9 +56,16 @@ void rt_init();
                        "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
     } while (0)
 
+/* optional per-kernel timing with CUDA events on the launching stream (b200_profile_enable) */
+extern int g_profile;
+int prof_begin(const char *name);
+void prof_end(int slot);
+
 #define B200_LAUNCH(kernel, grid, block, smem, ...)                  \
     do {                                                             \
+        int _ps = g_profile ? prof_begin(#kernel) : -1;              \
         kernel<<<(grid), (block), (smem), g_stream>>>(__VA_ARGS__);  \
+        if (_ps >= 0) prof_end(_ps);                                 \
         g_stats.launches++;                                          \
         CUDA_CHECK(cudaGetLastError());                              \
     } while (0)
@@ -66,11 +73,16 @@ void rt_init();
 #define DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _dyn_smem[]; \
     type *name = reinterpret_cast<type *>(_dyn_smem)
 
+#ifdef __CUDACC__
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
 template <typename T> DEV T ldg(const T *p) { return __ldg(p); }
 DEV void atomic_add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 DEV void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
+#else /* host-only translation units (host_physics.cpp, host_numerics.cpp) built by g++ */
+#define HD inline
+#define DEV inline
+#endif
 
 #else
 /* ------------------------------------------------------------------ host emulation */

