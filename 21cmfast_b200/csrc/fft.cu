@@ -285,7 +285,7 @@ struct ZArgs {
     float scale;
     int clip;
     float clip_lo, clip_hi;
-    float *minmax_partial;      /* [2 * gridDim.x] or null */
+    int *minmax_keys;           /* {min, max} order keys or null */
     long long real_row_stride;  /* floats between rows of the real side */
     float premul;
 };
@@ -320,8 +320,9 @@ __global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict
             dst[row * a.real_row_stride + z] = val;
         }
     }
-    if (a.minmax_partial) {
-        /* block reduction through shared memory (reuse A: all reads of res are done) */
+    if (a.minmax_keys) {
+        /* block reduction through shared memory (reuse A: all reads of res are done), then one
+           pair of integer atomics per CTA on order-preserving keys */
         __syncthreads();
         float *red = reinterpret_cast<float *>(smem);
         red[threadIdx.x] = lmin;
@@ -336,8 +337,8 @@ __global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            a.minmax_partial[2 * blockIdx.x] = red[0];
-            a.minmax_partial[2 * blockIdx.x + 1] = red[blockDim.x];
+            atomic_min_i32(&a.minmax_keys[0], float_order_key(float_as_int_bits(red[0])));
+            atomic_max_i32(&a.minmax_keys[1], float_order_key(float_as_int_bits(red[blockDim.x])));
         }
     }
 }
@@ -377,32 +378,6 @@ __global__ void __launch_bounds__(256) fft_r2c_z_kernel(const float *__restrict_
     }
 }
 
-/* min/max partials -> 2 floats */
-__global__ void minmax_finish_kernel(const float *__restrict__ partial, int nblocks,
-                                     float *__restrict__ out) {
-    DYN_SMEM(float, red);
-    float lmin = 3.0e38f, lmax = -3.0e38f;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
-        lmin = fminf(lmin, partial[2 * i]);
-        lmax = fmaxf(lmax, partial[2 * i + 1]);
-    }
-    red[threadIdx.x] = lmin;
-    red[blockDim.x + threadIdx.x] = lmax;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + s]);
-            red[blockDim.x + threadIdx.x] =
-                fmaxf(red[blockDim.x + threadIdx.x], red[blockDim.x + threadIdx.x + s]);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        out[0] = red[0];
-        out[1] = red[blockDim.x];
-    }
-}
-
 /* ------------------------------------------------------------------ plans */
 static bool factorize(int n, FftFactors &f) {
     f.nf = 0;
@@ -426,7 +401,6 @@ static bool factorize(int n, FftFactors &f) {
 
 static std::map<int, Fft1D> g_plans1d;
 static std::map<std::tuple<int, int, int>, Fft3D *> g_plans3d;
-static DevBuf<float> g_minmax_partial;
 
 static Fft1D &plan1d(int n) {
     auto it = g_plans1d.find(n);
@@ -463,7 +437,6 @@ void fft_plans_drop() {
     g_plans3d.clear();
     for (auto &kv : g_plans1d) dev_free(kv.second.tw);
     g_plans1d.clear();
-    g_minmax_partial.release();
 }
 
 /* tile width: as many lines per CTA as fit ~72 KB (3 CTAs/SM), else 110 KB, else 220 KB */
@@ -534,16 +507,10 @@ void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZE
     float *dst = epi.dst ? epi.dst : reinterpret_cast<float *>(work);
     a.real_row_stride = epi.dst ? epi.dst_row_stride : 2LL * nzc;
     const int nblocks = (a.nrows + a.L - 1) / a.L;
-    if (epi.minmax) {
-        g_minmax_partial.ensure(2 * (size_t)nblocks);
-        a.minmax_partial = g_minmax_partial;
-    }
+    a.minmax_keys = epi.minmax_keys;
     size_t smem = tile_smem(a.n, a.L);
     allow_smem(fft_c2r_z_kernel, smem);
     B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, work, dst, a);
-    if (epi.minmax)
-        B200_LAUNCH(minmax_finish_kernel, dim3(1), 256, 2 * 256 * sizeof(float),
-                    (const float *)g_minmax_partial, nblocks, epi.minmax);
 }
 
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {

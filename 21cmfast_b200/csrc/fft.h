@@ -64,7 +64,8 @@ struct ZEpilogue {
     float scale = 1.f;          /* multiply (e.g. 1/VOLUME) */
     int clip = 0;               /* clamp to [clip_lo, clip_hi] after min/max were taken */
     float clip_lo = 0.f, clip_hi = 0.f;
-    float *minmax = nullptr;    /* device float[2]: global min / max of the unclipped values */
+    int *minmax_keys = nullptr; /* device int[2] = {min key, max key} of the unclipped values, combined with
+                                   integer atomics on float_order_key(); caller presets {INT_MAX, INT_MIN} */
     float *dst = nullptr;       /* optional separate real destination (else in place, padded) */
     long long dst_row_stride = 0; /* floats between consecutive (x,y) rows of dst */
 };

@@ -670,6 +670,55 @@ void build_fgtrm_table(FcollTable *t, double min_dens, double max_dens, double g
     }
 }
 
+/* Everything in the Gauss-Legendre integrand that does not depend on the cell density: the same
+   factors, evaluated once per node instead of once per (density, node).  The per-density
+   expression below multiplies them in the order of cmf() / integrate_gl(), so the table values
+   are the same doubles. */
+struct GLNode {
+    double w, nf, dsig, taylor, barrier, sdi, sdi15, sqrt_sdi;
+    bool below; /* sigma(M) < sigma_cond: the conditional mass function vanishes */
+};
+static void gl_prepare_nodes(GLNode *nd, const MFParams &p) {
+    for (int i = 1; i < NGL_INT + 1; i++) {
+        GLNode &n = nd[i];
+        const double lnM = xi_GL[i];
+        const double sigma1 = EvaluateSigma(lnM);
+        n.w = wi_GL[i];
+        n.nf = nion_fraction(lnM, p);
+        n.dsig = EvaluatedSigmasqdm(lnM);
+        n.below = sigma1 < p.sigma_cond;
+        n.sdi = sigma1 == p.sigma_cond ? 1e6 : 1 / (sigma1 * sigma1 - p.sigma_cond * p.sigma_cond);
+        n.sdi15 = pow(n.sdi, 1.5);
+        n.sqrt_sdi = sqrt(n.sdi);
+        n.taylor = n.barrier = 0.;
+        if (p.HMF == HMF_ST && !n.below) n.taylor = st_taylor_factor(sigma1, p.sigma_cond, p.growthf, &n.barrier);
+    }
+}
+static double gl_integral(const GLNode *nd, const MFParams &p, double delta) {
+    double integral = 0;
+    const double delta_0 = delta / p.growthf;
+    for (int i = 1; i < NGL_INT + 1; i++) {
+        const GLNode &n = nd[i];
+        double c;
+        if (n.below) {
+            c = 0.;
+        } else if (p.HMF == HMF_ST) {
+            const double factor = n.taylor - delta_0;
+            c = -n.dsig * factor * n.sdi15 * exp(-(n.barrier - delta_0) * (n.barrier - delta_0) * 0.5 * (n.sdi)) /
+                sqrt(2. * M_PI);
+        } else if (p.HMF == HMF_DELOS) {
+            const double nu = (pc::delta_c_delos - delta) * n.sqrt_sdi / p.growthf;
+            const double dfdnu = 0.519 * pow(nu, 0.582) * exp(-0.469 * nu * nu);
+            c = dfdnu * fabs(n.dsig * 0.5) * n.sdi;
+        } else {
+            const double del = (pc::delta_c_sph - delta) / p.growthf;
+            c = -del * n.dsig * n.sdi15 * exp(-del * del * 0.5 * n.sdi) / sqrt(2. * M_PI);
+        }
+        integral += n.w * (n.nf * c);
+    }
+    return integral;
+}
+
 void build_nion_table(FcollTable *t, double redshift, double min_dens, double max_dens, double Mmin,
                       double Mmax, const ScalingConstants *sc, int method, int n_threads) {
     /* initialise_Nion_Conditional_spline without mini-halos, interp_tables.c:291-408 */
@@ -681,11 +730,28 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
     t->log_valued = 1;
     int err_code = 0;
     if (n_threads < 1) n_threads = 1;
+
+    MFParams p = mf_params(growthf, sc->mturn_a_nofb, sc);
+    p.sigma_cond = sigma2;
+    if (p.HMF != HMF_PS && p.HMF != HMF_ST && p.HMF != HMF_DELOS) p.HMF = HMF_PS;
+    GLNode nodes[NGL_INT + 1];
+    const bool gl_fast = method == INTEG_GL && lnMmin < lnMcond;
+    if (gl_fast) {
+        if ((float)lnMmin != (float)GL_limit[0] || (float)lnMmax != (float)GL_limit[1])
+            b200_throw(B200_TableGenerationError, "integral limits do not match the Gauss-Legendre nodes");
+        gl_prepare_nodes(nodes, p);
+    }
+    const double dcrit_lim = (float)0.99 * get_delta_crit(matter_options_global->HMF, sigma2, growthf);
 #pragma omp parallel for num_threads(n_threads) schedule(dynamic, 8)
     for (int i = 0; i < N_DENS_INTERP; i++) {
         try {
             const double dens = min_dens + (float)i / ((float)N_DENS_INTERP - 1.) * (max_dens - min_dens);
-            float y = log(Nion_ConditionalM(growthf, lnMmin, lnMmax, lnMcond, sigma2, dens, sc->mturn_a_nofb, sc, method));
+            double v;
+            if (gl_fast && !(dens > dcrit_lim) && !(dens > 1.2))
+                v = gl_integral(nodes, p, dens);
+            else
+                v = Nion_ConditionalM(growthf, lnMmin, lnMmax, lnMcond, sigma2, dens, sc->mturn_a_nofb, sc, method);
+            float y = log(v);
             if (y < -40.) y = -40.;
             t->y[i] = y;
             if (!std::isfinite(y)) err_code = B200_TableGenerationError;

@@ -13,13 +13,15 @@
  *                                                   [copy_filter_transform + clip_and_get_extrema]
  *     2 floats D2H -> host builds the 400-point f_coll(delta) table -> 1.6 KB H2D
  *                                                   [setup_integration_tables]
- *     sweep 1: table lookup per cell, deterministic double sum  [calculate_fcoll_grid]
- *     sweep 2: lookup again (float-rounded like the stored grid), mean fix, barrier test,
- *              flags / z_reion / partial ionisation             [find_ionised_regions]
+ *     sweep 1: table lookup per cell -> float f_coll grid + deterministic double block sums
+ *                                                               [calculate_fcoll_grid]
+ *     sweep 2: mean fix, barrier test, flags / z_reion / partial ionisation
+ *                                                               [find_ionised_regions]
  *   temperatures of ionised cells, D2H of the outputs           [set_ionized_temperatures]
  *
- * The f_coll grid is never materialised except for the radius whose values the reference
- * leaves in `unnormalised_nion`: sweep 2 recomputes the lookup instead of re-reading 4N bytes.
+ * The radius loop is software-pipelined: while the host waits for the two min/max keys of radius
+ * k and integrates its table, the stream already filters and transforms radius k+1 into the
+ * other work box, so the GPU does not idle on the host-side table build.
  */
 #include "fft.h"
 #include "host_physics.h"
@@ -30,21 +32,17 @@
 
 /* ------------------------------------------------------------------ device side */
 struct DevTable {
-    double x_min, x_width;
+    double x_min, x_width, inv_width;
     int log_valued;
     float y[N_DENS_INTERP];
 };
 
 /* EvaluateRGTable1D_f (interpolation.c:123-131) on a table staged in shared memory */
-DEV double table_eval(double x, double x_min, double x_width, const float *y) {
-    const int idx = (int)floor((x - x_min) / x_width);
-    const double table_val = x_min + x_width * (float)idx;
-    const double t = (x - table_val) / x_width;
+DEV double table_eval(double x, const DevTable *h, const float *y) {
+    const int idx = (int)floor((x - h->x_min) * h->inv_width);
+    const double table_val = h->x_min + h->x_width * (float)idx;
+    const double t = (x - table_val) * h->inv_width;
     return (double)y[idx] * (1 - t) + (double)y[idx + 1] * t;
-}
-DEV double fcoll_of_delta(float dens, const DevTable *hdr, const float *y) {
-    const double v = table_eval((double)dens, hdr->x_min, hdr->x_width, y);
-    return hdr->log_valued ? exp(v) : v;
 }
 
 struct SweepArgs {
@@ -52,7 +50,7 @@ struct SweepArgs {
     const float *filtered;   /* padded real rows, already clipped to [-1, 1e6] */
     const DevTable *table;
     double *partial;         /* [gridDim.x] block sums */
-    float *nion_out;         /* unnormalised_nion[0] or null */
+    float *fcoll;            /* unpadded f_coll grid of this radius */
 };
 
 /* sweep 1: f_coll per cell + block partial sums (calculate_fcoll_grid, IonisationBox.c:773-962) */
@@ -63,14 +61,16 @@ __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     __syncthreads();
     const long long nrows = (long long)a.nx * a.ny;
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
+    const int log_valued = a.table->log_valued;
     double acc = 0.;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const float *src = a.filtered + row * 2 * a.nzc;
         for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
             const float d = fmaxf(src[z], dens_floor);
-            const double fc = fcoll_of_delta(d, a.table, ytab);
+            double fc = table_eval((double)d, a.table, ytab);
+            if (log_valued) fc = exp(fc);
             acc += fc;
-            if (a.nion_out) a.nion_out[row * a.nz + z] = (float)fc;
+            a.fcoll[row * a.nz + z] = (float)fc;
         }
     }
     red[threadIdx.x] = acc;
@@ -82,30 +82,16 @@ __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
 }
 
-/* fixed-order finish so the grid mean is bit-reproducible run to run */
-__global__ void sum_finish_kernel(const double *partial, int n, double *out) {
-    __shared__ double red[256];
-    double acc = 0.;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *out = red[0];
-}
-
 struct CritArgs {
-    int nx, ny, nz, nzc;
-    const float *filtered;
-    const DevTable *table;
-    const double *fcoll_total;
+    long long n;
+    const float *fcoll;      /* f_coll grid written by sweep 1 */
+    const double *partial;   /* block sums of sweep 1 */
+    int n_partial;
     const float *density;    /* unfiltered perturbed density, unpadded */
     const float *prev_zre;   /* previous box z_reion or null (= all -1) */
     float *xH, *z_reion, *Tk;
     double n_cells, mean_f_coll, f_limit, ion_eff_factor;
-    int mass_dep_zeta, last_radius, R_index;
+    int mass_dep_zeta, R_index;
     double redshift, TK_nofluct, adia_TK_term, T_re;
 };
 
@@ -117,42 +103,42 @@ DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { 
 
 /* sweep 2: find_ionised_regions (IonisationBox.c:1008-1201), centre-cell method */
 __global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
-    DYN_SMEM(float, ytab);
-    for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) ytab[i] = a.table->y[i];
+    __shared__ double red[256];
+    /* every CTA re-adds the block sums of sweep 1 in the same fixed order: the grid mean is
+       bit-reproducible and no separate finishing launch is needed */
+    double acc = 0.;
+    for (int i = threadIdx.x; i < a.n_partial; i += blockDim.x) acc += a.partial[i];
+    red[threadIdx.x] = acc;
     __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
     /* grid mean with the reference's floor (IonisationBox.c:1566-1576), then the mean fix */
-    double grid_mean = *a.fcoll_total / a.n_cells;
+    double grid_mean = red[0] / a.n_cells;
     if (a.mass_dep_zeta) {
         if (grid_mean <= a.f_limit) grid_mean = a.f_limit;
     } else {
         if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
     }
     const double mean_fix = a.mean_f_coll / grid_mean;
-    const long long nrows = (long long)a.nx * a.ny;
-    const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
-    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const float *src = a.filtered + row * 2 * a.nzc;
-        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
-            const long long idx = row * a.nz + z;
-            const float d = fmaxf(src[z], dens_floor);
-            /* the reference reads f_coll back from the float grid it stored in sweep 1 */
-            double curr_fcoll = (double)(float)fcoll_of_delta(d, a.table, ytab);
-            curr_fcoll = mean_fix * curr_fcoll;
-            if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
-            if (curr_fcoll * a.ion_eff_factor > 1.0) {
-                const float pz = a.prev_zre ? a.prev_zre[idx] : -1.f;
-                a.z_reion[idx] = (pz < 0) ? (float)a.redshift : pz;
-                a.xH[idx] = 0.f;
-            } else if (a.R_index == 0 && (a.xH[idx] > pc::TINY)) {
-                double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
-                if (a.Tk) {
-                    const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
-                    a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
-                }
-                if (res_xH < 0) res_xH = 0;
-                else if (res_xH > 1) res_xH = 1;
-                a.xH[idx] = (float)res_xH;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double curr_fcoll = mean_fix * (double)a.fcoll[idx];
+        if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
+        if (curr_fcoll * a.ion_eff_factor > 1.0) {
+            const float pz = a.prev_zre ? a.prev_zre[idx] : -1.f;
+            a.z_reion[idx] = (pz < 0) ? (float)a.redshift : pz;
+            a.xH[idx] = 0.f;
+        } else if (a.R_index == 0 && (a.xH[idx] > pc::TINY)) {
+            double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
+            if (a.Tk) {
+                const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
+                a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
             }
+            if (res_xH < 0) res_xH = 0;
+            else if (res_xH > 1) res_xH = 1;
+            a.xH[idx] = (float)res_xH;
         }
     }
 }
@@ -207,6 +193,16 @@ __global__ void fill_kernel(FillArgs a) {
          i += (long long)gridDim.x * blockDim.x)
         a.p[i] = a.v;
 }
+struct KeyInitArgs {
+    int n;
+    int *keys;
+};
+__global__ void minmax_key_init_kernel(KeyInitArgs a) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        a.keys[2 * i] = 2147483647;
+        a.keys[2 * i + 1] = -2147483647 - 1;
+    }
+}
 
 struct NeutralArgs {
     long long n;
@@ -237,6 +233,26 @@ struct IonDeviceIO {
     float *xH, *z_reion, *Tk, *nion; /* device, N each; Tk / nion may be null */
 };
 
+/* pinned staging that outlives a call (cudaMallocHost is too slow to repeat per call) */
+struct IonStaging {
+    int cap = 0;
+    int *h_keys = nullptr;       /* [cap][2] */
+    DevTable *h_tables = nullptr; /* [cap] */
+    void *events[64];
+    ~IonStaging() {}
+    void ensure(int n) {
+        if (n <= cap) return;
+        if (n > 64) b200_throw(B200_ValueError, "more than 64 filter radii");
+        host_pinned_free(h_keys);
+        host_pinned_free(h_tables);
+        h_keys = (int *)host_pinned_alloc(sizeof(int) * 2 * 64);
+        h_tables = (DevTable *)host_pinned_alloc(sizeof(DevTable) * 64);
+        for (int i = cap; i < 64; i++) events[i] = dev_event_create();
+        cap = 64;
+    }
+};
+static IonStaging g_stage;
+
 static void ionize_core(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box) {
     const SimulationOptions *so = simulation_options_global;
     const AstroOptions *ao = astro_options_global;
@@ -247,10 +263,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         ao->PHOTON_CONS_TYPE != 0)
         b200_throw(B200_ValueError, "USE_TS_FLUCT / RECOMB_MODEL / USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / "
                                     "photon conservation are outside the scoped IonizeBox path");
-    if (mo->SOURCE_MODEL == SRC_E_INTEGRAL && mo->USE_INTERPOLATION_TABLES != 2)
-        b200_throw(B200_ValueError, "E-INTEGRAL needs USE_INTERPOLATION_TABLES='hmf-interpolation' in this build");
-    if (mo->SOURCE_MODEL == SRC_CONST_ION_EFF && mo->USE_INTERPOLATION_TABLES != 2)
-        b200_throw(B200_ValueError, "CONST-ION-EFF needs USE_INTERPOLATION_TABLES='hmf-interpolation' in this build");
+    if (mo->USE_INTERPOLATION_TABLES != 2)
+        b200_throw(B200_ValueError, "this build needs USE_INTERPOLATION_TABLES='hmf-interpolation'");
 
     const double redshift = redshift_f, prev_redshift = prev_redshift_f;
     IonConsts c;
@@ -297,13 +311,29 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         return;
     }
 
-    DevBuf<float2> k_unfiltered(plan->n_cplx()), work(plan->n_cplx());
-    DevBuf<float> d_minmax(2);
-    DevBuf<DevTable> d_table(1);
+    /* radii that will actually be processed, largest first (IonisationBox.c:1531-1541) */
+    std::vector<int> todo;
+    for (int R_ct = n_radii; R_ct--;) {
+        if (c.M_min > RtoM(radii[R_ct].R)) break;
+        todo.push_back(R_ct);
+    }
+    const int n_todo = (int)todo.size();
+
+    DevBuf<float2> k_unfiltered(plan->n_cplx()), work0(plan->n_cplx()), work1(plan->n_cplx());
+    float2 *work[2] = {work0.p, work1.p};
+    DevBuf<float> d_fcoll;
+    if (!io.nion || n_todo > 1) d_fcoll.alloc(N);
+    DevBuf<int> d_keys(2 * (size_t)(n_todo > 0 ? n_todo : 1));
+    DevBuf<DevTable> d_tables((size_t)(n_todo > 0 ? n_todo : 1));
     const int sweep_blocks = grid_for((long long)nx * ny, 1);
-    DevBuf<double> d_partial(sweep_blocks), d_total(1);
+    DevBuf<double> d_partial(sweep_blocks);
     DevBuf<int> d_flag(1);
     dev_zero(d_flag, sizeof(int));
+    g_stage.ensure(n_todo);
+    if (n_todo > 0) {
+        KeyInitArgs ka = {n_todo, d_keys};
+        B200_LAUNCH(minmax_key_init_kernel, 1, 64, 0, ka);
+    }
 
     /* prepare_box_for_filtering (IonisationBox.c:323-360) */
     ZPrologue pro;
@@ -312,62 +342,64 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     pro.post_scale = 1.f / (float)N;
     fft_r2c(plan, k_unfiltered, pro);
 
-    /* the radius whose f_coll the reference leaves in unnormalised_nion (last one processed) */
-    int last_Rct = -1;
-    for (int R_ct = n_radii; R_ct--;) {
-        if (c.M_min > RtoM(radii[R_ct].R)) break;
-        last_Rct = R_ct;
-    }
-
     const double dk0 = 2.0 * M_PI / so->BOX_LEN;
     const double dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
-    FcollTable htab;
-    DevTable stage;
-    for (int R_ct = n_radii; R_ct--;) {
-        const RadiusSpec &rs = radii[R_ct];
-        if (c.M_min > RtoM(rs.R)) break;
 
+    /* stage A of radius k: filter + c2r + clip + min/max keys; the two keys travel to pinned host
+       memory behind an event, so the host can wait for exactly this radius while the stream
+       already runs the next one (copy_filter_transform + clip_and_get_extrema) */
+    auto enqueue_transform = [&](int k) {
+        const RadiusSpec &rs = radii[todo[k]];
         KMul km;
         if (rs.R_index > 0) {
             km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
         }
         ZEpilogue epi;
-        epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f; epi.minmax = d_minmax;
-        fft_c2r(plan, k_unfiltered, work, km, epi);
+        epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
+        epi.minmax_keys = d_keys.p + 2 * k;
+        fft_c2r(plan, k_unfiltered, work[k & 1], km, epi);
+        d2h_async(g_stage.h_keys + 2 * k, d_keys.p + 2 * k, 2 * sizeof(int));
+        dev_event_record(g_stage.events[k]);
+    };
 
-        float mm[2];
-        d2h(mm, d_minmax, sizeof(mm));
-        g_stats.d2h -= (long long)sizeof(mm); /* control scalars, not payload */
-        const double min_density = (double)mm[0] - 0.001, max_density = (double)mm[1] + 0.001;
+    FcollTable htab;
+    if (n_todo > 0) enqueue_transform(0);
+    for (int k = 0; k < n_todo; k++) {
+        const RadiusSpec &rs = radii[todo[k]];
+        if (k + 1 < n_todo) enqueue_transform(k + 1);
+        dev_event_wait_host(g_stage.events[k]);
+        const double min_density = (double)float_from_order_key(g_stage.h_keys[2 * k]) - 0.001;
+        const double max_density = (double)float_from_order_key(g_stage.h_keys[2 * k + 1]) + 0.001;
 
+        /* setup_integration_tables (IonisationBox.c:702-768) on the host while the stream works */
         if (c.mass_dep_zeta) {
             if (method == INTEG_GL) initialise_GL(c.lnMmin, rs.ln_M_max_R);
             build_nion_table(&htab, c.redshift, min_density, max_density, c.M_min, rs.M_max_R, &c.sc, method, so->N_THREADS);
         } else {
             build_fgtrm_table(&htab, min_density, max_density, c.growth_factor, c.sigma_minmass, rs.sigma_maxmass);
         }
-        stage.x_min = htab.x_min; stage.x_width = htab.x_width; stage.log_valued = htab.log_valued;
-        memcpy(stage.y, htab.y, sizeof(stage.y));
-        h2d(d_table, &stage, sizeof(DevTable));
-        g_stats.h2d -= (long long)sizeof(DevTable);
+        DevTable *st = &g_stage.h_tables[k];
+        st->x_min = htab.x_min; st->x_width = htab.x_width; st->inv_width = 1.0 / htab.x_width;
+        st->log_valued = htab.log_valued;
+        memcpy(st->y, htab.y, sizeof(st->y));
+        h2d_async(d_tables.p + k, st, sizeof(DevTable));
 
-        SweepArgs sa = {nx, ny, nz, plan->nzc, reinterpret_cast<const float *>(work.p), d_table, d_partial,
-                        (R_ct == last_Rct) ? io.nion : nullptr};
+        /* the reference leaves the last processed radius' f_coll in unnormalised_nion */
+        float *fc = (k == n_todo - 1 && io.nion) ? io.nion : d_fcoll.p;
+        SweepArgs sa = {nx, ny, nz, plan->nzc, reinterpret_cast<const float *>(work[k & 1]), d_tables.p + k, d_partial, fc};
         B200_LAUNCH(fcoll_sum_kernel, sweep_blocks, 256, N_DENS_INTERP * sizeof(float), sa);
-        B200_LAUNCH(sum_finish_kernel, 1, 256, 0, (const double *)d_partial, sweep_blocks, (double *)d_total);
 
         CritArgs ca;
         memset(&ca, 0, sizeof(ca));
-        ca.nx = nx; ca.ny = ny; ca.nz = nz; ca.nzc = plan->nzc;
-        ca.filtered = reinterpret_cast<const float *>(work.p);
-        ca.table = d_table; ca.fcoll_total = d_total; ca.density = io.density; ca.prev_zre = io.prev_zre;
+        ca.n = N; ca.fcoll = fc; ca.partial = d_partial; ca.n_partial = sweep_blocks;
+        ca.density = io.density; ca.prev_zre = io.prev_zre;
         ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
         ca.n_cells = (double)N; ca.mean_f_coll = box->mean_f_coll; ca.f_limit = f_limit;
         ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
         ca.R_index = rs.R_index; ca.redshift = c.redshift;
         ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
-        B200_LAUNCH(ionise_kernel, sweep_blocks, 256, N_DENS_INTERP * sizeof(float), ca);
+        B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
     }
 
     if (io.Tk) {
@@ -377,6 +409,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         d2h(&flag, d_flag, sizeof(int));
         g_stats.d2h -= (long long)sizeof(int);
         if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
+    } else {
+        dev_sync(); /* pinned staging and the work boxes must outlive the queued kernels */
     }
 }
 

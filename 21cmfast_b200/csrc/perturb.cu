@@ -140,6 +140,148 @@ __global__ void __launch_bounds__(256) move_cic_kernel(MoveArgs a) {
     }
 }
 
+/* Integer DIM/HII_DIM ratio F: the F^3 particles whose nearest velocity cell is the same low-res
+   cell share one displacement, so along each axis their F positions span less than one output
+   cell and touch at most 3 cells.  One thread owns such a group: it contracts the F^3 masses with
+   the three per-axis F x 3 CIC weight matrices (z, then y, then x) into a 3x3x3 block and issues
+   27 fixed-point adds instead of 8 F^3.  Same positions and weights as the generic kernel. */
+struct GroupArgs {
+    MoveArgs m;
+    int gbrick[3];  /* source (low-res) cells per CTA */
+    int gtiles[3];
+};
+
+template <int F> DEV void axis_weights(int c, int n_hi, double disp, double r, int &base, double W[F][3]) {
+    /* hi-res indices whose nearest velocity cell is c: istart .. istart + F - 1 (may be -1 at c = 0) */
+    const int istart = (int)ceil((double)F * c - 0.5 * F);
+    int b0 = 0;
+#pragma unroll
+    for (int t = 0; t < F; t++) {
+        double pos = (double)(istart + t);
+        pos += disp;
+        pos *= r;
+        const double fl = floor(pos);
+        const int b = (int)fl;
+        if (t == 0) b0 = b;
+        const int o = b - b0; /* 0 or 1 */
+        const double w1 = pos - fl, w0 = 1. - w1;
+        W[t][0] = (o == 0) ? w0 : 0.;
+        W[t][1] = (o == 0) ? w1 : w0;
+        W[t][2] = (o == 0) ? 0. : w1;
+    }
+    base = b0;
+    (void)n_hi;
+}
+
+template <int F> __global__ void __launch_bounds__(256) move_cic_grouped_kernel(GroupArgs g) {
+    const MoveArgs &a = g.m;
+    DYN_SMEM(unsigned long long, tile);
+    const int tx = g.gbrick[0] + 2 * a.halo, ty = g.gbrick[1] + 2 * a.halo, tz = g.gbrick[2] + 2 * a.halo;
+    const int tcells = tx * ty * tz;
+    for (int i = threadIdx.x; i < tcells; i += blockDim.x) tile[i] = 0ULL;
+    __syncthreads();
+    const int bz = blockIdx.x % g.gtiles[2];
+    const int by = (blockIdx.x / g.gtiles[2]) % g.gtiles[1];
+    const int bx = blockIdx.x / (g.gtiles[2] * g.gtiles[1]);
+    const int c0x = bx * g.gbrick[0], c0y = by * g.gbrick[1], c0z = bz * g.gbrick[2];
+    const int ox = c0x - a.halo, oy = c0y - a.halo, oz = c0z - a.halo;
+    const int np = g.gbrick[0] * g.gbrick[1] * g.gbrick[2];
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        const int cz = c0z + p % g.gbrick[2];
+        const int cy = c0y + (p / g.gbrick[2]) % g.gbrick[1];
+        const int cx = c0x + p / (g.gbrick[2] * g.gbrick[1]);
+        if (cx >= a.vn[0] || cy >= a.vn[1] || cz >= a.vn[2]) continue;
+        const long long vidx = (long long)cz + (long long)a.vn[2] * ((long long)cy + (long long)a.vn[1] * cx);
+        double disp[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            /* pos = i; pos += v*vdf; pos -= v2*vdf2 (map_mass.c:190-196); (i + d1) - d2 is kept as
+               two steps inside axis_weights by folding only the part independent of i */
+            disp[ax] = (double)a.v[ax][vidx] * a.vdf[ax];
+            if (a.v2[0]) disp[ax] -= (double)a.v2[ax][vidx] * a.vdf2[ax];
+        }
+        double Wx[F][3], Wy[F][3], Wz[F][3];
+        int Bx, By, Bz;
+        axis_weights<F>(cx, a.dn[0], disp[0], a.ratio_out, Bx, Wx);
+        axis_weights<F>(cy, a.dn[1], disp[1], a.ratio_out, By, Wy);
+        axis_weights<F>(cz, a.dn[2], disp[2], a.ratio_out, Bz, Wz);
+        const int isx = (int)ceil((double)F * cx - 0.5 * F), isy = (int)ceil((double)F * cy - 0.5 * F),
+                  isz = (int)ceil((double)F * cz - 0.5 * F);
+        double A[3][3][3];
+#pragma unroll
+        for (int i = 0; i < 27; i++) (&A[0][0][0])[i] = 0.;
+#pragma unroll
+        for (int t0 = 0; t0 < F; t0++) {
+            const int hi = wrap_index(isx + t0, a.dn[0]);
+            double Cy[3][3];
+#pragma unroll
+            for (int i = 0; i < 9; i++) (&Cy[0][0])[i] = 0.;
+#pragma unroll
+            for (int t1 = 0; t1 < F; t1++) {
+                const int hj = wrap_index(isy + t1, a.dn[1]);
+                const long long rowbase = (long long)a.dn[2] * ((long long)hj + (long long)a.dn[1] * hi);
+                double Bzv[3] = {0., 0., 0.};
+#pragma unroll
+                for (int t2 = 0; t2 < F; t2++) {
+                    const int hk = wrap_index(isz + t2, a.dn[2]);
+                    const double mass = 1.0 + (double)a.dens[rowbase + hk] * a.init_growth;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) Bzv[c] += mass * Wz[t2][c];
+                }
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) Cy[b][c] += Wy[t1][b] * Bzv[c];
+            }
+#pragma unroll
+            for (int aa = 0; aa < 3; aa++)
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) A[aa][b][c] += Wx[t0][aa] * Cy[b][c];
+        }
+#pragma unroll
+        for (int aa = 0; aa < 3; aa++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const long long q = llrint(A[aa][b][c] * FIXED_SCALE);
+                    if (q == 0) continue;
+                    const int gx = Bx + aa, gy = By + b, gz = Bz + c;
+                    const int lx = gx - ox, ly = gy - oy, lz = gz - oz;
+                    if (lx >= 0 && lx < tx && ly >= 0 && ly < ty && lz >= 0 && lz < tz) {
+                        atomic_add_u64(&tile[(lx * ty + ly) * tz + lz], (unsigned long long)q);
+                    } else {
+                        const int wx = wrap_index(gx, a.on[0]), wy = wrap_index(gy, a.on[1]), wz = wrap_index(gz, a.on[2]);
+                        atomic_add_u64(&a.acc[(long long)wz + (long long)a.on[2] * ((long long)wy + (long long)a.on[1] * wx)],
+                                       (unsigned long long)q);
+                    }
+                }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tcells; t += blockDim.x) {
+        const unsigned long long q = tile[t];
+        if (q == 0ULL) continue;
+        const int lz = t % tz, ly = (t / tz) % ty, lx = t / (tz * ty);
+        const int wx = wrap_index(ox + lx, a.on[0]), wy = wrap_index(oy + ly, a.on[1]), wz = wrap_index(oz + lz, a.on[2]);
+        atomic_add_u64(&a.acc[(long long)wz + (long long)a.on[2] * ((long long)wy + (long long)a.on[1] * wx)], q);
+    }
+}
+
+template <int F> static void launch_grouped(const MoveArgs &a) {
+    GroupArgs g;
+    g.m = a;
+    const int want[3] = {4, 8, 8};
+    for (int ax = 0; ax < 3; ax++) {
+        g.gbrick[ax] = a.vn[ax] < want[ax] ? a.vn[ax] : want[ax];
+        g.gtiles[ax] = (a.vn[ax] + g.gbrick[ax] - 1) / g.gbrick[ax];
+    }
+    const size_t smem = sizeof(unsigned long long) * (size_t)(g.gbrick[0] + 2 * a.halo) *
+                        (g.gbrick[1] + 2 * a.halo) * (g.gbrick[2] + 2 * a.halo);
+    B200_LAUNCH(move_cic_grouped_kernel<F>, g.gtiles[0] * g.gtiles[1] * g.gtiles[2], 256, smem, g);
+}
+
 struct AccToDeltaArgs {
     long long nrows;
     int nz, nzc;
@@ -231,13 +373,24 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
             a.tiles[ax] = (dn[ax] + a.brick[ax] - 1) / a.brick[ax];
             a.tile0[ax] = (int)ceil(a.brick[ax] * a.ratio_out) + 1;
         }
-        const size_t smem = sizeof(unsigned long long) * (size_t)(a.tile0[0] + 2 * a.halo) *
-                            (a.tile0[1] + 2 * a.halo) * (a.tile0[2] + 2 * a.halo);
+        /* integer hi/lo ratio (the default DIM = 3 HII_DIM): grouped kernel, else the generic one */
+        const int F = dn[0] / hn[0];
+        const bool integer_ratio = F * hn[0] == dn[0] && F * hn[1] == dn[1] && F * hn[2] == dn[2] && F >= 1 && F <= 4;
+        const char *force = getenv("B200_CIC_GENERIC");
+        if (integer_ratio && !(force && force[0] == '1')) {
+            if (F == 1) launch_grouped<1>(a);
+            else if (F == 2) launch_grouped<2>(a);
+            else if (F == 3) launch_grouped<3>(a);
+            else launch_grouped<4>(a);
+        } else {
+            const size_t smem = sizeof(unsigned long long) * (size_t)(a.tile0[0] + 2 * a.halo) *
+                                (a.tile0[1] + 2 * a.halo) * (a.tile0[2] + 2 * a.halo);
 #ifndef B200_EMU
-        if (smem > 48 * 1024)
-            CUDA_CHECK(cudaFuncSetAttribute(move_cic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 48 * 1024)
+                CUDA_CHECK(cudaFuncSetAttribute(move_cic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-        B200_LAUNCH(move_cic_kernel, a.tiles[0] * a.tiles[1] * a.tiles[2], 256, smem, a);
+            B200_LAUNCH(move_cic_kernel, a.tiles[0] * a.tiles[1] * a.tiles[2], 256, smem, a);
+        }
         AccToDeltaArgs ca = {(long long)hn[0] * hn[1], hn[2], plan->nzc, acc, padded, (double)N / (double)M};
         B200_LAUNCH(acc_to_delta_kernel, row_blocks, 256, 0, ca);
         /* acc returns to the pool at scope exit; reuse is stream-ordered (single stream) */

@@ -102,6 +102,26 @@ void d2d(void *dst, const void *src, size_t bytes) {
     CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
 }
 void dev_sync() { CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+void *host_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    CUDA_CHECK(cudaMallocHost(&p, bytes));
+    return p;
+}
+void host_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+void h2d_async(void *dst, const void *src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+}
+void d2h_async(void *dst, const void *src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+}
+void *dev_event_create() {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return e;
+}
+void dev_event_record(void *ev) { CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev, g_stream)); }
+void dev_event_wait_host(void *ev) { CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)ev)); }
+void dev_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
 
 void DevTimer::start() {
     rt_init();
@@ -191,6 +211,14 @@ void h2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_
 void d2h(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_stats.d2h += bytes; }
 void d2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void dev_sync() {}
+void *host_pinned_alloc(size_t bytes) { return malloc(bytes); }
+void host_pinned_free(void *p) { free(p); }
+void h2d_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void d2h_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void *dev_event_create() { return nullptr; }
+void dev_event_record(void *) {}
+void dev_event_wait_host(void *) {}
+void dev_event_destroy(void *) {}
 void DevTimer::start() { t0 = omp_get_wtime(); }
 double DevTimer::stop_ms() { return (omp_get_wtime() - t0) * 1e3; }
 #endif

@@ -79,6 +79,9 @@ void prof_end(int slot);
 template <typename T> DEV T ldg(const T *p) { return __ldg(p); }
 DEV void atomic_add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 DEV void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
+DEV void atomic_min_i32(int *p, int v) { atomicMin(p, v); }
+DEV void atomic_max_i32(int *p, int v) { atomicMax(p, v); }
+DEV int float_as_int_bits(float f) { return __float_as_int(f); }
 #else /* host-only translation units (host_physics.cpp, host_numerics.cpp) built by g++ */
 #define HD inline
 #define DEV inline
@@ -122,6 +125,15 @@ inline void atomic_add_f64(double *p, double v) {
 #pragma omp atomic
     *p += v;
 }
+inline void atomic_min_i32(int *p, int v) {
+#pragma omp critical(b200_minmax)
+    { if (v < *p) *p = v; }
+}
+inline void atomic_max_i32(int *p, int v) {
+#pragma omp critical(b200_minmax)
+    { if (v > *p) *p = v; }
+}
+inline int float_as_int_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
@@ -161,6 +173,24 @@ void d2h(void *dst, const void *src, size_t bytes);
 void d2d(void *dst, const void *src, size_t bytes);
 void dev_sync();
 int dev_num_sms();
+/* pinned host staging + asynchronous copies + events, for pipelines that must not stall the stream */
+void *host_pinned_alloc(size_t bytes);
+void host_pinned_free(void *p);
+void h2d_async(void *dst, const void *pinned_src, size_t bytes);
+void d2h_async(void *pinned_dst, const void *src, size_t bytes);
+void *dev_event_create();
+void dev_event_record(void *ev);
+void dev_event_wait_host(void *ev);
+void dev_event_destroy(void *ev);
+
+/* order-preserving float <-> int key (so that integer atomicMin/Max order floats) */
+HD int float_order_key(int bits) { return bits >= 0 ? bits : bits ^ 0x7fffffff; }
+inline float float_from_order_key(int key) {
+    int bits = key >= 0 ? key : key ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
 
 /* RAII device buffer */
 template <typename T> struct DevBuf {

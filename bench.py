@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- coeval cells/sec for perturb + ionize at one redshift (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's own C, host cores
+
+One "step" = ComputePerturbedField + ComputeIonizedBox for one coeval box with the initial
+conditions already generated (ICs are outside the metric).
+
+b200 arm, per rank (one process per GPU, independent boxes -> weak scaling, no collective on the
+data path):
+  value : steps with every input/output already resident in HBM (device-pointer entry points),
+          timed with CUDA events on the library's stream, max over ranks.
+  e2e   : the same steps through the reference-facing C-ABI (ComputePerturbedField /
+          ComputeIonizedBox) with pinned HOST buffers; H2D of the initial conditions and D2H of
+          every output box are inside the timed region (IC device cache disabled).
+  roofline : dominant kernel by summed CUDA-event time inside the timed steps; achieved =
+          algorithmic bytes per launch / mean launch time (DESIGN.md "Algorithmic bytes").
+  cpu_baseline : oracle/_ref (the reference's C sources compiled here against the FFTW/GSL
+          shims) on a bounded sample of the same workload, on this host's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hii-dim", type=int, default=256)
+    ap.add_argument("--dim", type=int, default=0, help="hi-res grid (default 3 x HII_DIM)")
+    ap.add_argument("--box-len", type=float, default=0.0, help="Mpc (default 300/256 per cell)")
+    ap.add_argument("--redshift", type=float, default=8.0)
+    ap.add_argument("--source", default="E-INTEGRAL", choices=["E-INTEGRAL", "CONST-ION-EFF"])
+    ap.add_argument("--r-bubble-max", type=float, default=15.0)
+    ap.add_argument("--ref-hii-dim", type=int, default=128, help="bounded CPU sample size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, hii=None):
+    hii = hii or args.hii_dim
+    dim = (args.dim if args.dim and hii == args.hii_dim else 0) or 3 * hii
+    cell = (args.box_len / args.hii_dim) if args.box_len else 300.0 / 256.0
+    return hii, dim, cell * hii
+
+
+def n_radii(hii, box_len, rmax):
+    rmin = max(0.620350491, 0.620350491 * box_len / hii)
+    rmx = min(rmax, 0.620350491 * box_len)
+    return int(np.log(rmx / rmin) / np.log(1.1) + 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def pinned_like(torch, arr):
+    t = torch.empty(arr.shape, dtype=torch.float32, pin_memory=True)
+    a = t.numpy()
+    a[...] = arr
+    return t, a
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref) on this host."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import common
+    pkg = common.pkg
+    ref = common.ref_backend()
+    ncpu = os.cpu_count() or 1
+    hii, dim, box_len = workload(args, args.ref_hii_dim)
+    full_hii, full_dim, full_box = workload(args)
+    base = {"impl": "reference", "metric": "coeval cells/sec (perturb+ionize, one redshift)",
+            "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"perturb_field+ionize_box z={args.redshift} HII_DIM={full_hii} "
+                                   f"DIM={full_dim} BOX_LEN={full_box:g} {args.source}"}}
+    if ref is None:
+        print(json.dumps({**base, "unavailable": "oracle/_ref/libref21cmfast.so not present"}))
+        return
+    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source,
+                                n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
+    ics = make_ics(pkg, common, inputs)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pf = pkg.perturb_field(redshift=args.redshift, initial_conditions=ics, backend=ref)
+        pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=ref)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = hii**3 / (ms / 1e3)
+    sample = (f"HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g} (same cell size and physics as the "
+              f"HII_DIM={full_hii} workload), N_THREADS={ncpu}; FFT back-end = MKL-DFTI shim, "
+              f"single-threaded as in the reference (dft.c), not FFTW")
+    print(json.dumps({**base, "value": value, "ms_per_step": ms,
+                      "cpu_baseline": {"value": value, "unit": "cells/s", "cores": ncpu,
+                                       "kind": "reference", "sample": sample},
+                      "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,
+                              "d2h_bytes_per_step": 0}}))
+
+
+def make_ics(pkg, common, inputs):
+    """Synthetic ICs from the product's own IC generator when a GPU is present (device RNG: the
+    field only needs the right P(k)), else from the compiled reference."""
+    try:
+        be = common.gpu_backend()
+        os.environ["B200_IC_RNG"] = "device"
+        os.environ["B200_SKIP_SCRATCH_OUTPUTS"] = "1"
+        ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+        os.environ.pop("B200_IC_RNG")
+        return ics
+    except Exception:
+        return pkg.compute_initial_conditions(inputs=inputs, backend=common.ref_backend())
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import common
+    pkg = common.pkg
+    _abi = importlib.import_module("21cmfast_b200._abi")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = pkg.get_backend()
+    be.set_table_path(common.table_dir())
+    lib = be.lib
+    assert lib.b200_set_device(local) == 0
+    lib.b200_profile_report.argtypes = [C.c_char_p, C.c_int]
+
+    ncpu = max(1, (os.cpu_count() or 1) // max(1, world))
+    hii, dim, box_len = workload(args)
+    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source, seed=1234 + rank,
+                                n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
+    N, M = hii**3, dim**3
+    nrad = n_radii(hii, box_len, args.r_bubble_max)
+    os.environ["B200_IC_RNG"] = "device"
+    os.environ["B200_SKIP_SCRATCH_OUTPUTS"] = "1"
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+    z = float(args.redshift)
+
+    def stats():
+        a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_double()
+        lib.b200_last_call_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg (`value`) ----------------
+    dev = torch.device("cuda", local)
+    names_ic = ["hires_density", "lowres_density", "lowres_vx", "lowres_vy", "lowres_vz",
+                "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+    d_ic = {k: torch.from_numpy(getattr(ics, k)).to(dev) for k in names_ic}
+    d_pf = {k: torch.zeros((hii,) * 3, dtype=torch.float32, device=dev) for k in ("density", "velocity_z")}
+    d_ib = {k: torch.zeros((hii,) * 3, dtype=torch.float32, device=dev)
+            for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion")}
+    s_ic = _abi.InitialConditionsStruct()
+    for k, t in d_ic.items():
+        setattr(s_ic, k, C.cast(t.data_ptr(), _abi.c_float_p))
+    s_pf = _abi.PerturbedFieldStruct()
+    for k, t in d_pf.items():
+        setattr(s_pf, k, C.cast(t.data_ptr(), _abi.c_float_p))
+    s_ib = _abi.IonizedBoxStruct()
+    for k, t in d_ib.items():
+        setattr(s_ib, k, C.cast(t.data_ptr(), _abi.c_float_p))
+    lib.b200_ComputePerturbedField_device.argtypes = [C.c_float, C.POINTER(_abi.InitialConditionsStruct),
+                                                      C.POINTER(_abi.PerturbedFieldStruct)]
+    lib.b200_ComputeIonizedBox_device.argtypes = [C.c_float, C.c_float, C.POINTER(_abi.PerturbedFieldStruct),
+                                                  C.POINTER(_abi.IonizedBoxStruct)]
+
+    def device_step():
+        d_ib["neutral_fraction"].fill_(1.0)
+        d_ib["kinetic_temperature"].zero_()
+        torch.cuda.synchronize()
+        st = lib.b200_ComputePerturbedField_device(C.c_float(z), C.byref(s_ic), C.byref(s_pf))
+        assert st == 0, st
+        l1, _, _, ms1 = stats()
+        st = lib.b200_ComputeIonizedBox_device(C.c_float(z), C.c_float(-1.0), C.byref(s_pf), C.byref(s_ib))
+        assert st == 0, st
+        l2, _, _, ms2 = stats()
+        return ms1, ms2, l1 + l2
+
+    for _ in range(args.warmup):
+        device_step()
+    lib.b200_profile_enable(1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    t_wall = time.perf_counter()
+    per, launches = [], 0
+    for _ in range(args.steps):
+        m1, m2, ln = device_step()
+        per.append((m1, m2))
+        launches += ln
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clk = clocks.stop()
+    buf = C.create_string_buffer(1 << 16)
+    lib.b200_profile_report(buf, len(buf))
+    lib.b200_profile_enable(0)
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        nm, cnt, tot = ln.split()
+        prof[nm] = (int(cnt), float(tot))
+    ms_perturb = float(np.mean([p[0] for p in per]))
+    ms_ionize = float(np.mean([p[1] for p in per]))
+    ms_step = ms_perturb + ms_ionize
+    xh_dev = float(d_ib["neutral_fraction"].mean().item())
+
+    # ---------------- end-to-end leg through the C-ABI with pinned host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        os.environ["B200_ICS_CACHE"] = "0"  # every step uploads its initial conditions
+        keep = []
+        h_ics = pkg.InitialConditions(inputs)
+        for k in names_ic:
+            t, a = pinned_like(torch, getattr(ics, k))
+            keep.append(t)
+            setattr(h_ics, k, a)
+        h_pf = pkg.PerturbedField(inputs, z)
+        h_ib = pkg.IonizedBox(inputs, z)
+        h_prev = pkg.IonizedBox(inputs, -1.0)
+        for obj, ks in ((h_pf, ("density", "velocity_z")),
+                        (h_ib, ("neutral_fraction", "ionisation_rate_G12", "mean_free_path", "z_reion",
+                                "kinetic_temperature", "unnormalised_nion")), (h_prev, ("z_reion",))):
+            for k in ks:
+                t, a = pinned_like(torch, np.zeros((hii,) * 3, np.float32))
+                keep.append(t)
+                setattr(obj, k, a)
+        ppf, ts, hb = pkg.PerturbedField(inputs, -1.0), pkg.outputs.TsBox.dummy(inputs), pkg.outputs.HaloBox.dummy(inputs)
+
+        def host_step():
+            h_ib.neutral_fraction[...] = 1.0
+            h_ib.kinetic_temperature[...] = 0.0
+            t0 = time.perf_counter()
+            st = lib.ComputePerturbedField(C.c_float(z), C.byref(h_ics.cstruct), C.byref(h_pf.cstruct))
+            assert st == 0, st
+            _, hb1, db1, _ = stats()
+            st = lib.ComputeIonizedBox(C.c_float(z), C.c_float(-1.0), C.byref(h_pf.cstruct), C.byref(ppf.cstruct),
+                                       C.byref(h_prev.cstruct), C.byref(ts.cstruct), C.byref(hb.cstruct),
+                                       C.byref(h_ics.cstruct), C.byref(h_ib.cstruct))
+            assert st == 0, st
+            _, hb2, db2, _ = stats()
+            return time.perf_counter() - t0, hb1 + hb2, db1 + db2
+
+        for _ in range(max(1, args.warmup - 1)):
+            host_step()
+        barrier()
+        tt, h2d_b, d2h_b = [], 0, 0
+        for _ in range(args.steps):
+            t, hb_, db_ = host_step()
+            tt.append(t)
+            h2d_b, d2h_b = hb_, db_
+        barrier()
+        e2e_s = float(np.mean(tt))
+        xh_host = float(h_ib.neutral_fraction.mean())
+        assert abs(xh_host - xh_dev) < 1e-6, (xh_host, xh_dev)
+        e2e = (e2e_s, h2d_b, d2h_b)
+        os.environ.pop("B200_ICS_CACHE")
+
+    # ---------------- reduce over ranks (max time) ----------------
+    vals = torch.tensor([ms_step, ms_perturb, ms_ionize, e2e[0] if e2e else 0.0, t_wall], device=dev,
+                        dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_step, ms_perturb, ms_ionize, e2e_s, t_wall = [float(x) for x in vals.tolist()]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = common.ref_backend()
+        if ref is not None:
+            rh, rd, rb = workload(args, args.ref_hii_dim)
+            rin = common.make_inputs(hii=rh, dim=rd, box_len=rb, source=args.source, n_threads=os.cpu_count() or 1,
+                                     R_BUBBLE_MAX=args.r_bubble_max)
+            os.environ["B200_IC_RNG"] = "device"
+            rics = pkg.compute_initial_conditions(inputs=rin, backend=be)
+            t0 = time.perf_counter()
+            rpf = pkg.perturb_field(redshift=z, initial_conditions=rics, backend=ref)
+            t1 = time.perf_counter()
+            pkg.compute_ionization_field(perturbed_field=rpf, initial_conditions=rics, backend=ref)
+            t2 = time.perf_counter()
+            cpu_baseline = {
+                "value": rh**3 / (t2 - t0), "unit": "cells/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                "sample": (f"oracle/_ref (reference C + FFTW/GSL shims, MKL-DFTI FFT single-threaded as in dft.c) "
+                           f"HII_DIM={rh} DIM={rd} BOX_LEN={rb:g} z={z}, one run: perturb {t1 - t0:.2f}s "
+                           f"ionize {t2 - t1:.2f}s, N_THREADS={os.cpu_count()}")}
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        Nk = hii * hii * (hii // 2 + 1)
+        alg = {  # algorithmic bytes per launch
+            "fft_strided_kernel": 16 * Nk, "fft_c2r_z_kernel": 8 * Nk + 4 * N, "fft_r2c_z_kernel": 8 * Nk + 4 * N,
+            "fcoll_sum_kernel": 4 * N, "ionise_kernel": 8 * N, "move_cic_kernel": 4 * M + 24 * N + 8 * N,
+            "acc_to_delta_kernel": 12 * N, "ionized_temperature_kernel": 16 * N, "fill_kernel": 4 * N}
+        dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+        roofline = None
+        if dom:
+            nm, (cnt, tot) = dom
+            avg_ms = tot / cnt
+            ach = alg.get(nm, 0) / (avg_ms * 1e-3) / 1e9
+            traffic = None
+            tp = ROOT / "profiles" / "traffic.json"
+            if tp.exists():
+                traffic = json.loads(tp.read_text()).get(f"{nm}@{hii}")
+            roofline = {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                        "launches": cnt, "avg_launch_ms": avg_ms,
+                        "share_of_kernel_time": tot / sum(v[1] for v in prof.values())}
+        step_bytes = (40 + 24 * nrad) * N + (4 * M + 72 * N)
+        out = {
+            "metric": "coeval cells/sec (perturb+ionize, one redshift)", "value": world * N / (ms_step * 1e-3),
+            "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"perturb_field+ionize_box z={z} HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g} "
+                                   f"{args.source} n_radii={nrad}",
+                       "parallelism": f"{world} independent coeval boxes (one per GPU)",
+                       "l2": "inputs larger than L2 (every box >= 67 MB at HII_DIM=256 is streamed per pass)",
+                       "ms_perturb": ms_perturb, "ms_ionize": ms_ionize, "global_xH": xh_dev,
+                       "wall_ms_per_step": 1e3 * t_wall / args.steps},
+            "clocks": clk, "gpu_launches": launches,
+            "roofline": roofline,
+            "step_roofline": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            "kernel_profile_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+            "cpu_baseline": cpu_baseline,
+        }
+        if e2e:
+            out["e2e"] = {"value": world * N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(e2e[1]),
+                          "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": 1e3 * e2e_s}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
