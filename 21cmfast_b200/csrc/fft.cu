@@ -200,7 +200,7 @@ struct StridedArgs {
     FftFactors f;
     const float2 *tw;
     /* KMUL geometry: the line axis is x; column m of a group is (y, kz) = (m / nzc, m % nzc) */
-    int kmul, filter_type, nx, ny, nz, nzc;
+    int kmul, filter_type, fast_window, nx, ny, nz, nzc, pitch;
     float R;
     double R_param, r_const, dkx, dky, dkz;
     int op, axis_a, axis_b;
@@ -211,6 +211,54 @@ struct StridedArgs {
 DEV double kd_of_index(int n, int dim, double dk) {
     const double buf = (n <= dim / 2) ? n : (n - dim);
     return buf * dk;
+}
+
+/* k-space multipliers of the x-pass load stage: derivative operator first (rounded to float),
+   then the window -- see KMul in fft.h.  (i = x index, col = flattened (y, kz) with row pitch) */
+DEV float2 apply_kmul(float2 v, int i, int col, const StridedArgs &a) {
+    const int iy = col / a.pitch, iz = col - iy * a.pitch;
+    if (iz >= a.nzc) return v; /* pad column */
+    if (a.op != KOP_NONE) {
+        if (i == 0 && iy == 0 && iz == 0) {
+            v = make_float2(0.f, 0.f);
+        } else if (a.op == KOP_VELOCITY_F) {
+            /* float wavenumbers straight from index_to_k's double value */
+            const float kx = (float)kd_of_index(i, a.nx, a.dkx), ky = (float)kd_of_index(iy, a.ny, a.dky),
+                        kz = (float)kd_of_index(iz, a.nz, a.dkz);
+            const float ksq = kmag_sq_f(kx, ky, kz);
+            const float ka = a.axis_a == 0 ? kx : (a.axis_a == 1 ? ky : kz);
+            const double g = a.op_factor * (double)ka / (double)ksq;
+            v = make_float2((float)(-(double)v.y * g), (float)((double)v.x * g)); /* (re + i im) * (i g) */
+        } else {
+            const double kx = kd_of_index(i, a.nx, a.dkx), ky = kd_of_index(iy, a.ny, a.dky),
+                         kz = kd_of_index(iz, a.nz, a.dkz);
+            const double ksq = kx * kx + ky * ky + kz * kz;
+            const double ka = a.axis_a == 0 ? kx : (a.axis_a == 1 ? ky : kz);
+            if (a.op == KOP_GRADIENT_D) {
+                const double g = ka / ksq;
+                v = make_float2((float)(-(double)v.y * g), (float)((double)v.x * g));
+            } else {
+                const double kb = a.axis_b == 0 ? kx : (a.axis_b == 1 ? ky : kz);
+                const double g = -ka * kb / ksq;
+                v = make_float2((float)((double)v.x * g), (float)((double)v.y * g));
+            }
+        }
+    }
+    if (a.kmul == KMUL_FILTER) {
+        const float kx = kf_of_index(i, a.nx, a.dkx);
+        const float ky = kf_of_index(iy, a.ny, a.dky);
+        const float kz = (float)((double)iz * a.dkz);
+        if (a.fast_window) {
+            const float W = window_value_fast(a.filter_type, kmag_sq_f(kx, ky, kz), a.R);
+            v.x *= W;
+            v.y *= W;
+        } else {
+            const double W = window_value(a.filter_type, kmag_sq_f(kx, ky, kz), a.R, a.R_param, a.r_const);
+            v.x = (float)((double)v.x * W);
+            v.y = (float)((double)v.y * W);
+        }
+    }
+    return v;
 }
 
 __global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restrict__ src,
@@ -226,41 +274,7 @@ __global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restri
         float2 v = make_float2(0.f, 0.f);
         if (col < a.ncols) {
             v = src[gbase + (long long)i * a.line_stride + col];
-            if (a.op != KOP_NONE) {
-                const int iy = col / a.nzc, iz = col - iy * a.nzc;
-                if (i == 0 && iy == 0 && iz == 0) {
-                    v = make_float2(0.f, 0.f);
-                } else if (a.op == KOP_VELOCITY_F) {
-                    /* float wavenumbers straight from index_to_k's double value */
-                    const float kv[3] = {(float)kd_of_index(i, a.nx, a.dkx), (float)kd_of_index(iy, a.ny, a.dky),
-                                         (float)kd_of_index(iz, a.nz, a.dkz)};
-                    const float ksq = kmag_sq_f(kv[0], kv[1], kv[2]);
-                    const double g = a.op_factor * (double)kv[a.axis_a] / (double)ksq;
-                    /* (re + i im) * (i g) */
-                    v = make_float2((float)(-(double)v.y * g), (float)((double)v.x * g));
-                } else {
-                    const double kv[3] = {kd_of_index(i, a.nx, a.dkx), kd_of_index(iy, a.ny, a.dky),
-                                          kd_of_index(iz, a.nz, a.dkz)};
-                    const double ksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
-                    if (a.op == KOP_GRADIENT_D) {
-                        const double g = kv[a.axis_a] / ksq;
-                        v = make_float2((float)(-(double)v.y * g), (float)((double)v.x * g));
-                    } else {
-                        const double g = -kv[a.axis_a] * kv[a.axis_b] / ksq;
-                        v = make_float2((float)((double)v.x * g), (float)((double)v.y * g));
-                    }
-                }
-            }
-            if (a.kmul == KMUL_FILTER) {
-                const int iy = col / a.nzc, iz = col - iy * a.nzc;
-                const float kx = kf_of_index(i, a.nx, a.dkx);
-                const float ky = kf_of_index(iy, a.ny, a.dky);
-                const float kz = (float)((double)iz * a.dkz);
-                const double W = window_value(a.filter_type, kmag_sq_f(kx, ky, kz), a.R,
-                                              a.R_param, a.r_const);
-                v.x = (float)((double)v.x * W);
-                v.y = (float)((double)v.y * W);
-            }
+            if (a.kmul != KMUL_NONE || a.op != KOP_NONE) v = apply_kmul(v, i, col, a);
         }
         A[i * a.Tp + c] = v;
     }
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restri
 
 /* ------------------------------------------------------------------ z-axis kernels */
 struct ZArgs {
-    int n, nzc, nrows, L, Tp;
+    int n, nzc, pitch, nrows, L, Tp;
     FftFactors f;
     const float2 *tw;
     float scale;
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict
         const int k = w % nzc, l = w / nzc;
         const long long row = row0 + l;
         float2 v = make_float2(0.f, 0.f);
-        if (row < a.nrows) v = src[row * nzc + k];
+        if (row < a.nrows) v = src[row * a.pitch + k];
         if (k == 0 || 2 * k == n) v.y = 0.f;
         A[k * a.Tp + l] = v;
         if (k > 0 && 2 * k < n) A[(n - k) * a.Tp + l] = make_float2(v.x, -v.y);
@@ -373,7 +387,7 @@ __global__ void __launch_bounds__(256) fft_r2c_z_kernel(const float *__restrict_
         if (row < a.nrows) {
             float2 v = res[k * a.Tp + l];
             if (a.scale != 1.f) { v.x *= a.scale; v.y *= a.scale; }
-            dst[row * nzc + k] = v;
+            dst[row * a.pitch + k] = v;
         }
     }
 }
@@ -427,6 +441,7 @@ Fft3D *fft_plan(int nx, int ny, int nz) {
     if (it != g_plans3d.end()) return it->second;
     Fft3D *p = new Fft3D();
     p->nx = nx; p->ny = ny; p->nz = nz; p->nzc = nz / 2 + 1;
+    p->pitch = (p->nzc + 7) / 8 * 8;
     p->px = plan1d(nx); p->py = plan1d(ny); p->pz = plan1d(nz);
     g_plans3d[key] = p;
     return p;
@@ -464,8 +479,12 @@ template <typename K> static void allow_smem(K kernel, size_t bytes) {
         cur = bytes;
     }
 }
+#include "fft_pow2.cuh"
 #else
 template <typename K> static void allow_smem(K, size_t) {}
+static bool pow2_strided(const float2 *, float2 *, const StridedArgs &, int) { return false; }
+static bool pow2_c2r_z(const float2 *, float *, const ZArgs &) { return false; }
+static bool pow2_r2c_z(const float *, float2 *, const ZArgs &) { return false; }
 #endif
 
 static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long long line_stride,
@@ -478,13 +497,19 @@ static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long lo
     a.f = p1.f; a.tw = p1.tw;
     a.kmul = KMUL_NONE;
     a.op = KOP_NONE;
+    a.nx = p3->nx; a.ny = p3->ny; a.nz = p3->nz; a.nzc = p3->nzc; a.pitch = p3->pitch;
     if (km && km->active()) {
         a.kmul = km->kind; a.filter_type = km->filter_type;
-        a.nx = p3->nx; a.ny = p3->ny; a.nz = p3->nz; a.nzc = p3->nzc;
+        {
+            static int exact = -1;
+            if (exact < 0) { const char *e = getenv("B200_EXACT_WINDOW"); exact = (e && e[0] == '1') ? 1 : 0; }
+            a.fast_window = (km->fast && !exact && (km->filter_type == 0 || km->filter_type == 2)) ? 1 : 0;
+        }
         a.R = km->R; a.R_param = km->R_param; a.r_const = km->r_const;
         a.dkx = km->dk[0]; a.dky = km->dk[1]; a.dkz = km->dk[2];
         a.op = km->op; a.axis_a = km->axis_a; a.axis_b = km->axis_b; a.op_factor = km->op_factor;
     }
+    if (pow2_strided(src, dst, a, ngroups)) return;
     size_t smem = tile_smem(a.n, a.T);
     allow_smem(fft_strided_kernel, smem);
     dim3 grid((ncols + a.T - 1) / a.T, ngroups, 1);
@@ -492,42 +517,45 @@ static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long lo
 }
 
 void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZEpilogue &epi) {
-    const int nx = p->nx, ny = p->ny, nzc = p->nzc;
-    /* x: lines over (y,kz) flattened, stride ny*nzc; filter rides on the load */
-    run_strided(p->px, src, work, (long long)ny * nzc, ny * nzc, 0, 1, +1, 1.f, &km, p);
-    /* y: for each x, lines over kz, stride nzc */
-    run_strided(p->py, work, work, nzc, nzc, (long long)ny * nzc, nx, +1, 1.f, nullptr, p);
+    const int nx = p->nx, ny = p->ny, pitch = p->pitch;
+    /* x: lines over (y,kz) flattened (pad columns included), stride ny*pitch; multipliers ride on the load */
+    run_strided(p->px, src, work, (long long)ny * pitch, ny * pitch, 0, 1, +1, 1.f, &km, p);
+    /* y: for each x, lines over kz, stride pitch */
+    run_strided(p->py, work, work, pitch, pitch, (long long)ny * pitch, nx, +1, 1.f, nullptr, p);
     /* z: contiguous rows, complex -> real */
     ZArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = p->nz; a.nzc = nzc; a.nrows = nx * ny;
+    a.n = p->nz; a.nzc = p->nzc; a.pitch = pitch; a.nrows = nx * ny;
     a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
     a.f = p->pz.f; a.tw = p->pz.tw;
     a.scale = epi.scale; a.clip = epi.clip; a.clip_lo = epi.clip_lo; a.clip_hi = epi.clip_hi;
     float *dst = epi.dst ? epi.dst : reinterpret_cast<float *>(work);
-    a.real_row_stride = epi.dst ? epi.dst_row_stride : 2LL * nzc;
-    const int nblocks = (a.nrows + a.L - 1) / a.L;
+    a.real_row_stride = epi.dst ? epi.dst_row_stride : 2LL * pitch;
     a.minmax_keys = epi.minmax_keys;
+    if (pow2_c2r_z(work, dst, a)) return;
+    const int nblocks = (a.nrows + a.L - 1) / a.L;
     size_t smem = tile_smem(a.n, a.L);
     allow_smem(fft_c2r_z_kernel, smem);
     B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, work, dst, a);
 }
 
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {
-    const int nx = p->nx, ny = p->ny, nzc = p->nzc;
+    const int nx = p->nx, ny = p->ny, pitch = p->pitch;
     ZArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = p->nz; a.nzc = nzc; a.nrows = nx * ny;
+    a.n = p->nz; a.nzc = p->nzc; a.pitch = pitch; a.nrows = nx * ny;
     a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
     a.f = p->pz.f; a.tw = p->pz.tw;
     a.scale = 1.f; a.premul = pro.premul; a.clip = pro.clip;
     a.clip_lo = pro.clip_lo; a.clip_hi = pro.clip_hi;
     const float *src = pro.src ? pro.src : reinterpret_cast<const float *>(box);
-    a.real_row_stride = pro.src ? pro.src_row_stride : 2LL * nzc;
-    const int nblocks = (a.nrows + a.L - 1) / a.L;
-    size_t smem = tile_smem(a.n, a.L);
-    allow_smem(fft_r2c_z_kernel, smem);
-    B200_LAUNCH(fft_r2c_z_kernel, dim3(nblocks), 256, smem, src, box, a);
-    run_strided(p->py, box, box, nzc, nzc, (long long)ny * nzc, nx, -1, 1.f, nullptr, p);
-    run_strided(p->px, box, box, (long long)ny * nzc, ny * nzc, 0, 1, -1, pro.post_scale, nullptr, p);
+    a.real_row_stride = pro.src ? pro.src_row_stride : 2LL * pitch;
+    if (!pow2_r2c_z(src, box, a)) {
+        const int nblocks = (a.nrows + a.L - 1) / a.L;
+        size_t smem = tile_smem(a.n, a.L);
+        allow_smem(fft_r2c_z_kernel, smem);
+        B200_LAUNCH(fft_r2c_z_kernel, dim3(nblocks), 256, smem, src, box, a);
+    }
+    run_strided(p->py, box, box, pitch, pitch, (long long)ny * pitch, nx, -1, 1.f, nullptr, p);
+    run_strided(p->px, box, box, (long long)ny * pitch, ny * pitch, 0, 1, -1, pro.post_scale, nullptr, p);
 }

@@ -97,6 +97,42 @@ double box_volume() { /* VOLUME macro, indexing.h:39-43 (float products, as in C
 #define CP cosmo_params_global
 #define MO matter_options_global
 
+/* ------------------------------------------------------------------ memo cache for host scalars
+ * sigma_z0 / Nion_General / Fcoll_General are pure functions of the broadcast input structs and
+ * their arguments; a coeval run asks for the same ~70 values at every call, each one an adaptive
+ * quadrature.  Results are memoised under a key that hashes the *contents* of the input structs
+ * (Python may re-use a pointer for new values), the function id and the argument bits. */
+#include <unordered_map>
+static std::unordered_map<unsigned long long, double> g_memo;
+static unsigned long long fnv(const void *p, size_t n, unsigned long long h) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ULL;
+    return h;
+}
+static unsigned long long params_signature(bool astro) {
+    unsigned long long h = 1469598103934665603ULL;
+    h = fnv(CP, sizeof(CosmoParams), h);
+    h = fnv(MO, sizeof(MatterOptions), h);
+    if (cosmo_tables_global) {
+        h = fnv(&cosmo_tables_global->ps_norm, sizeof(double), h);
+        h = fnv(&cosmo_tables_global->USE_SIGMA_8, sizeof(bool), h);
+    }
+    if (astro && astro_params_global) h = fnv(astro_params_global, sizeof(AstroParams), h);
+    if (astro && astro_options_global) h = fnv(astro_options_global, sizeof(AstroOptions), h);
+    return h;
+}
+template <typename F> static double memoised(int fn_id, bool astro, const double *args, int nargs, F &&compute) {
+    unsigned long long h = params_signature(astro);
+    h = fnv(&fn_id, sizeof(int), h);
+    h = fnv(args, sizeof(double) * nargs, h);
+    auto it = g_memo.find(h);
+    if (it != g_memo.end()) return it->second;
+    const double v = compute();
+    if (g_memo.size() > 100000) g_memo.clear();
+    g_memo[h] = v;
+    return v;
+}
+
 /* ------------------------------------------------------------------ background cosmology */
 double hubble_H0() { return (double)(CP->hlittle * 3.2407e-18); } /* Constants.h:92 */
 double rho_crit() {                                                /* Constants.h:94-98 */
@@ -260,7 +296,12 @@ static double dw2dm_of_k(double k, double R, int filter) { /* filtering.c:49-78 
     return 2 * w * dwdr * drdm;
 }
 
-extern "C" double sigma_z0(double M) { /* cosmology.c:369-404 */
+static double sigma_z0_compute(double M);
+extern "C" double sigma_z0(double M) {
+    if (omp_in_parallel()) return sigma_z0_compute(M); /* the memo map is not thread-safe */
+    return memoised(1, false, &M, 1, [&] { return sigma_z0_compute(M); });
+}
+static double sigma_z0_compute(double M) { /* cosmology.c:369-404 */
     const double R = MtoR(M);
     const int filt = MO->FILTER;
     double res, err;
@@ -318,11 +359,12 @@ static void init_ps_impl() { /* cosmology.c:459-557 */
     if (cosmo_tables_global->USE_SIGMA_8) {
         const double Radius_8 = 8.0 / CP->hlittle;
         cc.sigma_norm = 1;
-        cc.sigma_norm = pow(cosmo_tables_global->ps_norm / sigma_z0(RtoM(Radius_8)), 2);
+        cc.sigma_norm = pow(cosmo_tables_global->ps_norm / sigma_z0_compute(RtoM(Radius_8)), 2);
     } else {
         cc.sigma_norm = 2.0 * M_PI * M_PI;
     }
     cc.ready = true;
+    g_memo.clear();
 }
 extern "C" void init_ps(void) {
     try { init_ps_impl(); } catch (B200Error &e) {
@@ -611,12 +653,18 @@ static MFParams mf_params(double growthf, double Mturn, const ScalingConstants *
 }
 
 double Fcoll_General(double z, double lnMmin, double lnMmax) { /* hmf.c:945-953 */
-    MFParams p = mf_params(dicke(z), 0., nullptr);
-    return integrate_qag(lnMmin, lnMmax, p, 0);
+    const double args[3] = {z, lnMmin, lnMmax};
+    return memoised(2, true, args, 3, [&] {
+        MFParams p = mf_params(dicke(z), 0., nullptr);
+        return integrate_qag(lnMmin, lnMmax, p, 0);
+    });
 }
 double Nion_General(double z, double lnMmin, double lnMmax, double Mturn, const ScalingConstants *sc) {
-    MFParams p = mf_params(dicke(z), Mturn, sc); /* hmf.c:955-971 */
-    return integrate_qag(lnMmin, lnMmax, p, 1);
+    const double args[4] = {z, lnMmin, lnMmax, Mturn}; /* sc derives from astro params (in the key) */
+    return memoised(3, true, args, 4, [&] {
+        MFParams p = mf_params(dicke(z), Mturn, sc); /* hmf.c:955-971 */
+        return integrate_qag(lnMmin, lnMmax, p, 1);
+    });
 }
 double Nion_ConditionalM(double growthf, double lnM1, double lnM2, double lnM_cond, double sigma2,
                          double delta2, double Mturn, const ScalingConstants *sc, int method) {
@@ -742,7 +790,7 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
         gl_prepare_nodes(nodes, p);
     }
     const double dcrit_lim = (float)0.99 * get_delta_crit(matter_options_global->HMF, sigma2, growthf);
-#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 8)
+#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 1)
     for (int i = 0; i < N_DENS_INTERP; i++) {
         try {
             const double dens = min_dens + (float)i / ((float)N_DENS_INTERP - 1.) * (max_dens - min_dens);

@@ -80,7 +80,7 @@ DEV void philox4x32(unsigned int ctr[4], unsigned int k0, unsigned int k1) {
 }
 
 struct ModeArgs {
-    int nx, ny, nz, nzc;
+    int nx, ny, nz, nzc, pitch;
     int x0, nxs;              /* x-slab handled by this launch */
     double dk[3], volume;
     PsConsts ps;
@@ -116,19 +116,19 @@ __global__ void __launch_bounds__(256) ic_modes_kernel(ModeArgs a) {
             ga = r * co;
             gb = r * s;
         }
-        a.box[((long long)ix * a.ny + iy) * a.nzc + iz] = make_float2((float)(amp * ga), (float)(amp * gb));
+        a.box[((long long)ix * a.ny + iy) * a.pitch + iz] = make_float2((float)(amp * ga), (float)(amp * gb));
     }
 }
 
 struct ConjArgs {
-    int nx, ny, nz, nzc;
+    int nx, ny, nz, nzc, pitch;
     float2 *box;
 };
 /* adj_complex_conj, InitialConditions.c:26-101: Hermitian symmetry on the kz = 0 and kz = Nyquist
    planes, real corners, zero DC.  One thread per (i, j) pair the reference's loops visit. */
 __global__ void ic_hermitian_kernel(ConjArgs a) {
     const int mx = a.nx / 2, my = a.ny / 2, mz = a.nz / 2;
-    const long long sy = a.nzc, sx = (long long)a.ny * a.nzc;
+    const long long sy = a.pitch, sx = (long long)a.ny * a.pitch;
     const int kplanes[2] = {0, mz};
     /* loop A: i in 1..mx-1, all j handled by the reference's two inner loops */
     const long long nA = (long long)(mx - 1) * (my + 1);
@@ -251,7 +251,8 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
         const float VOLUME = so->BOX_LEN * so->BOX_LEN * so->NON_CUBIC_FACTOR * so->BOX_LEN;
         const double ratio = hn[0] / (double)ln[0];
         Fft3D *plan = fft_plan(hn[0], hn[1], hn[2]);
-        const int nzc = plan->nzc;
+        const int nzc = plan->pitch; /* row pitch of the padded / complex layouts */
+        const int nzc_modes = plan->nzc;
         const long long Mk = (long long)plan->n_cplx();
         const double box_len[3] = {so->BOX_LEN, so->BOX_LEN, so->NON_CUBIC_FACTOR * so->BOX_LEN};
         const double dk[3] = {2. * M_PI / box_len[0], 2. * M_PI / box_len[1], 2. * M_PI / box_len[2]};
@@ -282,7 +283,7 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
             const bool device_rng = mode && strcmp(mode, "device") == 0;
             ModeArgs ma;
             memset(&ma, 0, sizeof(ma));
-            ma.nx = hn[0]; ma.ny = hn[1]; ma.nz = hn[2]; ma.nzc = nzc;
+            ma.nx = hn[0]; ma.ny = hn[1]; ma.nz = hn[2]; ma.nzc = nzc_modes; ma.pitch = nzc;
             ma.dk[0] = dk[0]; ma.dk[1] = dk[1]; ma.dk[2] = dk[2];
             ma.volume = VOLUME; ma.ps = ps; ma.box = K0; ma.seed = random_seed;
             if (device_rng) {
@@ -292,7 +293,7 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
                 unsigned int seeds[1];
                 hostnum::derive_thread_seeds(random_seed, 1, seeds);
                 hostnum::Mt19937 rng(seeds[0]);
-                const long long plane = (long long)hn[1] * nzc;
+                const long long plane = (long long)hn[1] * nzc_modes;
                 int slab = (int)(((long long)1 << 24) / plane);
                 if (slab < 1) slab = 1;
                 if (slab > hn[0]) slab = hn[0];
@@ -308,7 +309,7 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
                     dev_sync(); /* host_g is refilled next iteration */
                 }
             }
-            ConjArgs ca = {hn[0], hn[1], hn[2], nzc, K0};
+            ConjArgs ca = {hn[0], hn[1], hn[2], nzc_modes, nzc, K0};
             B200_LAUNCH(ic_hermitian_kernel, 64, 256, 0, ca);
             /* hires_density = c2r(K0) / VOLUME  (InitialConditions.c:667-692) */
             DevBuf<float> d_hi(M);

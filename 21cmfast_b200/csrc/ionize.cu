@@ -26,6 +26,7 @@
 #include "fft.h"
 #include "host_physics.h"
 
+#include <omp.h>
 #include <vector>
 
 #define HII_ROUND_ERR (1e-5)
@@ -53,7 +54,15 @@ struct SweepArgs {
     float *fcoll;            /* unpadded f_coll grid of this radius */
 };
 
-/* sweep 1: f_coll per cell + block partial sums (calculate_fcoll_grid, IonisationBox.c:773-962) */
+/* sweep 1: f_coll per cell + block partial sums (calculate_fcoll_grid, IonisationBox.c:773-962).
+   Four cells per thread and iteration (128-bit loads/stores) when the row length allows. */
+DEV float fcoll_cell(float dens, float dens_floor, const DevTable *tab, const float *ytab, int log_valued, double &acc) {
+    const float d = fmaxf(dens, dens_floor);
+    double fc = table_eval((double)d, tab, ytab);
+    if (log_valued) fc = exp(fc);
+    acc += fc;
+    return (float)fc;
+}
 __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     DYN_SMEM(float, ytab);
     __shared__ double red[256];
@@ -63,14 +72,26 @@ __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
     const int log_valued = a.table->log_valued;
     double acc = 0.;
-    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const float *src = a.filtered + row * 2 * a.nzc;
-        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
-            const float d = fmaxf(src[z], dens_floor);
-            double fc = table_eval((double)d, a.table, ytab);
-            if (log_valued) fc = exp(fc);
-            acc += fc;
-            a.fcoll[row * a.nz + z] = (float)fc;
+    if ((a.nz & 3) == 0) {
+        const int q = a.nz >> 2; /* float4 chunks per row */
+        const long long nchunks = nrows * q;
+        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks;
+             id += (long long)gridDim.x * blockDim.x) {
+            const long long row = id / q;
+            const int zc = (int)(id - row * q);
+            const float4 d4 = *reinterpret_cast<const float4 *>(a.filtered + row * 2 * a.nzc + 4 * zc);
+            float4 o;
+            o.x = fcoll_cell(d4.x, dens_floor, a.table, ytab, log_valued, acc);
+            o.y = fcoll_cell(d4.y, dens_floor, a.table, ytab, log_valued, acc);
+            o.z = fcoll_cell(d4.z, dens_floor, a.table, ytab, log_valued, acc);
+            o.w = fcoll_cell(d4.w, dens_floor, a.table, ytab, log_valued, acc);
+            *reinterpret_cast<float4 *>(a.fcoll + row * a.nz + 4 * zc) = o;
+        }
+    } else {
+        for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+            const float *src = a.filtered + row * 2 * a.nzc;
+            for (int z = threadIdx.x; z < a.nz; z += blockDim.x)
+                a.fcoll[row * a.nz + z] = fcoll_cell(src[z], dens_floor, a.table, ytab, log_valued, acc);
         }
     }
     red[threadIdx.x] = acc;
@@ -101,7 +122,27 @@ DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { 
     return T_HI * res_xH + T_re * (1. - res_xH);
 }
 
-/* sweep 2: find_ionised_regions (IonisationBox.c:1008-1201), centre-cell method */
+/* one cell of find_ionised_regions (IonisationBox.c:1040-1196), centre-cell method */
+DEV void ionise_cell(const CritArgs &a, long long idx, float fcoll, double mean_fix) {
+    double curr_fcoll = mean_fix * (double)fcoll;
+    if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
+    if (curr_fcoll * a.ion_eff_factor > 1.0) {
+        const float pz = a.prev_zre ? a.prev_zre[idx] : -1.f;
+        a.z_reion[idx] = (pz < 0) ? (float)a.redshift : pz;
+        a.xH[idx] = 0.f;
+    } else if (a.R_index == 0 && (a.xH[idx] > pc::TINY)) {
+        double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
+        if (a.Tk) {
+            const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
+            a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
+        }
+        if (res_xH < 0) res_xH = 0;
+        else if (res_xH > 1) res_xH = 1;
+        a.xH[idx] = (float)res_xH;
+    }
+}
+
+/* sweep 2: find_ionised_regions (IonisationBox.c:1008-1201) */
 __global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
     __shared__ double red[256];
     /* every CTA re-adds the block sums of sweep 1 in the same fixed order: the grid mean is
@@ -122,24 +163,33 @@ __global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
         if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
     }
     const double mean_fix = a.mean_f_coll / grid_mean;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        double curr_fcoll = mean_fix * (double)a.fcoll[idx];
-        if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
-        if (curr_fcoll * a.ion_eff_factor > 1.0) {
-            const float pz = a.prev_zre ? a.prev_zre[idx] : -1.f;
-            a.z_reion[idx] = (pz < 0) ? (float)a.redshift : pz;
-            a.xH[idx] = 0.f;
-        } else if (a.R_index == 0 && (a.xH[idx] > pc::TINY)) {
-            double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
-            if (a.Tk) {
-                const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
-                a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
+    if ((a.n & 3) == 0) {
+        const long long n4 = a.n >> 2;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        const float4 *f4p = reinterpret_cast<const float4 *>(a.fcoll);
+        for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += 4 * stride) {
+            /* four independent 128-bit loads in flight per thread */
+            float4 f4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long j = i4 + u * stride;
+                f4[u] = (j < n4) ? f4p[j] : float4{0.f, 0.f, 0.f, 0.f};
             }
-            if (res_xH < 0) res_xH = 0;
-            else if (res_xH > 1) res_xH = 1;
-            a.xH[idx] = (float)res_xH;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long j = i4 + u * stride;
+                if (j < n4) {
+                    ionise_cell(a, 4 * j + 0, f4[u].x, mean_fix);
+                    ionise_cell(a, 4 * j + 1, f4[u].y, mean_fix);
+                    ionise_cell(a, 4 * j + 2, f4[u].z, mean_fix);
+                    ionise_cell(a, 4 * j + 3, f4[u].w, mean_fix);
+                }
+            }
         }
+    } else {
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n;
+             idx += (long long)gridDim.x * blockDim.x)
+            ionise_cell(a, idx, a.fcoll[idx], mean_fix);
     }
 }
 
@@ -352,7 +402,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         const RadiusSpec &rs = radii[todo[k]];
         KMul km;
         if (rs.R_index > 0) {
-            km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R;
+            km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R; km.fast = 1;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
         }
         ZEpilogue epi;
@@ -364,11 +414,16 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     };
 
     FcollTable htab;
+    double t_wait = 0, t_table = 0, t_launch = 0;
+    const bool verbose = getenv("B200_TIMING") != nullptr;
     if (n_todo > 0) enqueue_transform(0);
     for (int k = 0; k < n_todo; k++) {
         const RadiusSpec &rs = radii[todo[k]];
+        double t0 = omp_get_wtime();
         if (k + 1 < n_todo) enqueue_transform(k + 1);
+        double t1 = omp_get_wtime();
         dev_event_wait_host(g_stage.events[k]);
+        double t2 = omp_get_wtime();
         const double min_density = (double)float_from_order_key(g_stage.h_keys[2 * k]) - 0.001;
         const double max_density = (double)float_from_order_key(g_stage.h_keys[2 * k + 1]) + 0.001;
 
@@ -379,6 +434,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         } else {
             build_fgtrm_table(&htab, min_density, max_density, c.growth_factor, c.sigma_minmass, rs.sigma_maxmass);
         }
+        double t3 = omp_get_wtime();
+        t_launch += t1 - t0; t_wait += t2 - t1; t_table += t3 - t2;
         DevTable *st = &g_stage.h_tables[k];
         st->x_min = htab.x_min; st->x_width = htab.x_width; st->inv_width = 1.0 / htab.x_width;
         st->log_valued = htab.log_valued;
@@ -387,7 +444,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 
         /* the reference leaves the last processed radius' f_coll in unnormalised_nion */
         float *fc = (k == n_todo - 1 && io.nion) ? io.nion : d_fcoll.p;
-        SweepArgs sa = {nx, ny, nz, plan->nzc, reinterpret_cast<const float *>(work[k & 1]), d_tables.p + k, d_partial, fc};
+        SweepArgs sa = {nx, ny, nz, plan->pitch, reinterpret_cast<const float *>(work[k & 1]), d_tables.p + k, d_partial, fc};
         B200_LAUNCH(fcoll_sum_kernel, sweep_blocks, 256, N_DENS_INTERP * sizeof(float), sa);
 
         CritArgs ca;
@@ -402,6 +459,9 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
     }
 
+    if (verbose)
+        fprintf(stderr, "[21cmfast_b200] ionize host: enqueue %.3f ms, event wait %.3f ms, tables %.3f ms (%d radii)\n",
+                1e3 * t_launch, 1e3 * t_wait, 1e3 * t_table, n_todo);
     if (io.Tk) {
         TempArgs ta = {N, io.xH, io.z_reion, io.density, io.Tk, d_flag, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term};
         B200_LAUNCH(ionized_temperature_kernel, grid_for(N, 1024), 256, 0, ta);

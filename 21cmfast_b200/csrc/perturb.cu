@@ -173,32 +173,20 @@ template <int F> DEV void axis_weights(int c, int n_hi, double disp, double r, i
     (void)n_hi;
 }
 
-template <int F> __global__ void __launch_bounds__(256) move_cic_grouped_kernel(GroupArgs g) {
+template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kernel(GroupArgs g) {
     const MoveArgs &a = g.m;
-    DYN_SMEM(unsigned long long, tile);
-    const int tx = g.gbrick[0] + 2 * a.halo, ty = g.gbrick[1] + 2 * a.halo, tz = g.gbrick[2] + 2 * a.halo;
-    const int tcells = tx * ty * tz;
-    for (int i = threadIdx.x; i < tcells; i += blockDim.x) tile[i] = 0ULL;
-    __syncthreads();
-    const int bz = blockIdx.x % g.gtiles[2];
-    const int by = (blockIdx.x / g.gtiles[2]) % g.gtiles[1];
-    const int bx = blockIdx.x / (g.gtiles[2] * g.gtiles[1]);
-    const int c0x = bx * g.gbrick[0], c0y = by * g.gbrick[1], c0z = bz * g.gbrick[2];
-    const int ox = c0x - a.halo, oy = c0y - a.halo, oz = c0z - a.halo;
-    const int np = g.gbrick[0] * g.gbrick[1] * g.gbrick[2];
-    for (int p = threadIdx.x; p < np; p += blockDim.x) {
-        const int cz = c0z + p % g.gbrick[2];
-        const int cy = c0y + (p / g.gbrick[2]) % g.gbrick[1];
-        const int cx = c0x + p / (g.gbrick[2] * g.gbrick[1]);
-        if (cx >= a.vn[0] || cy >= a.vn[1] || cz >= a.vn[2]) continue;
-        const long long vidx = (long long)cz + (long long)a.vn[2] * ((long long)cy + (long long)a.vn[1] * cx);
+    const int nzg = a.vn[2], nyg = a.vn[1], nxg = a.vn[0];
+    const long long ngroups = (long long)nxg * nyg * nzg;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < ngroups;
+         p += (long long)gridDim.x * blockDim.x) {
+        const int cz = (int)(p % nzg);
+        const int cy = (int)((p / nzg) % nyg);
+        const int cx = (int)(p / ((long long)nzg * nyg));
         double disp[3];
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) {
-            /* pos = i; pos += v*vdf; pos -= v2*vdf2 (map_mass.c:190-196); (i + d1) - d2 is kept as
-               two steps inside axis_weights by folding only the part independent of i */
-            disp[ax] = (double)a.v[ax][vidx] * a.vdf[ax];
-            if (a.v2[0]) disp[ax] -= (double)a.v2[ax][vidx] * a.vdf2[ax];
+            disp[ax] = (double)a.v[ax][p] * a.vdf[ax];
+            if (a.v2[0]) disp[ax] -= (double)a.v2[ax][p] * a.vdf2[ax];
         }
         double Wx[F][3], Wy[F][3], Wz[F][3];
         int Bx, By, Bz;
@@ -207,24 +195,27 @@ template <int F> __global__ void __launch_bounds__(256) move_cic_grouped_kernel(
         axis_weights<F>(cz, a.dn[2], disp[2], a.ratio_out, Bz, Wz);
         const int isx = (int)ceil((double)F * cx - 0.5 * F), isy = (int)ceil((double)F * cy - 0.5 * F),
                   isz = (int)ceil((double)F * cz - 0.5 * F);
+        /* groups away from the periodic boundary need no index wrapping */
+        const bool interior = isx >= 0 && isy >= 0 && isz >= 0 && isx + F <= a.dn[0] && isy + F <= a.dn[1] &&
+                              isz + F <= a.dn[2];
         double A[3][3][3];
 #pragma unroll
         for (int i = 0; i < 27; i++) (&A[0][0][0])[i] = 0.;
 #pragma unroll
         for (int t0 = 0; t0 < F; t0++) {
-            const int hi = wrap_index(isx + t0, a.dn[0]);
+            const int hi = interior ? isx + t0 : wrap_index(isx + t0, a.dn[0]);
             double Cy[3][3];
 #pragma unroll
             for (int i = 0; i < 9; i++) (&Cy[0][0])[i] = 0.;
 #pragma unroll
             for (int t1 = 0; t1 < F; t1++) {
-                const int hj = wrap_index(isy + t1, a.dn[1]);
-                const long long rowbase = (long long)a.dn[2] * ((long long)hj + (long long)a.dn[1] * hi);
+                const int hj = interior ? isy + t1 : wrap_index(isy + t1, a.dn[1]);
+                const float *row = a.dens + (long long)a.dn[2] * ((long long)hj + (long long)a.dn[1] * hi);
                 double Bzv[3] = {0., 0., 0.};
 #pragma unroll
                 for (int t2 = 0; t2 < F; t2++) {
-                    const int hk = wrap_index(isz + t2, a.dn[2]);
-                    const double mass = 1.0 + (double)a.dens[rowbase + hk] * a.init_growth;
+                    const int hk = interior ? isz + t2 : wrap_index(isz + t2, a.dn[2]);
+                    const double mass = 1.0 + (double)ldg(&row[hk]) * a.init_growth;
 #pragma unroll
                     for (int c = 0; c < 3; c++) Bzv[c] += mass * Wz[t2][c];
                 }
@@ -240,6 +231,9 @@ template <int F> __global__ void __launch_bounds__(256) move_cic_grouped_kernel(
 #pragma unroll
                     for (int c = 0; c < 3; c++) A[aa][b][c] += Wx[t0][aa] * Cy[b][c];
         }
+        /* 27 fixed-point adds straight into the global accumulator (64-bit integer reductions
+           resolve in L2; no ordering dependence) */
+        const bool inside = Bx >= 0 && By >= 0 && Bz >= 0 && Bx + 2 < a.on[0] && By + 2 < a.on[1] && Bz + 2 < a.on[2];
 #pragma unroll
         for (int aa = 0; aa < 3; aa++)
 #pragma unroll
@@ -248,38 +242,24 @@ template <int F> __global__ void __launch_bounds__(256) move_cic_grouped_kernel(
                 for (int c = 0; c < 3; c++) {
                     const long long q = llrint(A[aa][b][c] * FIXED_SCALE);
                     if (q == 0) continue;
-                    const int gx = Bx + aa, gy = By + b, gz = Bz + c;
-                    const int lx = gx - ox, ly = gy - oy, lz = gz - oz;
-                    if (lx >= 0 && lx < tx && ly >= 0 && ly < ty && lz >= 0 && lz < tz) {
-                        atomic_add_u64(&tile[(lx * ty + ly) * tz + lz], (unsigned long long)q);
-                    } else {
-                        const int wx = wrap_index(gx, a.on[0]), wy = wrap_index(gy, a.on[1]), wz = wrap_index(gz, a.on[2]);
-                        atomic_add_u64(&a.acc[(long long)wz + (long long)a.on[2] * ((long long)wy + (long long)a.on[1] * wx)],
-                                       (unsigned long long)q);
-                    }
+                    int gx = Bx + aa, gy = By + b, gz = Bz + c;
+                    if (!inside) { gx = wrap_index(gx, a.on[0]); gy = wrap_index(gy, a.on[1]); gz = wrap_index(gz, a.on[2]); }
+                    atomic_add_u64(&a.acc[(long long)gz + (long long)a.on[2] * ((long long)gy + (long long)a.on[1] * gx)],
+                                   (unsigned long long)q);
                 }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < tcells; t += blockDim.x) {
-        const unsigned long long q = tile[t];
-        if (q == 0ULL) continue;
-        const int lz = t % tz, ly = (t / tz) % ty, lx = t / (tz * ty);
-        const int wx = wrap_index(ox + lx, a.on[0]), wy = wrap_index(oy + ly, a.on[1]), wz = wrap_index(oz + lz, a.on[2]);
-        atomic_add_u64(&a.acc[(long long)wz + (long long)a.on[2] * ((long long)wy + (long long)a.on[1] * wx)], q);
     }
 }
 
 template <int F> static void launch_grouped(const MoveArgs &a) {
     GroupArgs g;
     g.m = a;
-    const int want[3] = {4, 8, 8};
-    for (int ax = 0; ax < 3; ax++) {
-        g.gbrick[ax] = a.vn[ax] < want[ax] ? a.vn[ax] : want[ax];
-        g.gtiles[ax] = (a.vn[ax] + g.gbrick[ax] - 1) / g.gbrick[ax];
-    }
-    const size_t smem = sizeof(unsigned long long) * (size_t)(g.gbrick[0] + 2 * a.halo) *
-                        (g.gbrick[1] + 2 * a.halo) * (g.gbrick[2] + 2 * a.halo);
-    B200_LAUNCH(move_cic_grouped_kernel<F>, g.gtiles[0] * g.gtiles[1] * g.gtiles[2], 256, smem, g);
+    for (int ax = 0; ax < 3; ax++) { g.gbrick[ax] = 0; g.gtiles[ax] = 0; }
+    const long long ngroups = (long long)a.vn[0] * a.vn[1] * a.vn[2];
+    long long blocks = (ngroups + 127) / 128;
+    const long long cap = (long long)dev_num_sms() * 64;
+    if (blocks > cap) blocks = cap;
+    auto kp = &move_cic_grouped_kernel<F>;
+    B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
 }
 
 struct AccToDeltaArgs {
@@ -340,7 +320,7 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
 
     const double growth = dicke(redshift);
     if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR) {
-        LinearArgs la = {(long long)hn[0] * hn[1], hn[2], plan->nzc, io.lowres_density, padded, growth};
+        LinearArgs la = {(long long)hn[0] * hn[1], hn[2], plan->pitch, io.lowres_density, padded, growth};
         B200_LAUNCH(linear_density_kernel, row_blocks, 256, 0, la);
     } else {
         /* move_grid_masses, map_mass.c:146-208 */
@@ -391,7 +371,7 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
 #endif
             B200_LAUNCH(move_cic_kernel, a.tiles[0] * a.tiles[1] * a.tiles[2], 256, smem, a);
         }
-        AccToDeltaArgs ca = {(long long)hn[0] * hn[1], hn[2], plan->nzc, acc, padded, (double)N / (double)M};
+        AccToDeltaArgs ca = {(long long)hn[0] * hn[1], hn[2], plan->pitch, acc, padded, (double)N / (double)M};
         B200_LAUNCH(acc_to_delta_kernel, row_blocks, 256, 0, ca);
         /* acc returns to the pool at scope exit; reuse is stream-ordered (single stream) */
     }

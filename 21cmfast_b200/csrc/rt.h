@@ -70,6 +70,16 @@ void prof_end(int slot);
         CUDA_CHECK(cudaGetLastError());                              \
     } while (0)
 
+/* same, for a kernel given as a function pointer (template instantiations) with an explicit label */
+#define B200_LAUNCH_T(label, kptr, grid, block, smem, ...)           \
+    do {                                                             \
+        int _ps = g_profile ? prof_begin(label) : -1;                \
+        kptr<<<(grid), (block), (smem), g_stream>>>(__VA_ARGS__);    \
+        if (_ps >= 0) prof_end(_ps);                                 \
+        g_stats.launches++;                                          \
+        CUDA_CHECK(cudaGetLastError());                              \
+    } while (0)
+
 #define DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _dyn_smem[]; \
     type *name = reinterpret_cast<type *>(_dyn_smem)
 
@@ -96,6 +106,7 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r; }
 extern thread_local uint3e blockIdx;
@@ -138,9 +149,11 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline void sincosf_emu(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 static inline void sincospi(double x, double *s, double *c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 
 #define DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(b200_emu_smem)
+#define B200_LAUNCH_T(label, kptr, grid, block, smem, ...) B200_LAUNCH(kptr, grid, block, smem, __VA_ARGS__)
 
 #define B200_LAUNCH(kernel, grid, block, smem, ...)                                         \
     do {                                                                                    \

@@ -1,11 +1,12 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -5
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_256b.json 2> gpurun_out/bench_256b.err; tail -3 gpurun_out/bench_256b.err
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_256f.json 2> gpurun_out/bench_256f.err; tail -2 gpurun_out/bench_256f.err
+python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --hii-dim 512 --dim 1024 --box-len 768 --r-bubble-max 40 > gpurun_out/bench_512c.json 2> gpurun_out/bench_512c.err; tail -2 gpurun_out/bench_512c.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_256b.json'))
-for k in ('value','ms_per_step','e2e','cpu_baseline','roofline','step_roofline','kernel_profile_ms_per_step','gpu_launches'):
-    print(k, d.get(k))
-print(d['config'])
+for f in ('gpurun_out/bench_256f.json','gpurun_out/bench_512c.json'):
+    d=json.load(open(f))
+    print(f, d['value'], d['ms_per_step'], d['config']['ms_perturb'], d['config']['ms_ionize'])
+    print(' ', d.get('kernel_profile_ms_per_step'))
 PY
