@@ -1,0 +1,146 @@
+"""Host-side logic on the CPU tier: the Python mirror of the reference's input structs, the host
+scalar chain of the *shipped* library (g++-compiled units of lib21cmfast_b200.so, no device
+work) against golden values produced by the compiled reference, and the full pipeline of the
+host-emulation build (tests/_emu, same kernel sources, one logical thread per block) against the
+golden fixtures."""
+import ctypes as C
+import math
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import common
+
+pkg = common.pkg
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "21cmfast_b200" / "csrc" / "lib21cmfast_b200.so"
+
+
+def test_input_defaults_and_transformers():
+    ap = pkg.AstroParams()
+    c = ap.cdict
+    assert math.isclose(c["F_STAR10"], 10**-1.3) and math.isclose(c["M_TURN"], 10**8.7)
+    assert math.isclose(c["F_STAR7_MINI"], 10 ** (-1.3 - 1.5)) and math.isclose(c["L_X_MINI"], 10**40.5)
+    assert math.isclose(c["SIGMA_STAR"], 0.25 * math.log(10))
+    so = pkg.SimulationOptions(HII_DIM=50)
+    assert so.dim == 150 and math.isclose(so.box_len, 75.0)
+    with pytest.raises(ValueError):
+        pkg.SimulationOptions(HII_DIM=50, DIM=100, HIRES_TO_LOWRES_FACTOR=2)
+    with pytest.raises(ValueError):
+        pkg.MatterOptions(FILTER="sharp-k")
+    mo = pkg.MatterOptions(SOURCE_MODEL="E-INTEGRAL")
+    assert mo.cdict["SOURCE_MODEL"] == 1 and mo.cdict["POWER_SPECTRUM"] == 0 and mo.cdict["HMF"] == 1
+    cp = pkg.CosmoParams()
+    assert math.isclose(cp.OMl, 1 - cp.OMm)
+    inp = common.make_inputs()
+    assert not inp.evolution_required
+    assert inp.evolve_input_structs(HII_DIM=16).simulation_options.HII_DIM == 16
+
+
+def test_output_struct_allocation_rules():
+    inp = common.make_inputs(hii=8, dim=16)
+    ics = pkg.InitialConditions.new(inp)
+    assert ics.hires_vx is None and ics.lowres_vx.shape == (8, 8, 8) and ics.hires_vx_2LPT.shape == (16, 16, 16)
+    ib = pkg.IonizedBox.new(inp, 8.0)
+    assert (ib.neutral_fraction == 1).all() and ib.unnormalised_nion.shape == (1, 8, 8, 8)
+    assert ib.cumulative_recombinations is None
+    s = ib.cstruct
+    assert not s.cumulative_recombinations and bool(s.neutral_fraction)
+
+
+def _host_backend():
+    if not LIB.exists():
+        pytest.skip("CUDA library not built")
+    be = pkg.Backend()
+    be.set_table_path(common.table_dir())
+    return be
+
+
+def test_shipped_library_host_scalars_match_reference_golden():
+    be = _host_backend()
+    g = np.load(common.GOLDEN / "host_scalars.npz")
+    be.state.init(common.make_inputs(), broadcast_inputs=True, ps=True, sigma=True, heat=True)
+    for z, d in zip(g["z"], g["dicke"]):
+        assert abs(be.lib.dicke(float(z)) - d) <= 1e-14 * abs(d)
+    for M, s, ds in zip(g["M"], g["sigma"], g["dsigmasqdm"]):
+        assert abs(be.lib.sigma_z0(float(M)) - s) <= 1e-10 * abs(s)
+        assert abs(be.lib.dsigmasqdm_z0(float(M)) - ds) <= 1e-8 * abs(ds)
+    for k, p in zip(g["k"], g["power"]):
+        assert abs(be.lib.power_in_k(float(k)) - p) <= 1e-12 * abs(p)
+
+
+@pytest.mark.parametrize("case", list(common.GOLDEN_CASES))
+def test_shipped_library_ionize_host_chain_matches_golden(case):
+    """mean_f_coll (QAG-61 over the mass function) from the shipped library's host code equals the
+    value the compiled reference produced, to 1e-12 -- the check that caught nvcc's float-overload
+    host pass."""
+    be = _host_backend()
+    inputs, _, _, g_ib = common.load_golden(case)
+    be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+    out = (C.c_double * 80)()
+    assert be.lib.b200_ionize_host_scalars(C.c_float(8.0), out, 80) == 0
+    assert abs(out[0] - g_ib.mean_f_coll) <= 1e-12 * g_ib.mean_f_coll
+    n_radii = int(out[7])
+    radii = np.array([out[8 + 2 * i] for i in range(n_radii)])
+    assert n_radii == int(math.log(min(15.0, 0.620350491 * 48) / max(0.620350491, 0.620350491 * 1.5)) / math.log(1.1) + 1)
+    np.testing.assert_allclose(radii[1:] / radii[:-1], 1.1, rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", list(common.GOLDEN_CASES))
+def test_emulated_kernels_reproduce_golden(case):
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built (run __graft_entry__.build())")
+    inputs, ics, g_pf, g_ib = common.load_golden(case)
+    pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+    common.compare_struct(pf, g_pf, tols={"velocity_z": common.TOL_VELOCITY})
+    ib = pkg.compute_ionization_field(perturbed_field=g_pf, initial_conditions=ics, backend=emu)
+    assert common.compare_ionized(ib, g_ib)["mask_mismatch"] == 0
+
+
+def test_emulated_initial_conditions_reproduce_golden_seed_stream():
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    inputs, g_ics, _, _ = common.load_golden(common.GOLDEN_BASE)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+    common.compare_struct(ics, g_ics)
+    # feeding hires_density back in reproduces every other field (reference
+    # tests/test_initial_conditions.py:153-178)
+    again = pkg.compute_initial_conditions(inputs=inputs, backend=emu, initial_density=ics.hires_density)
+    common.compare_struct(again, ics, tol=1e-5, skip=("hires_density", "hires_vx_2LPT", "hires_vy_2LPT", "hires_vz_2LPT"))
+
+
+def test_emulated_generic_cic_equals_grouped():
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    inputs, ics, _, _ = common.load_golden(common.GOLDEN_BASE)
+    a = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+    os.environ["B200_CIC_GENERIC"] = "1"
+    try:
+        b = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+    finally:
+        os.environ.pop("B200_CIC_GENERIC")
+    assert np.abs(a.density - b.density).max() <= 2e-7 * np.abs(a.density).max() + 1e-7
+
+
+def test_error_codes_follow_reference_convention():
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    inputs = common.make_inputs(hii=8, dim=16)
+    bad = inputs.clone(astro_options=pkg.AstroOptions(USE_EXP_FILTER=False, CELL_RECOMB=False, USE_TS_FLUCT=True))
+    ics = pkg.InitialConditions.new(inputs)
+    pf = pkg.PerturbedField.new(bad, 8.0)
+    emu.state.init(bad, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+    ib = pkg.IonizedBox.new(bad, 8.0)
+    prev = pkg.IonizedBox.initial(bad)
+    ts, hb = pkg.outputs.TsBox.dummy(bad), pkg.outputs.HaloBox.dummy(bad)
+    st = emu.lib.ComputeIonizedBox(C.c_float(8.0), C.c_float(-1.0), C.byref(pf.cstruct), C.byref(pf.cstruct),
+                                   C.byref(prev.cstruct), C.byref(ts.cstruct), C.byref(hb.cstruct),
+                                   C.byref(ics.cstruct), C.byref(ib.cstruct))
+    assert st == 3  # ValueError: outside the scoped path, reported through the status code
+    assert (prev.z_reion == -1).all()  # first-snapshot side effect on the previous box is preserved

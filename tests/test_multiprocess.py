@@ -1,0 +1,51 @@
+"""N > 1 host logic on CPU: the path shards by independent coeval boxes (one per rank, no data
+path collective); the only exchange is the max-over-ranks timing reduction bench.py does.  Two
+gloo ranks each run the host-emulation pipeline on their own seed and agree on the reduction."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
+import numpy as np, torch, torch.distributed as dist
+import common
+pkg = common.pkg
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+emu = common.emu_backend()
+inputs = common.make_inputs(hii=16, dim=32, seed=100 + rank)
+ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+ib = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
+xh = torch.tensor([ib.global_xH], dtype=torch.float64)
+allx = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(allx, xh)
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert t.item() == world
+vals = [x.item() for x in allx]
+assert all(0 < v < 1 for v in vals) and len(set(round(v, 9) for v in vals)) == world, vals
+cells = torch.tensor([16.0**3]); dist.all_reduce(cells)
+assert cells.item() == world * 16**3
+if rank == 0: print("OK", vals)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_independent_boxes(tmp_path):
+    if not (ROOT / "tests" / "_emu" / "libb200_emu.so").exists():
+        pytest.skip("tests/_emu not built")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "OK" in r.stdout
