@@ -205,6 +205,7 @@ struct StridedArgs {
     double R_param, r_const, dkx, dky, dkz;
     int op, axis_a, axis_b;
     double op_factor;
+    const float *wtab;
 };
 
 /* index_to_k (indexing.h:116-120): double wavenumber of a grid index */
@@ -244,7 +245,12 @@ DEV float2 apply_kmul(float2 v, int i, int col, const StridedArgs &a) {
             }
         }
     }
-    if (a.kmul == KMUL_FILTER) {
+    if (a.kmul == KMUL_FILTER && a.wtab) {
+        const int sx = (i > a.nx / 2) ? i - a.nx : i, sy = (iy > a.ny / 2) ? iy - a.ny : iy;
+        const float W = ldg(&a.wtab[sx * sx + sy * sy + iz * iz]);
+        v.x *= W;
+        v.y *= W;
+    } else if (a.kmul == KMUL_FILTER) {
         const float kx = kf_of_index(i, a.nx, a.dkx);
         const float ky = kf_of_index(iy, a.ny, a.dky);
         const float kz = (float)((double)iz * a.dkz);
@@ -505,6 +511,7 @@ static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long lo
             if (exact < 0) { const char *e = getenv("B200_EXACT_WINDOW"); exact = (e && e[0] == '1') ? 1 : 0; }
             a.fast_window = (km->fast && !exact && (km->filter_type == 0 || km->filter_type == 2)) ? 1 : 0;
         }
+        a.wtab = (a.fast_window && km->wtab) ? km->wtab : nullptr;
         a.R = km->R; a.R_param = km->R_param; a.r_const = km->r_const;
         a.dkx = km->dk[0]; a.dky = km->dk[1]; a.dkz = km->dk[2];
         a.op = km->op; a.axis_a = km->axis_a; a.axis_b = km->axis_b; a.op_factor = km->op_factor;
@@ -558,4 +565,21 @@ void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {
     }
     run_strided(p->py, box, box, pitch, pitch, (long long)ny * pitch, nx, -1, 1.f, nullptr, p);
     run_strided(p->px, box, box, (long long)ny * pitch, ny * pitch, 0, 1, -1, pro.post_scale, nullptr, p);
+}
+
+/* ------------------------------------------------------------------ window table */
+struct WTabArgs {
+    int type, n;
+    float R;
+    double dk;
+    float *out;
+};
+__global__ void window_table_kernel(WTabArgs a) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
+        a.out[i] = window_of_n2(a.type, i, a.dk, a.R);
+}
+int window_table_size(const Fft3D *p) { return 3 * (p->nx / 2) * (p->nx / 2) + 1; }
+void window_table_build(const Fft3D *p, int type, float R, double dk, float *out) {
+    WTabArgs a = {type, window_table_size(p), R, dk, out};
+    B200_LAUNCH(window_table_kernel, (a.n + 255) / 256, 256, 0, a);
 }

@@ -57,6 +57,8 @@ struct KMul {
     double r_const = 0.;       /* exp(-R/R_param) for type 3 */
     double dk[3] = {0, 0, 0};  /* 2 pi / box length per axis (filtering.c:310-314) */
     int fast = 0;              /* 1: single-precision window (window_value_fast) for the hot sweep */
+    const float *wtab = nullptr; /* optional window table indexed by nx^2+ny^2+nz^2 (cubic boxes) */
+    int wtab_n = 0;
     int op = KOP_NONE;         /* derivative operator */
     int axis_a = 0, axis_b = 0;
     double op_factor = 1.;     /* c in KOP_VELOCITY_F */
@@ -85,6 +87,9 @@ struct ZPrologue {
 };
 
 Fft3D *fft_plan(int nx, int ny, int nz);
+/* table of the window over |n|^2 for cubic boxes (see KMul::wtab) */
+int window_table_size(const Fft3D *p);
+void window_table_build(const Fft3D *p, int type, float R, double dk, float *out);
 
 /* forward: real (padded or pro.src) -> complex in `box` */
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro);
@@ -166,6 +171,23 @@ DEV float window_value_fast(int type, float kmag_sq, float R) {
     /* gaussian */
     const float kR2 = kmag_sq * (R * R);
     return expf(-0.5f * 0.643f * 0.643f * kR2);
+}
+
+/* Window as a function of the integer |n|^2 = nx^2 + ny^2 + nz^2 (cubic boxes): the exact double
+   formula at k = dk sqrt(n2), rounded to float.  Differs from the per-mode evaluation only through
+   the float rounding of the wavenumber components (<= 1 ulp of kR). */
+HD float window_of_n2(int type, long long n2, double dk, float R) {
+    const double k = dk * sqrt((double)n2);
+    const float kmag_sq = (float)(k * k);
+    if (type == 0) {
+        const double x = (double)(float)(k * (double)R);
+        if (x < 1e-4) return (float)(1.0 - x * x * 0.1);
+        double sn, cs;
+        sincos(x, &sn, &cs);
+        return (float)((3.0 / (x * x * x)) * (sn - x * cs));
+    }
+    const float kR2 = kmag_sq * (R * R);
+    return (float)exp(-0.643 * 0.643 * (double)kR2 / 2.);
 }
 
 /* float wavenumber of grid index n on an axis of `dim` cells: the reference computes

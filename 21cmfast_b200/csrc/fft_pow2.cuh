@@ -149,8 +149,25 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::THREADS, Pow2Cfg<N>::MIN_CTAS) fft
             }
         }
         if (has_kmul && live) {
+            if (a.wtab && a.op == KOP_NONE) {
+                /* window from the |n|^2 table: the (y, kz) part is a per-thread constant of the tile */
+                const int iy = col / a.pitch, iz = col - iy * a.pitch;
+                if (iz < a.nzc) {
+                    const int sy = (iy > a.ny / 2) ? iy - a.ny : iy;
+                    const int syz = sy * sy + iz * iz;
 #pragma unroll
-            for (int m = 0; m < 8; m++) v[m] = apply_kmul(v[m], t + m * STEP, col, a);
+                    for (int m = 0; m < 8; m++) {
+                        const int i = t + m * STEP;
+                        const int sx = (i > N / 2) ? i - N : i;
+                        const float W = ldg(&a.wtab[sx * sx + syz]);
+                        v[m].x *= W;
+                        v[m].y *= W;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; m++) v[m] = apply_kmul(v[m], t + m * STEP, col, a);
+            }
         }
         fft_line_regs<N, SIGN, TL>(v, t, c, S, a.tw, 1);
         if (live) {

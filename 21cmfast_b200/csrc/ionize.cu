@@ -110,6 +110,7 @@ struct CritArgs {
     int n_partial;
     const float *density;    /* unfiltered perturbed density, unpadded */
     const float *prev_zre;   /* previous box z_reion or null (= all -1) */
+    unsigned char *mask;     /* 1 = ionised at some radius so far */
     float *xH, *z_reion, *Tk;
     double n_cells, mean_f_coll, f_limit, ion_eff_factor;
     int mass_dep_zeta, R_index;
@@ -122,15 +123,16 @@ DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { 
     return T_HI * res_xH + T_re * (1. - res_xH);
 }
 
-/* one cell of find_ionised_regions (IonisationBox.c:1040-1196), centre-cell method */
+/* one cell of find_ionised_regions (IonisationBox.c:1040-1196), centre-cell method.  Radii above
+   the last one only record "ionised" in a byte mask (the reference rewrites xH = 0 and z_reion at
+   every radius that ionises the cell; both are functions of the mask alone and are materialised
+   once by finalize_kernel).  The last radius also assigns the partial ionisations. */
 DEV void ionise_cell(const CritArgs &a, long long idx, float fcoll, double mean_fix) {
     double curr_fcoll = mean_fix * (double)fcoll;
     if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
     if (curr_fcoll * a.ion_eff_factor > 1.0) {
-        const float pz = a.prev_zre ? a.prev_zre[idx] : -1.f;
-        a.z_reion[idx] = (pz < 0) ? (float)a.redshift : pz;
-        a.xH[idx] = 0.f;
-    } else if (a.R_index == 0 && (a.xH[idx] > pc::TINY)) {
+        a.mask[idx] = 1;
+    } else if (a.R_index == 0 && !a.mask[idx] && (a.xH[idx] > pc::TINY)) {
         double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
         if (a.Tk) {
             const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
@@ -211,25 +213,37 @@ DEV float fully_ionized_temperature(float z_re, float z, float delta, float T_re
     return result;
 }
 
-struct TempArgs {
+struct FinalArgs {
     long long n;
-    const float *xH, *z_reion, *density;
-    float *Tk;
+    const unsigned char *mask;
+    const float *density, *prev_zre;
+    float *xH, *z_reion, *Tk;
     int *nonfinite;
-    double stored_redshift, T_re, TK_nofluct, adia_TK_term;
+    double redshift, stored_redshift, T_re, TK_nofluct, adia_TK_term;
 };
-/* set_ionized_temperatures (IonisationBox.c:1203-1256) */
-__global__ void __launch_bounds__(256) ionized_temperature_kernel(TempArgs a) {
+/* materialise the flags (xH = 0, z_reion; IonisationBox.c:1142-1151) and set_ionized_temperatures
+   (IonisationBox.c:1203-1256) in one pass */
+__global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
          i += (long long)gridDim.x * blockDim.x) {
-        float tk = a.Tk[i];
-        if ((a.z_reion[i] > 0) && (a.xH[i] < pc::TINY)) {
-            tk = fully_ionized_temperature(a.z_reion[i], (float)a.stored_redshift, a.density[i], (float)a.T_re);
-            const float thistk = a.TK_nofluct * (1 + a.adia_TK_term * a.density[i]);
-            if (tk < thistk) tk = thistk;
-            a.Tk[i] = tk;
+        float zre = -1.0f;
+        if (a.mask[i]) {
+            const float pz = a.prev_zre ? a.prev_zre[i] : -1.f;
+            zre = (pz < 0) ? (float)a.redshift : pz;
+            a.xH[i] = 0.f;
         }
-        if (!isfinite(tk)) *a.nonfinite = 1;
+        a.z_reion[i] = zre;
+        if (a.Tk) {
+            float tk = a.Tk[i];
+            if (a.mask[i] && zre > 0) {
+                const float d = a.density[i];
+                tk = fully_ionized_temperature(zre, (float)a.stored_redshift, d, (float)a.T_re);
+                const float thistk = a.TK_nofluct * (1 + a.adia_TK_term * d);
+                if (tk < thistk) tk = thistk;
+                a.Tk[i] = tk;
+            }
+            if (!isfinite(tk)) *a.nonfinite = 1;
+        }
     }
 }
 
@@ -323,7 +337,6 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const long long N = (long long)nx * ny * nz;
     Fft3D *plan = fft_plan(nx, ny, nz);
 
-    { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
 
     std::vector<RadiusSpec> radii = setup_radii(c);
     const int n_radii = (int)radii.size();
@@ -356,6 +369,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 
     const double exp_global_hii = box->mean_f_coll * c.ion_eff_factor_gl;
     if (exp_global_hii < HII_ROUND_ERR) {
+        { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
         NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term};
         B200_LAUNCH(neutral_box_kernel, grid_for(N, 1024), 256, 0, na);
         return;
@@ -379,6 +393,13 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     DevBuf<double> d_partial(sweep_blocks);
     DevBuf<int> d_flag(1);
     dev_zero(d_flag, sizeof(int));
+    DevBuf<unsigned char> d_mask((size_t)N);
+    dev_zero(d_mask, (size_t)N);
+    /* window tables over |n|^2 (cubic boxes, top-hat / gaussian): two slots, stream-ordered reuse */
+    const bool cubic = nx == ny && ny == nz && so->NON_CUBIC_FACTOR == 1.0f;
+    const bool use_wtab = cubic && (c.hii_filter == 0 || c.hii_filter == 2);
+    const int wtab_n = use_wtab ? window_table_size(plan) : 0;
+    DevBuf<float> d_wtab(use_wtab ? 2 * (size_t)wtab_n : 0);
     g_stage.ensure(n_todo);
     if (n_todo > 0) {
         KeyInitArgs ka = {n_todo, d_keys};
@@ -404,6 +425,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         if (rs.R_index > 0) {
             km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R; km.fast = 1;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
+            if (use_wtab) {
+                float *slot = d_wtab.p + (size_t)(k & 1) * wtab_n;
+                window_table_build(plan, c.hii_filter, km.R, dk0, slot);
+                km.wtab = slot; km.wtab_n = wtab_n;
+            }
         }
         ZEpilogue epi;
         epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
@@ -451,7 +477,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         memset(&ca, 0, sizeof(ca));
         ca.n = N; ca.fcoll = fc; ca.partial = d_partial; ca.n_partial = sweep_blocks;
         ca.density = io.density; ca.prev_zre = io.prev_zre;
-        ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
+        ca.mask = d_mask; ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
         ca.n_cells = (double)N; ca.mean_f_coll = box->mean_f_coll; ca.f_limit = f_limit;
         ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
         ca.R_index = rs.R_index; ca.redshift = c.redshift;
@@ -462,15 +488,14 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     if (verbose)
         fprintf(stderr, "[21cmfast_b200] ionize host: enqueue %.3f ms, event wait %.3f ms, tables %.3f ms (%d radii)\n",
                 1e3 * t_launch, 1e3 * t_wait, 1e3 * t_table, n_todo);
-    if (io.Tk) {
-        TempArgs ta = {N, io.xH, io.z_reion, io.density, io.Tk, d_flag, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term};
-        B200_LAUNCH(ionized_temperature_kernel, grid_for(N, 1024), 256, 0, ta);
+    {
+        FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
+                        c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term};
+        B200_LAUNCH(finalize_kernel, grid_for(N, 1024), 256, 0, fa);
         int flag = 0;
-        d2h(&flag, d_flag, sizeof(int));
+        d2h(&flag, d_flag, sizeof(int)); /* also drains the stream before the work boxes are released */
         g_stats.d2h -= (long long)sizeof(int);
         if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
-    } else {
-        dev_sync(); /* pinned staging and the work boxes must outlive the queued kernels */
     }
 }
 

@@ -151,8 +151,10 @@ struct GroupArgs {
     int gtiles[3];
 };
 
-template <int F> DEV void axis_weights(int c, int n_hi, double disp, double r, int &base, double W[F][3]) {
-    /* hi-res indices whose nearest velocity cell is c: istart .. istart + F - 1 (may be -1 at c = 0) */
+/* per-axis CIC data of one group: position of sub-particle t -> (cell offset o_t in {0,1} relative
+   to the base cell, weight w1_t of the upper cell).  The F x 3 weight matrix row is
+   W[t][a] = (a == o_t) ? 1 - w1_t : (a == o_t + 1) ? w1_t : 0. */
+template <int F> DEV void axis_cic(int c, double disp, double r, int &base, double (&w1)[F], int (&o)[F]) {
     const int istart = (int)ceil((double)F * c - 0.5 * F);
     int b0 = 0;
 #pragma unroll
@@ -163,20 +165,18 @@ template <int F> DEV void axis_weights(int c, int n_hi, double disp, double r, i
         const double fl = floor(pos);
         const int b = (int)fl;
         if (t == 0) b0 = b;
-        const int o = b - b0; /* 0 or 1 */
-        const double w1 = pos - fl, w0 = 1. - w1;
-        W[t][0] = (o == 0) ? w0 : 0.;
-        W[t][1] = (o == 0) ? w1 : w0;
-        W[t][2] = (o == 0) ? 0. : w1;
+        o[t] = b - b0;
+        w1[t] = pos - fl;
     }
     base = b0;
-    (void)n_hi;
 }
+DEV double cic_w(int a, int o, double w1) { return a == o ? 1. - w1 : (a == o + 1 ? w1 : 0.); }
 
 template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kernel(GroupArgs g) {
     const MoveArgs &a = g.m;
     const int nzg = a.vn[2], nyg = a.vn[1], nxg = a.vn[0];
     const long long ngroups = (long long)nxg * nyg * nzg;
+    const long long out_sx = (long long)a.on[1] * a.on[2];
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < ngroups;
          p += (long long)gridDim.x * blockDim.x) {
         const int cz = (int)(p % nzg);
@@ -188,25 +188,24 @@ template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kern
             disp[ax] = (double)a.v[ax][p] * a.vdf[ax];
             if (a.v2[0]) disp[ax] -= (double)a.v2[ax][p] * a.vdf2[ax];
         }
-        double Wx[F][3], Wy[F][3], Wz[F][3];
+        double w1x[F], w1y[F], w1z[F];
+        int ox_[F], oy_[F], oz_[F];
         int Bx, By, Bz;
-        axis_weights<F>(cx, a.dn[0], disp[0], a.ratio_out, Bx, Wx);
-        axis_weights<F>(cy, a.dn[1], disp[1], a.ratio_out, By, Wy);
-        axis_weights<F>(cz, a.dn[2], disp[2], a.ratio_out, Bz, Wz);
+        axis_cic<F>(cx, disp[0], a.ratio_out, Bx, w1x, ox_);
+        axis_cic<F>(cy, disp[1], a.ratio_out, By, w1y, oy_);
+        axis_cic<F>(cz, disp[2], a.ratio_out, Bz, w1z, oz_);
         const int isx = (int)ceil((double)F * cx - 0.5 * F), isy = (int)ceil((double)F * cy - 0.5 * F),
                   isz = (int)ceil((double)F * cz - 0.5 * F);
         /* groups away from the periodic boundary need no index wrapping */
         const bool interior = isx >= 0 && isy >= 0 && isz >= 0 && isx + F <= a.dn[0] && isy + F <= a.dn[1] &&
                               isz + F <= a.dn[2];
-        double A[3][3][3];
-#pragma unroll
-        for (int i = 0; i < 27; i++) (&A[0][0][0])[i] = 0.;
+        /* contract z then y for each x-slice of the group: Cy[t0][b][c] */
+        double Cy[F][3][3];
 #pragma unroll
         for (int t0 = 0; t0 < F; t0++) {
             const int hi = interior ? isx + t0 : wrap_index(isx + t0, a.dn[0]);
-            double Cy[3][3];
 #pragma unroll
-            for (int i = 0; i < 9; i++) (&Cy[0][0])[i] = 0.;
+            for (int i = 0; i < 9; i++) (&Cy[t0][0][0])[i] = 0.;
 #pragma unroll
             for (int t1 = 0; t1 < F; t1++) {
                 const int hj = interior ? isy + t1 : wrap_index(isy + t1, a.dn[1]);
@@ -217,36 +216,44 @@ template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kern
                     const int hk = interior ? isz + t2 : wrap_index(isz + t2, a.dn[2]);
                     const double mass = 1.0 + (double)ldg(&row[hk]) * a.init_growth;
 #pragma unroll
-                    for (int c = 0; c < 3; c++) Bzv[c] += mass * Wz[t2][c];
+                    for (int c = 0; c < 3; c++) Bzv[c] += mass * cic_w(c, oz_[t2], w1z[t2]);
                 }
 #pragma unroll
-                for (int b = 0; b < 3; b++)
+                for (int b = 0; b < 3; b++) {
+                    const double wy = cic_w(b, oy_[t1], w1y[t1]);
 #pragma unroll
-                    for (int c = 0; c < 3; c++) Cy[b][c] += Wy[t1][b] * Bzv[c];
+                    for (int c = 0; c < 3; c++) Cy[t0][b][c] += wy * Bzv[c];
+                }
             }
-#pragma unroll
-            for (int aa = 0; aa < 3; aa++)
-#pragma unroll
-                for (int b = 0; b < 3; b++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) A[aa][b][c] += Wx[t0][aa] * Cy[b][c];
         }
-        /* 27 fixed-point adds straight into the global accumulator (64-bit integer reductions
-           resolve in L2; no ordering dependence) */
+        /* x contraction one output plane at a time (rolled loop keeps the kernel inside the
+           instruction cache), 9 fixed-point 64-bit reductions per plane straight into L2 */
         const bool inside = Bx >= 0 && By >= 0 && Bz >= 0 && Bx + 2 < a.on[0] && By + 2 < a.on[1] && Bz + 2 < a.on[2];
+#pragma unroll 1
+        for (int aa = 0; aa < 3; aa++) {
+            double A[3][3];
 #pragma unroll
-        for (int aa = 0; aa < 3; aa++)
+            for (int i = 0; i < 9; i++) (&A[0][0])[i] = 0.;
 #pragma unroll
-            for (int b = 0; b < 3; b++)
+            for (int t0 = 0; t0 < F; t0++) {
+                const double wx = cic_w(aa, ox_[t0], w1x[t0]);
+#pragma unroll
+                for (int i = 0; i < 9; i++) (&A[0][0])[i] += wx * (&Cy[t0][0][0])[i];
+            }
+            const int gx = inside ? Bx + aa : wrap_index(Bx + aa, a.on[0]);
+            unsigned long long *plane = a.acc + (long long)gx * out_sx;
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const int gy = inside ? By + b : wrap_index(By + b, a.on[1]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const long long q = llrint(A[aa][b][c] * FIXED_SCALE);
+                    const long long q = llrint(A[b][c] * FIXED_SCALE);
                     if (q == 0) continue;
-                    int gx = Bx + aa, gy = By + b, gz = Bz + c;
-                    if (!inside) { gx = wrap_index(gx, a.on[0]); gy = wrap_index(gy, a.on[1]); gz = wrap_index(gz, a.on[2]); }
-                    atomic_add_u64(&a.acc[(long long)gz + (long long)a.on[2] * ((long long)gy + (long long)a.on[1] * gx)],
-                                   (unsigned long long)q);
+                    const int gz = inside ? Bz + c : wrap_index(Bz + c, a.on[2]);
+                    atomic_add_u64(&plane[(long long)gy * a.on[2] + gz], (unsigned long long)q);
                 }
+            }
+        }
     }
 }
 

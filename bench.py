@@ -377,11 +377,15 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        Nk = hii * hii * (hii // 2 + 1)
-        alg = {  # algorithmic bytes per launch (DESIGN.md)
-            "fft_strided_kernel": 16 * Nk, "fft_c2r_z_kernel": 8 * Nk + 4 * N, "fft_r2c_z_kernel": 8 * Nk + 4 * N,
-            "fcoll_sum_kernel": 4 * N, "ionise_kernel": 8 * N, "move_cic_kernel": 4 * M + 24 * N + 8 * N,
-            "acc_to_delta_kernel": 12 * N, "ionized_temperature_kernel": 16 * N, "fill_kernel": 4 * N}
+        pitch = ((hii // 2 + 1) + 7) // 8 * 8
+        Nk = hii * hii * pitch
+        alg = {  # algorithmic bytes per launch (DESIGN.md section 4)
+            "fft_strided_pow2_kernel": 16 * Nk, "fft_strided_kernel": 16 * Nk,
+            "fft_c2r_z_pow2_kernel": 8 * Nk + 4 * N, "fft_c2r_z_kernel": 8 * Nk + 4 * N,
+            "fft_r2c_z_pow2_kernel": 8 * Nk + 4 * N, "fft_r2c_z_kernel": 8 * Nk + 4 * N,
+            "fcoll_sum_kernel": 8 * N, "ionise_kernel": 4 * N,
+            "move_cic_grouped_kernel": 4 * M + 24 * N + 8 * N, "move_cic_kernel": 4 * M + 24 * N + 8 * N,
+            "acc_to_delta_kernel": 12 * N, "finalize_kernel": 17 * N, "fill_kernel": 4 * N}
         dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
         roofline = None
         if dom:
