@@ -47,9 +47,26 @@ DEV void stage_regs(float2 (&v)[R], int t, const float2 *__restrict__ tw, int tw
     }
 }
 
+/* where a line's point p lives in shared memory and how the owners of a line synchronise */
+template <int TL> struct TilePolicy { /* TL lines interleaved, whole CTA works on the tile */
+    float2 *S;
+    int c;
+    DEV float2 &at(int p) const { return S[sidx<TL>(p, c)]; }
+    DEV void sync() const { __syncthreads(); }
+};
+template <int LT> struct LinePolicy { /* one line per LT threads, padded by one slot every 8 points */
+    float2 *L;
+    int bar_id;
+    DEV float2 &at(int p) const { return L[p + (p >> 3)]; }
+    DEV void sync() const {
+        if (LT <= 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(LT) : "memory");
+    }
+};
+
 /* transpose between stages: outputs of stage (RAD, NS) -> inputs t + m STEP of the next stage */
-template <int N, int R, int RAD, int NS, int TL>
-DEV void exchange(float2 (&v)[R], int t, int c, float2 *S) {
+template <int N, int R, int RAD, int NS, class Pol>
+DEV void exchange(float2 (&v)[R], int t, const Pol &pol) {
     constexpr int NB = R / RAD;
     constexpr int STEP = N / R;
 #pragma unroll
@@ -58,20 +75,20 @@ DEV void exchange(float2 (&v)[R], int t, int c, float2 *S) {
         const int k = j & (NS - 1);
         const int j0 = (j - k) * RAD + k;
 #pragma unroll
-        for (int q = 0; q < RAD; q++) S[sidx<TL>(j0 + q * NS, c)] = v[b + NB * q];
+        for (int q = 0; q < RAD; q++) pol.at(j0 + q * NS) = v[b + NB * q];
     }
-    __syncthreads();
+    pol.sync();
 #pragma unroll
-    for (int m = 0; m < R; m++) v[m] = S[sidx<TL>(t + m * STEP, c)];
-    __syncthreads();
+    for (int m = 0; m < R; m++) v[m] = pol.at(t + m * STEP);
+    pol.sync();
 }
 
 /* full length-N transform of the line whose points t + m N/8 live in v */
-template <int N, int SIGN, int TL>
-DEV void fft_line_regs(float2 (&v)[8], int t, int c, float2 *S, const float2 *__restrict__ tw, int tws) {
+template <int N, int SIGN, class Pol>
+DEV void fft_line_regs(float2 (&v)[8], int t, const Pol &pol, const float2 *__restrict__ tw, int tws) {
     static_assert(N >= 16 && N <= 2048 && (N & (N - 1)) == 0, "power of two 16..2048");
     stage_regs<N, 8, 8, 1, SIGN>(v, t, tw, tws);
-    exchange<N, 8, 8, 1, TL>(v, t, c, S);
+    exchange<N, 8, 8, 1>(v, t, pol);
     if constexpr (N == 16) {
         stage_regs<N, 8, 2, 8, SIGN>(v, t, tw, tws);
     } else if constexpr (N == 32) {
@@ -80,7 +97,7 @@ DEV void fft_line_regs(float2 (&v)[8], int t, int c, float2 *S, const float2 *__
         stage_regs<N, 8, 8, 8, SIGN>(v, t, tw, tws);
     } else {
         stage_regs<N, 8, 8, 8, SIGN>(v, t, tw, tws);
-        exchange<N, 8, 8, 8, TL>(v, t, c, S);
+        exchange<N, 8, 8, 8>(v, t, pol);
         if constexpr (N == 128) {
             stage_regs<N, 8, 2, 64, SIGN>(v, t, tw, tws);
         } else if constexpr (N == 256) {
@@ -89,7 +106,7 @@ DEV void fft_line_regs(float2 (&v)[8], int t, int c, float2 *S, const float2 *__
             stage_regs<N, 8, 8, 64, SIGN>(v, t, tw, tws);
         } else {
             stage_regs<N, 8, 8, 64, SIGN>(v, t, tw, tws);
-            exchange<N, 8, 8, 64, TL>(v, t, c, S);
+            exchange<N, 8, 8, 64>(v, t, pol);
             if constexpr (N == 1024) stage_regs<N, 8, 2, 512, SIGN>(v, t, tw, tws);
             else stage_regs<N, 8, 4, 512, SIGN>(v, t, tw, tws);
         }
@@ -169,7 +186,7 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::THREADS, Pow2Cfg<N>::MIN_CTAS) fft
                 for (int m = 0; m < 8; m++) v[m] = apply_kmul(v[m], t + m * STEP, col, a);
             }
         }
-        fft_line_regs<N, SIGN, TL>(v, t, c, S, a.tw, 1);
+        fft_line_regs<N, SIGN>(v, t, TilePolicy<TL>{S, c}, a.tw, 1);
         if (live) {
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -235,106 +252,95 @@ static bool pow2_strided(const float2 *src, float2 *dst, const StridedArgs &a, i
 }
 
 /* ------------------------------------------------------------------ contiguous axis (z) */
-/* complex rows (NH + 1 values) -> NR = 2 NH reals per row.  Persistent CTAs; the half spectrum of
-   the next tile is prefetched into registers while the current tile is transformed. */
+/* complex rows (NH + 1 values) -> NR = 2 NH reals per row.
+   The z axis is contiguous, so a line can be owned by NH/8 consecutive lanes (one warp at
+   nz = 512): spectrum loads and real stores are coalesced straight from/to registers, the
+   inter-stage transposes use a private padded strip of shared memory, and lines synchronise with
+   __syncwarp / a per-line named barrier -- no CTA-wide barrier anywhere. */
+template <int NH> struct ZLineCfg {
+    static constexpr int LT = NH / 8;                       /* threads per line */
+    static constexpr int THREADS = LT > 256 ? LT : 256;
+    static constexpr int LINES = THREADS / LT;              /* lines per CTA */
+    static constexpr int STRIP = NH + NH / 8;               /* padded points per line */
+};
 template <int NH>
-__global__ void __launch_bounds__(Pow2Cfg<NH>::THREADS, Pow2Cfg<NH>::MIN_CTAS)
-fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, ZArgs a, int ntiles) {
-    constexpr int TL = Pow2Cfg<NH>::TL;
-    constexpr int STEP = NH / 8;
-    constexpr int NT = Pow2Cfg<NH>::THREADS;
-    static_assert(TL * NH == 8 * NT, "eight spectrum values per thread");
+__global__ void __launch_bounds__(ZLineCfg<NH>::THREADS)
+fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, ZArgs a) {
+    using Cfg = ZLineCfg<NH>;
+    constexpr int LT = Cfg::LT, STEP = NH / 8;
     DYN_SMEM(float2, S);
-    const int c = threadIdx.x & (TL - 1), t = threadIdx.x / TL;
-    float2 pre[8], pre_ny = make_float2(0.f, 0.f);
-    float lmin = 3.0e38f, lmax = -3.0e38f;
+    __shared__ float red_min[32], red_max[32];
+    const int line = threadIdx.x / LT, t = threadIdx.x - line * LT;
+    const LinePolicy<LT> pol{S + line * Cfg::STRIP, 1 + line};
     float2 *dst2 = reinterpret_cast<float2 *>(dst);
     const long long row_stride2 = a.real_row_stride / 2;
-
-    auto load_tile = [&](int tile) {
-        const long long row0 = (long long)tile * TL;
+    float lmin = 3.0e38f, lmax = -3.0e38f;
+    /* uniform trip count for every thread of the CTA (the line barriers need all owners) */
+    for (long long row0 = (long long)blockIdx.x * Cfg::LINES; row0 < a.nrows;
+         row0 += (long long)gridDim.x * Cfg::LINES) {
+        const long long row = row0 + line;
+        const bool live = row < a.nrows;
+        const float2 *X = src + row * a.pitch;
+        float2 xa[8], xb[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int e = threadIdx.x + j * NT;
-            const int l = e / NH, k = e - l * NH;
-            pre[j] = make_float2(0.f, 0.f);
-            if (row0 + l < a.nrows) pre[j] = src[(row0 + l) * a.pitch + k];
+        for (int m = 0; m < 8; m++) {
+            const int n = t + m * STEP;
+            xa[m] = live ? X[n] : make_float2(0.f, 0.f);
+            xb[m] = live ? X[NH - n] : make_float2(0.f, 0.f);
         }
-        if (threadIdx.x < TL) {
-            pre_ny = make_float2(0.f, 0.f);
-            if (row0 + threadIdx.x < a.nrows) pre_ny = src[(row0 + threadIdx.x) * a.pitch + NH];
-        }
-    };
-
-    int tile = blockIdx.x;
-    if (tile < ntiles) load_tile(tile);
-    for (; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = (long long)tile * TL;
-        /* phase A: staged half spectrum -> tile (lanes along k) */
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int e = threadIdx.x + j * NT;
-            const int l = e / NH, k = e - l * NH;
-            float2 x = pre[j];
-            if (k == 0) x.y = 0.f;
-            S[sidx<TL>(k, l)] = x;
-        }
-        if (threadIdx.x < TL) S[sidx<TL>(NH, threadIdx.x)] = make_float2(pre_ny.x, 0.f);
-        __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);
-        /* phase B: Z[n] = (X[n] + conj X[NH-n]) + i e^{+2 pi i n / NR} (X[n] - conj X[NH-n]) */
+        if (t == 0) { xa[0].y = 0.f; xb[0].y = 0.f; } /* DC and Nyquist are real */
+        /* Z[n] = (X[n] + conj X[NH-n]) + i e^{+2 pi i n / NR} (X[n] - conj X[NH-n]) */
         float2 v[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             const int n = t + m * STEP;
-            const float2 A = S[sidx<TL>(n, c)];
-            float2 B = S[sidx<TL>(NH - n, c)];
+            float2 B = xb[m];
             B.y = -B.y;
-            const float2 sum = cadd(A, B), dif = csub(A, B);
+            const float2 sum = cadd(xa[m], B), dif = csub(xa[m], B);
             float2 w = ldg(&a.tw[n]); /* e^{-2 pi i n / NR} */
             w.y = -w.y;
             const float2 p = cmul(w, dif);
             v[m] = make_float2(sum.x - p.y, sum.y + p.x);
         }
-        __syncthreads();
-        fft_line_regs<NH, 1, TL>(v, t, c, S, a.tw, 2);
-        /* phase C: z[n] = (x[2n], x[2n+1]) back through the tile for a coalesced store */
+        fft_line_regs<NH, 1>(v, t, pol, a.tw, 2);
+        /* z[n] = (x[2n], x[2n+1]) */
 #pragma unroll
-        for (int m = 0; m < 8; m++) S[sidx<TL>(t + m * STEP, c)] = v[m];
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int e = threadIdx.x + j * NT;
-            const int l = e / NH, n = e - l * NH;
-            if (row0 + l < a.nrows) {
-                float2 x = S[sidx<TL>(n, l)];
-                x.x *= a.scale; x.y *= a.scale;
+        for (int m = 0; m < 8; m++) {
+            float2 x = v[m];
+            x.x *= a.scale; x.y *= a.scale;
+            if (live) {
                 lmin = fminf(lmin, fminf(x.x, x.y));
                 lmax = fmaxf(lmax, fmaxf(x.x, x.y));
-                if (a.clip) {
-                    x.x = fmaxf(fminf(x.x, a.clip_hi), a.clip_lo);
-                    x.y = fmaxf(fminf(x.y, a.clip_hi), a.clip_lo);
-                }
-                dst2[(row0 + l) * row_stride2 + n] = x;
             }
+            if (a.clip) {
+                x.x = fmaxf(fminf(x.x, a.clip_hi), a.clip_lo);
+                x.y = fmaxf(fminf(x.y, a.clip_hi), a.clip_lo);
+            }
+            if (live) dst2[row * row_stride2 + t + m * STEP] = x;
         }
-        __syncthreads();
     }
     if (a.minmax_keys) {
-        float *red = reinterpret_cast<float *>(S);
-        red[threadIdx.x] = lmin;
-        red[NT + threadIdx.x] = lmax;
-        __syncthreads();
-        for (int s = NT / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) {
-                red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + s]);
-                red[NT + threadIdx.x] = fmaxf(red[NT + threadIdx.x], red[NT + threadIdx.x + s]);
-            }
-            __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         }
-        if (threadIdx.x == 0) {
-            atomic_min_i32(&a.minmax_keys[0], float_order_key(float_as_int_bits(red[0])));
-            atomic_max_i32(&a.minmax_keys[1], float_order_key(float_as_int_bits(red[NT])));
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) { red_min[warp] = lmin; red_max[warp] = lmax; }
+        __syncthreads();
+        if (warp == 0) {
+            const int nw = Cfg::THREADS / 32;
+            lmin = lane < nw ? red_min[lane] : 3.0e38f;
+            lmax = lane < nw ? red_max[lane] : -3.0e38f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+                lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            }
+            if (lane == 0) {
+                atomic_min_i32(&a.minmax_keys[0], float_order_key(float_as_int_bits(lmin)));
+                atomic_max_i32(&a.minmax_keys[1], float_order_key(float_as_int_bits(lmax)));
+            }
         }
     }
 }
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(Pow2Cfg<NH>::THREADS) fft_r2c_z_pow2_kernel(co
 #pragma unroll
     for (int m = 0; m < 8; m++) v[m] = S[sidx<TL>(t + m * STEP, c)];
     __syncthreads();
-    fft_line_regs<NH, -1, TL>(v, t, c, S, a.tw, 2);
+    fft_line_regs<NH, -1>(v, t, TilePolicy<TL>{S, c}, a.tw, 2);
 #pragma unroll
     for (int m = 0; m < 8; m++) S[sidx<TL>(t + m * STEP, c)] = v[m];
     __syncthreads();
@@ -402,21 +408,19 @@ __global__ void __launch_bounds__(Pow2Cfg<NH>::THREADS) fft_r2c_z_pow2_kernel(co
 }
 
 template <int NH> static void launch_c2r_z_pow2(const float2 *src, float *dst, const ZArgs &a) {
-    constexpr int TL = Pow2Cfg<NH>::TL;
-    size_t smem = (size_t)(NH + 1) * TL * sizeof(float2);
-    const size_t red = 2 * (size_t)Pow2Cfg<NH>::THREADS * sizeof(float);
-    if (smem < red) smem = red;
+    using Cfg = ZLineCfg<NH>;
+    const size_t smem = (size_t)Cfg::LINES * Cfg::STRIP * sizeof(float2);
     auto k = &fft_c2r_z_pow2_kernel<NH>;
     allow_smem(k, smem);
     static int per_sm = 0;
     if (per_sm == 0) {
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, Pow2Cfg<NH>::THREADS, smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, Cfg::THREADS, smem));
         if (per_sm < 1) per_sm = 1;
     }
-    const int ntiles = (a.nrows + TL - 1) / TL;
-    int grid = dev_num_sms() * per_sm;
-    if (grid > ntiles) grid = ntiles;
-    B200_LAUNCH_T("fft_c2r_z_pow2_kernel", k, dim3(grid), Pow2Cfg<NH>::THREADS, smem, src, dst, a, ntiles);
+    const long long groups = ((long long)a.nrows + Cfg::LINES - 1) / Cfg::LINES;
+    long long grid = (long long)dev_num_sms() * per_sm;
+    if (grid > groups) grid = groups;
+    B200_LAUNCH_T("fft_c2r_z_pow2_kernel", k, dim3((unsigned)grid), Cfg::THREADS, smem, src, dst, a);
 }
 template <int NH> static void launch_r2c_z_pow2(const float *src, float2 *dst, const ZArgs &a) {
     constexpr int TL = Pow2Cfg<NH>::TL;
