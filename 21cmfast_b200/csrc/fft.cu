@@ -479,7 +479,7 @@ static size_t tile_smem(int n, int T) {
 template <typename K> static void allow_smem(K kernel, size_t bytes) {
     static std::map<const void *, size_t> done;
     size_t &cur = done[(const void *)kernel];
-    if (bytes > cur && bytes > 48 * 1024) {
+    if (bytes > cur && bytes > 32 * 1024) { /* static + dynamic may pass 48 KB before dynamic alone does */
         CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)bytes));
         cur = bytes;
@@ -523,27 +523,52 @@ static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long lo
     B200_LAUNCH(fft_strided_kernel, grid, 256, smem, src, dst, a);
 }
 
+/* x-planes per (y pass, z pass) chunk of fft_c2r: the y pass leaves its output dirty in L2 and the z
+   pass of the same planes reads it back from there, so the intermediate box never makes the round
+   trip through HBM.  B200_FFT_CHUNK_MB sets the chunk size (0 = one chunk = whole box, the default). */
+static int c2r_chunk_planes(const Fft3D *p) {
+    static int mb = -1;
+    if (mb < 0) {
+        const char *e = getenv("B200_FFT_CHUNK_MB");
+        mb = e ? atoi(e) : 0; /* measured on B200 at 512^3: per-chunk launches cost more than the L2 hits save */
+    }
+    const size_t plane = (size_t)p->ny * p->pitch * sizeof(float2);
+    if (mb <= 0 || plane * p->nx <= (size_t)mb << 20) return p->nx;
+    long long planes = ((long long)mb << 20) / (long long)plane;
+    if (planes < 1) planes = 1;
+    /* equal chunks */
+    const int nchunks = (int)((p->nx + planes - 1) / planes);
+    return (p->nx + nchunks - 1) / nchunks;
+}
+
 void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZEpilogue &epi) {
     const int nx = p->nx, ny = p->ny, pitch = p->pitch;
     /* x: lines over (y,kz) flattened (pad columns included), stride ny*pitch; multipliers ride on the load */
     run_strided(p->px, src, work, (long long)ny * pitch, ny * pitch, 0, 1, +1, 1.f, &km, p);
-    /* y: for each x, lines over kz, stride pitch */
-    run_strided(p->py, work, work, pitch, pitch, (long long)ny * pitch, nx, +1, 1.f, nullptr, p);
-    /* z: contiguous rows, complex -> real */
     ZArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = p->nz; a.nzc = p->nzc; a.pitch = pitch; a.nrows = nx * ny;
+    a.n = p->nz; a.nzc = p->nzc; a.pitch = pitch;
     a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
     a.f = p->pz.f; a.tw = p->pz.tw;
     a.scale = epi.scale; a.clip = epi.clip; a.clip_lo = epi.clip_lo; a.clip_hi = epi.clip_hi;
     float *dst = epi.dst ? epi.dst : reinterpret_cast<float *>(work);
     a.real_row_stride = epi.dst ? epi.dst_row_stride : 2LL * pitch;
     a.minmax_keys = epi.minmax_keys;
-    if (pow2_c2r_z(work, dst, a)) return;
-    const int nblocks = (a.nrows + a.L - 1) / a.L;
-    size_t smem = tile_smem(a.n, a.L);
-    allow_smem(fft_c2r_z_kernel, smem);
-    B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, work, dst, a);
+    const int xc = c2r_chunk_planes(p);
+    for (int x0 = 0; x0 < nx; x0 += xc) {
+        const int planes = (x0 + xc <= nx) ? xc : nx - x0;
+        float2 *w = work + (long long)x0 * ny * pitch;
+        /* y: for each x, lines over kz, stride pitch */
+        run_strided(p->py, w, w, pitch, pitch, (long long)ny * pitch, planes, +1, 1.f, nullptr, p);
+        /* z: contiguous rows, complex -> real */
+        a.nrows = planes * ny;
+        float *d = dst + (long long)x0 * ny * a.real_row_stride;
+        if (pow2_c2r_z(w, d, a)) continue;
+        const int nblocks = (a.nrows + a.L - 1) / a.L;
+        size_t smem = tile_smem(a.n, a.L);
+        allow_smem(fft_c2r_z_kernel, smem);
+        B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, w, d, a);
+    }
 }
 
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {

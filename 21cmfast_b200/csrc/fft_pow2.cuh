@@ -1,16 +1,22 @@
 /*
  * fft_pow2.cuh -- power-of-two fast path of the batched 1-D FFTs (included by fft.cu, CUDA only).
  *
- * Each line of N points is owned by N/R threads; a thread keeps R = 8 points in registers for the
- * whole transform (positions t + m N/R) and runs radix-8/4/2 Stockham stages on them.  Between
- * stages the CTA's TL lines are transposed through ONE shared-memory tile (no ping-pong buffer):
- * write outputs at their Stockham positions, barrier, read back positions t + m N/R.  The last
- * stage's outputs already sit at t + m N/R, so the first load and the final store go straight
- * between registers and global memory.
+ * Each line of N points is owned by N/8 threads; a thread keeps 8 points in registers for the
+ * whole transform (positions t + m N/8) and runs radix-8/4/2 Stockham stages on them.  Between
+ * stages the lines are transposed through shared memory: write outputs at their Stockham
+ * positions, barrier, read back positions t + m N/8.  Two tile buffers alternate between the
+ * exchanges, so every exchange costs ONE barrier.  The last stage's outputs already sit at
+ * t + m N/8, so the first load and the final store go straight between registers and global memory.
  *
- * Tile layout: point i of line c at [i * TL + (c ^ (i & (TL-1)))].  With TL = 16 a half-warp of
- * the butterfly phase touches exactly one 128-byte row (conflict-free for every stage pattern),
- * and the XOR keeps the column-wise accesses of the contiguous-axis (z) kernels conflict-free too.
+ * Instruction diet (the strided passes are issue-bound before they are HBM-bound):
+ *   - complex arithmetic on Blackwell's packed FADD2 / FMUL2 / FFMA2 (two floats per instruction;
+ *     the +-i rotations ride on the operand swizzles),
+ *   - the stage twiddles live in shared memory as (w, i w) float4 rows indexed by the thread's
+ *     butterfly phase: one LDS.128 + FMUL2 + FFMA2 per complex multiply, no index arithmetic,
+ *   - tile rows are unswizzled [point][line]: a half-warp owns one 128-byte row, every exchange
+ *     access is a per-thread base plus a compile-time offset,
+ *   - the k-space multipliers are a template parameter, so the hot instantiations carry no
+ *     double-precision window code.
  *
  * z axis: a length-NR real transform runs as a length-NR/2 complex FFT on (even, odd) pairs with
  * the standard Hermitian split/merge step, so the z pass costs half the butterflies and half the
@@ -18,46 +24,118 @@
  */
 #pragma once
 
-template <int TL> DEV int sidx(int i, int c) { return i * TL + (c ^ (i & (TL - 1))); }
+/* ------------------------------------------------------------------ packed complex helpers */
+DEV float2 pk_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DEV float2 pk_sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+template <int S> DEV float2 pk_rot(float2 a) { return S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+DEV float2 pk_scale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+/* a * w with w given as (w.x, w.y, -w.y, w.x) */
+DEV float2 pk_cmul4(float2 a, float4 w) {
+    const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(w.z, w.w));
+    return __ffma2_rn(make_float2(a.x, a.x), make_float2(w.x, w.y), t);
+}
+DEV float2 pk_cmul(float2 a, float2 w) { return pk_cmul4(a, make_float4(w.x, w.y, -w.y, w.x)); }
 
-/* one Stockham stage on the registers of a thread; RAD <= R, NS = product of earlier radices */
-template <int N, int R, int RAD, int NS, int SIGN>
-DEV void stage_regs(float2 (&v)[R], int t, const float2 *__restrict__ tw, int tw_stride) {
-    constexpr int NB = R / RAD;   /* butterflies per thread */
-    constexpr int STEP = N / R;   /* distance between the positions a thread holds */
+template <int S> DEV void pk_bfly2(float2 *v) {
+    const float2 a = v[0], b = v[1];
+    v[0] = pk_add(a, b);
+    v[1] = pk_sub(a, b);
+}
+template <int S> DEV void pk_bfly4(float2 *v) {
+    const float2 a = pk_add(v[0], v[2]), b = pk_sub(v[0], v[2]);
+    const float2 c = pk_add(v[1], v[3]), d = pk_rot<S>(pk_sub(v[1], v[3]));
+    v[0] = pk_add(a, c);
+    v[1] = pk_add(b, d);
+    v[2] = pk_sub(a, c);
+    v[3] = pk_sub(b, d);
+}
+template <int S> DEV void pk_bfly8(float2 *v) {
+    const float h = 0.70710678118654752440f;
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    pk_bfly4<S>(e);
+    pk_bfly4<S>(o);
+    /* W8^k o[k], W8 = exp(S 2 pi i / 8): (1 + S i)/sqrt2, S i, (-1 + S i)/sqrt2 */
+    const float2 t1 = pk_scale(pk_add(o[1], pk_rot<S>(o[1])), h);
+    const float2 t2 = pk_rot<S>(o[2]);
+    const float2 t3 = pk_scale(pk_sub(pk_rot<S>(o[3]), o[3]), h);
+    v[0] = pk_add(e[0], o[0]); v[4] = pk_sub(e[0], o[0]);
+    v[1] = pk_add(e[1], t1);   v[5] = pk_sub(e[1], t1);
+    v[2] = pk_add(e[2], t2);   v[6] = pk_sub(e[2], t2);
+    v[3] = pk_add(e[3], t3);   v[7] = pk_sub(e[3], t3);
+}
+template <int RAD, int S> DEV void pk_dft(float2 *v) {
+    if constexpr (RAD == 8) pk_bfly8<S>(v);
+    else if constexpr (RAD == 4) pk_bfly4<S>(v);
+    else pk_bfly2<S>(v);
+}
+
+/* ------------------------------------------------------------------ stage plan of a length-N line
+ * stages: radix 8 at NS = 1, 8, 64 while they fit, then one radix 2/4/8 stage that completes N. */
+template <int N> struct Pow2Plan {
+    static_assert(N >= 16 && N <= 2048 && (N & (N - 1)) == 0, "power of two 16..2048");
+    static constexpr int STEP = N / 8;
+    static constexpr int NSTAGE = N <= 64 ? 2 : (N <= 512 ? 3 : 4);
+    static constexpr int ns(int s) { return s == 0 ? 1 : (s == 1 ? 8 : (s == 2 ? 64 : 512)); }
+    static constexpr int rad(int s) { return (s == NSTAGE - 1) ? N / ns(s) : 8; }
+    /* float4 twiddle rows: stage s (s >= 1) holds ns(s) phases x (rad - 1) multipliers */
+    static constexpr int tw_base(int s) { return s <= 1 ? 0 : (s == 2 ? 56 : 504); }
+    static constexpr int TW_TOTAL = tw_base(NSTAGE - 1) + ns(NSTAGE - 1) * (rad(NSTAGE - 1) - 1);
+};
+
+/* fill the shared twiddle table from the global exp(-2 pi i k / (tws N)) table (tws = 1 or 2) */
+template <int N, int SIGN> DEV void fill_twiddles(float4 *twS, const float2 *__restrict__ tw, int tws, int nthreads) {
+    using P = Pow2Plan<N>;
+#pragma unroll
+    for (int s = 1; s < P::NSTAGE; s++) {
+        const int NS = P::ns(s), RAD = P::rad(s);
+        for (int e = threadIdx.x; e < NS * (RAD - 1); e += nthreads) {
+            const int k = e / (RAD - 1), q = 1 + e - k * (RAD - 1);
+            float2 w = ldg(&tw[q * k * (N / (NS * RAD)) * tws]);
+            if (SIGN > 0) w.y = -w.y;
+            twS[P::tw_base(s) + e] = make_float4(w.x, w.y, -w.y, w.x);
+        }
+    }
+}
+
+/* one Stockham stage on the registers of a thread.  twp = row of the thread's phase for
+   butterfly 0 (phases of butterfly b are b * STEP rows further: only in the last stage, where
+   t + b STEP < NS, see Pow2Plan) */
+template <int N, int RAD, int NS, int SIGN> DEV void stage_regs(float2 (&v)[8], const float4 *twp) {
+    constexpr int NB = 8 / RAD;
+    constexpr int STEP = N / 8;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        const int j = t + b * STEP;
         float2 u[RAD];
 #pragma unroll
         for (int q = 0; q < RAD; q++) u[q] = v[b + NB * q];
-        if (NS > 1) {
-            const int k = j & (NS - 1);
-            const int base = k * (N / (NS * RAD)) * tw_stride;
+        if constexpr (NS > 1) {
 #pragma unroll
-            for (int q = 1; q < RAD; q++) {
-                float2 w = ldg(&tw[q * base]);
-                if (SIGN > 0) w.y = -w.y;
-                u[q] = cmul(u[q], w);
-            }
+            for (int q = 1; q < RAD; q++) u[q] = pk_cmul4(u[q], twp[b * STEP * (RAD - 1) + (q - 1)]);
         }
-        small_dft<RAD>(u, SIGN);
+        pk_dft<RAD, SIGN>(u);
 #pragma unroll
         for (int q = 0; q < RAD; q++) v[b + NB * q] = u[q];
     }
 }
 
-/* where a line's point p lives in shared memory and how the owners of a line synchronise */
-template <int TL> struct TilePolicy { /* TL lines interleaved, whole CTA works on the tile */
-    float2 *S;
+/* where a line's point p lives in shared memory; offq<D>(p0, q) addresses point p0 + q D with the
+   q-dependent part a compile-time constant wherever the layout allows */
+template <int TL> struct TilePolicy { /* TL lines interleaved: [point][line] */
+    float2 *A, *B; /* the two exchange buffers */
     int c;
-    DEV float2 &at(int p) const { return S[sidx<TL>(p, c)]; }
+    DEV int off(int p) const { return p * TL + c; }
+    template <int D> DEV int offq(int p0, int q) const { return off(p0) + q * D * TL; }
     DEV void sync() const { __syncthreads(); }
 };
 template <int LT> struct LinePolicy { /* one line per LT threads, padded by one slot every 8 points */
-    float2 *L;
+    float2 *A, *B;
     int bar_id;
-    DEV float2 &at(int p) const { return L[p + (p >> 3)]; }
+    DEV int off(int p) const { return p + (p >> 3); }
+    template <int D> DEV int offq(int p0, int q) const {
+        if constexpr (D % 8 == 0) return off(p0) + q * (D + D / 8);
+        else return off(p0 + q * D);
+    }
     DEV void sync() const {
         if (LT <= 32) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(LT) : "memory");
@@ -65,53 +143,54 @@ template <int LT> struct LinePolicy { /* one line per LT threads, padded by one 
 };
 
 /* transpose between stages: outputs of stage (RAD, NS) -> inputs t + m STEP of the next stage */
-template <int N, int R, int RAD, int NS, class Pol>
-DEV void exchange(float2 (&v)[R], int t, const Pol &pol) {
-    constexpr int NB = R / RAD;
-    constexpr int STEP = N / R;
+template <int N, int RAD, int NS, class Pol> DEV void exchange(float2 (&v)[8], int t, float2 *buf, const Pol &pol) {
+    constexpr int NB = 8 / RAD;
+    constexpr int STEP = N / 8;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         const int j = t + b * STEP;
         const int k = j & (NS - 1);
         const int j0 = (j - k) * RAD + k;
 #pragma unroll
-        for (int q = 0; q < RAD; q++) pol.at(j0 + q * NS) = v[b + NB * q];
+        for (int q = 0; q < RAD; q++) buf[pol.template offq<NS>(j0, q)] = v[b + NB * q];
     }
     pol.sync();
 #pragma unroll
-    for (int m = 0; m < R; m++) v[m] = pol.at(t + m * STEP);
-    pol.sync();
+    for (int m = 0; m < 8; m++) v[m] = buf[pol.template offq<STEP>(t, m)];
 }
 
-/* full length-N transform of the line whose points t + m N/8 live in v */
-template <int N, int SIGN, class Pol>
-DEV void fft_line_regs(float2 (&v)[8], int t, const Pol &pol, const float2 *__restrict__ tw, int tws) {
-    static_assert(N >= 16 && N <= 2048 && (N & (N - 1)) == 0, "power of two 16..2048");
-    stage_regs<N, 8, 8, 1, SIGN>(v, t, tw, tws);
-    exchange<N, 8, 8, 1>(v, t, pol);
-    if constexpr (N == 16) {
-        stage_regs<N, 8, 2, 8, SIGN>(v, t, tw, tws);
-    } else if constexpr (N == 32) {
-        stage_regs<N, 8, 4, 8, SIGN>(v, t, tw, tws);
-    } else if constexpr (N == 64) {
-        stage_regs<N, 8, 8, 8, SIGN>(v, t, tw, tws);
+/* full length-N transform of the line whose points t + m N/8 live in v.  Exchanges alternate
+   between pol.A and pol.B; a caller that loops must keep one barrier between two transforms
+   only if N has a single exchange (N <= 64), see the kernels. */
+template <int N, int SIGN, class Pol> DEV void fft_line_regs(float2 (&v)[8], int t, const Pol &pol, const float4 *twS) {
+    using P = Pow2Plan<N>;
+    constexpr int STEP = N / 8;
+    stage_regs<N, 8, 1, SIGN>(v, nullptr);
+    exchange<N, 8, 1>(v, t, pol.A, pol);
+    if constexpr (P::NSTAGE == 2) {
+        stage_regs<N, P::rad(1), 8, SIGN>(v, twS + (t & 7) * (P::rad(1) - 1));
     } else {
-        stage_regs<N, 8, 8, 8, SIGN>(v, t, tw, tws);
-        exchange<N, 8, 8, 8>(v, t, pol);
-        if constexpr (N == 128) {
-            stage_regs<N, 8, 2, 64, SIGN>(v, t, tw, tws);
-        } else if constexpr (N == 256) {
-            stage_regs<N, 8, 4, 64, SIGN>(v, t, tw, tws);
-        } else if constexpr (N == 512) {
-            stage_regs<N, 8, 8, 64, SIGN>(v, t, tw, tws);
+        stage_regs<N, 8, 8, SIGN>(v, twS + (t & 7) * 7);
+        exchange<N, 8, 8>(v, t, pol.B, pol);
+        if constexpr (P::NSTAGE == 3) {
+            stage_regs<N, P::rad(2), 64, SIGN>(v, twS + P::tw_base(2) + (t & 63) * (P::rad(2) - 1));
         } else {
-            stage_regs<N, 8, 8, 64, SIGN>(v, t, tw, tws);
-            exchange<N, 8, 8, 64>(v, t, pol);
-            if constexpr (N == 1024) stage_regs<N, 8, 2, 512, SIGN>(v, t, tw, tws);
-            else stage_regs<N, 8, 4, 512, SIGN>(v, t, tw, tws);
+            stage_regs<N, 8, 64, SIGN>(v, twS + P::tw_base(2) + (t & 63) * 7);
+            /* A again: every thread read it before the barrier of the second exchange */
+            exchange<N, 8, 64>(v, t, pol.A, pol);
+            stage_regs<N, P::rad(3), 512, SIGN>(v, twS + P::tw_base(3) + (t & 511) * (P::rad(3) - 1));
         }
     }
+    (void)STEP;
 }
+/* number of exchanges that touch buffer A / need a trailing barrier before the next transform */
+template <int N> struct Pow2Sync {
+    /* after fft_line_regs returns, the last exchange buffer may still be read by slower threads of
+       the line; the next transform's first write goes to A.  With >= 2 exchanges the barrier of
+       the second exchange already orders "all reads of A done" before anyone returns -- unless
+       the last exchange itself used A (4 stages). */
+    static constexpr bool NEED_TAIL_SYNC = (Pow2Plan<N>::NSTAGE != 3);
+};
 
 /* lines per CTA: 16 while the CTA stays within 1024 threads */
 template <int N> struct Pow2Cfg {
@@ -124,88 +203,95 @@ template <int N> struct Pow2Cfg {
  * Persistent CTAs: each loops over tiles of TL adjacent lines and issues the global loads of its
  * NEXT tile into a second register set before it transforms the current one, so the HBM latency
  * of tile k+1 hides behind the butterflies, barriers and stores of tile k even with one CTA per
- * SM. */
-template <int N, int SIGN>
-__global__ void __launch_bounds__(Pow2Cfg<N>::THREADS, Pow2Cfg<N>::MIN_CTAS) fft_strided_pow2_kernel(const float2 *__restrict__ src,
-                                                                               float2 *__restrict__ dst,
-                                                                               StridedArgs a, int tiles_per_group,
-                                                                               int ntiles) {
+ * SM.  MODE: 0 plain, 1 window from the |n|^2 table, 2 generic k-space multiplier (apply_kmul). */
+enum { PM_PLAIN = 0, PM_WTAB = 1, PM_GENERIC = 2 };
+template <int N, int SIGN, int MODE>
+__global__ void __launch_bounds__(Pow2Cfg<N>::THREADS, Pow2Cfg<N>::MIN_CTAS)
+fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst, StridedArgs a, int tiles_per_group,
+                        int ntiles) {
+    using P = Pow2Plan<N>;
     constexpr int TL = Pow2Cfg<N>::TL;
     constexpr int STEP = N / 8;
     DYN_SMEM(float2, S);
+    float4 *twS = reinterpret_cast<float4 *>(S + 2 * N * TL);
+    fill_twiddles<N, SIGN>(twS, a.tw, 1, Pow2Cfg<N>::THREADS);
     const int c = threadIdx.x & (TL - 1), t = threadIdx.x / TL;
-    const bool has_kmul = a.kmul != KMUL_NONE || a.op != KOP_NONE;
+    const TilePolicy<TL> pol{S, S + N * TL, c};
+    const long long rs = (long long)STEP * a.line_stride; /* elements between a thread's points */
+    const long long toff = (long long)t * a.line_stride;
     float2 v[8], vn[8];
     int tile = blockIdx.x;
     /* prologue: first tile */
     {
         const int g = tile / tiles_per_group, col = (tile - g * tiles_per_group) * TL + c;
-        const long long base = (long long)g * a.group_stride + col;
+        const float2 *p = src + ((long long)g * a.group_stride + col + toff);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             vn[m] = make_float2(0.f, 0.f);
-            if (tile < ntiles && col < a.ncols) vn[m] = src[base + (long long)(t + m * STEP) * a.line_stride];
+            if (tile < ntiles && col < a.ncols) vn[m] = p[m * rs];
         }
     }
+    __syncthreads(); /* twiddle table visible */
     for (; tile < ntiles; tile += gridDim.x) {
         const int g = tile / tiles_per_group, col = (tile - g * tiles_per_group) * TL + c;
         const bool live = col < a.ncols;
-        const long long base = (long long)g * a.group_stride + col;
+        const long long base = (long long)g * a.group_stride + col + toff;
 #pragma unroll
         for (int m = 0; m < 8; m++) v[m] = vn[m];
         /* prefetch the next tile of this CTA */
         {
             const int nt = tile + gridDim.x;
             const int gn = nt / tiles_per_group, coln = (nt - gn * tiles_per_group) * TL + c;
-            const long long basen = (long long)gn * a.group_stride + coln;
+            const float2 *p = src + ((long long)gn * a.group_stride + coln + toff);
             const bool liven = nt < ntiles && coln < a.ncols;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 vn[m] = make_float2(0.f, 0.f);
-                if (liven) vn[m] = src[basen + (long long)(t + m * STEP) * a.line_stride];
+                if (liven) vn[m] = p[m * rs];
             }
         }
-        if (has_kmul && live) {
-            if (a.wtab && a.op == KOP_NONE) {
-                /* window from the |n|^2 table: the (y, kz) part is a per-thread constant of the tile */
-                const int iy = col / a.pitch, iz = col - iy * a.pitch;
-                if (iz < a.nzc) {
-                    const int sy = (iy > a.ny / 2) ? iy - a.ny : iy;
-                    const int syz = sy * sy + iz * iz;
+        if constexpr (MODE == PM_WTAB) {
+            /* window from the |n|^2 table: the (y, kz) part is a per-thread constant of the tile */
+            const int iy = col / a.pitch, iz = col - iy * a.pitch;
+            if (live && iz < a.nzc) {
+                const int sy = (iy > a.ny / 2) ? iy - a.ny : iy;
+                const float *wt = a.wtab + (sy * sy + iz * iz);
 #pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        const int i = t + m * STEP;
-                        const int sx = (i > N / 2) ? i - N : i;
-                        const float W = ldg(&a.wtab[sx * sx + syz]);
-                        v[m].x *= W;
-                        v[m].y *= W;
-                    }
+                for (int m = 0; m < 8; m++) {
+                    const int i = t + m * STEP;
+                    const int sx = m < 4 ? i : i - N; /* i = N/2 (m = 4, t = 0): (-N/2)^2 is the same entry */
+                    v[m] = pk_scale(v[m], ldg(&wt[sx * sx]));
                 }
-            } else {
+            }
+        } else if constexpr (MODE == PM_GENERIC) {
+            if (live) {
 #pragma unroll
                 for (int m = 0; m < 8; m++) v[m] = apply_kmul(v[m], t + m * STEP, col, a);
             }
         }
-        fft_line_regs<N, SIGN>(v, t, TilePolicy<TL>{S, c}, a.tw, 1);
+        fft_line_regs<N, SIGN>(v, t, pol, twS);
         if (live) {
+            float2 *q = dst + base;
+            if (a.scale != 1.f) {
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                float2 x = v[m];
-                if (a.scale != 1.f) { x.x *= a.scale; x.y *= a.scale; }
-                dst[base + (long long)(t + m * STEP) * a.line_stride] = x;
+                for (int m = 0; m < 8; m++) q[m * rs] = pk_scale(v[m], a.scale);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; m++) q[m * rs] = v[m];
             }
         }
-        __syncthreads(); /* the tile buffer is reused by the next iteration */
+        if (Pow2Sync<N>::NEED_TAIL_SYNC) __syncthreads();
     }
 }
 
-template <int N> static void launch_strided_pow2(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
+template <int N, int MODE> static void launch_strided_pow2_mode(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
+    using P = Pow2Plan<N>;
     constexpr int TL = Pow2Cfg<N>::TL;
-    const size_t smem = (size_t)N * TL * sizeof(float2);
+    const size_t smem = (size_t)2 * N * TL * sizeof(float2) + (size_t)P::TW_TOTAL * sizeof(float4);
     const int tiles_per_group = (a.ncols + TL - 1) / TL;
     const long long ntiles = (long long)tiles_per_group * ngroups;
-    auto kf = &fft_strided_pow2_kernel<N, -1>;
-    auto ki = &fft_strided_pow2_kernel<N, 1>;
+    auto kf = &fft_strided_pow2_kernel<N, -1, MODE>;
+    auto ki = &fft_strided_pow2_kernel<N, 1, MODE>;
     /* persistent grid: exactly the CTAs that are resident at once */
     allow_smem(kf, smem);
     allow_smem(ki, smem);
@@ -217,14 +303,18 @@ template <int N> static void launch_strided_pow2(const float2 *src, float2 *dst,
     long long grid = (long long)dev_num_sms() * per_sm;
     if (grid > ntiles) grid = ntiles;
     if (a.sign < 0) {
-        allow_smem(kf, smem);
         B200_LAUNCH_T("fft_strided_pow2_kernel", kf, dim3((unsigned)grid), Pow2Cfg<N>::THREADS, smem, src, dst, a,
                       tiles_per_group, (int)ntiles);
     } else {
-        allow_smem(ki, smem);
         B200_LAUNCH_T("fft_strided_pow2_kernel", ki, dim3((unsigned)grid), Pow2Cfg<N>::THREADS, smem, src, dst, a,
                       tiles_per_group, (int)ntiles);
     }
+}
+template <int N> static void launch_strided_pow2(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
+    const bool has_kmul = a.kmul != KMUL_NONE || a.op != KOP_NONE;
+    if (!has_kmul) launch_strided_pow2_mode<N, PM_PLAIN>(src, dst, a, ngroups);
+    else if (a.wtab && a.op == KOP_NONE) launch_strided_pow2_mode<N, PM_WTAB>(src, dst, a, ngroups);
+    else launch_strided_pow2_mode<N, PM_GENERIC>(src, dst, a, ngroups);
 }
 
 static bool pow2_enabled() {
@@ -255,13 +345,15 @@ static bool pow2_strided(const float2 *src, float2 *dst, const StridedArgs &a, i
 /* complex rows (NH + 1 values) -> NR = 2 NH reals per row.
    The z axis is contiguous, so a line can be owned by NH/8 consecutive lanes (one warp at
    nz = 512): spectrum loads and real stores are coalesced straight from/to registers, the
-   inter-stage transposes use a private padded strip of shared memory, and lines synchronise with
-   __syncwarp / a per-line named barrier -- no CTA-wide barrier anywhere. */
+   inter-stage transposes use private padded strips of shared memory, and lines synchronise with
+   __syncwarp / a per-line named barrier -- no CTA-wide barrier in the loop. */
 template <int NH> struct ZLineCfg {
     static constexpr int LT = NH / 8;                       /* threads per line */
     static constexpr int THREADS = LT > 256 ? LT : 256;
     static constexpr int LINES = THREADS / LT;              /* lines per CTA */
-    static constexpr int STRIP = NH + NH / 8;               /* padded points per line */
+    static constexpr int STRIP = NH + NH / 8;               /* padded points per line and buffer */
+    static constexpr size_t SMEM = (size_t)2 * LINES * STRIP * sizeof(float2) + (size_t)Pow2Plan<NH>::TW_TOTAL * sizeof(float4) +
+                                   (size_t)NH * sizeof(float2);
 };
 template <int NH>
 __global__ void __launch_bounds__(ZLineCfg<NH>::THREADS)
@@ -270,8 +362,16 @@ fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, Z
     constexpr int LT = Cfg::LT, STEP = NH / 8;
     DYN_SMEM(float2, S);
     __shared__ float red_min[32], red_max[32];
+    float4 *twS = reinterpret_cast<float4 *>(S + 2 * Cfg::LINES * Cfg::STRIP);
+    float2 *mrg = reinterpret_cast<float2 *>(twS + Pow2Plan<NH>::TW_TOTAL); /* e^{+2 pi i n / NR}, n < NH */
+    fill_twiddles<NH, 1>(twS, a.tw, 2, Cfg::THREADS);
+    for (int n = threadIdx.x; n < NH; n += Cfg::THREADS) {
+        float2 w = ldg(&a.tw[n]);
+        mrg[n] = make_float2(w.x, -w.y);
+    }
+    __syncthreads();
     const int line = threadIdx.x / LT, t = threadIdx.x - line * LT;
-    const LinePolicy<LT> pol{S + line * Cfg::STRIP, 1 + line};
+    const LinePolicy<LT> pol{S + (2 * line) * Cfg::STRIP, S + (2 * line + 1) * Cfg::STRIP, 1 + line};
     float2 *dst2 = reinterpret_cast<float2 *>(dst);
     const long long row_stride2 = a.real_row_stride / 2;
     float lmin = 3.0e38f, lmax = -3.0e38f;
@@ -293,21 +393,16 @@ fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, Z
         float2 v[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            const int n = t + m * STEP;
-            float2 B = xb[m];
-            B.y = -B.y;
-            const float2 sum = cadd(xa[m], B), dif = csub(xa[m], B);
-            float2 w = ldg(&a.tw[n]); /* e^{-2 pi i n / NR} */
-            w.y = -w.y;
-            const float2 p = cmul(w, dif);
-            v[m] = make_float2(sum.x - p.y, sum.y + p.x);
+            const float2 B = make_float2(xb[m].x, -xb[m].y);
+            const float2 sum = pk_add(xa[m], B), dif = pk_sub(xa[m], B);
+            const float2 p = pk_cmul(dif, mrg[t + m * STEP]);
+            v[m] = pk_add(sum, pk_rot<1>(p));
         }
-        fft_line_regs<NH, 1>(v, t, pol, a.tw, 2);
+        fft_line_regs<NH, 1>(v, t, pol, twS);
         /* z[n] = (x[2n], x[2n+1]) */
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            float2 x = v[m];
-            x.x *= a.scale; x.y *= a.scale;
+            float2 x = pk_scale(v[m], a.scale);
             if (live) {
                 lmin = fminf(lmin, fminf(x.x, x.y));
                 lmax = fmaxf(lmax, fmaxf(x.x, x.y));
@@ -318,6 +413,7 @@ fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, Z
             }
             if (live) dst2[row * row_stride2 + t + m * STEP] = x;
         }
+        if (Pow2Sync<NH>::NEED_TAIL_SYNC) pol.sync();
     }
     if (a.minmax_keys) {
 #pragma unroll
@@ -345,23 +441,35 @@ fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, Z
     }
 }
 
-/* NR = 2 NH reals per row -> NH + 1 complex values */
+/* NR = 2 NH reals per row -> NH + 1 complex values.  Same line-per-LT-threads layout: the real row
+   is read as NH (even, odd) pairs, coalesced, straight into the FFT registers; the Hermitian
+   split needs Z[k] and Z[NH-k] of the same line, exchanged through the line's strip. */
 template <int NH>
-__global__ void __launch_bounds__(Pow2Cfg<NH>::THREADS) fft_r2c_z_pow2_kernel(const float *__restrict__ src,
-                                                                             float2 *__restrict__ dst, ZArgs a) {
-    constexpr int TL = Pow2Cfg<NH>::TL;
-    constexpr int STEP = NH / 8;
-    constexpr int NT = Pow2Cfg<NH>::THREADS;
+__global__ void __launch_bounds__(ZLineCfg<NH>::THREADS)
+fft_r2c_z_pow2_kernel(const float *__restrict__ src, float2 *__restrict__ dst, ZArgs a) {
+    using Cfg = ZLineCfg<NH>;
+    constexpr int LT = Cfg::LT, STEP = NH / 8;
     DYN_SMEM(float2, S);
-    const long long row0 = (long long)blockIdx.x * TL;
+    float4 *twS = reinterpret_cast<float4 *>(S + 2 * Cfg::LINES * Cfg::STRIP);
+    float2 *mrg = reinterpret_cast<float2 *>(twS + Pow2Plan<NH>::TW_TOTAL); /* e^{-2 pi i k / NR}, k < NH */
+    fill_twiddles<NH, -1>(twS, a.tw, 2, Cfg::THREADS);
+    for (int n = threadIdx.x; n < NH; n += Cfg::THREADS) mrg[n] = ldg(&a.tw[n]);
+    __syncthreads();
+    const int line = threadIdx.x / LT, t = threadIdx.x - line * LT;
+    const LinePolicy<LT> pol{S + (2 * line) * Cfg::STRIP, S + (2 * line + 1) * Cfg::STRIP, 1 + line};
     const float2 *src2 = reinterpret_cast<const float2 *>(src);
     const long long row_stride2 = a.real_row_stride / 2;
-    for (int e = threadIdx.x; e < TL * NH; e += NT) {
-        const int l = e / NH, n = e - l * NH;
-        float2 x = make_float2(0.f, 0.f);
-        if (row0 + l < a.nrows) {
-            x = src2[(row0 + l) * row_stride2 + n];
-            if (a.premul != 1.f || a.clip) {
+    const bool pre = a.premul != 1.f || a.clip;
+    for (long long row0 = (long long)blockIdx.x * Cfg::LINES; row0 < a.nrows;
+         row0 += (long long)gridDim.x * Cfg::LINES) {
+        const long long row = row0 + line;
+        const bool live = row < a.nrows;
+        float2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            float2 x = live ? src2[row * row_stride2 + t + m * STEP] : make_float2(0.f, 0.f);
+            if (pre) {
+                /* prepare_box_for_filtering (IonisationBox.c:343-346): double product, clamp */
                 double c0 = (double)x.x * (double)a.premul, c1 = (double)x.y * (double)a.premul;
                 if (a.clip) {
                     c0 = fmax(fmin(c0, (double)a.clip_hi), (double)a.clip_lo);
@@ -369,65 +477,59 @@ __global__ void __launch_bounds__(Pow2Cfg<NH>::THREADS) fft_r2c_z_pow2_kernel(co
                 }
                 x = make_float2((float)c0, (float)c1);
             }
+            v[m] = x;
         }
-        S[sidx<TL>(n, l)] = x;
-    }
-    __syncthreads();
-    const int c = threadIdx.x & (TL - 1), t = threadIdx.x / TL;
-    float2 v[8];
+        fft_line_regs<NH, -1>(v, t, pol, twS);
+        /* Z[k] at k = t + m STEP; partner Z[(NH - k) mod NH] through the strip that the last
+           exchange did NOT use (no hazard with slower threads still reading the other one) */
+        float2 *strip = (Pow2Plan<NH>::NSTAGE == 3) ? pol.A : pol.B;
 #pragma unroll
-    for (int m = 0; m < 8; m++) v[m] = S[sidx<TL>(t + m * STEP, c)];
-    __syncthreads();
-    fft_line_regs<NH, -1>(v, t, TilePolicy<TL>{S, c}, a.tw, 2);
+        for (int m = 0; m < 8; m++) strip[pol.off(t + m * STEP)] = v[m];
+        pol.sync();
+        /* X[k] = (Z[k] + conj Z[NH-k]) / 2 - (i/2) e^{-2 pi i k / NR} (Z[k] - conj Z[NH-k]) */
 #pragma unroll
-    for (int m = 0; m < 8; m++) S[sidx<TL>(t + m * STEP, c)] = v[m];
-    __syncthreads();
-    /* X[k] = (Z[k] + conj Z[NH-k]) / 2 - (i/2) e^{-2 pi i k / NR} (Z[k] - conj Z[NH-k]) */
-    for (int e = threadIdx.x; e < TL * NH; e += NT) {
-        const int l = e / NH, k = e - l * NH;
-        if (row0 + l < a.nrows) {
-            const float2 Zk = S[sidx<TL>(k, l)];
-            float2 Zc = S[sidx<TL>((NH - k) & (NH - 1), l)];
-            Zc.y = -Zc.y;
-            const float2 s = cadd(Zk, Zc), d = csub(Zk, Zc);
-            const float2 p = cmul(ldg(&a.tw[k]), d);
-            float2 X = make_float2(0.5f * (s.x + p.y), 0.5f * (s.y - p.x));
-            if (a.scale != 1.f) { X.x *= a.scale; X.y *= a.scale; }
-            dst[(row0 + l) * a.pitch + k] = X;
+        for (int m = 0; m < 8; m++) {
+            const int k = t + m * STEP;
+            const float2 zc = strip[pol.off((NH - k) & (NH - 1))];
+            const float2 Zc = make_float2(zc.x, -zc.y);
+            const float2 s = pk_add(v[m], Zc), d = pk_sub(v[m], Zc);
+            const float2 p = pk_cmul(d, mrg[k]);
+            float2 X = pk_scale(pk_add(s, pk_rot<-1>(p)), 0.5f * a.scale);
+            if (live) dst[row * a.pitch + k] = X;
+            if (k == 0 && live) dst[row * a.pitch + NH] = make_float2((v[m].x - v[m].y) * a.scale, 0.f);
         }
-    }
-    if (threadIdx.x < TL) {
-        const int l = threadIdx.x;
-        if (row0 + l < a.nrows) {
-            const float2 Z0 = S[sidx<TL>(0, l)];
-            float2 X = make_float2(Z0.x - Z0.y, 0.f);
-            if (a.scale != 1.f) X.x *= a.scale;
-            dst[(row0 + l) * a.pitch + NH] = X;
-        }
+        pol.sync();
     }
 }
 
-template <int NH> static void launch_c2r_z_pow2(const float2 *src, float *dst, const ZArgs &a) {
+template <int NH> static int z_grid(int per_sm, int nrows) {
     using Cfg = ZLineCfg<NH>;
-    const size_t smem = (size_t)Cfg::LINES * Cfg::STRIP * sizeof(float2);
-    auto k = &fft_c2r_z_pow2_kernel<NH>;
-    allow_smem(k, smem);
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, Cfg::THREADS, smem));
-        if (per_sm < 1) per_sm = 1;
-    }
-    const long long groups = ((long long)a.nrows + Cfg::LINES - 1) / Cfg::LINES;
+    const long long groups = ((long long)nrows + Cfg::LINES - 1) / Cfg::LINES;
     long long grid = (long long)dev_num_sms() * per_sm;
     if (grid > groups) grid = groups;
-    B200_LAUNCH_T("fft_c2r_z_pow2_kernel", k, dim3((unsigned)grid), Cfg::THREADS, smem, src, dst, a);
+    return (int)grid;
+}
+template <int NH> static void launch_c2r_z_pow2(const float2 *src, float *dst, const ZArgs &a) {
+    using Cfg = ZLineCfg<NH>;
+    auto k = &fft_c2r_z_pow2_kernel<NH>;
+    allow_smem(k, Cfg::SMEM);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, Cfg::THREADS, Cfg::SMEM));
+        if (per_sm < 1) per_sm = 1;
+    }
+    B200_LAUNCH_T("fft_c2r_z_pow2_kernel", k, dim3((unsigned)z_grid<NH>(per_sm, a.nrows)), Cfg::THREADS, Cfg::SMEM, src, dst, a);
 }
 template <int NH> static void launch_r2c_z_pow2(const float *src, float2 *dst, const ZArgs &a) {
-    constexpr int TL = Pow2Cfg<NH>::TL;
-    const size_t smem = (size_t)(NH + 1) * TL * sizeof(float2);
+    using Cfg = ZLineCfg<NH>;
     auto k = &fft_r2c_z_pow2_kernel<NH>;
-    allow_smem(k, smem);
-    B200_LAUNCH_T("fft_r2c_z_pow2_kernel", k, dim3((a.nrows + TL - 1) / TL), Pow2Cfg<NH>::THREADS, smem, src, dst, a);
+    allow_smem(k, Cfg::SMEM);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, Cfg::THREADS, Cfg::SMEM));
+        if (per_sm < 1) per_sm = 1;
+    }
+    B200_LAUNCH_T("fft_r2c_z_pow2_kernel", k, dim3((unsigned)z_grid<NH>(per_sm, a.nrows)), Cfg::THREADS, Cfg::SMEM, src, dst, a);
 }
 
 static bool z_ok(const ZArgs &a, const void *real_ptr) {

@@ -38,60 +38,154 @@ struct DevTable {
     float y[N_DENS_INTERP];
 };
 
-/* EvaluateRGTable1D_f (interpolation.c:123-131) on a table staged in shared memory */
-DEV double table_eval(double x, const DevTable *h, const float *y) {
-    const int idx = (int)floor((x - h->x_min) * h->inv_width);
-    const double table_val = h->x_min + h->x_width * (float)idx;
-    const double t = (x - table_val) * h->inv_width;
-    return (double)y[idx] * (1 - t) + (double)y[idx + 1] * t;
-}
-
 struct SweepArgs {
     int nx, ny, nz, nzc;
     const float *filtered;   /* padded real rows, already clipped to [-1, 1e6] */
     const DevTable *table;
     double *partial;         /* [gridDim.x] block sums */
-    float *fcoll;            /* unpadded f_coll grid of this radius */
+    float *fcoll;            /* unpadded f_coll grid of this radius, or null (sum only) */
 };
 
-/* sweep 1: f_coll per cell + block partial sums (calculate_fcoll_grid, IonisationBox.c:773-962).
-   Four cells per thread and iteration (128-bit loads/stores) when the row length allows. */
-DEV float fcoll_cell(float dens, float dens_floor, const DevTable *tab, const float *ytab, int log_valued, double &acc) {
-    const float d = fmaxf(dens, dens_floor);
-    double fc = table_eval((double)d, tab, ytab);
-    if (log_valued) fc = exp(fc);
-    acc += fc;
-    return (float)fc;
+/* Shared-memory copy of the radius' table in the forms the sweeps use.
+ *
+ * The sweeps are HBM-bound only if a cell costs ~25 single-precision instructions: on B200 a cell
+ * of a 4-byte stream has a budget of ~0.2 SM cycles, i.e. ~13 double-precision or ~3 64-bit
+ * conversion instructions.  The reference's arithmetic (double interpolation of a float table,
+ * interpolation.c:123-131, double exp) is therefore kept for what is stored or decided, and a
+ * single-precision evaluation is used where its error cannot reach the result:
+ *   - grid SUM of radii whose f_coll grid is not an output: per-cell relative error ~1e-7, unbiased,
+ *     so the mean over >= 32^3 cells moves by < 1e-9 relative;
+ *   - ionised FLAG: decided in single precision only when the value is further from the threshold
+ *     than a band that covers the single-precision evaluation error (1e-5 + 1e-4 |dy| of the bin);
+ *     inside the band the reference arithmetic decides.
+ * Log-valued (E-INTEGRAL) table: exp(y0 (1-t) + y1 t) = exp(y0) exp(t dy) with exp(y0) tabulated
+ * per bin and exp(u), |u| <= 1/4, a degree-6 Taylor series (remainder < 1.3e-8, typical |u| << 1/4);
+ * steeper bins take the reference path. */
+struct SweepTable {
+    float y[N_DENS_INTERP];        /* the table as uploaded (reference path) */
+    float2 yd[N_DENS_INTERP];      /* {y0, y1 - y0} */
+    float2 ed[N_DENS_INTERP];      /* {exp(y0), y1 - y0} (log-valued tables) */
+    double x_min, x_width, inv_width;
+    float x_min_f, inv_width_f;
+    int log_valued;
+};
+DEV void sweep_table_load(SweepTable *st, const DevTable *t) {
+    for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) {
+        const float y0 = t->y[i];
+        const float y1 = t->y[i + 1 < N_DENS_INTERP ? i + 1 : i];
+        const float dy = (float)((double)y1 - (double)y0);
+        st->y[i] = y0;
+        st->yd[i] = make_float2(y0, dy);
+        st->ed[i] = make_float2(t->log_valued ? (float)exp((double)y0) : y0, dy);
+    }
+    if (threadIdx.x == 0) {
+        st->x_min = t->x_min; st->x_width = t->x_width; st->inv_width = t->inv_width;
+        st->x_min_f = (float)t->x_min; st->inv_width_f = (float)t->inv_width;
+        st->log_valued = t->log_valued;
+    }
 }
+/* reference arithmetic: EvaluateRGTable1D_f (interpolation.c:123-131), exp for log-valued tables */
+DEV double fcoll_exact(float d, const SweepTable *h) {
+    const double x = (double)d;
+    const int idx = (int)floor((x - h->x_min) * h->inv_width);
+    const double table_val = h->x_min + h->x_width * (float)idx;
+    const double t = (x - table_val) * h->inv_width;
+    const double v = (double)h->y[idx] * (1 - t) + (double)h->y[idx + 1] * t;
+    return h->log_valued ? exp(v) : v;
+}
+/* single-precision bin coordinates; idx is clamped so that a rounding slip at the table ends
+   stays inside the table */
+DEV void table_coords_f(float d, const SweepTable *h, int &idx, float &t) {
+    const float pos = (d - h->x_min_f) * h->inv_width_f;
+    const float fl = floorf(pos);
+    idx = (int)fl;
+    idx = idx < 0 ? 0 : (idx > N_DENS_INTERP - 2 ? N_DENS_INTERP - 2 : idx);
+    t = pos - (float)idx;
+}
+DEV float exp_small_f(float u) { /* Taylor series of exp, |u| <= 1/4 */
+    float p = 1.0f / 720.0f;
+    p = fmaf(p, u, 1.0f / 120.0f);
+    p = fmaf(p, u, 1.0f / 24.0f);
+    p = fmaf(p, u, 1.0f / 6.0f);
+    p = fmaf(p, u, 0.5f);
+    p = fmaf(p, u, 1.0f);
+    return fmaf(p, u, 1.0f);
+}
+/* f_coll of one cell for the grid sum only */
+DEV float fcoll_fast(float dens, float dens_floor, const SweepTable *h, int log_valued) {
+    const float d = fmaxf(dens, dens_floor);
+    int idx;
+    float t;
+    table_coords_f(d, h, idx, t);
+    const float2 e = h->ed[idx];
+    const float u = t * e.y;
+    if (!log_valued) return e.x + u;
+    if (fabsf(u) <= 0.25f) return e.x * exp_small_f(u);
+    return (float)fcoll_exact(d, h);
+}
+
+/* row / chunk decomposition of a flat float4 index over rows of q chunks */
+struct RowSplit {
+    int q, shift; /* shift >= 0: q is a power of two */
+};
+DEV RowSplit row_split(int q) {
+    RowSplit r;
+    r.q = q;
+    r.shift = (q & (q - 1)) == 0 ? 31 - __builtin_clz((unsigned)q) : -1;
+    return r;
+}
+DEV void row_of(const RowSplit &r, long long id, long long &row, int &zc) {
+    if (r.shift >= 0) { row = id >> r.shift; zc = (int)(id & (r.q - 1)); }
+    else { row = id / r.q; zc = (int)(id - row * r.q); }
+}
+
+/* sweep 1: sum of f_coll over the grid as deterministic double block sums (calculate_fcoll_grid,
+   IonisationBox.c:773-962).  With a.fcoll set (last radius: the grid is the unnormalised_nion
+   output) every cell takes the reference arithmetic and the float grid is written. */
 __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
-    DYN_SMEM(float, ytab);
+    __shared__ SweepTable st;
     __shared__ double red[256];
-    for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) ytab[i] = a.table->y[i];
+    sweep_table_load(&st, a.table);
     __syncthreads();
     const long long nrows = (long long)a.nx * a.ny;
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
-    const int log_valued = a.table->log_valued;
+    const int log_valued = st.log_valued;
     double acc = 0.;
-    if ((a.nz & 3) == 0) {
-        const int q = a.nz >> 2; /* float4 chunks per row */
-        const long long nchunks = nrows * q;
-        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks;
-             id += (long long)gridDim.x * blockDim.x) {
-            const long long row = id / q;
-            const int zc = (int)(id - row * q);
-            const float4 d4 = *reinterpret_cast<const float4 *>(a.filtered + row * 2 * a.nzc + 4 * zc);
-            float4 o;
-            o.x = fcoll_cell(d4.x, dens_floor, a.table, ytab, log_valued, acc);
-            o.y = fcoll_cell(d4.y, dens_floor, a.table, ytab, log_valued, acc);
-            o.z = fcoll_cell(d4.z, dens_floor, a.table, ytab, log_valued, acc);
-            o.w = fcoll_cell(d4.w, dens_floor, a.table, ytab, log_valued, acc);
-            *reinterpret_cast<float4 *>(a.fcoll + row * a.nz + 4 * zc) = o;
+    if ((a.nz & 3) == 0 && !a.fcoll) {
+        const RowSplit rs = row_split(a.nz >> 2);
+        const long long nchunks = nrows * rs.q;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks; id += 4 * stride) {
+            float4 d4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { /* four independent 128-bit loads in flight per thread */
+                const long long j = id + u * stride;
+                long long row;
+                int zc;
+                row_of(rs, j < nchunks ? j : id, row, zc);
+                d4[u] = *reinterpret_cast<const float4 *>(a.filtered + row * 2 * a.nzc + 4 * zc);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (id + u * stride < nchunks) {
+                    const float f = (fcoll_fast(d4[u].x, dens_floor, &st, log_valued) + fcoll_fast(d4[u].y, dens_floor, &st, log_valued)) +
+                                    (fcoll_fast(d4[u].z, dens_floor, &st, log_valued) + fcoll_fast(d4[u].w, dens_floor, &st, log_valued));
+                    acc += (double)f;
+                }
+            }
         }
     } else {
         for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
             const float *src = a.filtered + row * 2 * a.nzc;
-            for (int z = threadIdx.x; z < a.nz; z += blockDim.x)
-                a.fcoll[row * a.nz + z] = fcoll_cell(src[z], dens_floor, a.table, ytab, log_valued, acc);
+            for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
+                if (a.fcoll) {
+                    const double f = fcoll_exact(fmaxf(src[z], dens_floor), &st);
+                    acc += f;
+                    a.fcoll[row * a.nz + z] = (float)f;
+                } else {
+                    acc += (double)fcoll_fast(src[z], dens_floor, &st, log_valued);
+                }
+            }
         }
     }
     red[threadIdx.x] = acc;
@@ -195,7 +289,113 @@ __global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
     }
 }
 
-DEV float fully_ionized_temperature(float z_re, float z, float delta, float T_re) { /* thermochem.c:31-56 */
+struct CritDeltaArgs {
+    int nx, ny, nz, nzc;
+    const float *filtered;   /* padded real rows of this radius (the sweep-1 input) */
+    const DevTable *table;
+    const double *partial;   /* block sums of sweep 1 */
+    int n_partial;
+    unsigned char *mask;     /* 1 = ionised at some radius so far */
+    double n_cells, mean_f_coll, f_limit, ion_eff_factor;
+    int mass_dep_zeta;
+};
+/* sweep 2 for every radius but the last one processed: only the flag "f_coll zeta > 1" is needed
+   (find_ionised_regions, IonisationBox.c:1040-1151, centre-cell method), so the f_coll grid is never
+   written: the criterion is re-evaluated from the filtered density.  The reference compares
+   mean_fix * (double)(float)f_coll * zeta with 1; for the log-valued table that is decided in log
+   space whenever the interpolated log f_coll is more than 1e-6 away from the threshold (float
+   rounding moves f_coll by < 6e-8 relative), and with the reference's exact arithmetic inside
+   that band. */
+__global__ void __launch_bounds__(256) ionise_delta_kernel(CritDeltaArgs a) {
+    __shared__ SweepTable st;
+    __shared__ double red[256];
+    sweep_table_load(&st, a.table);
+    double acc = 0.;
+    for (int i = threadIdx.x; i < a.n_partial; i += blockDim.x) acc += a.partial[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    double grid_mean = red[0] / a.n_cells;
+    if (a.mass_dep_zeta) {
+        if (grid_mean <= a.f_limit) grid_mean = a.f_limit;
+    } else {
+        if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
+    }
+    const double mean_fix = a.mean_f_coll / grid_mean;
+    const double gain = mean_fix * a.ion_eff_factor;
+    const bool floor_ionises = a.mass_dep_zeta && (a.f_limit * a.ion_eff_factor > 1.0);
+    const int log_valued = st.log_valued;
+    /* threshold in the table's own units: log f_coll or f_coll */
+    const float thr = log_valued ? (float)(-log(gain)) : (float)(1.0 / gain);
+    const float band0 = log_valued ? 1e-5f : 1e-5f * fabsf(thr);
+    const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
+    const long long nrows = (long long)a.nx * a.ny;
+    auto ionised = [&](float dens) -> bool {
+        const float d = fmaxf(dens, dens_floor);
+        int idx;
+        float t;
+        table_coords_f(d, &st, idx, t);
+        const float2 yd = st.yd[idx];
+        const float diff = fmaf(t, yd.y, yd.x) - thr;
+        const float band = fmaf(1e-4f, fabsf(yd.y), band0);
+        if (diff > band) return true;
+        if (diff < -band) return floor_ionises;
+        /* inside the band: the reference arithmetic on the float-rounded f_coll decides */
+        double curr = mean_fix * (double)(float)fcoll_exact(d, &st);
+        if (a.mass_dep_zeta && curr < a.f_limit) curr = a.f_limit;
+        return curr * a.ion_eff_factor > 1.0;
+    };
+    if ((a.nz & 3) == 0) {
+        const RowSplit rs = row_split(a.nz >> 2);
+        const long long nchunks = nrows * rs.q;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks; id += 4 * stride) {
+            float4 d4[4];
+            long long cell[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long j = id + u * stride;
+                long long row;
+                int zc;
+                row_of(rs, j < nchunks ? j : id, row, zc);
+                d4[u] = *reinterpret_cast<const float4 *>(a.filtered + row * 2 * a.nzc + 4 * zc);
+                cell[u] = row * a.nz + 4 * zc;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (id + u * stride < nchunks) {
+                    const bool i0 = ionised(d4[u].x), i1 = ionised(d4[u].y), i2 = ionised(d4[u].z), i3 = ionised(d4[u].w);
+                    if (i0 || i1 || i2 || i3) {
+                        unsigned char *m = a.mask + cell[u];
+                        if (i0 && i1 && i2 && i3) {
+                            *reinterpret_cast<unsigned int *>(m) = 0x01010101u;
+                        } else {
+                            if (i0) m[0] = 1;
+                            if (i1) m[1] = 1;
+                            if (i2) m[2] = 1;
+                            if (i3) m[3] = 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+            const float *src = a.filtered + row * 2 * a.nzc;
+            for (int z = threadIdx.x; z < a.nz; z += blockDim.x)
+                if (ionised(src[z])) a.mask[row * a.nz + z] = 1;
+        }
+    }
+}
+
+/* ComputeFullyIonizedTemperature (thermochem.c:31-56).  The two powers that do not depend on the
+   cell, pow(T_re, 1.7) and pow(1e4 (1+z)/4, 1.7), are evaluated once per launch (c_Tre17, c_z17);
+   the remaining ones are written as exp(p log x), which costs half of a general pow. */
+DEV double pow_pos(double x, double p) { return exp(p * log(x)); }
+DEV float fully_ionized_temperature(float z_re, float z, float delta, double c_Tre17, double c_z17) {
     float result, delta_re;
     if (fabs(z - z_re) < 1e-4)
         result = 1;
@@ -203,13 +403,13 @@ DEV float fully_ionized_temperature(float z_re, float z, float delta, float T_re
         delta_re = delta * (1. + z) / (1. + z_re);
         if (delta_re <= -1) delta_re = -1. + 9e-8;
         if (delta <= -1) delta = -1. + 9e-8;
-        result = pow((1. + delta) / (1. + delta_re), 1.1333);
-        result *= pow((1. + z) / (1. + z_re), 3.4);
-        result *= expf(pow((1. + z) / 7.1, 2.5) - pow((1. + z_re) / 7.1, 2.5));
+        result = pow_pos((1. + delta) / (1. + delta_re), 1.1333);
+        result *= pow_pos((1. + z) / (1. + z_re), 3.4);
+        result *= expf(pow_pos((1. + z) / 7.1, 2.5) - pow_pos((1. + z_re) / 7.1, 2.5));
     }
-    result *= pow((double)T_re, 1.7);
-    result += pow(1e4 * ((1. + z) / 4.), 1.7) * (1 + delta);
-    result = pow((double)result, 0.5882);
+    result *= c_Tre17;
+    result += c_z17 * (1 + delta);
+    result = pow_pos((double)result, 0.5882);
     return result;
 }
 
@@ -220,6 +420,7 @@ struct FinalArgs {
     float *xH, *z_reion, *Tk;
     int *nonfinite;
     double redshift, stored_redshift, T_re, TK_nofluct, adia_TK_term;
+    double c_Tre17, c_z17; /* pow(T_re, 1.7), pow(1e4 (1 + z) / 4, 1.7) */
 };
 /* materialise the flags (xH = 0, z_reion; IonisationBox.c:1142-1151) and set_ionized_temperatures
    (IonisationBox.c:1203-1256) in one pass */
@@ -237,7 +438,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
             float tk = a.Tk[i];
             if (a.mask[i] && zre > 0) {
                 const float d = a.density[i];
-                tk = fully_ionized_temperature(zre, (float)a.stored_redshift, d, (float)a.T_re);
+                tk = fully_ionized_temperature(zre, (float)a.stored_redshift, d, a.c_Tre17, a.c_z17);
                 const float thistk = a.TK_nofluct * (1 + a.adia_TK_term * d);
                 if (tk < thistk) tk = thistk;
                 a.Tk[i] = tk;
@@ -386,7 +587,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     DevBuf<float2> k_unfiltered(plan->n_cplx()), work0(plan->n_cplx()), work1(plan->n_cplx());
     float2 *work[2] = {work0.p, work1.p};
     DevBuf<float> d_fcoll;
-    if (!io.nion || n_todo > 1) d_fcoll.alloc(N);
+    if (!io.nion) d_fcoll.alloc(N);
     DevBuf<int> d_keys(2 * (size_t)(n_todo > 0 ? n_todo : 1));
     DevBuf<DevTable> d_tables((size_t)(n_todo > 0 ? n_todo : 1));
     const int sweep_blocks = grid_for((long long)nx * ny, 1);
@@ -468,29 +669,46 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         memcpy(st->y, htab.y, sizeof(st->y));
         h2d_async(d_tables.p + k, st, sizeof(DevTable));
 
-        /* the reference leaves the last processed radius' f_coll in unnormalised_nion */
-        float *fc = (k == n_todo - 1 && io.nion) ? io.nion : d_fcoll.p;
-        SweepArgs sa = {nx, ny, nz, plan->pitch, reinterpret_cast<const float *>(work[k & 1]), d_tables.p + k, d_partial, fc};
-        B200_LAUNCH(fcoll_sum_kernel, sweep_blocks, 256, N_DENS_INTERP * sizeof(float), sa);
+        /* the reference leaves the last processed radius' f_coll in unnormalised_nion; every
+           other radius only needs the grid sum and the ionised flags, so its f_coll grid is never
+           materialised */
+        const bool last = (k == n_todo - 1);
+        float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : nullptr;
+        const float *filtered = reinterpret_cast<const float *>(work[k & 1]);
+        SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
+        B200_LAUNCH(fcoll_sum_kernel, sweep_blocks, 256, 0, sa);
 
-        CritArgs ca;
-        memset(&ca, 0, sizeof(ca));
-        ca.n = N; ca.fcoll = fc; ca.partial = d_partial; ca.n_partial = sweep_blocks;
-        ca.density = io.density; ca.prev_zre = io.prev_zre;
-        ca.mask = d_mask; ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
-        ca.n_cells = (double)N; ca.mean_f_coll = box->mean_f_coll; ca.f_limit = f_limit;
-        ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
-        ca.R_index = rs.R_index; ca.redshift = c.redshift;
-        ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
-        B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
+        if (!last) {
+            CritDeltaArgs cd;
+            memset(&cd, 0, sizeof(cd));
+            cd.nx = nx; cd.ny = ny; cd.nz = nz; cd.nzc = plan->pitch;
+            cd.filtered = filtered; cd.table = d_tables.p + k;
+            cd.partial = d_partial; cd.n_partial = sweep_blocks; cd.mask = d_mask;
+            cd.n_cells = (double)N; cd.mean_f_coll = box->mean_f_coll; cd.f_limit = f_limit;
+            cd.ion_eff_factor = c.ion_eff_factor; cd.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
+            B200_LAUNCH(ionise_delta_kernel, sweep_blocks, 256, 0, cd);
+        } else {
+            CritArgs ca;
+            memset(&ca, 0, sizeof(ca));
+            ca.n = N; ca.fcoll = fc; ca.partial = d_partial; ca.n_partial = sweep_blocks;
+            ca.density = io.density; ca.prev_zre = io.prev_zre;
+            ca.mask = d_mask; ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
+            ca.n_cells = (double)N; ca.mean_f_coll = box->mean_f_coll; ca.f_limit = f_limit;
+            ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
+            ca.R_index = rs.R_index; ca.redshift = c.redshift;
+            ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
+            B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
+        }
     }
 
     if (verbose)
         fprintf(stderr, "[21cmfast_b200] ionize host: enqueue %.3f ms, event wait %.3f ms, tables %.3f ms (%d radii)\n",
                 1e3 * t_launch, 1e3 * t_wait, 1e3 * t_table, n_todo);
     {
+        const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
         FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
-                        c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term};
+                        c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
+                        pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7)};
         B200_LAUNCH(finalize_kernel, grid_for(N, 1024), 256, 0, fa);
         int flag = 0;
         d2h(&flag, d_flag, sizeof(int)); /* also drains the stream before the work boxes are released */
