@@ -206,6 +206,8 @@ struct StridedArgs {
     int op, axis_a, axis_b;
     double op_factor;
     const float *wtab;
+    const float *wtab3;      /* expanded [|nx|][|ny|][pitch] form of wtab, or null */
+    long long w3_xstride;    /* (ny/2+1) * pitch */
 };
 
 /* index_to_k (indexing.h:116-120): double wavenumber of a grid index */
@@ -512,6 +514,8 @@ static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long lo
             a.fast_window = (km->fast && !exact && (km->filter_type == 0 || km->filter_type == 2)) ? 1 : 0;
         }
         a.wtab = (a.fast_window && km->wtab) ? km->wtab : nullptr;
+        a.wtab3 = a.wtab ? km->wtab3 : nullptr;
+        a.w3_xstride = (long long)(p3->ny / 2 + 1) * p3->pitch;
         a.R = km->R; a.R_param = km->R_param; a.r_const = km->r_const;
         a.dkx = km->dk[0]; a.dky = km->dk[1]; a.dkz = km->dk[2];
         a.op = km->op; a.axis_a = km->axis_a; a.axis_b = km->axis_b; a.op_factor = km->op_factor;
@@ -602,6 +606,34 @@ struct WTabArgs {
 __global__ void window_table_kernel(WTabArgs a) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
         a.out[i] = window_of_n2(a.type, i, a.dk, a.R);
+}
+struct WExpandArgs {
+    int nax, nay, pitch, nzc;
+    const float *tab;
+    float *out;
+};
+__global__ void window_expand_kernel(WExpandArgs a) {
+    /* the table is symmetric in (ax, ay) for a cubic box: gather each row once, write it twice */
+    const bool sym = a.nax == a.nay;
+    const long long rows = (long long)a.nax * a.nay;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int ax = (int)(row / a.nay), ay = (int)(row - (long long)ax * a.nay);
+        if (sym && ax > ay) continue;
+        const int n2 = ax * ax + ay * ay;
+        const long long mirror = (long long)ay * a.nay + ax;
+        for (int iz = threadIdx.x; iz < a.pitch; iz += blockDim.x) {
+            const float w = iz < a.nzc ? ldg(&a.tab[n2 + iz * iz]) : 1.0f;
+            a.out[row * a.pitch + iz] = w;
+            if (sym && ax != ay) a.out[mirror * a.pitch + iz] = w;
+        }
+    }
+}
+size_t window_table3_size(const Fft3D *p) { return (size_t)(p->nx / 2 + 1) * (p->ny / 2 + 1) * p->pitch; }
+void window_table_expand(const Fft3D *p, const float *tab, float *out3) {
+    WExpandArgs a = {p->nx / 2 + 1, p->ny / 2 + 1, p->pitch, p->nzc, tab, out3};
+    const long long rows = (long long)a.nax * a.nay;
+    const int cap = dev_num_sms() * 16;
+    B200_LAUNCH(window_expand_kernel, (int)(rows < cap ? rows : cap), 256, 0, a);
 }
 int window_table_size(const Fft3D *p) { return 3 * (p->nx / 2) * (p->nx / 2) + 1; }
 void window_table_build(const Fft3D *p, int type, float R, double dk, float *out) {

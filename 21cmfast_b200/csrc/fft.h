@@ -59,6 +59,8 @@ struct KMul {
     int fast = 0;              /* 1: single-precision window (window_value_fast) for the hot sweep */
     const float *wtab = nullptr; /* optional window table indexed by nx^2+ny^2+nz^2 (cubic boxes) */
     int wtab_n = 0;
+    const float *wtab3 = nullptr; /* the same window expanded to [|nx|][|ny|][kz] rows (window_table_expand):
+                                     the x pass reads it with the lanes along kz, i.e. coalesced */
     int op = KOP_NONE;         /* derivative operator */
     int axis_a = 0, axis_b = 0;
     double op_factor = 1.;     /* c in KOP_VELOCITY_F */
@@ -90,6 +92,9 @@ Fft3D *fft_plan(int nx, int ny, int nz);
 /* table of the window over |n|^2 for cubic boxes (see KMul::wtab) */
 int window_table_size(const Fft3D *p);
 void window_table_build(const Fft3D *p, int type, float R, double dk, float *out);
+/* expanded form for the power-of-two x pass: out3[(ax * (ny/2+1) + ay) * pitch + kz] = tab[ax^2 + ay^2 + kz^2] */
+size_t window_table3_size(const Fft3D *p);
+void window_table_expand(const Fft3D *p, const float *tab, float *out3);
 
 /* forward: real (padded or pro.src) -> complex in `box` */
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro);

@@ -119,6 +119,69 @@ template <int N, int RAD, int NS, int SIGN> DEV void stage_regs(float2 (&v)[8], 
     }
 }
 
+/* Register-resident twiddles for kernels whose threads keep the same butterfly phases for every
+   line they transform (the z kernels: one line per LT lanes, so the shared-memory rows would be
+   read with 32 distinct addresses per warp, 4 wavefronts per LDS.128, for every line).  A radix-8
+   stage keeps w, w^2, w^4 and derives the other four powers with one complex multiply each (two
+   roundings at most); the final radix-4 / radix-2 stage keeps (w, w^2) resp. w per butterfly. */
+template <int N> struct RegTwiddles {
+    float2 w[Pow2Plan<N>::NSTAGE - 1][4];
+};
+template <int N> DEV void load_reg_twiddles(RegTwiddles<N> &r, int t, const float4 *twS) {
+    using P = Pow2Plan<N>;
+    constexpr int STEP = N / 8;
+#pragma unroll
+    for (int s = 1; s < P::NSTAGE; s++) {
+        const int NS = P::ns(s), RAD = P::rad(s);
+        const float4 *row = twS + P::tw_base(s) + (t & (NS - 1)) * (RAD - 1);
+        if (RAD == 8) {
+            r.w[s - 1][0] = make_float2(row[0].x, row[0].y);
+            r.w[s - 1][1] = make_float2(row[1].x, row[1].y);
+            r.w[s - 1][2] = make_float2(row[3].x, row[3].y);
+            r.w[s - 1][3] = make_float2(0.f, 0.f);
+        } else if (RAD == 4) {
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                r.w[s - 1][2 * b] = make_float2(row[b * STEP * 3].x, row[b * STEP * 3].y);
+                r.w[s - 1][2 * b + 1] = make_float2(row[b * STEP * 3 + 1].x, row[b * STEP * 3 + 1].y);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) r.w[s - 1][b] = make_float2(row[b * STEP].x, row[b * STEP].y);
+        }
+    }
+}
+template <int N, int RAD, int SIGN> DEV void stage_regs_rt(float2 (&v)[8], const float2 (&w)[4]) {
+    constexpr int NB = 8 / RAD;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        float2 u[RAD];
+#pragma unroll
+        for (int q = 0; q < RAD; q++) u[q] = v[b + NB * q];
+        if constexpr (RAD == 8) {
+            const float2 w1 = w[0], w2 = w[1], w4 = w[2];
+            const float2 w3 = pk_cmul(w1, w2);
+            u[1] = pk_cmul(u[1], w1);
+            u[2] = pk_cmul(u[2], w2);
+            u[3] = pk_cmul(u[3], w3);
+            u[4] = pk_cmul(u[4], w4);
+            u[5] = pk_cmul(u[5], pk_cmul(w4, w1));
+            u[6] = pk_cmul(u[6], pk_cmul(w4, w2));
+            u[7] = pk_cmul(u[7], pk_cmul(w4, w3));
+        } else if constexpr (RAD == 4) {
+            const float2 w1 = w[2 * b], w2 = w[2 * b + 1];
+            u[1] = pk_cmul(u[1], w1);
+            u[2] = pk_cmul(u[2], w2);
+            u[3] = pk_cmul(u[3], pk_cmul(w1, w2));
+        } else {
+            u[1] = pk_cmul(u[1], w[b]);
+        }
+        pk_dft<RAD, SIGN>(u);
+#pragma unroll
+        for (int q = 0; q < RAD; q++) v[b + NB * q] = u[q];
+    }
+}
+
 /* where a line's point p lives in shared memory; offq<D>(p0, q) addresses point p0 + q D with the
    q-dependent part a compile-time constant wherever the layout allows */
 template <int TL> struct TilePolicy { /* TL lines interleaved: [point][line] */
@@ -143,7 +206,15 @@ template <int LT> struct LinePolicy { /* one line per LT threads, padded by one 
 };
 
 /* transpose between stages: outputs of stage (RAD, NS) -> inputs t + m STEP of the next stage */
-template <int N, int RAD, int NS, class Pol> DEV void exchange(float2 (&v)[8], int t, float2 *buf, const Pol &pol) {
+DEV void cp_async_16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int N, int RAD, int NS, class Pol, bool WAIT_ASYNC = false>
+DEV void exchange(float2 (&v)[8], int t, float2 *buf, const Pol &pol) {
     constexpr int NB = 8 / RAD;
     constexpr int STEP = N / 8;
 #pragma unroll
@@ -154,6 +225,7 @@ template <int N, int RAD, int NS, class Pol> DEV void exchange(float2 (&v)[8], i
 #pragma unroll
         for (int q = 0; q < RAD; q++) buf[pol.template offq<NS>(j0, q)] = v[b + NB * q];
     }
+    if (WAIT_ASYNC) cp_async_wait_all(); /* this thread's staged copies land before the barrier publishes them */
     pol.sync();
 #pragma unroll
     for (int m = 0; m < 8; m++) v[m] = buf[pol.template offq<STEP>(t, m)];
@@ -162,26 +234,44 @@ template <int N, int RAD, int NS, class Pol> DEV void exchange(float2 (&v)[8], i
 /* full length-N transform of the line whose points t + m N/8 live in v.  Exchanges alternate
    between pol.A and pol.B; a caller that loops must keep one barrier between two transforms
    only if N has a single exchange (N <= 64), see the kernels. */
-template <int N, int SIGN, class Pol> DEV void fft_line_regs(float2 (&v)[8], int t, const Pol &pol, const float4 *twS) {
+template <int N, int SIGN, class Pol, bool WAIT_ASYNC = false>
+DEV void fft_line_regs(float2 (&v)[8], int t, const Pol &pol, const float4 *twS) {
     using P = Pow2Plan<N>;
-    constexpr int STEP = N / 8;
     stage_regs<N, 8, 1, SIGN>(v, nullptr);
-    exchange<N, 8, 1>(v, t, pol.A, pol);
+    exchange<N, 8, 1, Pol, WAIT_ASYNC && P::NSTAGE == 2>(v, t, pol.A, pol);
     if constexpr (P::NSTAGE == 2) {
         stage_regs<N, P::rad(1), 8, SIGN>(v, twS + (t & 7) * (P::rad(1) - 1));
     } else {
         stage_regs<N, 8, 8, SIGN>(v, twS + (t & 7) * 7);
-        exchange<N, 8, 8>(v, t, pol.B, pol);
+        exchange<N, 8, 8, Pol, WAIT_ASYNC && P::NSTAGE == 3>(v, t, pol.B, pol);
         if constexpr (P::NSTAGE == 3) {
             stage_regs<N, P::rad(2), 64, SIGN>(v, twS + P::tw_base(2) + (t & 63) * (P::rad(2) - 1));
         } else {
             stage_regs<N, 8, 64, SIGN>(v, twS + P::tw_base(2) + (t & 63) * 7);
             /* A again: every thread read it before the barrier of the second exchange */
-            exchange<N, 8, 64>(v, t, pol.A, pol);
+            exchange<N, 8, 64, Pol, WAIT_ASYNC>(v, t, pol.A, pol);
             stage_regs<N, P::rad(3), 512, SIGN>(v, twS + P::tw_base(3) + (t & 511) * (P::rad(3) - 1));
         }
     }
-    (void)STEP;
+}
+/* same transform with the twiddles of RegTwiddles (z kernels) */
+template <int N, int SIGN, class Pol> DEV void fft_line_regs_rt(float2 (&v)[8], int t, const Pol &pol, const RegTwiddles<N> &rt) {
+    using P = Pow2Plan<N>;
+    stage_regs<N, 8, 1, SIGN>(v, nullptr);
+    exchange<N, 8, 1, Pol>(v, t, pol.A, pol);
+    if constexpr (P::NSTAGE == 2) {
+        stage_regs_rt<N, P::rad(1), SIGN>(v, rt.w[0]);
+    } else {
+        stage_regs_rt<N, 8, SIGN>(v, rt.w[0]);
+        exchange<N, 8, 8, Pol>(v, t, pol.B, pol);
+        if constexpr (P::NSTAGE == 3) {
+            stage_regs_rt<N, P::rad(2), SIGN>(v, rt.w[1]);
+        } else {
+            stage_regs_rt<N, 8, SIGN>(v, rt.w[1]);
+            exchange<N, 8, 64, Pol>(v, t, pol.A, pol);
+            stage_regs_rt<N, P::rad(3), SIGN>(v, rt.w[2]);
+        }
+    }
 }
 /* number of exchanges that touch buffer A / need a trailing barrier before the next transform */
 template <int N> struct Pow2Sync {
@@ -205,6 +295,25 @@ template <int N> struct Pow2Cfg {
  * of tile k+1 hides behind the butterflies, barriers and stores of tile k even with one CTA per
  * SM.  MODE: 0 plain, 1 window from the |n|^2 table, 2 generic k-space multiplier (apply_kmul). */
 enum { PM_PLAIN = 0, PM_WTAB = 1, PM_GENERIC = 2 };
+/* cp.async the window rows of one tile of the x pass into shared memory: row |nx| holds the TL
+   columns of the tile, fetched as 16-byte chunks of 4 columns (a chunk never straddles a (y)
+   row because the pitch is a multiple of 8).  Source: KMul::wtab3. */
+template <int N, int TL> DEV void stage_window(float *Wbuf, const StridedArgs &a, int tile, int tiles_per_group, int ntiles) {
+    constexpr int NA = N / 2 + 1, CH = TL / 4;
+    if (tile < ntiles) {
+        const int col0 = (tile % tiles_per_group) * TL;
+        for (int e = threadIdx.x; e < NA * CH; e += Pow2Cfg<N>::THREADS) {
+            const int ax = e / CH, j = e - ax * CH;
+            const int col = col0 + 4 * j;
+            if (col < a.ncols) {
+                const int iy = col / a.pitch, iz = col - iy * a.pitch;
+                const int ay = (iy > a.ny / 2) ? a.ny - iy : iy;
+                cp_async_16(Wbuf + ax * TL + 4 * j, a.wtab3 + ((long long)ax * a.w3_xstride + (long long)ay * a.pitch + iz));
+            }
+        }
+    }
+    cp_async_commit();
+}
 template <int N, int SIGN, int MODE>
 __global__ void __launch_bounds__(Pow2Cfg<N>::THREADS, Pow2Cfg<N>::MIN_CTAS)
 fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst, StridedArgs a, int tiles_per_group,
@@ -214,6 +323,8 @@ fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst
     constexpr int STEP = N / 8;
     DYN_SMEM(float2, S);
     float4 *twS = reinterpret_cast<float4 *>(S + 2 * N * TL);
+    constexpr int WROWS = N / 2 + 1;
+    float *Wst = reinterpret_cast<float *>(twS + P::TW_TOTAL); /* [2][WROWS][TL] staged window rows (PM_WTAB) */
     fill_twiddles<N, SIGN>(twS, a.tw, 1, Pow2Cfg<N>::THREADS);
     const int c = threadIdx.x & (TL - 1), t = threadIdx.x / TL;
     const TilePolicy<TL> pol{S, S + N * TL, c};
@@ -231,8 +342,12 @@ fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst
             if (tile < ntiles && col < a.ncols) vn[m] = p[m * rs];
         }
     }
-    __syncthreads(); /* twiddle table visible */
-    for (; tile < ntiles; tile += gridDim.x) {
+    if constexpr (MODE == PM_WTAB) {
+        stage_window<N, TL>(Wst, a, tile, tiles_per_group, ntiles);
+        cp_async_wait_all();
+    }
+    __syncthreads(); /* twiddle table (and the first tile's window rows) visible */
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
         const int g = tile / tiles_per_group, col = (tile - g * tiles_per_group) * TL + c;
         const bool live = col < a.ncols;
         const long long base = (long long)g * a.group_stride + col + toff;
@@ -251,16 +366,15 @@ fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst
             }
         }
         if constexpr (MODE == PM_WTAB) {
-            /* window from the |n|^2 table: the (y, kz) part is a per-thread constant of the tile */
-            const int iy = col / a.pitch, iz = col - iy * a.pitch;
-            if (live && iz < a.nzc) {
-                const int sy = (iy > a.ny / 2) ? iy - a.ny : iy;
-                const float *wt = a.wtab + (sy * sy + iz * iz);
+            /* stage the window rows of the NEXT tile (landed before this tile's last barrier), then
+               multiply by this tile's rows: |nx| = t + m STEP (m < 4) or N - (t + m STEP) */
+            stage_window<N, TL>(Wst + ((it + 1) & 1) * WROWS * TL, a, tile + gridDim.x, tiles_per_group, ntiles);
+            if (live) {
+                const float *w = Wst + (it & 1) * WROWS * TL + c;
 #pragma unroll
                 for (int m = 0; m < 8; m++) {
-                    const int i = t + m * STEP;
-                    const int sx = m < 4 ? i : i - N; /* i = N/2 (m = 4, t = 0): (-N/2)^2 is the same entry */
-                    v[m] = pk_scale(v[m], ldg(&wt[sx * sx]));
+                    const int ax = m < 4 ? t + m * STEP : N - (t + m * STEP);
+                    v[m] = pk_scale(v[m], w[ax * TL]);
                 }
             }
         } else if constexpr (MODE == PM_GENERIC) {
@@ -269,7 +383,7 @@ fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst
                 for (int m = 0; m < 8; m++) v[m] = apply_kmul(v[m], t + m * STEP, col, a);
             }
         }
-        fft_line_regs<N, SIGN>(v, t, pol, twS);
+        fft_line_regs<N, SIGN, TilePolicy<TL>, MODE == PM_WTAB>(v, t, pol, twS);
         if (live) {
             float2 *q = dst + base;
             if (a.scale != 1.f) {
@@ -287,7 +401,8 @@ fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst
 template <int N, int MODE> static void launch_strided_pow2_mode(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
     using P = Pow2Plan<N>;
     constexpr int TL = Pow2Cfg<N>::TL;
-    const size_t smem = (size_t)2 * N * TL * sizeof(float2) + (size_t)P::TW_TOTAL * sizeof(float4);
+    const size_t smem = (size_t)2 * N * TL * sizeof(float2) + (size_t)P::TW_TOTAL * sizeof(float4) +
+                        (MODE == PM_WTAB ? (size_t)2 * (N / 2 + 1) * TL * sizeof(float) : 0);
     const int tiles_per_group = (a.ncols + TL - 1) / TL;
     const long long ntiles = (long long)tiles_per_group * ngroups;
     auto kf = &fft_strided_pow2_kernel<N, -1, MODE>;
@@ -313,7 +428,7 @@ template <int N, int MODE> static void launch_strided_pow2_mode(const float2 *sr
 template <int N> static void launch_strided_pow2(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
     const bool has_kmul = a.kmul != KMUL_NONE || a.op != KOP_NONE;
     if (!has_kmul) launch_strided_pow2_mode<N, PM_PLAIN>(src, dst, a, ngroups);
-    else if (a.wtab && a.op == KOP_NONE) launch_strided_pow2_mode<N, PM_WTAB>(src, dst, a, ngroups);
+    else if (a.wtab3 && a.op == KOP_NONE) launch_strided_pow2_mode<N, PM_WTAB>(src, dst, a, ngroups);
     else launch_strided_pow2_mode<N, PM_GENERIC>(src, dst, a, ngroups);
 }
 
@@ -372,6 +487,8 @@ fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, Z
     __syncthreads();
     const int line = threadIdx.x / LT, t = threadIdx.x - line * LT;
     const LinePolicy<LT> pol{S + (2 * line) * Cfg::STRIP, S + (2 * line + 1) * Cfg::STRIP, 1 + line};
+    RegTwiddles<NH> rtw;
+    load_reg_twiddles<NH>(rtw, t, twS);
     float2 *dst2 = reinterpret_cast<float2 *>(dst);
     const long long row_stride2 = a.real_row_stride / 2;
     float lmin = 3.0e38f, lmax = -3.0e38f;
@@ -398,7 +515,7 @@ fft_c2r_z_pow2_kernel(const float2 *__restrict__ src, float *__restrict__ dst, Z
             const float2 p = pk_cmul(dif, mrg[t + m * STEP]);
             v[m] = pk_add(sum, pk_rot<1>(p));
         }
-        fft_line_regs<NH, 1>(v, t, pol, twS);
+        fft_line_regs_rt<NH, 1>(v, t, pol, rtw);
         /* z[n] = (x[2n], x[2n+1]) */
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -457,6 +574,8 @@ fft_r2c_z_pow2_kernel(const float *__restrict__ src, float2 *__restrict__ dst, Z
     __syncthreads();
     const int line = threadIdx.x / LT, t = threadIdx.x - line * LT;
     const LinePolicy<LT> pol{S + (2 * line) * Cfg::STRIP, S + (2 * line + 1) * Cfg::STRIP, 1 + line};
+    RegTwiddles<NH> rtw;
+    load_reg_twiddles<NH>(rtw, t, twS);
     const float2 *src2 = reinterpret_cast<const float2 *>(src);
     const long long row_stride2 = a.real_row_stride / 2;
     const bool pre = a.premul != 1.f || a.clip;
@@ -479,7 +598,7 @@ fft_r2c_z_pow2_kernel(const float *__restrict__ src, float2 *__restrict__ dst, Z
             }
             v[m] = x;
         }
-        fft_line_regs<NH, -1>(v, t, pol, twS);
+        fft_line_regs_rt<NH, -1>(v, t, pol, rtw);
         /* Z[k] at k = t + m STEP; partner Z[(NH - k) mod NH] through the strip that the last
            exchange did NOT use (no hazard with slower threads still reading the other one) */
         float2 *strip = (Pow2Plan<NH>::NSTAGE == 3) ? pol.A : pol.B;

@@ -63,29 +63,42 @@ struct SweepArgs {
  * steeper bins take the reference path. */
 struct SweepTable {
     float y[N_DENS_INTERP];        /* the table as uploaded (reference path) */
-    float2 yd[N_DENS_INTERP];      /* {y0, y1 - y0} */
-    float2 ed[N_DENS_INTERP];      /* {exp(y0), y1 - y0} (log-valued tables) */
+    float2 *rep;                   /* dynamic shared memory: the bin table the fast path reads, SWEEP_REP copies
+                                      interleaved as rep[idx * SWEEP_REP + (lane & (SWEEP_REP - 1))].
+                                      Entry = {y0 or exp(y0), y1 - y0}, see sweep_table_load(.., as_exp) */
     double x_min, x_width, inv_width;
     float x_min_f, inv_width_f;
     int log_valued;
 };
-DEV void sweep_table_load(SweepTable *st, const DevTable *t) {
+#define SWEEP_REP 1 /* copies of the bin table; 16 interleaved copies make the loads bank-conflict-free but
+                       measured slower on B200 (the sweeps are not shared-memory bound) */
+#define SWEEP_REP_BYTES (N_DENS_INTERP * SWEEP_REP * sizeof(float2))
+DEV int sweep_rep_lane() { return threadIdx.x & (SWEEP_REP - 1); }
+/* as_exp: first component exp(y0) (grid sum of a log-valued table) instead of y0 */
+DEV void sweep_table_load(SweepTable *st, const DevTable *t, float2 *rep, bool as_exp) {
     for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) {
         const float y0 = t->y[i];
         const float y1 = t->y[i + 1 < N_DENS_INTERP ? i + 1 : i];
         const float dy = (float)((double)y1 - (double)y0);
         st->y[i] = y0;
-        st->yd[i] = make_float2(y0, dy);
-        st->ed[i] = make_float2(t->log_valued ? (float)exp((double)y0) : y0, dy);
+        const float2 e = make_float2(as_exp ? (float)exp((double)y0) : y0, dy);
+#pragma unroll
+        for (int r = 0; r < SWEEP_REP; r++) rep[i * SWEEP_REP + r] = e;
     }
     if (threadIdx.x == 0) {
+        st->rep = rep;
         st->x_min = t->x_min; st->x_width = t->x_width; st->inv_width = t->inv_width;
         st->x_min_f = (float)t->x_min; st->inv_width_f = (float)t->inv_width;
         st->log_valued = t->log_valued;
     }
 }
 /* reference arithmetic: EvaluateRGTable1D_f (interpolation.c:123-131), exp for log-valued tables */
-DEV double fcoll_exact(float d, const SweepTable *h) {
+#ifndef B200_EMU
+__device__ __noinline__
+#else
+inline
+#endif
+double fcoll_exact(float d, const SweepTable *h) {
     const double x = (double)d;
     const int idx = (int)floor((x - h->x_min) * h->inv_width);
     const double table_val = h->x_min + h->x_width * (float)idx;
@@ -93,87 +106,111 @@ DEV double fcoll_exact(float d, const SweepTable *h) {
     const double v = (double)h->y[idx] * (1 - t) + (double)h->y[idx + 1] * t;
     return h->log_valued ? exp(v) : v;
 }
-/* single-precision bin coordinates; idx is clamped so that a rounding slip at the table ends
-   stays inside the table */
-DEV void table_coords_f(float d, const SweepTable *h, int &idx, float &t) {
-    const float pos = (d - h->x_min_f) * h->inv_width_f;
-    const float fl = floorf(pos);
-    idx = (int)fl;
-    idx = idx < 0 ? 0 : (idx > N_DENS_INTERP - 2 ? N_DENS_INTERP - 2 : idx);
-    t = pos - (float)idx;
+/* single-precision bin coordinates of TWO cells at a time (packed arithmetic).  pos is clamped into
+   the table so that a rounding slip at the table ends cannot index outside it. */
+struct SweepConstsF {
+    float inv, c0, floor;   /* pos = d * inv + c0,  c0 = -x_min * inv */
+    float pos_lo, pos_hi;   /* clamp of pos: the density floor and the table ends in one min/max pair */
+};
+DEV SweepConstsF sweep_consts(const SweepTable *h, float dens_floor) {
+    SweepConstsF k;
+    k.inv = h->inv_width_f;
+    k.c0 = -h->x_min_f * h->inv_width_f;
+    k.floor = dens_floor;
+    k.pos_lo = fmaxf(fmaf(dens_floor, k.inv, k.c0), 0.f);
+    k.pos_hi = (float)(N_DENS_INTERP - 1) - 1e-3f;
+    return k;
 }
-DEV float exp_small_f(float u) { /* Taylor series of exp, |u| <= 1/4 */
-    float p = 1.0f / 720.0f;
-    p = fmaf(p, u, 1.0f / 120.0f);
-    p = fmaf(p, u, 1.0f / 24.0f);
-    p = fmaf(p, u, 1.0f / 6.0f);
-    p = fmaf(p, u, 0.5f);
-    p = fmaf(p, u, 1.0f);
-    return fmaf(p, u, 1.0f);
+DEV void table_coords_f2(float2 d, const SweepConstsF &k, int &i0, int &i1, float2 &t) {
+    float2 pos = f2_fma(d, make_float2(k.inv, k.inv), make_float2(k.c0, k.c0));
+    pos.x = fminf(fmaxf(pos.x, k.pos_lo), k.pos_hi);
+    pos.y = fminf(fmaxf(pos.y, k.pos_lo), k.pos_hi);
+    i0 = float_to_int_floor(pos.x);
+    i1 = float_to_int_floor(pos.y);
+    t = f2_add(pos, make_float2(-(float)i0, -(float)i1));
 }
-/* f_coll of one cell for the grid sum only */
-DEV float fcoll_fast(float dens, float dens_floor, const SweepTable *h, int log_valued) {
-    const float d = fmaxf(dens, dens_floor);
-    int idx;
-    float t;
-    table_coords_f(d, h, idx, t);
-    const float2 e = h->ed[idx];
-    const float u = t * e.y;
-    if (!log_valued) return e.x + u;
-    if (fabsf(u) <= 0.25f) return e.x * exp_small_f(u);
-    return (float)fcoll_exact(d, h);
+DEV float2 exp_small_f2(float2 u) { /* Taylor series of exp, |u| <= 1/4, two lanes */
+    float2 p = make_float2(1.0f / 720.0f, 1.0f / 720.0f);
+    p = f2_fma(p, u, make_float2(1.0f / 120.0f, 1.0f / 120.0f));
+    p = f2_fma(p, u, make_float2(1.0f / 24.0f, 1.0f / 24.0f));
+    p = f2_fma(p, u, make_float2(1.0f / 6.0f, 1.0f / 6.0f));
+    p = f2_fma(p, u, make_float2(0.5f, 0.5f));
+    p = f2_fma(p, u, make_float2(1.0f, 1.0f));
+    return f2_fma(p, u, make_float2(1.0f, 1.0f));
+}
+/* f_coll of two cells for the grid sum only */
+template <bool LOG> DEV float2 fcoll_fast2(float2 d, const SweepTable *h, const SweepConstsF &k) {
+    int i0, i1;
+    float2 t;
+    table_coords_f2(d, k, i0, i1, t);
+    const float2 *rep = h->rep + sweep_rep_lane();
+    const float2 e0 = rep[i0 * SWEEP_REP], e1 = rep[i1 * SWEEP_REP];
+    const float2 u = f2_mul(t, make_float2(e0.y, e1.y));
+    if (!LOG) return f2_add(make_float2(e0.x, e1.x), u);
+    if (fabsf(u.x) > 0.25f || fabsf(u.y) > 0.25f) /* steep bin: reference arithmetic */
+        return make_float2((float)fcoll_exact(fmaxf(d.x, k.floor), h), (float)fcoll_exact(fmaxf(d.y, k.floor), h));
+    return f2_mul(make_float2(e0.x, e1.x), exp_small_f2(u));
 }
 
-/* row / chunk decomposition of a flat float4 index over rows of q chunks */
-struct RowSplit {
-    int q, shift; /* shift >= 0: q is a power of two */
-};
-DEV RowSplit row_split(int q) {
-    RowSplit r;
-    r.q = q;
-    r.shift = (q & (q - 1)) == 0 ? 31 - __builtin_clz((unsigned)q) : -1;
-    return r;
-}
-DEV void row_of(const RowSplit &r, long long id, long long &row, int &zc) {
-    if (r.shift >= 0) { row = id >> r.shift; zc = (int)(id & (r.q - 1)); }
-    else { row = id / r.q; zc = (int)(id - row * r.q); }
+/* Visit every float4 chunk of the padded real box [nrows][2 pitch] (nz valid floats per row, nz a
+   multiple of 4): f(d4, row, zc) with zc the chunk index inside the row.  When a 256-thread CTA
+   covers a whole number of rows (256 % (nz/4) == 0, i.e. nz a power of two <= 1024) a thread keeps
+   its (row offset, zc) for the whole kernel and an iteration is four independent 128-bit loads
+   at constant row strides: no per-chunk index arithmetic. */
+template <class F> DEV void for_each_chunk(const float *filtered, long long nrows, int nz, int pitch, F &&f) {
+    const int q = nz >> 2;
+    const long long rstride = 2LL * pitch; /* floats per padded row */
+    if (blockDim.x == 256 && q <= 256 && (256 % q) == 0) {
+        const int rows_per_step = 256 / q;
+        const int r = threadIdx.x / q, zc = threadIdx.x - r * q;
+        const long long step_rows = 4LL * rows_per_step;
+        /* (a register double-buffer that prefetches the next iteration was measured slower: the
+           sweeps are bound by the per-cell arithmetic, and the extra registers cost a CTA per SM) */
+        for (long long row0 = (long long)blockIdx.x * step_rows; row0 < nrows; row0 += (long long)gridDim.x * step_rows) {
+            const float *p = filtered + (row0 + r) * rstride + 4 * zc;
+            float4 d4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long row = row0 + r + (long long)u * rows_per_step;
+                d4[u] = row < nrows ? *reinterpret_cast<const float4 *>(p + (long long)u * rows_per_step * rstride)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long row = row0 + r + (long long)u * rows_per_step;
+                if (row < nrows) f(d4[u], row, zc);
+            }
+        }
+    } else {
+        const long long nchunks = nrows * q;
+        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks;
+             id += (long long)gridDim.x * blockDim.x) {
+            const long long row = id / q;
+            const int zc = (int)(id - row * q);
+            f(*reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc), row, zc);
+        }
+    }
 }
 
 /* sweep 1: sum of f_coll over the grid as deterministic double block sums (calculate_fcoll_grid,
    IonisationBox.c:773-962).  With a.fcoll set (last radius: the grid is the unnormalised_nion
    output) every cell takes the reference arithmetic and the float grid is written. */
-__global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
+template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     __shared__ SweepTable st;
     __shared__ double red[256];
-    sweep_table_load(&st, a.table);
+    DYN_SMEM(float2, rep);
+    sweep_table_load(&st, a.table, rep, LOG);
     __syncthreads();
     const long long nrows = (long long)a.nx * a.ny;
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
-    const int log_valued = st.log_valued;
+    const SweepConstsF kf = sweep_consts(&st, dens_floor);
     double acc = 0.;
     if ((a.nz & 3) == 0 && !a.fcoll) {
-        const RowSplit rs = row_split(a.nz >> 2);
-        const long long nchunks = nrows * rs.q;
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks; id += 4 * stride) {
-            float4 d4[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) { /* four independent 128-bit loads in flight per thread */
-                const long long j = id + u * stride;
-                long long row;
-                int zc;
-                row_of(rs, j < nchunks ? j : id, row, zc);
-                d4[u] = *reinterpret_cast<const float4 *>(a.filtered + row * 2 * a.nzc + 4 * zc);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (id + u * stride < nchunks) {
-                    const float f = (fcoll_fast(d4[u].x, dens_floor, &st, log_valued) + fcoll_fast(d4[u].y, dens_floor, &st, log_valued)) +
-                                    (fcoll_fast(d4[u].z, dens_floor, &st, log_valued) + fcoll_fast(d4[u].w, dens_floor, &st, log_valued));
-                    acc += (double)f;
-                }
-            }
-        }
+        for_each_chunk(a.filtered, nrows, a.nz, a.nzc, [&](const float4 &d, long long, int) {
+            const float2 f = f2_add(fcoll_fast2<LOG>(make_float2(d.x, d.y), &st, kf),
+                                    fcoll_fast2<LOG>(make_float2(d.z, d.w), &st, kf));
+            acc += (double)(f.x + f.y);
+        });
     } else {
         for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
             const float *src = a.filtered + row * 2 * a.nzc;
@@ -183,7 +220,7 @@ __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
                     acc += f;
                     a.fcoll[row * a.nz + z] = (float)f;
                 } else {
-                    acc += (double)fcoll_fast(src[z], dens_floor, &st, log_valued);
+                    acc += (double)fcoll_fast2<LOG>(make_float2(src[z], src[z]), &st, kf).x;
                 }
             }
         }
@@ -306,10 +343,11 @@ struct CritDeltaArgs {
    space whenever the interpolated log f_coll is more than 1e-6 away from the threshold (float
    rounding moves f_coll by < 6e-8 relative), and with the reference's exact arithmetic inside
    that band. */
-__global__ void __launch_bounds__(256) ionise_delta_kernel(CritDeltaArgs a) {
+template <bool LOG> __global__ void __launch_bounds__(256) ionise_delta_kernel(CritDeltaArgs a) {
     __shared__ SweepTable st;
     __shared__ double red[256];
-    sweep_table_load(&st, a.table);
+    DYN_SMEM(float2, rep);
+    sweep_table_load(&st, a.table, rep, false);
     double acc = 0.;
     for (int i = threadIdx.x; i < a.n_partial; i += blockDim.x) acc += a.partial[i];
     red[threadIdx.x] = acc;
@@ -327,66 +365,52 @@ __global__ void __launch_bounds__(256) ionise_delta_kernel(CritDeltaArgs a) {
     const double mean_fix = a.mean_f_coll / grid_mean;
     const double gain = mean_fix * a.ion_eff_factor;
     const bool floor_ionises = a.mass_dep_zeta && (a.f_limit * a.ion_eff_factor > 1.0);
-    const int log_valued = st.log_valued;
     /* threshold in the table's own units: log f_coll or f_coll */
-    const float thr = log_valued ? (float)(-log(gain)) : (float)(1.0 / gain);
-    const float band0 = log_valued ? 1e-5f : 1e-5f * fabsf(thr);
+    const float thr = LOG ? (float)(-log(gain)) : (float)(1.0 / gain);
+    const float band0 = LOG ? 1e-5f : 1e-5f * fabsf(thr);
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
+    const SweepConstsF kf = sweep_consts(&st, dens_floor);
     const long long nrows = (long long)a.nx * a.ny;
-    auto ionised = [&](float dens) -> bool {
-        const float d = fmaxf(dens, dens_floor);
-        int idx;
-        float t;
-        table_coords_f(d, &st, idx, t);
-        const float2 yd = st.yd[idx];
-        const float diff = fmaf(t, yd.y, yd.x) - thr;
-        const float band = fmaf(1e-4f, fabsf(yd.y), band0);
-        if (diff > band) return true;
-        if (diff < -band) return floor_ionises;
-        /* inside the band: the reference arithmetic on the float-rounded f_coll decides */
-        double curr = mean_fix * (double)(float)fcoll_exact(d, &st);
+    /* inside the band: the reference arithmetic on the float-rounded f_coll decides */
+    auto exact = [&](float dens) -> bool {
+        double curr = mean_fix * (double)(float)fcoll_exact(fmaxf(dens, dens_floor), &st);
         if (a.mass_dep_zeta && curr < a.f_limit) curr = a.f_limit;
         return curr * a.ion_eff_factor > 1.0;
     };
+    /* two cells at a time; returns bit 0 / bit 1 = ionised */
+    auto ionised2 = [&](float2 d) -> unsigned {
+        int i0, i1;
+        float2 t;
+        table_coords_f2(d, kf, i0, i1, t);
+        const float2 *rep = st.rep + sweep_rep_lane();
+        const float2 y0 = rep[i0 * SWEEP_REP], y1 = rep[i1 * SWEEP_REP];
+        const float2 diff = f2_add(f2_fma(t, make_float2(y0.y, y1.y), make_float2(y0.x, y1.x)), make_float2(-thr, -thr));
+        const float b0 = fmaf(1e-4f, fabsf(y0.y), band0), b1 = fmaf(1e-4f, fabsf(y1.y), band0);
+        bool r0 = diff.x > 0.f ? true : floor_ionises, r1 = diff.y > 0.f ? true : floor_ionises;
+        if (fabsf(diff.x) <= b0) r0 = exact(d.x);
+        if (fabsf(diff.y) <= b1) r1 = exact(d.y);
+        return (r0 ? 1u : 0u) | (r1 ? 2u : 0u);
+    };
     if ((a.nz & 3) == 0) {
-        const RowSplit rs = row_split(a.nz >> 2);
-        const long long nchunks = nrows * rs.q;
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks; id += 4 * stride) {
-            float4 d4[4];
-            long long cell[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const long long j = id + u * stride;
-                long long row;
-                int zc;
-                row_of(rs, j < nchunks ? j : id, row, zc);
-                d4[u] = *reinterpret_cast<const float4 *>(a.filtered + row * 2 * a.nzc + 4 * zc);
-                cell[u] = row * a.nz + 4 * zc;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (id + u * stride < nchunks) {
-                    const bool i0 = ionised(d4[u].x), i1 = ionised(d4[u].y), i2 = ionised(d4[u].z), i3 = ionised(d4[u].w);
-                    if (i0 || i1 || i2 || i3) {
-                        unsigned char *m = a.mask + cell[u];
-                        if (i0 && i1 && i2 && i3) {
-                            *reinterpret_cast<unsigned int *>(m) = 0x01010101u;
-                        } else {
-                            if (i0) m[0] = 1;
-                            if (i1) m[1] = 1;
-                            if (i2) m[2] = 1;
-                            if (i3) m[3] = 1;
-                        }
-                    }
+        for_each_chunk(a.filtered, nrows, a.nz, a.nzc, [&](const float4 &d, long long row, int zc) {
+            const unsigned m4 = ionised2(make_float2(d.x, d.y)) | (ionised2(make_float2(d.z, d.w)) << 2);
+            if (m4) {
+                unsigned char *m = a.mask + (row * a.nz + 4 * zc);
+                if (m4 == 15u) {
+                    *reinterpret_cast<unsigned int *>(m) = 0x01010101u;
+                } else {
+                    if (m4 & 1u) m[0] = 1;
+                    if (m4 & 2u) m[1] = 1;
+                    if (m4 & 4u) m[2] = 1;
+                    if (m4 & 8u) m[3] = 1;
                 }
             }
-        }
+        });
     } else {
         for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
             const float *src = a.filtered + row * 2 * a.nzc;
             for (int z = threadIdx.x; z < a.nz; z += blockDim.x)
-                if (ionised(src[z])) a.mask[row * a.nz + z] = 1;
+                if (ionised2(make_float2(src[z], src[z])) & 1u) a.mask[row * a.nz + z] = 1;
         }
     }
 }
@@ -486,6 +510,18 @@ __global__ void neutral_box_kernel(NeutralArgs a) {
 }
 
 /* ------------------------------------------------------------------ orchestration */
+static void sweep_smem_optin() {
+#ifndef B200_EMU
+    static bool done = false;
+    if (done) return;
+    const int bytes = (int)SWEEP_REP_BYTES;
+    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ionise_delta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ionise_delta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done = true;
+#endif
+}
 static int grid_for(long long n_items, int per_block) {
     long long want = (n_items + per_block - 1) / per_block;
     long long cap = (long long)dev_num_sms() * 8;
@@ -601,6 +637,10 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const bool use_wtab = cubic && (c.hii_filter == 0 || c.hii_filter == 2);
     const int wtab_n = use_wtab ? window_table_size(plan) : 0;
     DevBuf<float> d_wtab(use_wtab ? 2 * (size_t)wtab_n : 0);
+    /* expanded [|nx|][|ny|][kz] copy for the coalesced x-pass lookup (power-of-two grids, <= 1 GB per slot) */
+    const size_t wtab3_n = use_wtab ? window_table3_size(plan) : 0;
+    const bool use_wtab3 = use_wtab && (nx & (nx - 1)) == 0 && nx >= 16 && wtab3_n * sizeof(float) <= ((size_t)1 << 30);
+    DevBuf<float> d_wtab3(use_wtab3 ? 2 * wtab3_n : 0);
     g_stage.ensure(n_todo);
     if (n_todo > 0) {
         KeyInitArgs ka = {n_todo, d_keys};
@@ -630,6 +670,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
                 float *slot = d_wtab.p + (size_t)(k & 1) * wtab_n;
                 window_table_build(plan, c.hii_filter, km.R, dk0, slot);
                 km.wtab = slot; km.wtab_n = wtab_n;
+                if (use_wtab3) {
+                    float *slot3 = d_wtab3.p + (size_t)(k & 1) * wtab3_n;
+                    window_table_expand(plan, slot, slot3);
+                    km.wtab3 = slot3;
+                }
             }
         }
         ZEpilogue epi;
@@ -676,7 +721,9 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : nullptr;
         const float *filtered = reinterpret_cast<const float *>(work[k & 1]);
         SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
-        B200_LAUNCH(fcoll_sum_kernel, sweep_blocks, 256, 0, sa);
+        sweep_smem_optin();
+        if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
+        else B200_LAUNCH(fcoll_sum_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
 
         if (!last) {
             CritDeltaArgs cd;
@@ -686,7 +733,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             cd.partial = d_partial; cd.n_partial = sweep_blocks; cd.mask = d_mask;
             cd.n_cells = (double)N; cd.mean_f_coll = box->mean_f_coll; cd.f_limit = f_limit;
             cd.ion_eff_factor = c.ion_eff_factor; cd.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
-            B200_LAUNCH(ionise_delta_kernel, sweep_blocks, 256, 0, cd);
+            if (htab.log_valued) B200_LAUNCH(ionise_delta_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
+            else B200_LAUNCH(ionise_delta_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
         } else {
             CritArgs ca;
             memset(&ca, 0, sizeof(ca));

@@ -154,7 +154,7 @@ struct GroupArgs {
 /* per-axis CIC data of one group: position of sub-particle t -> (cell offset o_t in {0,1} relative
    to the base cell, weight w1_t of the upper cell).  The F x 3 weight matrix row is
    W[t][a] = (a == o_t) ? 1 - w1_t : (a == o_t + 1) ? w1_t : 0. */
-template <int F> DEV void axis_cic(int c, double disp, double r, int &base, double (&w1)[F], int (&o)[F]) {
+template <int F, typename T> DEV void axis_cic(int c, double disp, double r, int &base, T (&w1)[F], int (&o)[F]) {
     const int istart = (int)ceil((double)F * c - 0.5 * F);
     int b0 = 0;
 #pragma unroll
@@ -166,17 +166,26 @@ template <int F> DEV void axis_cic(int c, double disp, double r, int &base, doub
         const int b = (int)fl;
         if (t == 0) b0 = b;
         o[t] = b - b0;
-        w1[t] = pos - fl;
+        w1[t] = (T)(pos - fl);
     }
     base = b0;
 }
-DEV double cic_w(int a, int o, double w1) { return a == o ? 1. - w1 : (a == o + 1 ? w1 : 0.); }
+template <typename T> DEV T cic_w(int a, int o, T w1) { return a == o ? (T)1 - w1 : (a == o + 1 ? w1 : (T)0); }
+DEV long long to_fixed(double v) { return llrint(v * FIXED_SCALE); }
+DEV long long to_fixed(float v) { return llrintf(v * (float)FIXED_SCALE); }
 
-template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kernel(GroupArgs g) {
+/* T = arithmetic of the F^3 -> 3x3x3 contraction.  Positions, cell indices and the CIC weights
+   are always derived in double (the weight is a difference of O(DIM) numbers); with T = float
+   (default) the weights and the masses 1 + delta D(z_i) are then rounded to float and contracted
+   in single precision: each of the 27 sums carries ~1e-7 relative error, which averages to
+   < 6e-8 of the cell total (itself rounded to float32 afterwards), at a third of the instruction
+   cost of the double contraction (B200_CIC_DOUBLE=1 selects T = double). */
+template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kernel(GroupArgs g) {
     const MoveArgs &a = g.m;
     const int nzg = a.vn[2], nyg = a.vn[1], nxg = a.vn[0];
     const long long ngroups = (long long)nxg * nyg * nzg;
     const long long out_sx = (long long)a.on[1] * a.on[2];
+    const T growth = (T)a.init_growth;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < ngroups;
          p += (long long)gridDim.x * blockDim.x) {
         const int cz = (int)(p % nzg);
@@ -188,39 +197,39 @@ template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kern
             disp[ax] = (double)a.v[ax][p] * a.vdf[ax];
             if (a.v2[0]) disp[ax] -= (double)a.v2[ax][p] * a.vdf2[ax];
         }
-        double w1x[F], w1y[F], w1z[F];
+        T w1x[F], w1y[F], w1z[F];
         int ox_[F], oy_[F], oz_[F];
         int Bx, By, Bz;
-        axis_cic<F>(cx, disp[0], a.ratio_out, Bx, w1x, ox_);
-        axis_cic<F>(cy, disp[1], a.ratio_out, By, w1y, oy_);
-        axis_cic<F>(cz, disp[2], a.ratio_out, Bz, w1z, oz_);
+        axis_cic<F, T>(cx, disp[0], a.ratio_out, Bx, w1x, ox_);
+        axis_cic<F, T>(cy, disp[1], a.ratio_out, By, w1y, oy_);
+        axis_cic<F, T>(cz, disp[2], a.ratio_out, Bz, w1z, oz_);
         const int isx = (int)ceil((double)F * cx - 0.5 * F), isy = (int)ceil((double)F * cy - 0.5 * F),
                   isz = (int)ceil((double)F * cz - 0.5 * F);
         /* groups away from the periodic boundary need no index wrapping */
         const bool interior = isx >= 0 && isy >= 0 && isz >= 0 && isx + F <= a.dn[0] && isy + F <= a.dn[1] &&
                               isz + F <= a.dn[2];
         /* contract z then y for each x-slice of the group: Cy[t0][b][c] */
-        double Cy[F][3][3];
+        T Cy[F][3][3];
 #pragma unroll
         for (int t0 = 0; t0 < F; t0++) {
             const int hi = interior ? isx + t0 : wrap_index(isx + t0, a.dn[0]);
 #pragma unroll
-            for (int i = 0; i < 9; i++) (&Cy[t0][0][0])[i] = 0.;
+            for (int i = 0; i < 9; i++) (&Cy[t0][0][0])[i] = (T)0;
 #pragma unroll
             for (int t1 = 0; t1 < F; t1++) {
                 const int hj = interior ? isy + t1 : wrap_index(isy + t1, a.dn[1]);
                 const float *row = a.dens + (long long)a.dn[2] * ((long long)hj + (long long)a.dn[1] * hi);
-                double Bzv[3] = {0., 0., 0.};
+                T Bzv[3] = {(T)0, (T)0, (T)0};
 #pragma unroll
                 for (int t2 = 0; t2 < F; t2++) {
                     const int hk = interior ? isz + t2 : wrap_index(isz + t2, a.dn[2]);
-                    const double mass = 1.0 + (double)ldg(&row[hk]) * a.init_growth;
+                    const T mass = (T)1 + (T)ldg(&row[hk]) * growth;
 #pragma unroll
-                    for (int c = 0; c < 3; c++) Bzv[c] += mass * cic_w(c, oz_[t2], w1z[t2]);
+                    for (int c = 0; c < 3; c++) Bzv[c] += mass * cic_w<T>(c, oz_[t2], w1z[t2]);
                 }
 #pragma unroll
                 for (int b = 0; b < 3; b++) {
-                    const double wy = cic_w(b, oy_[t1], w1y[t1]);
+                    const T wy = cic_w<T>(b, oy_[t1], w1y[t1]);
 #pragma unroll
                     for (int c = 0; c < 3; c++) Cy[t0][b][c] += wy * Bzv[c];
                 }
@@ -231,12 +240,12 @@ template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kern
         const bool inside = Bx >= 0 && By >= 0 && Bz >= 0 && Bx + 2 < a.on[0] && By + 2 < a.on[1] && Bz + 2 < a.on[2];
 #pragma unroll 1
         for (int aa = 0; aa < 3; aa++) {
-            double A[3][3];
+            T A[3][3];
 #pragma unroll
-            for (int i = 0; i < 9; i++) (&A[0][0])[i] = 0.;
+            for (int i = 0; i < 9; i++) (&A[0][0])[i] = (T)0;
 #pragma unroll
             for (int t0 = 0; t0 < F; t0++) {
-                const double wx = cic_w(aa, ox_[t0], w1x[t0]);
+                const T wx = cic_w<T>(aa, ox_[t0], w1x[t0]);
 #pragma unroll
                 for (int i = 0; i < 9; i++) (&A[0][0])[i] += wx * (&Cy[t0][0][0])[i];
             }
@@ -247,7 +256,7 @@ template <int F> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kern
                 const int gy = inside ? By + b : wrap_index(By + b, a.on[1]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const long long q = llrint(A[b][c] * FIXED_SCALE);
+                    const long long q = to_fixed(A[b][c]);
                     if (q == 0) continue;
                     const int gz = inside ? Bz + c : wrap_index(Bz + c, a.on[2]);
                     atomic_add_u64(&plane[(long long)gy * a.on[2] + gz], (unsigned long long)q);
@@ -265,8 +274,15 @@ template <int F> static void launch_grouped(const MoveArgs &a) {
     long long blocks = (ngroups + 127) / 128;
     const long long cap = (long long)dev_num_sms() * 64;
     if (blocks > cap) blocks = cap;
-    auto kp = &move_cic_grouped_kernel<F>;
-    B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
+    static int dbl = -1;
+    if (dbl < 0) { const char *e = getenv("B200_CIC_DOUBLE"); dbl = (e && e[0] == '1') ? 1 : 0; }
+    if (dbl) {
+        auto kp = &move_cic_grouped_kernel<F, double>;
+        B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
+    } else {
+        auto kp = &move_cic_grouped_kernel<F, float>;
+        B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
+    }
 }
 
 struct AccToDeltaArgs {

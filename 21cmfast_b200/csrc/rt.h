@@ -92,6 +92,11 @@ DEV void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 DEV void atomic_min_i32(int *p, int v) { atomicMin(p, v); }
 DEV void atomic_max_i32(int *p, int v) { atomicMax(p, v); }
 DEV int float_as_int_bits(float f) { return __float_as_int(f); }
+/* two single-precision lanes per instruction (Blackwell FFMA2 / FADD2 / FMUL2) */
+DEV float2 f2_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+DEV float2 f2_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DEV float2 f2_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+DEV int float_to_int_floor(float x) { return __float2int_rd(x); }
 #else /* host-only translation units (host_physics.cpp, host_numerics.cpp) built by g++ */
 #define HD inline
 #define DEV inline
@@ -109,6 +114,7 @@ struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r; }
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r = {a, b, c, d}; return r; }
 extern thread_local uint3e blockIdx;
 extern thread_local uint3e gridDim;
 extern thread_local unsigned char *b200_emu_smem;
@@ -145,6 +151,10 @@ inline void atomic_max_i32(int *p, int v) {
     { if (v > *p) *p = v; }
 }
 inline int float_as_int_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float2 f2_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float2 f2_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 f2_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline int float_to_int_floor(float x) { return (int)floorf(x); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
