@@ -206,13 +206,6 @@ template <int LT> struct LinePolicy { /* one line per LT threads, padded by one 
 };
 
 /* transpose between stages: outputs of stage (RAD, NS) -> inputs t + m STEP of the next stage */
-DEV void cp_async_16(void *smem_dst, const void *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 template <int N, int RAD, int NS, class Pol, bool WAIT_ASYNC = false>
 DEV void exchange(float2 (&v)[8], int t, float2 *buf, const Pol &pol) {
     constexpr int NB = 8 / RAD;

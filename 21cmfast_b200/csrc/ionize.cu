@@ -72,7 +72,7 @@ struct SweepTable {
 };
 #define SWEEP_REP 1 /* copies of the bin table; 16 interleaved copies make the loads bank-conflict-free but
                        measured slower on B200 (the sweeps are not shared-memory bound) */
-#define SWEEP_REP_BYTES (N_DENS_INTERP * SWEEP_REP * sizeof(float2))
+#define SWEEP_REP_BYTES (N_DENS_INTERP * SWEEP_REP * sizeof(float2) + 2 * 4 * 256 * sizeof(float4)) /* table + load ring */
 DEV int sweep_rep_lane() { return threadIdx.x & (SWEEP_REP - 1); }
 /* as_exp: first component exp(y0) (grid sum of a log-valued table) instead of y0 */
 DEV void sweep_table_load(SweepTable *st, const DevTable *t, float2 *rep, bool as_exp) {
@@ -138,8 +138,9 @@ DEV float2 exp_small_f2(float2 u) { /* Taylor series of exp, |u| <= 1/4, two lan
     p = f2_fma(p, u, make_float2(1.0f, 1.0f));
     return f2_fma(p, u, make_float2(1.0f, 1.0f));
 }
-/* f_coll of two cells for the grid sum only */
-template <bool LOG> DEV float2 fcoll_fast2(float2 d, const SweepTable *h, const SweepConstsF &k) {
+/* f_coll of two cells for the grid sum only: straight-line code; `steep` is raised when a lane's
+   |t dy| leaves the range of the series and the caller must redo the chunk with fcoll_exact */
+template <bool LOG> DEV float2 fcoll_fast2(float2 d, const SweepTable *h, const SweepConstsF &k, bool &steep) {
     int i0, i1;
     float2 t;
     table_coords_f2(d, k, i0, i1, t);
@@ -147,8 +148,7 @@ template <bool LOG> DEV float2 fcoll_fast2(float2 d, const SweepTable *h, const 
     const float2 e0 = rep[i0 * SWEEP_REP], e1 = rep[i1 * SWEEP_REP];
     const float2 u = f2_mul(t, make_float2(e0.y, e1.y));
     if (!LOG) return f2_add(make_float2(e0.x, e1.x), u);
-    if (fabsf(u.x) > 0.25f || fabsf(u.y) > 0.25f) /* steep bin: reference arithmetic */
-        return make_float2((float)fcoll_exact(fmaxf(d.x, k.floor), h), (float)fcoll_exact(fmaxf(d.y, k.floor), h));
+    steep = steep || (fmaxf(fabsf(u.x), fabsf(u.y)) > 0.25f);
     return f2_mul(make_float2(e0.x, e1.x), exp_small_f2(u));
 }
 
@@ -157,39 +157,77 @@ template <bool LOG> DEV float2 fcoll_fast2(float2 d, const SweepTable *h, const 
    covers a whole number of rows (256 % (nz/4) == 0, i.e. nz a power of two <= 1024) a thread keeps
    its (row offset, zc) for the whole kernel and an iteration is four independent 128-bit loads
    at constant row strides: no per-chunk index arithmetic. */
-template <class F> DEV void for_each_chunk(const float *filtered, long long nrows, int nz, int pitch, F &&f) {
+#define SWEEP_RING_BYTES (2 * 4 * 256 * sizeof(float4)) /* two iterations of four chunks per thread */
+template <class R, class F1, class F2>
+DEV void for_each_chunk(const float *filtered, long long nrows, int nz, int pitch, float4 *ring, F1 &&fast, F2 &&finish) {
+    /* fast(d4) -> R must be straight-line code (the four chunks of an iteration are evaluated
+       back to back so that their dependency chains interleave); finish(R, d4, row, zc) holds the
+       rare branches and the side effects */
     const int q = nz >> 2;
     const long long rstride = 2LL * pitch; /* floats per padded row */
+#ifndef B200_EMU
     if (blockDim.x == 256 && q <= 256 && (256 % q) == 0) {
+        /* A thread keeps its (row offset, zc) for the whole kernel.  Its loads travel as cp.async
+           copies into a private slot of a shared-memory ring, one iteration ahead of the
+           arithmetic: the bytes in flight per SM stay at 16 KB per resident CTA all the time
+           without holding registers (ncu: the register-staged version stalled on the loads,
+           long_scoreboard ~8 of ~12 cycles per issue).  A thread only ever reads the slots it
+           filled itself, so no barrier is involved. */
         const int rows_per_step = 256 / q;
         const int r = threadIdx.x / q, zc = threadIdx.x - r * q;
         const long long step_rows = 4LL * rows_per_step;
-        /* (a register double-buffer that prefetches the next iteration was measured slower: the
-           sweeps are bound by the per-cell arithmetic, and the extra registers cost a CTA per SM) */
-        for (long long row0 = (long long)blockIdx.x * step_rows; row0 < nrows; row0 += (long long)gridDim.x * step_rows) {
-            const float *p = filtered + (row0 + r) * rstride + 4 * zc;
-            float4 d4[4];
+        const long long gstride = (long long)gridDim.x * step_rows;
+        auto issue = [&](long long row0, int slot) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const long long row = row0 + r + (long long)u * rows_per_step;
-                d4[u] = row < nrows ? *reinterpret_cast<const float4 *>(p + (long long)u * rows_per_step * rstride)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                long long row = row0 + r + (long long)u * rows_per_step;
+                if (row >= nrows) row = nrows - 1; /* harmless duplicate, discarded below */
+                cp_async_16(&ring[(slot * 4 + u) * 256 + threadIdx.x], filtered + row * rstride + 4 * zc);
             }
+            cp_async_commit();
+        };
+        long long row0 = (long long)blockIdx.x * step_rows;
+        if (row0 < nrows) issue(row0, 0);
+        for (int it = 0; row0 < nrows; row0 += gstride, it++) {
+            if (row0 + gstride < nrows) issue(row0 + gstride, (it + 1) & 1);
+            else cp_async_commit(); /* keep one group per iteration so that wait_group 1 is uniform */
+            cp_async_wait_group<1>();
+            float4 d4[4];
+            R res[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) d4[u] = ring[((it & 1) * 4 + u) * 256 + threadIdx.x];
+#pragma unroll
+            for (int u = 0; u < 4; u++) res[u] = fast(d4[u]);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const long long row = row0 + r + (long long)u * rows_per_step;
-                if (row < nrows) f(d4[u], row, zc);
+                if (row < nrows) finish(res[u], d4[u], row, zc);
             }
         }
+        cp_async_wait_all();
     } else {
         const long long nchunks = nrows * q;
         for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks;
              id += (long long)gridDim.x * blockDim.x) {
             const long long row = id / q;
             const int zc = (int)(id - row * q);
-            f(*reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc), row, zc);
+            const float4 d = *reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc);
+            finish(fast(d), d, row, zc);
         }
     }
+#else
+    (void)ring;
+    {
+        const long long nchunks = nrows * q;
+        for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < nchunks;
+             id += (long long)gridDim.x * blockDim.x) {
+            const long long row = id / q;
+            const int zc = (int)(id - row * q);
+            const float4 d = *reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc);
+            finish(fast(d), d, row, zc);
+        }
+    }
+#endif
 }
 
 /* sweep 1: sum of f_coll over the grid as deterministic double block sums (calculate_fcoll_grid,
@@ -206,11 +244,24 @@ template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(Swee
     const SweepConstsF kf = sweep_consts(&st, dens_floor);
     double acc = 0.;
     if ((a.nz & 3) == 0 && !a.fcoll) {
-        for_each_chunk(a.filtered, nrows, a.nz, a.nzc, [&](const float4 &d, long long, int) {
-            const float2 f = f2_add(fcoll_fast2<LOG>(make_float2(d.x, d.y), &st, kf),
-                                    fcoll_fast2<LOG>(make_float2(d.z, d.w), &st, kf));
-            acc += (double)(f.x + f.y);
-        });
+        struct SumRes { float sum; bool steep; };
+        for_each_chunk<SumRes>(
+            a.filtered, nrows, a.nz, a.nzc, reinterpret_cast<float4 *>(rep + N_DENS_INTERP * SWEEP_REP),
+            [&](const float4 &d) -> SumRes {
+                SumRes r;
+                r.steep = false;
+                const float2 f = f2_add(fcoll_fast2<LOG>(make_float2(d.x, d.y), &st, kf, r.steep),
+                                        fcoll_fast2<LOG>(make_float2(d.z, d.w), &st, kf, r.steep));
+                r.sum = f.x + f.y;
+                return r;
+            },
+            [&](const SumRes &r, const float4 &d, long long, int) {
+                if (r.steep) /* a steep bin somewhere in the chunk: reference arithmetic for its cells */
+                    acc += (fcoll_exact(fmaxf(d.x, dens_floor), &st) + fcoll_exact(fmaxf(d.y, dens_floor), &st)) +
+                           (fcoll_exact(fmaxf(d.z, dens_floor), &st) + fcoll_exact(fmaxf(d.w, dens_floor), &st));
+                else
+                    acc += (double)r.sum;
+            });
     } else {
         for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
             const float *src = a.filtered + row * 2 * a.nzc;
@@ -220,7 +271,9 @@ template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(Swee
                     acc += f;
                     a.fcoll[row * a.nz + z] = (float)f;
                 } else {
-                    acc += (double)fcoll_fast2<LOG>(make_float2(src[z], src[z]), &st, kf).x;
+                    bool steep = false;
+                    const float f = fcoll_fast2<LOG>(make_float2(src[z], src[z]), &st, kf, steep).x;
+                    acc += steep ? fcoll_exact(fmaxf(src[z], dens_floor), &st) : (double)f;
                 }
             }
         }
@@ -377,7 +430,8 @@ template <bool LOG> __global__ void __launch_bounds__(256) ionise_delta_kernel(C
         if (a.mass_dep_zeta && curr < a.f_limit) curr = a.f_limit;
         return curr * a.ion_eff_factor > 1.0;
     };
-    /* two cells at a time; returns bit 0 / bit 1 = ionised */
+    /* two cells at a time, straight-line: bits 0/1 = ionised by the single-precision test,
+       bits 4/5 = inside the band (the reference arithmetic must decide) */
     auto ionised2 = [&](float2 d) -> unsigned {
         int i0, i1;
         float2 t;
@@ -386,31 +440,44 @@ template <bool LOG> __global__ void __launch_bounds__(256) ionise_delta_kernel(C
         const float2 y0 = rep[i0 * SWEEP_REP], y1 = rep[i1 * SWEEP_REP];
         const float2 diff = f2_add(f2_fma(t, make_float2(y0.y, y1.y), make_float2(y0.x, y1.x)), make_float2(-thr, -thr));
         const float b0 = fmaf(1e-4f, fabsf(y0.y), band0), b1 = fmaf(1e-4f, fabsf(y1.y), band0);
-        bool r0 = diff.x > 0.f ? true : floor_ionises, r1 = diff.y > 0.f ? true : floor_ionises;
-        if (fabsf(diff.x) <= b0) r0 = exact(d.x);
-        if (fabsf(diff.y) <= b1) r1 = exact(d.y);
-        return (r0 ? 1u : 0u) | (r1 ? 2u : 0u);
+        const bool r0 = diff.x > 0.f ? true : floor_ionises, r1 = diff.y > 0.f ? true : floor_ionises;
+        return (r0 ? 1u : 0u) | (r1 ? 2u : 0u) | (fabsf(diff.x) <= b0 ? 16u : 0u) | (fabsf(diff.y) <= b1 ? 32u : 0u);
+    };
+    auto set_mask = [&](unsigned m4, long long cell) {
+        if (!m4) return;
+        unsigned char *m = a.mask + cell;
+        if (m4 == 15u) {
+            *reinterpret_cast<unsigned int *>(m) = 0x01010101u;
+        } else {
+            if (m4 & 1u) m[0] = 1;
+            if (m4 & 2u) m[1] = 1;
+            if (m4 & 4u) m[2] = 1;
+            if (m4 & 8u) m[3] = 1;
+        }
     };
     if ((a.nz & 3) == 0) {
-        for_each_chunk(a.filtered, nrows, a.nz, a.nzc, [&](const float4 &d, long long row, int zc) {
-            const unsigned m4 = ionised2(make_float2(d.x, d.y)) | (ionised2(make_float2(d.z, d.w)) << 2);
-            if (m4) {
-                unsigned char *m = a.mask + (row * a.nz + 4 * zc);
-                if (m4 == 15u) {
-                    *reinterpret_cast<unsigned int *>(m) = 0x01010101u;
-                } else {
-                    if (m4 & 1u) m[0] = 1;
-                    if (m4 & 2u) m[1] = 1;
-                    if (m4 & 4u) m[2] = 1;
-                    if (m4 & 8u) m[3] = 1;
+        for_each_chunk<unsigned>(
+            a.filtered, nrows, a.nz, a.nzc, reinterpret_cast<float4 *>(rep + N_DENS_INTERP * SWEEP_REP),
+            [&](const float4 &d) -> unsigned { return ionised2(make_float2(d.x, d.y)) | (ionised2(make_float2(d.z, d.w)) << 2); },
+            [&](unsigned res, const float4 &d, long long row, int zc) {
+                unsigned m4 = res & 15u;
+                if (res & 0xf0u) { /* some cell of the chunk sits inside the band */
+                    const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (res & (16u << i)) m4 = (m4 & ~(1u << i)) | (exact(dd[i]) ? (1u << i) : 0u);
                 }
-            }
-        });
+                set_mask(m4, row * a.nz + 4 * zc);
+            });
     } else {
         for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
             const float *src = a.filtered + row * 2 * a.nzc;
             for (int z = threadIdx.x; z < a.nz; z += blockDim.x)
-                if (ionised2(make_float2(src[z], src[z])) & 1u) a.mask[row * a.nz + z] = 1;
+            {
+                const unsigned res = ionised2(make_float2(src[z], src[z]));
+                const bool ion = (res & 16u) ? exact(src[z]) : (res & 1u) != 0;
+                if (ion) a.mask[row * a.nz + z] = 1;
+            }
         }
     }
 }

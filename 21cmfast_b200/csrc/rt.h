@@ -92,6 +92,14 @@ DEV void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 DEV void atomic_min_i32(int *p, int v) { atomicMin(p, v); }
 DEV void atomic_max_i32(int *p, int v) { atomicMax(p, v); }
 DEV int float_as_int_bits(float f) { return __float_as_int(f); }
+/* asynchronous 16-byte global -> shared copies (LDGSTS): in-flight loads that hold no registers */
+DEV void cp_async_16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N> DEV void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 /* two single-precision lanes per instruction (Blackwell FFMA2 / FADD2 / FMUL2) */
 DEV float2 f2_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 DEV float2 f2_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
