@@ -599,6 +599,8 @@ struct IonDeviceIO {
     const float *density;   /* device, N */
     const float *prev_zre;  /* device or null */
     float *xH, *z_reion, *Tk, *nion; /* device, N each; Tk / nion may be null */
+    int wait_slot = -1;     /* copy-stream event that must have fired before xH / Tk / prev_zre are read
+                               (their upload overlaps the radius ladder), or -1 */
 };
 
 /* pinned staging that outlives a call (cudaMallocHost is too slow to repeat per call) */
@@ -673,6 +675,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 
     const double exp_global_hii = box->mean_f_coll * c.ion_eff_factor_gl;
     if (exp_global_hii < HII_ROUND_ERR) {
+        if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
         { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
         NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term};
         B200_LAUNCH(neutral_box_kernel, grid_for(N, 1024), 256, 0, na);
@@ -803,6 +806,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             if (htab.log_valued) B200_LAUNCH(ionise_delta_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
             else B200_LAUNCH(ionise_delta_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
         } else {
+            if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
             CritArgs ca;
             memset(&ca, 0, sizeof(ca));
             ca.n = N; ca.fcoll = fc; ca.partial = d_partial; ca.n_partial = sweep_blocks;
@@ -820,6 +824,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         fprintf(stderr, "[21cmfast_b200] ionize host: enqueue %.3f ms, event wait %.3f ms, tables %.3f ms (%d radii)\n",
                 1e3 * t_launch, 1e3 * t_wait, 1e3 * t_table, n_todo);
     {
+        if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
         const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
         FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
                         c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
@@ -857,15 +862,20 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
 
         DevBuf<float> d_density(N), d_xH(N), d_zre(N), d_prev, d_Tk, d_nion;
         h2d(d_density, perturbed_field->density, N * sizeof(float));
-        h2d(d_xH, box->neutral_fraction, N * sizeof(float));
+        /* neutral_fraction / kinetic_temperature / previous z_reion are first read at the last
+           radius: their upload rides on the copy stream behind the radius ladder */
+        const int slot = 60;
+        copy_wait_main();
+        h2d_copy_stream(d_xH, box->neutral_fraction, N * sizeof(float));
         const bool want_Tk = !matter_options_global->MINIMIZE_MEMORY && box->kinetic_temperature;
-        if (want_Tk) { d_Tk.alloc(N); h2d(d_Tk, box->kinetic_temperature, N * sizeof(float)); }
+        if (want_Tk) { d_Tk.alloc(N); h2d_copy_stream(d_Tk, box->kinetic_temperature, N * sizeof(float)); }
         if (box->unnormalised_nion) d_nion.alloc(N);
         if (!first && previous_ionize_box && previous_ionize_box->z_reion) {
             d_prev.alloc(N);
-            h2d(d_prev, previous_ionize_box->z_reion, N * sizeof(float));
+            h2d_copy_stream(d_prev, previous_ionize_box->z_reion, N * sizeof(float));
         }
-        IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p};
+        copy_event_record(slot);
+        IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p, slot};
         ionize_core(redshift, prev_redshift, io, box);
 
         d2h(box->neutral_fraction, d_xH, N * sizeof(float));
@@ -874,6 +884,7 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         if (d_nion.p) d2h(box->unnormalised_nion, d_nion, N * sizeof(float));
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
+        try { copy_stream_sync(); } catch (B200Error &) {} /* no copy may outlive the buffers released above */
         if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
             fprintf(stderr, "[21cmfast_b200] ComputeIonizedBox: %s\n", e.msg);
         return e.code;

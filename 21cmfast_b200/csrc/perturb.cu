@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) move_cic_kernel(MoveArgs a) {
    27 fixed-point adds instead of 8 F^3.  Same positions and weights as the generic kernel. */
 struct GroupArgs {
     MoveArgs m;
+    long long p_begin, p_end; /* range of groups (x-major flat index) this launch deposits */
     int gbrick[3];  /* source (low-res) cells per CTA */
     int gtiles[3];
 };
@@ -186,7 +187,8 @@ template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_
     const long long ngroups = (long long)nxg * nyg * nzg;
     const long long out_sx = (long long)a.on[1] * a.on[2];
     const T growth = (T)a.init_growth;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < ngroups;
+    (void)ngroups;
+    for (long long p = g.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < g.p_end;
          p += (long long)gridDim.x * blockDim.x) {
         const int cz = (int)(p % nzg);
         const int cy = (int)((p / nzg) % nyg);
@@ -266,11 +268,13 @@ template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_
     }
 }
 
-template <int F> static void launch_grouped(const MoveArgs &a) {
+template <int F> static void launch_grouped(const MoveArgs &a, long long p_begin, long long p_end) {
     GroupArgs g;
     g.m = a;
+    g.p_begin = p_begin; g.p_end = p_end;
     for (int ax = 0; ax < 3; ax++) { g.gbrick[ax] = 0; g.gtiles[ax] = 0; }
-    const long long ngroups = (long long)a.vn[0] * a.vn[1] * a.vn[2];
+    const long long ngroups = p_end - p_begin;
+    if (ngroups <= 0) return;
     long long blocks = (ngroups + 127) / 128;
     const long long cap = (long long)dev_num_sms() * 64;
     if (blocks > cap) blocks = cap;
@@ -319,6 +323,21 @@ __global__ void linear_density_kernel(LinearArgs a) {
 }
 
 /* ------------------------------------------------------------------ orchestration */
+/* host arrays still to be uploaded when perturb_core starts: the deposit then runs slab by slab
+   behind the copies (ComputePerturbedField with a cold IC cache) */
+struct PendingUpload {
+    const float *h_hires = nullptr;          /* host DIM^3 */
+    const float *h_v[3] = {nullptr, nullptr, nullptr}, *h_v2[3] = {nullptr, nullptr, nullptr}; /* host HII^3 */
+    float *d_hires = nullptr, *d_v[3] = {nullptr, nullptr, nullptr}, *d_v2[3] = {nullptr, nullptr, nullptr};
+};
+static void upload_all(const PendingUpload &u, long long M, long long N) {
+    h2d(u.d_hires, u.h_hires, M * sizeof(float));
+    for (int a = 0; a < 3; a++) {
+        if (u.h_v[a]) h2d(u.d_v[a], u.h_v[a], N * sizeof(float));
+        if (u.h_v2[a]) h2d(u.d_v2[a], u.h_v2[a], N * sizeof(float));
+    }
+}
+
 struct PerturbDeviceIO {
     const float *hires_density; /* device, DIM^3 (2LPT / ZA) */
     const float *lowres_density; /* device, HII^3 (LINEAR only) */
@@ -326,7 +345,7 @@ struct PerturbDeviceIO {
     float *density, *vel[3];     /* device outputs (vel[a] may be null) */
 };
 
-static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
+static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const PendingUpload *pending = nullptr) {
     const SimulationOptions *so = simulation_options_global;
     const MatterOptions *mo = matter_options_global;
     if (mo->PERTURB_ON_HIGH_RES)
@@ -343,6 +362,7 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
 
     const double growth = dicke(redshift);
     if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR) {
+        if (pending) h2d(pending->d_hires, pending->h_hires, N * sizeof(float));
         LinearArgs la = {(long long)hn[0] * hn[1], hn[2], plan->pitch, io.lowres_density, padded, growth};
         B200_LAUNCH(linear_density_kernel, row_blocks, 256, 0, la);
     } else {
@@ -380,12 +400,44 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io) {
         const int F = dn[0] / hn[0];
         const bool integer_ratio = F * hn[0] == dn[0] && F * hn[1] == dn[1] && F * hn[2] == dn[2] && F >= 1 && F <= 4;
         const char *force = getenv("B200_CIC_GENERIC");
+        auto deposit = [&](long long p0, long long p1) {
+            if (F == 1) launch_grouped<1>(a, p0, p1);
+            else if (F == 2) launch_grouped<2>(a, p0, p1);
+            else if (F == 3) launch_grouped<3>(a, p0, p1);
+            else launch_grouped<4>(a, p0, p1);
+        };
+        const long long plane_groups = (long long)hn[1] * hn[2];
         if (integer_ratio && !(force && force[0] == '1')) {
-            if (F == 1) launch_grouped<1>(a);
-            else if (F == 2) launch_grouped<2>(a);
-            else if (F == 3) launch_grouped<3>(a);
-            else launch_grouped<4>(a);
+            if (pending && hn[0] >= 8) {
+                /* Pipeline the upload with the deposit: x-slabs of the hi-res density (and of the
+                   low-res velocity boxes) travel on the copy stream; the groups of slab k are
+                   deposited as soon as its copy has landed.  Group cx reads hi-res planes
+                   ceil(F cx - F/2) .. + F - 1, i.e. it starts at most one plane below F cx: inside
+                   slab k or the (earlier) slab k - 1.  Only cx = 0 reaches back to plane DIM - 1; it
+                   is deposited last. */
+                const int nslab = hn[0] >= 64 ? 16 : (hn[0] >= 16 ? 4 : 2);
+                const long long hplane = (long long)dn[1] * dn[2];
+                copy_wait_main(); /* the destination buffers may still be in use by earlier work */
+                for (int k = 0; k < nslab; k++) {
+                    const int cx0 = (int)((long long)hn[0] * k / nslab), cx1 = (int)((long long)hn[0] * (k + 1) / nslab);
+                    const long long lo = (long long)cx0 * plane_groups, cnt = (long long)(cx1 - cx0) * plane_groups;
+                    for (int ax = 0; ax < 3; ax++) {
+                        if (pending->h_v[ax]) h2d_copy_stream(pending->d_v[ax] + lo, pending->h_v[ax] + lo, cnt * sizeof(float));
+                        if (pending->h_v2[ax]) h2d_copy_stream(pending->d_v2[ax] + lo, pending->h_v2[ax] + lo, cnt * sizeof(float));
+                    }
+                    const long long hlo = (long long)F * cx0 * hplane, hcnt = (long long)F * (cx1 - cx0) * hplane;
+                    h2d_copy_stream(pending->d_hires + hlo, pending->h_hires + hlo, hcnt * sizeof(float));
+                    copy_event_record(k);
+                    main_wait_copy_event(k);
+                    deposit((k == 0 ? 1 : cx0) * plane_groups, (long long)cx1 * plane_groups);
+                }
+                deposit(0, plane_groups);
+            } else {
+                if (pending) upload_all(*pending, M, N);
+                deposit(0, (long long)hn[0] * plane_groups);
+            }
         } else {
+            if (pending) upload_all(*pending, M, N);
             const size_t smem = sizeof(unsigned long long) * (size_t)(a.tile0[0] + 2 * a.halo) *
                                 (a.tile0[1] + 2 * a.halo) * (a.tile0[2] + 2 * a.halo);
 #ifndef B200_EMU
@@ -463,17 +515,19 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
             sig[i] = sample_signature(hv[i], hn[i]);
             if (hit && (g_ics.host[i] != hv[i] || g_ics.sig[i] != sig[i])) hit = false;
         }
+        PendingUpload pending;
         if (!hit) {
             ics_cache_drop();
             g_ics.hires.alloc(hn[0]);
-            h2d(g_ics.hires, hv[0], hn[0] * sizeof(float));
+            pending.h_hires = hv[0]; pending.d_hires = g_ics.hires;
             for (int a = 0; a < 3 && nuse > 1; a++) {
                 g_ics.v[a].alloc(N);
-                h2d(g_ics.v[a], hv[1 + a], N * sizeof(float));
-                if (lpt2) { g_ics.v2[a].alloc(N); h2d(g_ics.v2[a], hv[4 + a], N * sizeof(float)); }
+                pending.h_v[a] = hv[1 + a]; pending.d_v[a] = g_ics.v[a];
+                if (lpt2) { g_ics.v2[a].alloc(N); pending.h_v2[a] = hv[4 + a]; pending.d_v2[a] = g_ics.v2[a]; }
             }
             for (int i = 0; i < 7; i++) { g_ics.host[i] = i < nuse ? hv[i] : nullptr; g_ics.sig[i] = sig[i]; }
-            g_ics.dim = so->DIM; g_ics.hii = so->HII_DIM; g_ics.valid = true;
+            g_ics.dim = so->DIM; g_ics.hii = so->HII_DIM;
+            g_ics.valid = false; /* becomes valid once the (pipelined) upload has been issued in full */
         }
         DevBuf<float> d_density(N), d_v[3];
         float *host_v[3] = {mo->KEEP_3D_VELOCITIES ? pf->velocity_x : nullptr,
@@ -486,13 +540,15 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
             if (host_v[a]) { d_v[a].alloc(N); io.vel[a] = d_v[a]; }
         }
         io.density = d_density;
-        perturb_core(redshift, io);
+        perturb_core(redshift, io, hit ? nullptr : &pending);
+        g_ics.valid = true;
         d2h(pf->density, d_density, N * sizeof(float));
         for (int a = 0; a < 3; a++)
             if (host_v[a]) d2h(host_v[a], d_v[a], N * sizeof(float));
         if (!use_cache) ics_cache_drop();
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
+        try { copy_stream_sync(); } catch (B200Error &) {}
         if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
             fprintf(stderr, "[21cmfast_b200] ComputePerturbedField: %s\n", e.msg);
         return e.code;

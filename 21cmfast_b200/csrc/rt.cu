@@ -26,6 +26,9 @@ static std::map<void *, size_t> g_live;
 
 #ifndef B200_EMU
 cudaStream_t g_stream = nullptr;
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_copy_events[64];
+static cudaEvent_t g_main_event = nullptr;
 static int g_device = -1;
 static int g_sms = 0;
 
@@ -51,6 +54,12 @@ extern "C" int b200_set_device(int device) {
             b200_release_device_cache();
             cudaStreamDestroy(g_stream);
             g_stream = nullptr;
+            if (g_copy_stream) {
+                cudaStreamDestroy(g_copy_stream);
+                g_copy_stream = nullptr;
+                for (int i = 0; i < 64; i++) cudaEventDestroy(g_copy_events[i]);
+                cudaEventDestroy(g_main_event);
+            }
         }
         g_device = device;
         rt_init();
@@ -114,6 +123,34 @@ void h2d_async(void *dst, const void *src, size_t bytes) {
 void d2h_async(void *dst, const void *src, size_t bytes) {
     CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
 }
+static void copy_stream_init() {
+    rt_init();
+    if (g_copy_stream) return;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; i++) CUDA_CHECK(cudaEventCreateWithFlags(&g_copy_events[i], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_main_event, cudaEventDisableTiming));
+}
+void h2d_copy_stream(void *dst, const void *src, size_t bytes) {
+    copy_stream_init();
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_copy_stream));
+    g_stats.h2d += (long long)bytes;
+}
+void d2h_copy_stream(void *dst, const void *src, size_t bytes) {
+    copy_stream_init();
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_copy_stream));
+    g_stats.d2h += (long long)bytes;
+}
+void copy_event_record(int slot) {
+    copy_stream_init();
+    CUDA_CHECK(cudaEventRecord(g_copy_events[slot & 63], g_copy_stream));
+}
+void main_wait_copy_event(int slot) { CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_copy_events[slot & 63], 0)); }
+void copy_wait_main() {
+    copy_stream_init();
+    CUDA_CHECK(cudaEventRecord(g_main_event, g_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(g_copy_stream, g_main_event, 0));
+}
+void copy_stream_sync() { if (g_copy_stream) CUDA_CHECK(cudaStreamSynchronize(g_copy_stream)); }
 void *dev_event_create() {
     cudaEvent_t e;
     CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -215,6 +252,12 @@ void *host_pinned_alloc(size_t bytes) { return malloc(bytes); }
 void host_pinned_free(void *p) { free(p); }
 void h2d_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void d2h_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void h2d_copy_stream(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_stats.h2d += bytes; }
+void d2h_copy_stream(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_stats.d2h += bytes; }
+void copy_event_record(int) {}
+void main_wait_copy_event(int) {}
+void copy_wait_main() {}
+void copy_stream_sync() {}
 void *dev_event_create() { return nullptr; }
 void dev_event_record(void *) {}
 void dev_event_wait_host(void *) {}

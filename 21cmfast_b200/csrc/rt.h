@@ -209,6 +209,16 @@ void *host_pinned_alloc(size_t bytes);
 void host_pinned_free(void *p);
 void h2d_async(void *dst, const void *pinned_src, size_t bytes);
 void d2h_async(void *pinned_dst, const void *src, size_t bytes);
+/* second stream for host<->device copies that overlap kernels on the main stream; `slot` indexes a
+   small pool of events (copy_event_record on the copy stream, main_wait_copy_event makes the
+   main stream wait; copy_wait_main makes the copy stream wait for everything enqueued so far
+   on the main stream).  In the emulation build the copies are synchronous and the rest no-ops. */
+void h2d_copy_stream(void *dst, const void *src, size_t bytes);
+void d2h_copy_stream(void *dst, const void *src, size_t bytes);
+void copy_event_record(int slot);
+void main_wait_copy_event(int slot);
+void copy_wait_main();
+void copy_stream_sync();
 void *dev_event_create();
 void dev_event_record(void *ev);
 void dev_event_wait_host(void *ev);

@@ -37,6 +37,7 @@ def test_golden_initial_conditions(gpu):
 
 @pytest.mark.parametrize("hii,dim,source,filt,perturb", [
     (64, 128, "E-INTEGRAL", "spherical-tophat", "2LPT"),
+    (128, 256, "E-INTEGRAL", "spherical-tophat", "2LPT"),   # N = 128 / 256 register FFTs, window-table x pass
     (64, 128, "CONST-ION-EFF", "sharp-k", "2LPT"),
     (35, 70, "CONST-ION-EFF", "spherical-tophat", "ZELDOVICH"),
     (50, 150, "E-INTEGRAL", "gaussian", "2LPT"),
@@ -56,6 +57,29 @@ def test_pipeline_vs_reference(gpu, hii, dim, source, filt, perturb):
     r_ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=r_ics, backend=ref)
     ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=r_ics, backend=gpu)
     common.compare_ionized(ib, r_ib)
+
+
+@pytest.mark.parametrize("filter_flag", [0, 1])
+def test_filter_512_vs_reference(gpu, filter_flag):
+    """The N = 512 kernels of the metric's grid size (three radix-8 stages, line-per-warp z passes):
+    lib.test_filter on a 512^3 box of noise + a delta function against the compiled reference."""
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    n = 512
+    inputs = common.make_inputs(hii=n, dim=n, box_len=768.0)
+    rng = np.random.default_rng(11)
+    box = rng.normal(size=(n,) * 3).astype(np.float32)
+    box[n // 2, n // 3, 5] += 100.0
+    out = np.zeros((n,) * 3, np.float64)
+    exp = np.zeros((n,) * 3, np.float64)
+    gpu.state.init(inputs, broadcast_inputs=True)
+    assert gpu.lib.test_filter(box.ctypes.data_as(C.POINTER(C.c_float)), 12.0, 0.0, 0.0, filter_flag,
+                               out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    ref.state.init(inputs, broadcast_inputs=True)
+    assert ref.lib.test_filter(box.ctypes.data_as(C.POINTER(C.c_float)), 12.0, 0.0, 0.0, filter_flag,
+                               exp.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    assert np.abs(out - exp).max() <= 5e-6 * np.abs(exp).max()
 
 
 def _tophat_profile(r, R):
