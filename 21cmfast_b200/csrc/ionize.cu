@@ -623,7 +623,20 @@ struct IonStaging {
 };
 static IonStaging g_stage;
 
-static void ionize_core(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box) {
+/* Radius-parallel execution of ONE box on several GPUs: given delta_k the radii
+   are independent units -- each needs only its own filtered grid, table, grid sum and flags, and
+   the flags combine by OR.  phase 0: this rank runs the radii k = part (mod nparts) except the last
+   one and leaves their flags in `mask` (N bytes, device); the caller ORs the masks of all ranks
+   (all-reduce MAX over bytes, the path's only collective).  phase 1: every rank runs the last
+   radius on the merged mask (it assigns the partial ionisations of the never-flagged cells) and
+   finalises, so every rank ends with the complete box.  phase -1: the whole ladder, no partition. */
+struct IonPartition {
+    int part = 0, nparts = 1, phase = -1;
+    unsigned char *mask = nullptr;
+};
+
+static void ionize_core(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box,
+                        const IonPartition &pt = IonPartition()) {
     const SimulationOptions *so = simulation_options_global;
     const AstroOptions *ao = astro_options_global;
     const MatterOptions *mo = matter_options_global;
@@ -675,6 +688,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 
     const double exp_global_hii = box->mean_f_coll * c.ion_eff_factor_gl;
     if (exp_global_hii < HII_ROUND_ERR) {
+        if (pt.phase == 0) { dev_zero(pt.mask, (size_t)N); dev_sync(); return; }
         if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
         { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
         NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term};
@@ -689,6 +703,14 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         todo.push_back(R_ct);
     }
     const int n_todo = (int)todo.size();
+    /* the ladder steps this call runs, in order */
+    std::vector<int> mine;
+    for (int k = 0; k < n_todo; k++) {
+        const bool last_k = (k == n_todo - 1);
+        if (pt.phase < 0 || (pt.phase == 0 && !last_k && k % pt.nparts == pt.part) || (pt.phase == 1 && last_k))
+            mine.push_back(k);
+    }
+    const int n_mine = (int)mine.size();
 
     DevBuf<float2> k_unfiltered(plan->n_cplx()), work0(plan->n_cplx()), work1(plan->n_cplx());
     float2 *work[2] = {work0.p, work1.p};
@@ -700,8 +722,10 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     DevBuf<double> d_partial(sweep_blocks);
     DevBuf<int> d_flag(1);
     dev_zero(d_flag, sizeof(int));
-    DevBuf<unsigned char> d_mask((size_t)N);
-    dev_zero(d_mask, (size_t)N);
+    DevBuf<unsigned char> own_mask;
+    unsigned char *d_mask = pt.mask;
+    if (pt.phase < 0) { own_mask.alloc((size_t)N); d_mask = own_mask; }
+    if (pt.phase <= 0) dev_zero(d_mask, (size_t)N); /* phase 1 continues on the merged mask */
     /* window tables over |n|^2 (cubic boxes, top-hat / gaussian): two slots, stream-ordered reuse */
     const bool cubic = nx == ny && ny == nz && so->NON_CUBIC_FACTOR == 1.0f;
     const bool use_wtab = cubic && (c.hii_filter == 0 || c.hii_filter == 2);
@@ -730,18 +754,19 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     /* stage A of radius k: filter + c2r + clip + min/max keys; the two keys travel to pinned host
        memory behind an event, so the host can wait for exactly this radius while the stream
        already runs the next one (copy_filter_transform + clip_and_get_extrema) */
-    auto enqueue_transform = [&](int k) {
+    auto enqueue_transform = [&](int j) {
+        const int k = mine[j];
         const RadiusSpec &rs = radii[todo[k]];
         KMul km;
         if (rs.R_index > 0) {
             km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R; km.fast = 1;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
             if (use_wtab) {
-                float *slot = d_wtab.p + (size_t)(k & 1) * wtab_n;
+                float *slot = d_wtab.p + (size_t)(j & 1) * wtab_n;
                 window_table_build(plan, c.hii_filter, km.R, dk0, slot);
                 km.wtab = slot; km.wtab_n = wtab_n;
                 if (use_wtab3) {
-                    float *slot3 = d_wtab3.p + (size_t)(k & 1) * wtab3_n;
+                    float *slot3 = d_wtab3.p + (size_t)(j & 1) * wtab3_n;
                     window_table_expand(plan, slot, slot3);
                     km.wtab3 = slot3;
                 }
@@ -750,7 +775,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         ZEpilogue epi;
         epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
         epi.minmax_keys = d_keys.p + 2 * k;
-        fft_c2r(plan, k_unfiltered, work[k & 1], km, epi);
+        fft_c2r(plan, k_unfiltered, work[j & 1], km, epi);
         d2h_async(g_stage.h_keys + 2 * k, d_keys.p + 2 * k, 2 * sizeof(int));
         dev_event_record(g_stage.events[k]);
     };
@@ -758,11 +783,12 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     FcollTable htab;
     double t_wait = 0, t_table = 0, t_launch = 0;
     const bool verbose = getenv("B200_TIMING") != nullptr;
-    if (n_todo > 0) enqueue_transform(0);
-    for (int k = 0; k < n_todo; k++) {
+    if (n_mine > 0) enqueue_transform(0);
+    for (int j = 0; j < n_mine; j++) {
+        const int k = mine[j];
         const RadiusSpec &rs = radii[todo[k]];
         double t0 = omp_get_wtime();
-        if (k + 1 < n_todo) enqueue_transform(k + 1);
+        if (j + 1 < n_mine) enqueue_transform(j + 1);
         double t1 = omp_get_wtime();
         dev_event_wait_host(g_stage.events[k]);
         double t2 = omp_get_wtime();
@@ -789,7 +815,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
            materialised */
         const bool last = (k == n_todo - 1);
         float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : nullptr;
-        const float *filtered = reinterpret_cast<const float *>(work[k & 1]);
+        const float *filtered = reinterpret_cast<const float *>(work[j & 1]);
         SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
         sweep_smem_optin();
         if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
@@ -822,7 +848,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 
     if (verbose)
         fprintf(stderr, "[21cmfast_b200] ionize host: enqueue %.3f ms, event wait %.3f ms, tables %.3f ms (%d radii)\n",
-                1e3 * t_launch, 1e3 * t_wait, 1e3 * t_table, n_todo);
+                1e3 * t_launch, 1e3 * t_wait, 1e3 * t_table, n_mine);
+    if (pt.phase == 0) {
+        dev_sync(); /* drain the stream before the work boxes are released */
+        return;
+    }
     {
         if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
         const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
@@ -906,6 +936,33 @@ extern "C" int b200_ComputeIonizedBox_device(float redshift, float prev_redshift
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
         fprintf(stderr, "[21cmfast_b200] b200_ComputeIonizedBox_device: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+/* Radius-parallel variant of the device-resident entry point (see IonPartition): d_mask is a device
+   buffer of HII_DIM^2 * HII_D_PARA bytes owned by the caller, who all-reduces it (MAX) between the
+   phase-0 and the phase-1 call. */
+extern "C" int b200_ComputeIonizedBox_device_part(float redshift, float prev_redshift, PerturbedField *d_pf,
+                                                  IonizedBox *d_box, unsigned char *d_mask, int part, int nparts,
+                                                  int phase) {
+    try {
+        require_params(true);
+        rt_init();
+        reset_stats();
+        if (!d_mask || nparts < 1 || part < 0 || part >= nparts || (phase != 0 && phase != 1))
+            b200_throw(B200_ValueError, "b200_ComputeIonizedBox_device_part: bad partition arguments");
+        DevTimer timer;
+        timer.start();
+        IonDeviceIO io = {d_pf->density, nullptr, d_box->neutral_fraction, d_box->z_reion, d_box->kinetic_temperature,
+                          d_box->unnormalised_nion};
+        IonPartition pt;
+        pt.part = part; pt.nparts = nparts; pt.phase = phase; pt.mask = d_mask;
+        ionize_core(redshift, prev_redshift, io, d_box, pt);
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ComputeIonizedBox_device_part: %s\n", e.msg);
         return e.code;
     }
     return 0;

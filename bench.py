@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--ref-hii-dim", type=int, default=256, help="bounded CPU sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--partition", default="boxes", choices=["boxes", "radius"],
+                    help="N > 1: 'boxes' = one independent coeval box per GPU (weak scaling, no collective); "
+                         "'radius' = ONE box, filter radii split over the GPUs + one all-reduce(MAX) of the "
+                         "ionised mask over NCCL (strong scaling; perturb is replicated)")
     return ap.parse_args()
 
 
@@ -215,7 +219,9 @@ def main():
 
     ncpu = max(1, (os.cpu_count() or 1) // max(1, world))
     hii, dim, box_len = workload(args)
-    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source, seed=1234 + rank,
+    radius_mode = args.partition == "radius" and world > 1
+    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source,
+                                seed=1234 + (0 if radius_mode else rank),
                                 n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
     N, M = hii**3, dim**3
     nrad = n_radii(hii, box_len, args.r_bubble_max)
@@ -258,7 +264,25 @@ def main():
     lib.b200_ComputeIonizedBox_device.argtypes = [C.c_float, C.c_float, C.POINTER(_abi.PerturbedFieldStruct),
                                                   C.POINTER(_abi.IonizedBoxStruct)]
 
+    def radius_step():
+        """one box on all ranks: perturb replicated, ionize split by radius, one all-reduce(MAX)"""
+        torch.cuda.synchronize()
+        st = lib.b200_ComputePerturbedField_device(C.c_float(z), C.byref(s_ic), C.byref(s_pf))
+        assert st == 0, st
+        l1, _, _, ms1 = stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        out = pkg.ionize_radius_parallel(redshift=z, density=d_pf["density"], inputs=inputs, backend=be)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms2 = 1e3 * (time.perf_counter() - t0)  # two library calls + the NCCL all-reduce, host clock around device syncs
+        d_ib["neutral_fraction"].copy_(out["neutral_fraction"])
+        return ms1, ms2, l1 + 2
+
     def device_step():
+        if radius_mode:
+            return radius_step()
         d_ib["neutral_fraction"].fill_(1.0)
         d_ib["kinetic_temperature"].zero_()
         torch.cuda.synchronize()
@@ -301,7 +325,7 @@ def main():
 
     # ---------------- end-to-end leg through the C-ABI with pinned host buffers ----------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not radius_mode:
         os.environ["B200_ICS_CACHE"] = "0"  # every step uploads its initial conditions
         keep = []
         h_ics = pkg.InitialConditions(inputs)
@@ -405,13 +429,17 @@ def main():
                         "share_of_kernel_time": tot / sum(v[1] for v in prof.values())}
         step_bytes = (40 + 24 * nrad) * N + (4 * M + 72 * N)
         out = {
-            "metric": "coeval cells/sec (perturb+ionize, one redshift)", "value": world * N / (ms_step * 1e-3),
+            "metric": "coeval cells/sec (perturb+ionize, one redshift)",
+            "value": (1 if radius_mode else world) * N / (ms_step * 1e-3),
             "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if radius_mode else "weak",
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"perturb_field+ionize_box z={z} HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g} "
                                    f"{args.source} n_radii={nrad}",
-                       "parallelism": f"{world} independent coeval boxes (one per GPU)",
+                       "parallelism": (f"one box, filter radii split over {world} GPUs + one all-reduce(MAX) of the mask "
+                                       f"(perturb replicated)") if radius_mode else
+                                      f"{world} independent coeval boxes (one per GPU)",
                        "l2": f"inputs larger than L2 (every pass streams a {4 * N / 1e6:.0f} MB box; L2 is 126 MB)",
                        "ms_perturb": ms_perturb, "ms_ionize": ms_ionize, "global_xH": xh_dev,
                        "wall_ms_per_step": 1e3 * t_wall / args.steps},

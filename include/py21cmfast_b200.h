@@ -275,6 +275,17 @@ int b200_ComputePerturbedField_device(float redshift, InitialConditions *d_boxes
                                       PerturbedField *d_perturbed_field);
 int b200_ComputeIonizedBox_device(float redshift, float prev_redshift,
                                   PerturbedField *d_perturbed_field, IonizedBox *d_box);
+/* Radius-parallel ionisation of ONE box across `nparts` GPUs (one process per GPU).  The filter
+   radii of find_HII_bubbles (IonisationBox.c:1531-1630) are independent given the k-space density
+   and their ionised flags combine by OR, so rank `part` runs the radii k = part (mod nparts):
+     phase 0: all assigned radii but the last one of the ladder -> d_mask (N bytes, 1 = ionised);
+              the caller then all-reduces d_mask with MAX over the ranks (the only collective);
+     phase 1: every rank runs the last radius (partial ionisations) on the merged mask and
+              finalises: d_box is complete on every rank.
+   Same device-pointer convention as b200_ComputeIonizedBox_device. */
+int b200_ComputeIonizedBox_device_part(float redshift, float prev_redshift,
+                                       PerturbedField *d_perturbed_field, IonizedBox *d_box,
+                                       unsigned char *d_mask, int part, int nparts, int phase);
 
 #ifdef __cplusplus
 }

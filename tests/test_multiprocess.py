@@ -49,3 +49,43 @@ def test_two_rank_gloo_independent_boxes(tmp_path):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     assert "OK" in r.stdout
+
+
+WORKER_RADIUS = r'''
+import os, sys
+sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
+import numpy as np, torch, torch.distributed as dist
+import common
+pkg = common.pkg
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+emu = common.emu_backend()
+inputs = common.make_inputs(hii=32, dim=64, seed=4242)            # the SAME box on every rank
+ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
+part = pkg.ionize_radius_parallel(redshift=8.0, density=torch.from_numpy(pf.density), inputs=inputs, backend=emu)
+for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion"):
+    a, b = part[k].numpy(), getattr(whole, k).reshape(part[k].shape)
+    assert np.array_equal(a, b), (k, np.abs(a - b).max())          # bit-identical to the one-rank ladder
+assert part["mean_f_coll"] == whole.mean_f_coll
+xh = float(part["neutral_fraction"].mean())
+assert 0.0 < xh < 1.0
+if rank == 0: print("OK radius-parallel", world, xh)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_radius_parallel_box(tmp_path):
+    """One box, radii split over two ranks, masks merged with all_reduce(MAX): bit-identical to the
+    single-rank ladder (the partition and the merge are the N > 1 host logic of SURVEY section 8e)."""
+    if not (ROOT / "tests" / "_emu" / "libb200_emu.so").exists():
+        pytest.skip("tests/_emu not built")
+    script = tmp_path / "worker_radius.py"
+    script.write_text(WORKER_RADIUS.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert "OK radius-parallel" in r.stdout
