@@ -14,6 +14,6 @@ from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  #
 from .outputs import (BrightnessTemp, InitialConditions, IonizedBox,  # noqa: F401
                       PerturbedField)
 from ._lib import Backend, BackendError, get_backend  # noqa: F401
-from .distributed import ionize_radius_parallel  # noqa: F401
+from .distributed import ionize_radius_parallel, perturb_slab_parallel  # noqa: F401
 
 __version__ = "0.1.0"

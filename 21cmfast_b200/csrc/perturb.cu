@@ -345,7 +345,19 @@ struct PerturbDeviceIO {
     float *density, *vel[3];     /* device outputs (vel[a] may be null) */
 };
 
-static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const PendingUpload *pending = nullptr) {
+/* Slab-parallel deposit of ONE box on several GPUs ("PerturbField move+CIC"):
+   phase 0: this rank deposits the groups of its x-slab [part, part+1) * HII_DIM / nparts into the
+   caller's fixed-point accumulator `acc` (N x u64, zeroed here) and returns; the caller sums the
+   accumulators over the ranks (all-reduce SUM on int64 -- integer addition, so the result is
+   bit-identical to the single-GPU deposit whatever the number of ranks); phase 1: every rank turns
+   the merged accumulator into delta and runs the (small) FFT chain.  phase -1: everything. */
+struct PerturbPartition {
+    int part = 0, nparts = 1, phase = -1;
+    unsigned long long *acc = nullptr;
+};
+
+static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const PendingUpload *pending = nullptr,
+                         const PerturbPartition &pt = PerturbPartition()) {
     const SimulationOptions *so = simulation_options_global;
     const MatterOptions *mo = matter_options_global;
     if (mo->PERTURB_ON_HIGH_RES)
@@ -361,6 +373,8 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
     const int row_blocks = (int)((long long)hn[0] * hn[1] < 4096 ? (long long)hn[0] * hn[1] : 4096);
 
     const double growth = dicke(redshift);
+    if (pt.phase >= 0 && mo->PERTURB_ALGORITHM == PERTURB_LINEAR)
+        b200_throw(B200_ValueError, "the slab-parallel deposit needs PERTURB_ALGORITHM = ZELDOVICH or 2LPT");
     if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR) {
         if (pending) h2d(pending->d_hires, pending->h_hires, N * sizeof(float));
         LinearArgs la = {(long long)hn[0] * hn[1], hn[2], plan->pitch, io.lowres_density, padded, growth};
@@ -384,8 +398,10 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
         a.ratio_vel = (double)hn[0] / (double)dn[0];
         a.ratio_out = (double)hn[0] / (double)dn[0];
         a.init_growth = init_growth;
-        DevBuf<unsigned long long> acc(N);
-        dev_zero(acc, N * sizeof(unsigned long long));
+        DevBuf<unsigned long long> own_acc;
+        unsigned long long *acc = pt.acc;
+        if (pt.phase < 0) { own_acc.alloc(N); acc = own_acc; }
+        if (pt.phase <= 0) dev_zero(acc, N * sizeof(unsigned long long));
         a.acc = acc;
         /* bricks of ~8 low-res cells per axis (fewer if the grid is small), halo of 4 cells */
         a.halo = 4;
@@ -407,7 +423,18 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
             else launch_grouped<4>(a, p0, p1);
         };
         const long long plane_groups = (long long)hn[1] * hn[2];
-        if (integer_ratio && !(force && force[0] == '1')) {
+        if (pt.phase >= 0 && !integer_ratio)
+            b200_throw(B200_ValueError, "the slab-parallel deposit needs an integer DIM / HII_DIM ratio <= 4");
+        if (pt.phase == 0) {
+            /* this rank's x-slab of groups only; the stream is drained before the caller's collective */
+            const int cx0 = (int)((long long)hn[0] * pt.part / pt.nparts), cx1 = (int)((long long)hn[0] * (pt.part + 1) / pt.nparts);
+            deposit((long long)cx0 * plane_groups, (long long)cx1 * plane_groups);
+            dev_sync();
+            return;
+        }
+        if (pt.phase == 1) {
+            /* merged accumulator supplied by the caller: nothing to deposit */
+        } else if (integer_ratio && !(force && force[0] == '1')) {
             if (pending && hn[0] >= 8) {
                 /* Pipeline the upload with the deposit: x-slabs of the hi-res density (and of the
                    low-res velocity boxes) travel on the copy stream; the groups of slab k are
@@ -551,6 +578,44 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
         try { copy_stream_sync(); } catch (B200Error &) {}
         if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
             fprintf(stderr, "[21cmfast_b200] ComputePerturbedField: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+static void fill_device_io(PerturbDeviceIO &io, InitialConditions *d_boxes, PerturbedField *d_pf) {
+    memset(&io, 0, sizeof(io));
+    io.hires_density = d_boxes->hires_density; io.lowres_density = d_boxes->lowres_density;
+    io.v[0] = d_boxes->lowres_vx; io.v[1] = d_boxes->lowres_vy; io.v[2] = d_boxes->lowres_vz;
+    io.v2[0] = d_boxes->lowres_vx_2LPT; io.v2[1] = d_boxes->lowres_vy_2LPT; io.v2[2] = d_boxes->lowres_vz_2LPT;
+    io.density = d_pf->density;
+    io.vel[0] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_x : nullptr;
+    io.vel[1] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_y : nullptr;
+    io.vel[2] = d_pf->velocity_z;
+}
+
+/* Slab-parallel variant of the device-resident entry point (see PerturbPartition): d_acc is a device
+   buffer of HII_DIM^2 * HII_D_PARA 64-bit integers owned by the caller, who all-reduces it (SUM)
+   between the phase-0 and the phase-1 call.  In phase 0 only the hi-res planes of the rank's own
+   slab (plus one plane below it) are read. */
+extern "C" int b200_ComputePerturbedField_device_part(float redshift, InitialConditions *d_boxes, PerturbedField *d_pf,
+                                                      unsigned long long *d_acc, int part, int nparts, int phase) {
+    try {
+        require_params(false);
+        rt_init();
+        reset_stats();
+        if (!d_acc || nparts < 1 || part < 0 || part >= nparts || (phase != 0 && phase != 1))
+            b200_throw(B200_ValueError, "b200_ComputePerturbedField_device_part: bad partition arguments");
+        DevTimer timer;
+        timer.start();
+        PerturbDeviceIO io;
+        fill_device_io(io, d_boxes, d_pf);
+        PerturbPartition pt;
+        pt.part = part; pt.nparts = nparts; pt.phase = phase; pt.acc = d_acc;
+        perturb_core(redshift, io, nullptr, pt);
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ComputePerturbedField_device_part: %s\n", e.msg);
         return e.code;
     }
     return 0;

@@ -56,8 +56,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--partition", default="boxes", choices=["boxes", "radius"],
                     help="N > 1: 'boxes' = one independent coeval box per GPU (weak scaling, no collective); "
-                         "'radius' = ONE box, filter radii split over the GPUs + one all-reduce(MAX) of the "
-                         "ionised mask over NCCL (strong scaling; perturb is replicated)")
+                         "'radius' = ONE box: particle deposit split by x-slab + all-reduce(SUM) of the fixed-point "
+                         "accumulator, filter radii split over the GPUs + all-reduce(MAX) of the ionised mask, both "
+                         "over NCCL (strong scaling)")
     return ap.parse_args()
 
 
@@ -231,6 +232,8 @@ def main():
     be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
     z = float(args.redshift)
 
+    d_ic_part = None
+
     def stats():
         a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_double()
         lib.b200_last_call_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
@@ -247,6 +250,7 @@ def main():
     names_ic = ["hires_density", "lowres_density", "lowres_vx", "lowres_vy", "lowres_vz",
                 "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
     d_ic = {k: torch.from_numpy(getattr(ics, k)).to(dev) for k in names_ic}
+    d_ic_part = {k: v for k, v in d_ic.items() if k != "lowres_density"}
     d_pf = {k: torch.zeros((hii,) * 3, dtype=torch.float32, device=dev) for k in ("density", "velocity_z")}
     d_ib = {k: torch.zeros((hii,) * 3, dtype=torch.float32, device=dev)
             for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion")}
@@ -265,20 +269,18 @@ def main():
                                                   C.POINTER(_abi.IonizedBoxStruct)]
 
     def radius_step():
-        """one box on all ranks: perturb replicated, ionize split by radius, one all-reduce(MAX)"""
+        """one box on all ranks: slab-parallel deposit + all-reduce(SUM), radius-parallel ionize +
+        all-reduce(MAX); host clock around device syncs (library stream + NCCL on torch's stream)"""
         torch.cuda.synchronize()
-        st = lib.b200_ComputePerturbedField_device(C.c_float(z), C.byref(s_ic), C.byref(s_pf))
-        assert st == 0, st
-        l1, _, _, ms1 = stats()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        ev0.record()
-        out = pkg.ionize_radius_parallel(redshift=z, density=d_pf["density"], inputs=inputs, backend=be)
-        ev1.record()
+        ppf = pkg.perturb_slab_parallel(redshift=z, ics=d_ic_part, inputs=inputs, backend=be)
         torch.cuda.synchronize()
-        ms2 = 1e3 * (time.perf_counter() - t0)  # two library calls + the NCCL all-reduce, host clock around device syncs
+        t1 = time.perf_counter()
+        out = pkg.ionize_radius_parallel(redshift=z, density=ppf["density"], inputs=inputs, backend=be)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
         d_ib["neutral_fraction"].copy_(out["neutral_fraction"])
-        return ms1, ms2, l1 + 2
+        return 1e3 * (t1 - t0), 1e3 * (t2 - t1), 4
 
     def device_step():
         if radius_mode:
@@ -437,8 +439,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"perturb_field+ionize_box z={z} HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g} "
                                    f"{args.source} n_radii={nrad}",
-                       "parallelism": (f"one box, filter radii split over {world} GPUs + one all-reduce(MAX) of the mask "
-                                       f"(perturb replicated)") if radius_mode else
+                       "parallelism": (f"one box over {world} GPUs: x-slab deposit + all-reduce(SUM), radii split + "
+                                       f"all-reduce(MAX) of the mask") if radius_mode else
                                       f"{world} independent coeval boxes (one per GPU)",
                        "l2": f"inputs larger than L2 (every pass streams a {4 * N / 1e6:.0f} MB box; L2 is 126 MB)",
                        "ms_perturb": ms_perturb, "ms_ionize": ms_ionize, "global_xH": xh_dev,

@@ -275,6 +275,16 @@ int b200_ComputePerturbedField_device(float redshift, InitialConditions *d_boxes
                                       PerturbedField *d_perturbed_field);
 int b200_ComputeIonizedBox_device(float redshift, float prev_redshift,
                                   PerturbedField *d_perturbed_field, IonizedBox *d_box);
+/* Slab-parallel particle deposit of ONE box across `nparts` GPUs (move_grid_masses,
+   map_mass.c:146-208: the deposit is a sum over particles).  phase 0: rank `part` deposits the
+   particles of its x-slab into d_acc (N 64-bit fixed-point integers, device, zeroed by the call);
+   the caller all-reduces d_acc with SUM over the ranks (integer addition: bit-identical to the
+   single-GPU deposit); phase 1: every rank normalises the merged accumulator and runs the
+   density / velocity FFT chain (PerturbedField.c:212-387).  ZELDOVICH / 2LPT with an integer
+   DIM / HII_DIM ratio only. */
+int b200_ComputePerturbedField_device_part(float redshift, InitialConditions *d_boxes,
+                                           PerturbedField *d_perturbed_field,
+                                           unsigned long long *d_acc, int part, int nparts, int phase);
 /* Radius-parallel ionisation of ONE box across `nparts` GPUs (one process per GPU).  The filter
    radii of find_HII_bubbles (IonisationBox.c:1531-1630) are independent given the k-space density
    and their ionised flags combine by OR, so rank `part` runs the radii k = part (mod nparts):

@@ -25,8 +25,12 @@ inputs = common.make_inputs(hii=64, dim=128, seed=777)
 ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
 pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=be)
 whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=be)
-dens = torch.from_numpy(pf.density).cuda()
-part = pkg.ionize_radius_parallel(redshift=8.0, density=dens, inputs=inputs, backend=be)
+names = ["hires_density", "lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+ppf = pkg.perturb_slab_parallel(redshift=8.0, ics={{k: torch.from_numpy(getattr(ics, k)).cuda() for k in names}},
+                                inputs=inputs, backend=be)
+for k in ("density", "velocity_z"):
+    assert np.array_equal(ppf[k].cpu().numpy(), getattr(pf, k)), k
+part = pkg.ionize_radius_parallel(redshift=8.0, density=ppf["density"], inputs=inputs, backend=be)
 for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion"):
     a, b = part[k].cpu().numpy(), getattr(whole, k).reshape(part[k].shape)
     assert np.array_equal(a, b), (k, float(np.abs(a - b).max()))

@@ -63,8 +63,13 @@ emu = common.emu_backend()
 inputs = common.make_inputs(hii=32, dim=64, seed=4242)            # the SAME box on every rank
 ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
 pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+names = ["hires_density", "lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+ppf = pkg.perturb_slab_parallel(redshift=8.0, ics={{k: torch.from_numpy(getattr(ics, k)) for k in names}},
+                                inputs=inputs, backend=emu)
+for k in ("density", "velocity_z"):                                 # slab deposit + all_reduce(SUM): bit-identical
+    assert np.array_equal(ppf[k].numpy(), getattr(pf, k)), k
 whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
-part = pkg.ionize_radius_parallel(redshift=8.0, density=torch.from_numpy(pf.density), inputs=inputs, backend=emu)
+part = pkg.ionize_radius_parallel(redshift=8.0, density=ppf["density"], inputs=inputs, backend=emu)
 for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion"):
     a, b = part[k].numpy(), getattr(whole, k).reshape(part[k].shape)
     assert np.array_equal(a, b), (k, np.abs(a - b).max())          # bit-identical to the one-rank ladder
