@@ -596,6 +596,38 @@ void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {
     run_strided(p->px, box, box, (long long)ny * pitch, ny * pitch, 0, 1, -1, pro.post_scale, nullptr, p);
 }
 
+/* ------------------------------------------------------------------ in-place k-space window */
+struct KWinArgs {
+    int nx, ny, nz, nzc, pitch;
+    int type;
+    float R;
+    double R_param, r_const, dkx, dky, dkz;
+    float2 *box;
+};
+/* filter_box (filtering.c:308-394) as a separate pass: box *= W(k R), rounded to float */
+__global__ void kspace_window_kernel(KWinArgs a) {
+    const long long rows = (long long)a.nx * a.ny;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int ix = (int)(row / a.ny), iy = (int)(row - (long long)ix * a.ny);
+        const float kx = kf_of_index(ix, a.nx, a.dkx), ky = kf_of_index(iy, a.ny, a.dky);
+        for (int iz = threadIdx.x; iz < a.nzc; iz += blockDim.x) {
+            const float kz = (float)((double)iz * a.dkz);
+            const double W = window_value(a.type, kmag_sq_f(kx, ky, kz), a.R, a.R_param, a.r_const);
+            float2 v = a.box[row * a.pitch + iz];
+            v.x = (float)((double)v.x * W);
+            v.y = (float)((double)v.y * W);
+            a.box[row * a.pitch + iz] = v;
+        }
+    }
+}
+void fft_apply_window(Fft3D *p, float2 *box, const KMul &km) {
+    KWinArgs a = {p->nx, p->ny, p->nz, p->nzc, p->pitch, km.filter_type, km.R, km.R_param, km.r_const,
+                  km.dk[0], km.dk[1], km.dk[2], box};
+    const long long rows = (long long)p->nx * p->ny;
+    const int cap = dev_num_sms() * 16;
+    B200_LAUNCH(kspace_window_kernel, (int)(rows < cap ? rows : cap), 128, 0, a);
+}
+
 /* ------------------------------------------------------------------ window table */
 struct WTabArgs {
     int type, n;

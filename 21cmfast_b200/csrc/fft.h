@@ -96,6 +96,8 @@ void window_table_build(const Fft3D *p, int type, float R, double dk, float *out
 size_t window_table3_size(const Fft3D *p);
 void window_table_expand(const Fft3D *p, const float *tab, float *out3);
 
+/* box *= W(kR) in place (the exact double window of filter_box, rounded to float per mode) */
+void fft_apply_window(Fft3D *p, float2 *box, const KMul &km);
 /* forward: real (padded or pro.src) -> complex in `box` */
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro);
 /* inverse: complex `src` -> real in `work` (src may equal work); optional k-space multiplier */

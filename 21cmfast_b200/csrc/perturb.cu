@@ -485,9 +485,12 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
     const double dk0 = 2.0 * M_PI / so->BOX_LEN, dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
     km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
     if (mo->SMOOTH_EVOLVED_DENSITY_FIELD) {
-        /* the smoothed k-space box is also what the velocities are derived from, so smooth in
-           place first (window only, no transform) */
-        b200_throw(B200_ValueError, "SMOOTH_EVOLVED_DENSITY_FIELD is outside the scoped path");
+        /* gaussian smoothing of the evolved field (PerturbedField.c:221-227); the smoothed k-space
+           box is also what the velocities are derived from, so it is smoothed in place */
+        KMul ks = km;
+        ks.kind = KMUL_FILTER; ks.filter_type = 2;
+        ks.R = (float)(so->DENSITY_SMOOTH_RADIUS * so->BOX_LEN / (float)so->HII_DIM);
+        fft_apply_window(plan, kbox, ks);
     }
     ZEpilogue epi;
     epi.scale = 1.f / (float)N;

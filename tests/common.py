@@ -24,13 +24,14 @@ TOL_MASK_FRACTION = 1e-4  # fraction of cells whose ionised flag may differ (thr
 
 
 def make_inputs(hii=32, dim=None, box_len=None, source="E-INTEGRAL", hii_filter="spherical-tophat",
-                seed=12345, perturb="2LPT", n_threads=1, **astro):
+                seed=12345, perturb="2LPT", n_threads=1, smooth_evolved=False, **astro):
     dim = dim or 2 * hii
     box_len = box_len or 1.5 * hii
     return pkg.InputParameters(
         random_seed=seed,
         simulation_options=pkg.SimulationOptions(HII_DIM=hii, DIM=dim, BOX_LEN=box_len, N_THREADS=n_threads),
-        matter_options=pkg.MatterOptions(SOURCE_MODEL=source, PERTURB_ALGORITHM=perturb),
+        matter_options=pkg.MatterOptions(SOURCE_MODEL=source, PERTURB_ALGORITHM=perturb,
+                                         SMOOTH_EVOLVED_DENSITY_FIELD=smooth_evolved),
         astro_params=pkg.AstroParams(**astro),
         astro_options=pkg.AstroOptions(USE_EXP_FILTER=False, CELL_RECOMB=False, USE_LYA_HEATING=False,
                                        USE_UPPER_STELLAR_TURNOVER=False, HII_FILTER=hii_filter),

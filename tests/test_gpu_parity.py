@@ -82,6 +82,22 @@ def test_filter_512_vs_reference(gpu, filter_flag):
     assert np.abs(out - exp).max() <= 5e-6 * np.abs(exp).max()
 
 
+def test_smoothed_evolved_density_vs_reference(gpu):
+    """SMOOTH_EVOLVED_DENSITY_FIELD=True (PerturbedField.c:221-227): gaussian smoothing of the evolved
+    field in k space, velocities derived from the smoothed box."""
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    inputs = common.make_inputs(hii=64, dim=128, smooth_evolved=True)
+    r_ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    r_pf = pkg.perturb_field(redshift=7.0, initial_conditions=r_ics, backend=ref)
+    pf = pkg.perturb_field(redshift=7.0, initial_conditions=r_ics, backend=gpu)
+    common.compare_struct(pf, r_pf, tols={"velocity_z": common.TOL_VELOCITY})
+    plain = pkg.perturb_field(redshift=7.0, initial_conditions=pkg.compute_initial_conditions(
+        inputs=common.make_inputs(hii=64, dim=128), backend=ref), backend=gpu)
+    assert pf.density.std() < plain.density.std()   # the smoothing did something
+
+
 def _tophat_profile(r, R):
     return np.where(r < R, 3.0 / (4 * np.pi * R**3), 0.0)
 

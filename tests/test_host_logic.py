@@ -144,3 +144,16 @@ def test_error_codes_follow_reference_convention():
                                    C.byref(ics.cstruct), C.byref(ib.cstruct))
     assert st == 3  # ValueError: outside the scoped path, reported through the status code
     assert (prev.z_reion == -1).all()  # first-snapshot side effect on the previous box is preserved
+
+
+def test_emulated_smoothed_perturb_matches_reference():
+    """SMOOTH_EVOLVED_DENSITY_FIELD through the host-emulated kernels against the compiled reference
+    (CPU tier twin of tests/test_gpu_parity.py::test_smoothed_evolved_density_vs_reference)."""
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    inputs = common.make_inputs(hii=16, dim=32, smooth_evolved=True)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    r_pf = pkg.perturb_field(redshift=7.0, initial_conditions=ics, backend=ref)
+    pf = pkg.perturb_field(redshift=7.0, initial_conditions=ics, backend=emu)
+    common.compare_struct(pf, r_pf, tols={"velocity_z": common.TOL_VELOCITY})
