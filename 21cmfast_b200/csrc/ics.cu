@@ -17,6 +17,12 @@
 #include "host_numerics.h"
 #include "host_physics.h"
 
+/* gslrng.cu */
+struct GslStream;
+GslStream *gsl_stream_create(unsigned long mt_seed);
+void gsl_stream_destroy(GslStream *s);
+void gsl_stream_gaussians(GslStream *s, double *d_out, long long want);
+
 #include <vector>
 
 /* ------------------------------------------------------------------ power spectrum on device */
@@ -279,8 +285,13 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
         } else {
             PsConsts ps;
             ps_export_consts(&ps);
+            /* B200_IC_RNG: unset / "stream" = the reference's GSL mt19937 polar-Gaussian stream generated
+               on the device in stream order (gslrng.cu; seed parity with N_THREADS = 1);
+               "host" = the same stream from the sequential host generator (slow: ~26 ns per Gaussian);
+               "device" = a counter-based Philox field with the same P(k) (no seed parity; benchmarks) */
             const char *mode = getenv("B200_IC_RNG");
             const bool device_rng = mode && strcmp(mode, "device") == 0;
+            const bool host_rng = mode && strcmp(mode, "host") == 0;
             ModeArgs ma;
             memset(&ma, 0, sizeof(ma));
             ma.nx = hn[0]; ma.ny = hn[1]; ma.nz = hn[2]; ma.nzc = nzc_modes; ma.pitch = nzc;
@@ -292,21 +303,38 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
             } else {
                 unsigned int seeds[1];
                 hostnum::derive_thread_seeds(random_seed, 1, seeds);
-                hostnum::Mt19937 rng(seeds[0]);
                 const long long plane = (long long)hn[1] * nzc_modes;
-                int slab = (int)(((long long)1 << 24) / plane);
+                /* x-slabs of up to 2^25 modes (2^26 Gaussians, 512 MB of doubles) */
+                int slab = (int)(((long long)1 << (host_rng ? 24 : 25)) / plane);
                 if (slab < 1) slab = 1;
                 if (slab > hn[0]) slab = hn[0];
-                std::vector<double> host_g((size_t)slab * plane * 2);
                 DevBuf<double> d_g((size_t)slab * plane * 2);
-                for (int x0 = 0; x0 < hn[0]; x0 += slab) {
-                    const int nxs = (x0 + slab <= hn[0]) ? slab : hn[0] - x0;
-                    const long long cnt = (long long)nxs * plane * 2;
-                    for (long long i = 0; i < cnt; i++) host_g[i] = rng.ugaussian();
-                    h2d(d_g, host_g.data(), cnt * sizeof(double));
-                    ma.x0 = x0; ma.nxs = nxs; ma.gauss = d_g;
-                    B200_LAUNCH(ic_modes_kernel, flat_blocks, 256, 0, ma);
-                    dev_sync(); /* host_g is refilled next iteration */
+                if (host_rng) {
+                    hostnum::Mt19937 rng(seeds[0]);
+                    std::vector<double> host_g((size_t)slab * plane * 2);
+                    for (int x0 = 0; x0 < hn[0]; x0 += slab) {
+                        const int nxs = (x0 + slab <= hn[0]) ? slab : hn[0] - x0;
+                        const long long cnt = (long long)nxs * plane * 2;
+                        for (long long i = 0; i < cnt; i++) host_g[i] = rng.ugaussian();
+                        h2d(d_g, host_g.data(), cnt * sizeof(double));
+                        ma.x0 = x0; ma.nxs = nxs; ma.gauss = d_g;
+                        B200_LAUNCH(ic_modes_kernel, flat_blocks, 256, 0, ma);
+                        dev_sync(); /* host_g is refilled next iteration */
+                    }
+                } else {
+                    GslStream *gs = gsl_stream_create(seeds[0]);
+                    try {
+                        for (int x0 = 0; x0 < hn[0]; x0 += slab) {
+                            const int nxs = (x0 + slab <= hn[0]) ? slab : hn[0] - x0;
+                            gsl_stream_gaussians(gs, d_g, (long long)nxs * plane * 2);
+                            ma.x0 = x0; ma.nxs = nxs; ma.gauss = d_g;
+                            B200_LAUNCH(ic_modes_kernel, flat_blocks, 256, 0, ma);
+                        }
+                    } catch (...) {
+                        gsl_stream_destroy(gs);
+                        throw;
+                    }
+                    gsl_stream_destroy(gs);
                 }
             }
             ConjArgs ca = {hn[0], hn[1], hn[2], nzc_modes, nzc, K0};

@@ -297,6 +297,14 @@ int b200_ComputeIonizedBox_device_part(float redshift, float prev_redshift,
                                        PerturbedField *d_perturbed_field, IonizedBox *d_box,
                                        unsigned char *d_mask, int part, int nparts, int phase);
 
+/* Test hooks for the random stream of sample_ic_modes (InitialConditions.c:103-139; rng.c:31-90):
+   n1 then n2 values of gsl_ran_ugaussian on gsl_rng_mt19937 seeded with mt_seed, produced by the
+   device pipeline (csrc/gslrng.cu) resp. by the sequential host generator; and the sequential
+   conversion rule on a given array of raw 32-bit words (returns the words consumed, -1 if short). */
+int b200_gsl_gaussian_stream(unsigned long mt_seed, long long n1, long long n2, double *host_out);
+int b200_host_gaussian_stream(unsigned long mt_seed, long long n, double *host_out);
+long long b200_gaussians_from_raw_host(const unsigned int *raw, long long n_raw, long long want, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,21 @@ def test_filter_512_vs_reference(gpu, filter_flag):
     assert np.abs(out - exp).max() <= 5e-6 * np.abs(exp).max()
 
 
+def test_device_gaussian_stream(gpu):
+    """The reference's mt19937 polar-Gaussian stream generated on the GPU (csrc/gslrng.cu) against the
+    sequential host generator: same values in the same order (the device's log() may differ from
+    glibc's in the last bit), across two consecutive requests (carried-over words)."""
+    lib = gpu.lib
+    lib.b200_gsl_gaussian_stream.argtypes = [C.c_ulong, C.c_longlong, C.c_longlong, C.POINTER(C.c_double)]
+    lib.b200_host_gaussian_stream.argtypes = [C.c_ulong, C.c_longlong, C.POINTER(C.c_double)]
+    for seed, n1, n2 in ((12345, 3_000_000, 1_000_001), (7, 17, 5)):
+        a = np.zeros(n1 + n2); b = np.zeros(n1 + n2)
+        assert lib.b200_gsl_gaussian_stream(seed, n1, n2, a.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert lib.b200_host_gaussian_stream(seed, n1 + n2, b.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert np.abs(a - b).max() <= 1e-14 * max(1.0, np.abs(b).max()), np.abs(a - b).max()
+        assert (a == b).mean() > 0.99
+
+
 def test_smoothed_evolved_density_vs_reference(gpu):
     """SMOOTH_EVOLVED_DENSITY_FIELD=True (PerturbedField.c:221-227): gaussian smoothing of the evolved
     field in k space, velocities derived from the smoothed box."""

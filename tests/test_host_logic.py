@@ -157,3 +157,68 @@ def test_emulated_smoothed_perturb_matches_reference():
     r_pf = pkg.perturb_field(redshift=7.0, initial_conditions=ics, backend=ref)
     pf = pkg.perturb_field(redshift=7.0, initial_conditions=ics, backend=emu)
     common.compare_struct(pf, r_pf, tols={"velocity_z": common.TOL_VELOCITY})
+
+
+def _np_gaussians_from_raw(raw, want):
+    """GSL rules in numpy/python: uniform_pos redraws zero words, polar Box-Muller keeps y."""
+    out, p = [], 0
+    def upos():
+        nonlocal p
+        while True:
+            w = int(raw[p]); p += 1
+            if w != 0:
+                return w / 4294967296.0
+    while len(out) < want:
+        x = -1 + 2 * upos(); y = -1 + 2 * upos()
+        r2 = x * x + y * y
+        if r2 > 1.0 or r2 == 0:
+            continue
+        out.append(y * math.sqrt(-2.0 * math.log(r2) / r2))
+    return np.array(out), p
+
+
+def test_device_gaussian_stream_equals_sequential_generator():
+    """csrc/gslrng.cu (three-step parallel MT19937 refresh, data-parallel polar attempts, prefix-sum
+    placement) through the host-emulated kernels == the sequential generator, bit for bit, across
+    refresh boundaries, chunk boundaries and carried-over words; and the MT19937 words themselves
+    against numpy's legacy seeding."""
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    lib = emu.lib
+    lib.b200_gsl_gaussian_stream.argtypes = [C.c_ulong, C.c_longlong, C.c_longlong, C.POINTER(C.c_double)]
+    lib.b200_host_gaussian_stream.argtypes = [C.c_ulong, C.c_longlong, C.POINTER(C.c_double)]
+    for seed, n1, n2 in ((12345, 1000, 3), (1, 5, 70001), (4357, 20000, 20000), (987654321, 1, 1)):
+        a = np.zeros(n1 + n2); b = np.zeros(n1 + n2)
+        assert lib.b200_gsl_gaussian_stream(seed, n1, n2, a.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert lib.b200_host_gaussian_stream(seed, n1 + n2, b.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert np.array_equal(a, b), (seed, n1, n2, np.flatnonzero(a != b)[:5])
+    # the sequential generator itself against numpy's MT19937 (legacy seeding = init_genrand)
+    rs = np.random.RandomState(12345)
+    raw = rs.randint(0, 2**32, size=4000, dtype=np.uint64).astype(np.uint32)
+    exp, _ = _np_gaussians_from_raw(raw, 1000)
+    got = np.zeros(1000)
+    lib.b200_host_gaussian_stream(12345, 1000, got.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.allclose(got, exp, rtol=0, atol=1e-15)
+
+
+def test_gaussians_from_raw_redraws_zero_words():
+    """The sequential fallback used for chunks that contain a zero word (GSL's uniform_pos redraws
+    it, which shifts the pairing of all later words)."""
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    lib = emu.lib
+    lib.b200_gaussians_from_raw_host.argtypes = [C.POINTER(C.c_uint), C.c_longlong, C.c_longlong, C.POINTER(C.c_double)]
+    lib.b200_gaussians_from_raw_host.restype = C.c_longlong
+    rng = np.random.default_rng(3)
+    raw = rng.integers(1, 2**32, size=5000, dtype=np.uint64).astype(np.uint32)
+    raw[[0, 7, 8, 1001, 2500]] = 0
+    exp, used = _np_gaussians_from_raw(raw, 1500)
+    got = np.zeros(1500)
+    n = lib.b200_gaussians_from_raw_host(raw.ctypes.data_as(C.POINTER(C.c_uint)), len(raw), 1500,
+                                         got.ctypes.data_as(C.POINTER(C.c_double)))
+    assert n == used
+    assert np.allclose(got, exp, rtol=0, atol=1e-15)
+    assert lib.b200_gaussians_from_raw_host(raw.ctypes.data_as(C.POINTER(C.c_uint)), 100, 1500,
+                                            got.ctypes.data_as(C.POINTER(C.c_double))) == -1
