@@ -15,7 +15,7 @@
  *   1. raw words: within one 624-word refresh, words 0..226 depend only on the old state, words
  *      227..453 on the old state and on new words 0..226, words 454..623 on new words 227..396 (and
  *      new word 0): three data-parallel steps per refresh, run by ONE CTA (the generator itself is a
- *      single chain; ~5 G words/s on one SM, while every other stage uses the whole GPU);
+ *      single chain; measured ~0.75 G words/s on one SM, while every other stage uses the whole GPU);
  *   2. every polar attempt consumes exactly two words, accepted or not, so attempt i always owns
  *      words 2i, 2i+1: acceptance is data-parallel, and the j-th Gaussian is the j-th accepted
  *      attempt -- an exclusive prefix sum over the accept flags gives each accepted attempt its place;
