@@ -601,6 +601,8 @@ struct IonDeviceIO {
     float *xH, *z_reion, *Tk, *nion; /* device, N each; Tk / nion may be null */
     int wait_slot = -1;     /* copy-stream event that must have fired before xH / Tk / prev_zre are read
                                (their upload overlaps the radius ladder), or -1 */
+    bool *nion_written = nullptr; /* out: the ladder stored a grid in `nion` (the reference leaves the
+                                     caller's zero-initialised array untouched when it exits early) */
 };
 
 /* pinned staging that outlives a call (cudaMallocHost is too slow to repeat per call) */
@@ -815,6 +817,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
            materialised */
         const bool last = (k == n_todo - 1);
         float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : nullptr;
+        if (last && io.nion && io.nion_written) *io.nion_written = true;
         const float *filtered = reinterpret_cast<const float *>(work[j & 1]);
         SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
         sweep_smem_optin();
@@ -905,13 +908,14 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
             h2d_copy_stream(d_prev, previous_ionize_box->z_reion, N * sizeof(float));
         }
         copy_event_record(slot);
-        IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p, slot};
+        bool nion_written = false;
+        IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p, slot, &nion_written};
         ionize_core(redshift, prev_redshift, io, box);
 
         d2h(box->neutral_fraction, d_xH, N * sizeof(float));
         d2h(box->z_reion, d_zre, N * sizeof(float));
         if (want_Tk) d2h(box->kinetic_temperature, d_Tk, N * sizeof(float));
-        if (d_nion.p) d2h(box->unnormalised_nion, d_nion, N * sizeof(float));
+        if (d_nion.p && nion_written) d2h(box->unnormalised_nion, d_nion, N * sizeof(float));
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
         try { copy_stream_sync(); } catch (B200Error &) {} /* no copy may outlive the buffers released above */

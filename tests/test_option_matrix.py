@@ -1,0 +1,125 @@
+"""Option matrix of the scoped path against the compiled reference (oracle/_ref): non-cubic boxes,
+3-D velocities, HMF / integration-method / filter variants, MINIMIZE_MEMORY, and the early exit of a
+(nearly) neutral box.  The same cases run on the CPU tier through the host-emulated kernels and on the
+GPU tier through the CUDA library."""
+import numpy as np
+import pytest
+
+import common
+
+pkg = common.pkg
+
+CASES = {
+    "noncubic": dict(sim=dict(NON_CUBIC_FACTOR=1.5)),
+    "keep_3d_velocities": dict(matter=dict(KEEP_3D_VELOCITIES=True)),
+    "hmf_ps": dict(matter=dict(HMF="PS")),
+    "hmf_ps_const_zeta": dict(matter=dict(HMF="PS", SOURCE_MODEL="CONST-ION-EFF")),
+    "qag_integrals": dict(aopt=dict(INTEGRATION_METHOD_ATOMIC="GSL-QAG")),
+    "minimize_memory": dict(matter=dict(MINIMIZE_MEMORY=True)),
+    "gaussian_filter_const_zeta": dict(matter=dict(SOURCE_MODEL="CONST-ION-EFF"), aopt=dict(HII_FILTER="gaussian")),
+    "sharp_k_zeldovich": dict(matter=dict(PERTURB_ALGORITHM="ZELDOVICH"), aopt=dict(HII_FILTER="sharp-k")),
+    "neutral_box_z25": dict(z=25.0),
+    "noncubic_neutral_z25": dict(sim=dict(NON_CUBIC_FACTOR=1.5), z=25.0),
+    "barely_ionised_z18": dict(z=18.0),
+}
+
+
+def _inputs(sim=None, matter=None, aopt=None, astro=None, seed=99, **_):
+    sim = {**dict(HII_DIM=24, DIM=48, BOX_LEN=36.0, N_THREADS=1), **(sim or {})}
+    matter = {**dict(SOURCE_MODEL="E-INTEGRAL", PERTURB_ALGORITHM="2LPT"), **(matter or {})}
+    aopt = {**dict(USE_EXP_FILTER=False, CELL_RECOMB=False, USE_LYA_HEATING=False,
+                   USE_UPPER_STELLAR_TURNOVER=False), **(aopt or {})}
+    return pkg.InputParameters(
+        random_seed=seed, simulation_options=pkg.SimulationOptions(**sim),
+        matter_options=pkg.MatterOptions(**matter), astro_params=pkg.AstroParams(**(astro or {})),
+        astro_options=pkg.AstroOptions(**aopt))
+
+
+def _run_case(be, ref, name):
+    kw = CASES[name]
+    z = kw.get("z", 8.0)
+    inputs = _inputs(**kw)
+    r_ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    common.compare_struct(ics, r_ics)
+    r_pf = pkg.perturb_field(redshift=z, initial_conditions=r_ics, backend=ref)
+    pf = pkg.perturb_field(redshift=z, initial_conditions=r_ics, backend=be)
+    common.compare_struct(pf, r_pf, tols={k: common.TOL_VELOCITY for k in ("velocity_x", "velocity_y", "velocity_z")})
+    r_ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=r_ics, backend=ref)
+    ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=r_ics, backend=be)
+    stats = common.compare_ionized(ib, r_ib)
+    assert stats["mask_mismatch"] == 0
+    for k in ("neutral_fraction", "z_reion", "unnormalised_nion"):
+        assert np.isfinite(getattr(ib, k)).all(), k
+    assert abs(ib.mean_f_coll - r_ib.mean_f_coll) <= 1e-12 * abs(r_ib.mean_f_coll)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_option_matrix_emulated_vs_reference(name):
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    _run_case(emu, ref, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_option_matrix_gpu_vs_reference(name):
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    _run_case(common.gpu_backend(), ref, name)
+
+
+def _status_of(fn):
+    try:
+        fn()
+    except pkg.BackendError as e:
+        return e.code
+    return 0
+
+
+def _unsupported_cases(be):
+    """Options outside the scoped path must fail loudly with the reference's ValueError code (3),
+    never fall back or return silently (exceptions.h:12-21)."""
+    base = _inputs()
+    ics = pkg.compute_initial_conditions(inputs=base, backend=be)
+    pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=be)
+    import dataclasses
+
+    def with_opts(**kw):
+        ao = dataclasses.replace(base.astro_options, **kw)
+        return dataclasses.replace(base, astro_options=ao)
+
+    for kw in (dict(USE_TS_FLUCT=True), dict(RECOMB_MODEL="homogeneous"), dict(IONISE_ENTIRE_SPHERE=True)):
+        inp = with_opts(**kw)
+        be.state.init(inp, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+        box = pkg.IonizedBox.new(inp, 8.0)
+        prev_pf, prev_ion = pkg.PerturbedField.initial(inp), pkg.IonizedBox.initial(inp)
+        ts, hb = pkg.outputs.TsBox.dummy(inp), pkg.outputs.HaloBox.dummy(inp)
+        import ctypes as C
+        st = be.lib.ComputeIonizedBox(C.c_float(8.0), C.c_float(-1.0), C.byref(pf.cstruct), C.byref(prev_pf.cstruct),
+                                      C.byref(prev_ion.cstruct), C.byref(ts.cstruct), C.byref(hb.cstruct),
+                                      C.byref(ics.cstruct), C.byref(box.cstruct))
+        assert st == 3, (kw, st)
+    hi = dataclasses.replace(base, matter_options=dataclasses.replace(base.matter_options, PERTURB_ON_HIGH_RES=True))
+    be.state.init(hi, broadcast_inputs=True)
+    assert _status_of(lambda: pkg.perturb_field(redshift=8.0, initial_conditions=dataclasses.replace(ics, inputs=hi)
+                                                if dataclasses.is_dataclass(ics) else _retag(ics, hi), backend=be)) == 3
+
+
+def _retag(struct, inputs):
+    struct.inputs = inputs
+    return struct
+
+
+def test_unsupported_options_fail_loudly_emulated():
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    _unsupported_cases(emu)
+
+
+@pytest.mark.gpu
+def test_unsupported_options_fail_loudly_gpu():
+    _unsupported_cases(common.gpu_backend())
