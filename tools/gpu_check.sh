@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > "$O/box.tx
 ( time python -m pytest tests -m gpu -q -x ) > "$O/pytest_gpu.log" 2>&1; tail -4 "$O/pytest_gpu.log"
 python __graft_entry__.py smoke > "$O/smoke.log" 2>&1; tail -2 "$O/smoke.log"
 python bench.py --steps 5 --warmup 3 > "$O/bench_512.json" 2> "$O/bench_512.err"; tail -2 "$O/bench_512.err"
-python bench.py --steps 5 --warmup 3 --hii-dim 256 --box-len 300 --r-bubble-max 15 --ref-hii-dim 128 > "$O/bench_256.json" 2> "$O/bench_256.err"; tail -2 "$O/bench_256.err"
+python bench.py --steps 5 --warmup 3 --hii-dim 256 --box-len 300 --r-bubble-max 15 --ref-hii-dim 128 --no-cpu-baseline > "$O/bench_256.json" 2> "$O/bench_256.err"; tail -2 "$O/bench_256.err"
 python bench.py --impl reference --steps 1 --warmup 1 > "$O/bench_ref.json" 2> "$O/bench_ref.err"; tail -2 "$O/bench_ref.err"
 # launch list (cold-cache, serialised): one warm-up + one timed step at the default workload
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file "$O/launches_256.csv" \
