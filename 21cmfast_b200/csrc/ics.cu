@@ -2,7 +2,8 @@
  * ics.cu -- ComputeInitialConditions: Gaussian random field + Zel'dovich / 2LPT displacement
  * fields (reference InitialConditions.c:26-772, rng.c:31-90).
  *
- * Scope: V_CB_MODEL without fluctuations, PERTURB_ON_HIGH_RES = False, analytic power spectra.
+ * Scope: V_CB_MODEL without fluctuations, analytic power spectra; velocities on the low-res grid
+ * (default) or, with PERTURB_ON_HIGH_RES, unfiltered on the hi-res grid.
  *
  * Random numbers: with the default B200_IC_RNG=gsl the Gaussian stream is the reference's own for
  * N_THREADS = 1 -- GSL-seeded MT19937 feeding the polar Box-Muller, two deviates per mode in
@@ -249,7 +250,6 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
         const MatterOptions *mo = matter_options_global;
         if (!boxes || !boxes->hires_density || !boxes->lowres_density)
             b200_throw(B200_ValueError, "ComputeInitialConditions: NULL struct/array");
-        if (mo->PERTURB_ON_HIGH_RES) b200_throw(B200_ValueError, "PERTURB_ON_HIGH_RES=True is outside the scoped path");
         if (mo->V_CB_MODEL == 2) b200_throw(B200_ValueError, "V_CB_MODEL=FLUCTS (CLASS tables) is outside the scoped path");
         const int hn[3] = {so->DIM, so->DIM, d_para()};
         const int ln[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
@@ -365,19 +365,36 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
         fft_c2r(plan, K0, W, lowpass, plain);
         to_lowres(boxes->lowres_density, 1.f / VOLUME);
 
-        /* Zel'dovich velocities (compute_velocity_fields, :299-364) */
-        float *vel[3] = {boxes->lowres_vx, boxes->lowres_vy, boxes->lowres_vz};
+        /* Zel'dovich velocities (compute_velocity_fields, :299-364): low-pass filtered and sub-sampled
+           onto the low-res grid, or (PERTURB_ON_HIGH_RES) unfiltered on the hi-res grid */
+        const bool on_hires = mo->PERTURB_ON_HIGH_RES;
+        DevBuf<float> d_hv(on_hires ? (size_t)M : 0);
+        auto to_hires = [&](float *host_dst, const KMul &km, const float2 *kbox_src, float scale) {
+            ZEpilogue e;
+            e.scale = scale; e.dst = d_hv; e.dst_row_stride = hn[2];
+            fft_c2r(plan, kbox_src, W, km, e);
+            d2h(host_dst, d_hv, M * sizeof(float));
+        };
+        float *vel[3] = {on_hires ? boxes->hires_vx : boxes->lowres_vx, on_hires ? boxes->hires_vy : boxes->lowres_vy,
+                         on_hires ? boxes->hires_vz : boxes->lowres_vz};
         for (int ax = 0; ax < 3; ax++) {
-            if (!vel[ax]) b200_throw(B200_ValueError, "lowres velocity array is NULL");
-            KMul km = lowpass;
+            if (!vel[ax]) b200_throw(B200_ValueError, "velocity array of the initial conditions is NULL");
+            KMul km = on_hires ? KMul() : lowpass;
+            km.dk[0] = dk[0]; km.dk[1] = dk[1]; km.dk[2] = dk[2];
             km.op = KOP_GRADIENT_D; km.axis_a = ax;
-            fft_c2r(plan, K0, W, km, plain);
-            to_lowres(vel[ax], 1.f / VOLUME);
+            if (on_hires) {
+                to_hires(vel[ax], km, K0, 1.f / VOLUME);
+            } else {
+                fft_c2r(plan, K0, W, km, plain);
+                to_lowres(vel[ax], 1.f / VOLUME);
+            }
         }
 
         /* 2LPT (compute_velocity_fields_2LPT, :366-544) */
         if (mo->PERTURB_ALGORITHM == PERTURB_2LPT) {
-            float *vel2[3] = {boxes->lowres_vx_2LPT, boxes->lowres_vy_2LPT, boxes->lowres_vz_2LPT};
+            float *vel2[3] = {on_hires ? boxes->hires_vx_2LPT : boxes->lowres_vx_2LPT,
+                              on_hires ? boxes->hires_vy_2LPT : boxes->lowres_vy_2LPT,
+                              on_hires ? boxes->hires_vz_2LPT : boxes->lowres_vz_2LPT};
             float *scratch_out[3] = {boxes->hires_vx_2LPT, boxes->hires_vy_2LPT, boxes->hires_vz_2LPT};
             DevBuf<float> diag[3];
             DevBuf<float2> S(Mk);
@@ -391,7 +408,7 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
                 fft_c2r(plan, K0, W, km, e);
                 /* the reference leaves phi_ii in the hires_v*_2LPT arrays it used as scratch */
                 const char *skip = getenv("B200_SKIP_SCRATCH_OUTPUTS");
-                if (scratch_out[c] && !(skip && skip[0] == '1')) d2h(scratch_out[c], diag[c], M * sizeof(float));
+                if (scratch_out[c] && !on_hires && !(skip && skip[0] == '1')) d2h(scratch_out[c], diag[c], M * sizeof(float));
             }
             const int pairs[3][2] = {{0, 1}, {0, 2}, {1, 2}};
             for (int c = 0; c < 3; c++) {
@@ -409,11 +426,16 @@ extern "C" int ComputeInitialConditions(unsigned long long random_seed, InitialC
             ZPrologue pro;
             fft_r2c(plan, S, pro);
             for (int ax = 0; ax < 3; ax++) {
-                if (!vel2[ax]) b200_throw(B200_ValueError, "lowres 2LPT velocity array is NULL");
-                KMul km = lowpass;
+                if (!vel2[ax]) b200_throw(B200_ValueError, "2LPT velocity array of the initial conditions is NULL");
+                KMul km = on_hires ? KMul() : lowpass;
+                km.dk[0] = dk[0]; km.dk[1] = dk[1]; km.dk[2] = dk[2];
                 km.op = KOP_GRADIENT_D; km.axis_a = ax;
-                fft_c2r(plan, S, W, km, plain);
-                to_lowres(vel2[ax], 1.f);
+                if (on_hires) {
+                    to_hires(vel2[ax], km, S, 1.f);
+                } else {
+                    fft_c2r(plan, S, W, km, plain);
+                    to_lowres(vel2[ax], 1.f);
+                }
             }
         }
         g_stats.ms = timer.stop_ms();

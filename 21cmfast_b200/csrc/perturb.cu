@@ -295,6 +295,7 @@ struct AccToDeltaArgs {
     const unsigned long long *acc;
     float *padded;
     double mass_factor;
+    int to_delta; /* 1: (m * mass_factor) - 1 (normalise_delta_grid); 0: plain double -> float copy */
 };
 /* double -> float copy into the FFT layout (PerturbedField.c:115-128) + normalise_delta_grid (:180-210) */
 __global__ void acc_to_delta_kernel(AccToDeltaArgs a) {
@@ -302,8 +303,10 @@ __global__ void acc_to_delta_kernel(AccToDeltaArgs a) {
         for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
             const double m = (double)(long long)a.acc[row * a.nz + z] * (1.0 / FIXED_SCALE);
             float v = (float)m;
-            v = (float)((double)v * a.mass_factor);
-            v = v - 1.0f;
+            if (a.to_delta) {
+                v = (float)((double)v * a.mass_factor);
+                v = v - 1.0f;
+            }
             a.padded[row * 2 * a.nzc + z] = v;
         }
 }
@@ -323,6 +326,28 @@ __global__ void linear_density_kernel(LinearArgs a) {
 }
 
 /* ------------------------------------------------------------------ orchestration */
+struct ResampleArgs {
+    int ln[3], hn[3], h_pitch, l_pitch;
+    double ratio;
+    const float *hi_padded;
+    float *lo;          /* padded (l_pitch > 0) or unpadded (l_pitch == 0) low-res destination */
+    float scale, offset;
+};
+/* nearest-cell sub-sampling hi -> lo through resample_index (indexing.h:110-114):
+   lo = hi * scale + offset */
+__global__ void resample_kernel(ResampleArgs a) {
+    const long long n = (long long)a.ln[0] * a.ln[1] * a.ln[2];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % a.ln[2]), j = (int)((t / a.ln[2]) % a.ln[1]), i = (int)(t / ((long long)a.ln[2] * a.ln[1]));
+        const int hi = (int)(i * a.ratio + 0.5), hj = (int)(j * a.ratio + 0.5), hk = (int)(k * a.ratio + 0.5);
+        float v = a.hi_padded[(long long)hk + 2LL * a.h_pitch * ((long long)hj + (long long)a.hn[1] * hi)] * a.scale;
+        v = v + a.offset;
+        const long long dst = a.l_pitch ? (long long)k + 2LL * a.l_pitch * ((long long)j + (long long)a.ln[1] * i) : t;
+        a.lo[dst] = v;
+    }
+}
+
 /* host arrays still to be uploaded when perturb_core starts: the deposit then runs slab by slab
    behind the copies (ComputePerturbedField with a cold IC cache) */
 struct PendingUpload {
@@ -345,6 +370,115 @@ struct PerturbDeviceIO {
     float *density, *vel[3];     /* device outputs (vel[a] may be null) */
 };
 
+/* PERTURB_ON_HIGH_RES = True (PerturbedField.c:24-178, 284-387): the particles are deposited on the
+   hi-res grid with the hi-res velocity boxes, the evolved field is low-pass filtered (real-space
+   top-hat at the low-res cell scale) and sub-sampled, and the velocities are derived from the
+   unfiltered hi-res k-space field, filtered and sub-sampled.  io.v / io.v2 are DIM^3 boxes here. */
+static void perturb_core_hires(float redshift_f, const PerturbDeviceIO &io) {
+    const SimulationOptions *so = simulation_options_global;
+    const MatterOptions *mo = matter_options_global;
+    const double redshift = redshift_f;
+    const int hn[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
+    const int dn[3] = {so->DIM, so->DIM, d_para()};
+    const long long N = (long long)hn[0] * hn[1] * hn[2];
+    const long long M = (long long)dn[0] * dn[1] * dn[2];
+    Fft3D *plan = fft_plan(hn[0], hn[1], hn[2]);
+    Fft3D *hplan = fft_plan(dn[0], dn[1], dn[2]);
+    DevBuf<float2> kbox(plan->n_cplx()), work(plan->n_cplx());
+    DevBuf<float2> hk(hplan->n_cplx()), hsaved(hplan->n_cplx()), hwork(hplan->n_cplx());
+    float *padded = reinterpret_cast<float *>(kbox.p);
+    float *hpadded = reinterpret_cast<float *>(hk.p);
+    const int hrow_blocks = (int)((long long)dn[0] * dn[1] < 4096 ? (long long)dn[0] * dn[1] : 4096);
+    const int flat_blocks = dev_num_sms() * 8;
+    const double growth = dicke(redshift);
+    const double dk0 = 2.0 * M_PI / so->BOX_LEN, dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
+
+    if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR) {
+        LinearArgs la = {(long long)dn[0] * dn[1], dn[2], hplan->pitch, io.hires_density, hpadded, growth};
+        B200_LAUNCH(linear_density_kernel, hrow_blocks, 256, 0, la);
+    } else {
+        MoveArgs a;
+        memset(&a, 0, sizeof(a));
+        const double box_size[3] = {so->BOX_LEN, so->BOX_LEN, so->BOX_LEN * so->NON_CUBIC_FACTOR};
+        const double init_growth = dicke(so->INITIAL_REDSHIFT);
+        const double d2 = -(3.0 / 7.0) * growth * growth, d2i = -(3.0 / 7.0) * init_growth * init_growth;
+        for (int ax = 0; ax < 3; ax++) {
+            a.dn[ax] = dn[ax]; a.vn[ax] = dn[ax]; a.on[ax] = dn[ax];
+            a.v[ax] = io.v[ax];
+            a.v2[ax] = (mo->PERTURB_ALGORITHM == PERTURB_2LPT) ? io.v2[ax] : nullptr;
+            a.vdf[ax] = (growth - init_growth) / box_size[ax] * dn[ax];
+            a.vdf2[ax] = (d2 - d2i) / box_size[ax] * dn[ax];
+        }
+        a.dens = io.hires_density;
+        a.ratio_vel = 1.0; a.ratio_out = 1.0;
+        a.init_growth = init_growth;
+        DevBuf<unsigned long long> acc(M);
+        dev_zero(acc, M * sizeof(unsigned long long));
+        a.acc = acc;
+        launch_grouped<1>(a, 0, M); /* every particle is its own group */
+        AccToDeltaArgs ca = {(long long)dn[0] * dn[1], dn[2], hplan->pitch, acc, hpadded, 1.0, 0};
+        B200_LAUNCH(acc_to_delta_kernel, hrow_blocks, 256, 0, ca);
+    }
+
+    /* assign_to_lowres_grid (PerturbedField.c:137-178) */
+    ZPrologue pro;
+    fft_r2c(hplan, hk, pro);
+    d2d(hsaved, hk, hplan->n_cplx() * sizeof(float2));
+    KMul lowpass;
+    lowpass.kind = KMUL_FILTER; lowpass.filter_type = 0;
+    lowpass.R = (float)(pc::l_factor * so->BOX_LEN / (hn[0] + 0.0));
+    lowpass.dk[0] = dk0; lowpass.dk[1] = dk0; lowpass.dk[2] = dkz;
+    ZEpilogue plain;
+    fft_c2r(hplan, hk, hwork, lowpass, plain);
+    {
+        /* normalise_delta_grid with mass_factor = 1 (:180-210) rides on the sub-sampling */
+        const bool to_delta = mo->PERTURB_ALGORITHM != PERTURB_LINEAR;
+        ResampleArgs ra = {{hn[0], hn[1], hn[2]}, {dn[0], dn[1], dn[2]}, hplan->pitch, plan->pitch,
+                           dn[0] / (double)hn[0], reinterpret_cast<const float *>(hwork.p), padded,
+                           1.0f / (float)M, 0.f};
+        B200_LAUNCH(resample_kernel, flat_blocks, 256, 0, ra);
+        (void)to_delta;
+    }
+    if (mo->PERTURB_ALGORITHM != PERTURB_LINEAR) {
+        /* "*cell *= 1.0; *cell -= 1": a second, in-place pass keeps the reference's rounding sequence */
+        ResampleArgs rb = {{hn[0], hn[1], hn[2]}, {hn[0], hn[1], hn[2]}, plan->pitch, plan->pitch, 1.0,
+                           padded, padded, 1.0f, -1.0f};
+        B200_LAUNCH(resample_kernel, flat_blocks, 256, 0, rb);
+    }
+
+    /* smooth_and_clip_density (:212-282); the saved k-space box is the hi-res one */
+    fft_r2c(plan, kbox, pro);
+    if (mo->SMOOTH_EVOLVED_DENSITY_FIELD) {
+        KMul ks;
+        ks.dk[0] = dk0; ks.dk[1] = dk0; ks.dk[2] = dkz;
+        ks.kind = KMUL_FILTER; ks.filter_type = 2;
+        ks.R = (float)(so->DENSITY_SMOOTH_RADIUS * so->BOX_LEN / (float)so->HII_DIM);
+        fft_apply_window(plan, kbox, ks);
+    }
+    ZEpilogue epi;
+    epi.scale = 1.f / (float)N;
+    epi.clip = 1; epi.clip_lo = (float)(-1.0 + pc::FRACT_FLOAT_ERR); epi.clip_hi = 3.0e38f;
+    epi.dst = io.density; epi.dst_row_stride = hn[2];
+    fft_c2r(plan, kbox, work, KMul(), epi);
+
+    /* compute_perturbed_velocities on the hi-res grid (:284-387) */
+    if (so->HII_DIM > 1) {
+        const double dDdt_over_D = ddickedt(redshift) / dicke(redshift);
+        for (int ax = 0; ax < 3; ax++) {
+            if (!io.vel[ax]) continue;
+            KMul kv;
+            kv.dk[0] = dk0; kv.dk[1] = dk0; kv.dk[2] = dkz;
+            kv.op = KOP_VELOCITY_F; kv.axis_a = ax; kv.op_factor = dDdt_over_D / (double)M;
+            if (so->DIM != so->HII_DIM) { kv.kind = KMUL_FILTER; kv.filter_type = 0; kv.R = lowpass.R; }
+            fft_c2r(hplan, hsaved, hwork, kv, plain);
+            ResampleArgs rv = {{hn[0], hn[1], hn[2]}, {dn[0], dn[1], dn[2]}, hplan->pitch, 0,
+                               dn[0] / (double)hn[0], reinterpret_cast<const float *>(hwork.p), io.vel[ax], 1.0f, 0.f};
+            B200_LAUNCH(resample_kernel, flat_blocks, 256, 0, rv);
+        }
+    }
+    dev_sync(); /* the hi-res work boxes are released on return */
+}
+
 /* Slab-parallel deposit of ONE box on several GPUs ("PerturbField move+CIC"):
    phase 0: this rank deposits the groups of its x-slab [part, part+1) * HII_DIM / nparts into the
    caller's fixed-point accumulator `acc` (N x u64, zeroed here) and returns; the caller sums the
@@ -360,8 +494,15 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
                          const PerturbPartition &pt = PerturbPartition()) {
     const SimulationOptions *so = simulation_options_global;
     const MatterOptions *mo = matter_options_global;
-    if (mo->PERTURB_ON_HIGH_RES)
-        b200_throw(B200_ValueError, "PERTURB_ON_HIGH_RES=True is outside the scoped path");
+    if (mo->PERTURB_ON_HIGH_RES) {
+        if (pt.phase >= 0) b200_throw(B200_ValueError, "the slab-parallel deposit is not built for PERTURB_ON_HIGH_RES");
+        if (pending) {
+            const long long Mh = (long long)so->DIM * so->DIM * d_para();
+            upload_all(*pending, Mh, Mh); /* density and velocity boxes are all hi-res here */
+        }
+        perturb_core_hires(redshift_f, io);
+        return;
+    }
     const double redshift = redshift_f;
     const int hn[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
     const int dn[3] = {so->DIM, so->DIM, d_para()};
@@ -473,7 +614,7 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
 #endif
             B200_LAUNCH(move_cic_kernel, a.tiles[0] * a.tiles[1] * a.tiles[2], 256, smem, a);
         }
-        AccToDeltaArgs ca = {(long long)hn[0] * hn[1], hn[2], plan->pitch, acc, padded, (double)N / (double)M};
+        AccToDeltaArgs ca = {(long long)hn[0] * hn[1], hn[2], plan->pitch, acc, padded, (double)N / (double)M, 1};
         B200_LAUNCH(acc_to_delta_kernel, row_blocks, 256, 0, ca);
         /* acc returns to the pool at scope exit; reuse is stream-ordered (single stream) */
     }
@@ -528,10 +669,17 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
         const long long M = (long long)so->DIM * so->DIM * d_para();
         const bool linear = mo->PERTURB_ALGORITHM == PERTURB_LINEAR;
         const bool lpt2 = mo->PERTURB_ALGORITHM == PERTURB_2LPT;
-        const float *hv[7] = {linear ? boxes->lowres_density : boxes->hires_density,
-                              boxes->lowres_vx, boxes->lowres_vy, boxes->lowres_vz,
-                              boxes->lowres_vx_2LPT, boxes->lowres_vy_2LPT, boxes->lowres_vz_2LPT};
-        const size_t hn[7] = {(size_t)(linear ? N : M), (size_t)N, (size_t)N, (size_t)N, (size_t)N, (size_t)N, (size_t)N};
+        const bool on_hires = mo->PERTURB_ON_HIGH_RES;
+        /* PERTURB_ON_HIGH_RES: hi-res density also for LINEAR, hi-res velocity boxes (make_density_grid,
+           PerturbedField.c:32-54) */
+        const float *hv[7] = {(linear && !on_hires) ? boxes->lowres_density : boxes->hires_density,
+                              on_hires ? boxes->hires_vx : boxes->lowres_vx, on_hires ? boxes->hires_vy : boxes->lowres_vy,
+                              on_hires ? boxes->hires_vz : boxes->lowres_vz,
+                              on_hires ? boxes->hires_vx_2LPT : boxes->lowres_vx_2LPT,
+                              on_hires ? boxes->hires_vy_2LPT : boxes->lowres_vy_2LPT,
+                              on_hires ? boxes->hires_vz_2LPT : boxes->lowres_vz_2LPT};
+        const size_t NV = (size_t)(on_hires ? M : N);
+        const size_t hn[7] = {(size_t)((linear && !on_hires) ? N : M), NV, NV, NV, NV, NV, NV};
         const int nuse = linear ? 1 : (lpt2 ? 7 : 4);
         for (int i = 0; i < nuse; i++)
             if (!hv[i]) b200_throw(B200_ValueError, "ComputePerturbedField: a required IC array is NULL");
@@ -551,9 +699,9 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
             g_ics.hires.alloc(hn[0]);
             pending.h_hires = hv[0]; pending.d_hires = g_ics.hires;
             for (int a = 0; a < 3 && nuse > 1; a++) {
-                g_ics.v[a].alloc(N);
+                g_ics.v[a].alloc(NV);
                 pending.h_v[a] = hv[1 + a]; pending.d_v[a] = g_ics.v[a];
-                if (lpt2) { g_ics.v2[a].alloc(N); pending.h_v2[a] = hv[4 + a]; pending.d_v2[a] = g_ics.v2[a]; }
+                if (lpt2) { g_ics.v2[a].alloc(NV); pending.h_v2[a] = hv[4 + a]; pending.d_v2[a] = g_ics.v2[a]; }
             }
             for (int i = 0; i < 7; i++) { g_ics.host[i] = i < nuse ? hv[i] : nullptr; g_ics.sig[i] = sig[i]; }
             g_ics.dim = so->DIM; g_ics.hii = so->HII_DIM;
@@ -589,8 +737,13 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
 static void fill_device_io(PerturbDeviceIO &io, InitialConditions *d_boxes, PerturbedField *d_pf) {
     memset(&io, 0, sizeof(io));
     io.hires_density = d_boxes->hires_density; io.lowres_density = d_boxes->lowres_density;
-    io.v[0] = d_boxes->lowres_vx; io.v[1] = d_boxes->lowres_vy; io.v[2] = d_boxes->lowres_vz;
-    io.v2[0] = d_boxes->lowres_vx_2LPT; io.v2[1] = d_boxes->lowres_vy_2LPT; io.v2[2] = d_boxes->lowres_vz_2LPT;
+    const bool on_hires = matter_options_global->PERTURB_ON_HIGH_RES;
+    io.v[0] = on_hires ? d_boxes->hires_vx : d_boxes->lowres_vx;
+    io.v[1] = on_hires ? d_boxes->hires_vy : d_boxes->lowres_vy;
+    io.v[2] = on_hires ? d_boxes->hires_vz : d_boxes->lowres_vz;
+    io.v2[0] = on_hires ? d_boxes->hires_vx_2LPT : d_boxes->lowres_vx_2LPT;
+    io.v2[1] = on_hires ? d_boxes->hires_vy_2LPT : d_boxes->lowres_vy_2LPT;
+    io.v2[2] = on_hires ? d_boxes->hires_vz_2LPT : d_boxes->lowres_vz_2LPT;
     io.density = d_pf->density;
     io.vel[0] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_x : nullptr;
     io.vel[1] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_y : nullptr;
@@ -632,14 +785,7 @@ extern "C" int b200_ComputePerturbedField_device(float redshift, InitialConditio
         DevTimer timer;
         timer.start();
         PerturbDeviceIO io;
-        memset(&io, 0, sizeof(io));
-        io.hires_density = d_boxes->hires_density; io.lowres_density = d_boxes->lowres_density;
-        io.v[0] = d_boxes->lowres_vx; io.v[1] = d_boxes->lowres_vy; io.v[2] = d_boxes->lowres_vz;
-        io.v2[0] = d_boxes->lowres_vx_2LPT; io.v2[1] = d_boxes->lowres_vy_2LPT; io.v2[2] = d_boxes->lowres_vz_2LPT;
-        io.density = d_pf->density;
-        io.vel[0] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_x : nullptr;
-        io.vel[1] = matter_options_global->KEEP_3D_VELOCITIES ? d_pf->velocity_y : nullptr;
-        io.vel[2] = d_pf->velocity_z;
+        fill_device_io(io, d_boxes, d_pf);
         perturb_core(redshift, io);
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {

@@ -18,6 +18,11 @@ CASES = {
     "minimize_memory": dict(matter=dict(MINIMIZE_MEMORY=True)),
     "gaussian_filter_const_zeta": dict(matter=dict(SOURCE_MODEL="CONST-ION-EFF"), aopt=dict(HII_FILTER="gaussian")),
     "sharp_k_zeldovich": dict(matter=dict(PERTURB_ALGORITHM="ZELDOVICH"), aopt=dict(HII_FILTER="sharp-k")),
+    "perturb_on_high_res": dict(matter=dict(PERTURB_ON_HIGH_RES=True)),
+    "perturb_on_high_res_zeldovich_3d": dict(matter=dict(PERTURB_ON_HIGH_RES=True, PERTURB_ALGORITHM="ZELDOVICH",
+                                                         KEEP_3D_VELOCITIES=True)),
+    "perturb_on_high_res_linear": dict(matter=dict(PERTURB_ON_HIGH_RES=True, PERTURB_ALGORITHM="LINEAR")),
+    "perturb_on_high_res_smoothed": dict(matter=dict(PERTURB_ON_HIGH_RES=True, SMOOTH_EVOLVED_DENSITY_FIELD=True)),
     "neutral_box_z25": dict(z=25.0),
     "noncubic_neutral_z25": dict(sim=dict(NON_CUBIC_FACTOR=1.5), z=25.0),
     "barely_ionised_z18": dict(z=18.0),
@@ -102,10 +107,6 @@ def _unsupported_cases(be):
                                       C.byref(prev_ion.cstruct), C.byref(ts.cstruct), C.byref(hb.cstruct),
                                       C.byref(ics.cstruct), C.byref(box.cstruct))
         assert st == 3, (kw, st)
-    hi = dataclasses.replace(base, matter_options=dataclasses.replace(base.matter_options, PERTURB_ON_HIGH_RES=True))
-    be.state.init(hi, broadcast_inputs=True)
-    assert _status_of(lambda: pkg.perturb_field(redshift=8.0, initial_conditions=dataclasses.replace(ics, inputs=hi)
-                                                if dataclasses.is_dataclass(ics) else _retag(ics, hi), backend=be)) == 3
 
 
 def _retag(struct, inputs):
