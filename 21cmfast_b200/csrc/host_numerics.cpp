@@ -1,6 +1,9 @@
 /* host_numerics.cpp -- see host_numerics.h */
 #include "host_numerics.h"
 
+#include <map>
+#include <mutex>
+
 #include <climits>
 #include <limits>
 
@@ -48,22 +51,45 @@ double CubicSpline::eval(double x) const {
 }
 
 void gauss_legendre(double a, double b, int n, double *x, double *w) {
+    /* gauleg (hmf.c:660-697).  The roots z_i of P_n and the derivatives pp_i do not depend on the
+       interval: they are found once per n (same Newton iteration, same values) and only the final
+       affine map is redone per call -- the ionisation ladder calls this once per filter radius. */
+    struct Roots { std::vector<double> z, pp; };
+    static std::map<int, Roots> cache;
+    static std::mutex mu;
     const int m = (n + 1) / 2;
+    const Roots *r;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(n);
+        if (it == cache.end()) {
+            Roots fresh;
+            fresh.z.resize(m + 1);
+            fresh.pp.resize(m + 1);
+            for (int i = 1; i <= m; i++) {
+                double z = std::cos(M_PI * (i - 0.25) / (n + 0.5)), z1, pp;
+                int iter = 0;
+                do {
+                    double p1 = 1.0, p2 = 0.0;
+                    for (int j = 1; j <= n; j++) {
+                        const double p3 = p2;
+                        p2 = p1;
+                        p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
+                    }
+                    pp = n * (z * p1 - p2) / (z * z - 1.0);
+                    z1 = z;
+                    z = z1 - p1 / pp;
+                } while (std::fabs(z - z1) > 3.0e-11 && ++iter < 100);
+                fresh.z[i] = z;
+                fresh.pp[i] = pp;
+            }
+            it = cache.emplace(n, std::move(fresh)).first;
+        }
+        r = &it->second;
+    }
     const double xm = 0.5 * (b + a), xl = 0.5 * (b - a);
     for (int i = 1; i <= m; i++) {
-        double z = std::cos(M_PI * (i - 0.25) / (n + 0.5)), z1, pp;
-        int it = 0;
-        do {
-            double p1 = 1.0, p2 = 0.0;
-            for (int j = 1; j <= n; j++) {
-                const double p3 = p2;
-                p2 = p1;
-                p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
-            }
-            pp = n * (z * p1 - p2) / (z * z - 1.0);
-            z1 = z;
-            z = z1 - p1 / pp;
-        } while (std::fabs(z - z1) > 3.0e-11 && ++it < 100);
+        const double z = r->z[i], pp = r->pp[i];
         x[i] = xm - xl * z;
         x[n + 1 - i] = xm + xl * z;
         w[i] = 2.0 * xl / ((1.0 - z * z) * pp * pp);

@@ -69,10 +69,40 @@ inline double gk61_panel(F &&f, double a, double b, double *abserr, double *resa
     return rk;
 }
 
+/* the 61 abscissae of a panel in the order gk61_panel evaluates them */
+inline void gk61_abscissae(double a, double b, double *x) {
+    const int n = 31;
+    const double center = 0.5 * (a + b), half = 0.5 * (b - a);
+    int k = 0;
+    x[k++] = center;
+    for (int j = 0; j < (n - 1) / 2; j++) {
+        const double dx = half * GK61_XGK[2 * j + 1];
+        x[k++] = center - dx;
+        x[k++] = center + dx;
+    }
+    for (int j = 0; j < n / 2; j++) {
+        const double dx = half * GK61_XGK[2 * j];
+        x[k++] = center - dx;
+        x[k++] = center + dx;
+    }
+}
+
+/* globally adaptive QAG on a panel evaluator pe(a, b, &abserr, &resabs, &resasc) -> Kronrod estimate
+   (lets a caller cache what its integrand needs per panel); returns a QAG_* status */
+template <typename PE>
+inline int qag61_panels(PE &&pe, double a, double b, double epsabs, double epsrel, size_t limit,
+                        double *result, double *abserr);
+
 /* globally adaptive QAG; returns a QAG_* status */
 template <typename F>
 inline int qag61(F &&f, double a, double b, double epsabs, double epsrel, size_t limit,
                  double *result, double *abserr) {
+    return qag61_panels([&](double pa, double pb, double *e, double *ra, double *rs) { return gk61_panel(f, pa, pb, e, ra, rs); },
+                        a, b, epsabs, epsrel, limit, result, abserr);
+}
+template <typename PE>
+inline int qag61_panels(PE &&pe, double a, double b, double epsabs, double epsrel, size_t limit,
+                        double *result, double *abserr) {
     const double eps = 2.2204460492503131e-16, tiny = 2.2250738585072014e-308;
     *result = 0; *abserr = 0;
     if (epsabs <= 0 && (epsrel < 50 * eps || epsrel < 0.5e-28)) return QAG_EBADTOL;
@@ -80,7 +110,7 @@ inline int qag61(F &&f, double a, double b, double epsabs, double epsrel, size_t
     std::vector<Seg> segs;
     segs.reserve(64);
     double e0, ra0, rs0;
-    const double r0 = gk61_panel(f, a, b, &e0, &ra0, &rs0);
+    const double r0 = pe(a, b, &e0, &ra0, &rs0);
     segs.push_back({a, b, r0, e0});
     double tol = std::fmax(epsabs, epsrel * std::fabs(r0));
     if (e0 <= 50 * eps * ra0 && e0 > tol) { *result = r0; *abserr = e0; return QAG_EROUND; }
@@ -96,8 +126,8 @@ inline int qag61(F &&f, double a, double b, double epsabs, double epsrel, size_t
         const Seg s = segs[im];
         const double a1 = s.a, b1 = 0.5 * (s.a + s.b), a2 = b1, b2 = s.b;
         double e1, e2, ra1, ra2, rs1, rs2;
-        const double r1 = gk61_panel(f, a1, b1, &e1, &ra1, &rs1);
-        const double r2 = gk61_panel(f, a2, b2, &e2, &ra2, &rs2);
+        const double r1 = pe(a1, b1, &e1, &ra1, &rs1);
+        const double r2 = pe(a2, b2, &e2, &ra2, &rs2);
         const double r12 = r1 + r2, e12 = e1 + e2;
         errsum += e12 - s.e;
         area += r12 - s.r;

@@ -8,6 +8,8 @@
 #include <omp.h>
 
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "host_numerics.h"
@@ -767,6 +769,74 @@ static double gl_integral(const GLNode *nd, const MFParams &p, double delta) {
     return integral;
 }
 
+/* The table entries above delta = 1.2 are adaptive QAG integrals (hmf.c:896-905) of the same
+   integrand at different delta.  Everything the integrand needs at an abscissa except one
+   exponential is independent of delta (sigma, d sigma^2/dM, the moving-barrier series, the
+   escape/stellar fractions), and QAG's abscissae depend only on the panel: the per-panel node data
+   is computed once per table and shared by all entries and threads.  Same arithmetic per node as
+   cmf() * nion_fraction(), so the integrals are bit-identical to the uncached evaluation. */
+struct PanelNodes { GLNode n[61]; };
+struct CondNodeCache {
+    std::map<std::pair<double, double>, PanelNodes> panels;
+    std::mutex mu;
+};
+static void cond_node(GLNode &n, double lnM, const MFParams &p) {
+    const double sigma1 = EvaluateSigma(lnM);
+    n.w = 1.;
+    n.nf = nion_fraction(lnM, p);
+    n.dsig = EvaluatedSigmasqdm(lnM);
+    n.below = sigma1 < p.sigma_cond;
+    n.sdi = sigma1 == p.sigma_cond ? 1e6 : 1 / (sigma1 * sigma1 - p.sigma_cond * p.sigma_cond);
+    n.sdi15 = pow(n.sdi, 1.5);
+    n.sqrt_sdi = sqrt(n.sdi);
+    n.taylor = n.barrier = 0.;
+    if (p.HMF == HMF_ST && !n.below) n.taylor = st_taylor_factor(sigma1, p.sigma_cond, p.growthf, &n.barrier);
+}
+static double cond_node_value(const GLNode &n, const MFParams &p, double delta) { /* nion_fraction * cmf */
+    double c;
+    if (n.below) {
+        c = 0.;
+    } else if (p.HMF == HMF_ST) {
+        const double delta_0 = delta / p.growthf;
+        const double factor = n.taylor - delta_0;
+        c = -n.dsig * factor * n.sdi15 * exp(-(n.barrier - delta_0) * (n.barrier - delta_0) * 0.5 * (n.sdi)) /
+            sqrt(2. * M_PI);
+    } else if (p.HMF == HMF_DELOS) {
+        const double nu = (pc::delta_c_delos - delta) * n.sqrt_sdi / p.growthf;
+        const double dfdnu = 0.519 * pow(nu, 0.582) * exp(-0.469 * nu * nu);
+        c = dfdnu * fabs(n.dsig * 0.5) * n.sdi;
+    } else {
+        const double del = (pc::delta_c_sph - delta) / p.growthf;
+        c = -del * n.dsig * n.sdi15 * exp(-del * del * 0.5 * n.sdi) / sqrt(2. * M_PI);
+    }
+    return n.nf * c;
+}
+static double integrate_qag_cond_cached(double lo, double hi, const MFParams &p, CondNodeCache &cache) {
+    double res, err;
+    auto panel = [&](double a, double b, double *e, double *ra, double *rs) {
+        const PanelNodes *pn = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(cache.mu);
+            auto it = cache.panels.find({a, b});
+            if (it != cache.panels.end()) pn = &it->second; /* std::map nodes are stable */
+        }
+        if (!pn) {
+            /* computed outside the lock (another thread may do the same work; the first insert wins) */
+            PanelNodes fresh;
+            double x[61];
+            hostnum::gk61_abscissae(a, b, x);
+            for (int i = 0; i < 61; i++) cond_node(fresh.n[i], x[i], p);
+            std::lock_guard<std::mutex> lk(cache.mu);
+            pn = &cache.panels.emplace(std::make_pair(a, b), fresh).first->second;
+        }
+        int k = 0;
+        return hostnum::gk61_panel([&](double) { return cond_node_value(pn->n[k++], p, p.delta); }, a, b, e, ra, rs);
+    };
+    const int st_ = hostnum::qag61_panels(panel, lo, hi, 0, 1e-3, 1000, &res, &err);
+    if (st_ != 0) b200_throw(B200_GSLError, "mass-function quadrature status %d", st_);
+    return res;
+}
+
 void build_nion_table(FcollTable *t, double redshift, double min_dens, double max_dens, double Mmin,
                       double Mmax, const ScalingConstants *sc, int method, int n_threads) {
     /* initialise_Nion_Conditional_spline without mini-halos, interp_tables.c:291-408 */
@@ -790,15 +860,22 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
         gl_prepare_nodes(nodes, p);
     }
     const double dcrit_lim = (float)0.99 * get_delta_crit(matter_options_global->HMF, sigma2, growthf);
+    CondNodeCache qag_cache;
 #pragma omp parallel for num_threads(n_threads) schedule(dynamic, 1)
     for (int i = 0; i < N_DENS_INTERP; i++) {
         try {
             const double dens = min_dens + (float)i / ((float)N_DENS_INTERP - 1.) * (max_dens - min_dens);
             double v;
-            if (gl_fast && !(dens > dcrit_lim) && !(dens > 1.2))
+            if (gl_fast && !(dens > dcrit_lim) && !(dens > 1.2)) {
                 v = gl_integral(nodes, p, dens);
-            else
+            } else if (lnMmin < lnMcond && !(dens > dcrit_lim) && (method == INTEG_QAG || (method == INTEG_GL && dens > 1.2))) {
+                /* Nion_ConditionalM's QAG branch (hmf.c:1106-1140, 896-905) with shared node data */
+                MFParams pd = p;
+                pd.delta = dens;
+                v = integrate_qag_cond_cached(lnMmin, lnMmax, pd, qag_cache);
+            } else {
                 v = Nion_ConditionalM(growthf, lnMmin, lnMmax, lnMcond, sigma2, dens, sc->mturn_a_nofb, sc, method);
+            }
             float y = log(v);
             if (y < -40.) y = -40.;
             t->y[i] = y;
