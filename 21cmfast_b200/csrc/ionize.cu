@@ -714,8 +714,20 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     }
     const int n_mine = (int)mine.size();
 
-    DevBuf<float2> k_unfiltered(plan->n_cplx()), work0(plan->n_cplx()), work1(plan->n_cplx());
-    float2 *work[2] = {work0.p, work1.p};
+    /* The stream runs the filter + transform of up to `ahead` later radii while the host waits for
+       the extrema of radius j and integrates its table.  One radius ahead hides the host at 512^3
+       (1.1 ms of kernels per radius against ~0.1 ms of table build); at 256^3 (0.2 ms of kernels per
+       radius) two ahead is measurably better (12.0 -> 11.3 ms per step), at 128^3 and below the
+       host is the serial resource and running further ahead only delays the sweeps (7.2 -> 7.5 ms).
+       B200_IONIZE_AHEAD = 1..3 overrides. */
+    const size_t work_bytes = plan->n_cplx() * sizeof(float2);
+    int ahead = (work_bytes >= ((size_t)32 << 20) && work_bytes <= ((size_t)256 << 20)) ? 2 : 1;
+    if (const char *e = getenv("B200_IONIZE_AHEAD")) { ahead = atoi(e); if (ahead < 1) ahead = 1; if (ahead > 3) ahead = 3; }
+    const int NW = ahead + 1;
+    DevBuf<float2> k_unfiltered(plan->n_cplx());
+    DevBuf<float2> work_ring[4];
+    float2 *work[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) { work_ring[i].alloc(plan->n_cplx()); work[i] = work_ring[i].p; }
     DevBuf<float> d_fcoll;
     if (!io.nion) d_fcoll.alloc(N);
     DevBuf<int> d_keys(2 * (size_t)(n_todo > 0 ? n_todo : 1));
@@ -728,15 +740,15 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     unsigned char *d_mask = pt.mask;
     if (pt.phase < 0) { own_mask.alloc((size_t)N); d_mask = own_mask; }
     if (pt.phase <= 0) dev_zero(d_mask, (size_t)N); /* phase 1 continues on the merged mask */
-    /* window tables over |n|^2 (cubic boxes, top-hat / gaussian): two slots, stream-ordered reuse */
+    /* window tables over |n|^2 (cubic boxes, top-hat / gaussian): one slot per work box, stream-ordered reuse */
     const bool cubic = nx == ny && ny == nz && so->NON_CUBIC_FACTOR == 1.0f;
     const bool use_wtab = cubic && (c.hii_filter == 0 || c.hii_filter == 2);
     const int wtab_n = use_wtab ? window_table_size(plan) : 0;
-    DevBuf<float> d_wtab(use_wtab ? 2 * (size_t)wtab_n : 0);
+    DevBuf<float> d_wtab(use_wtab ? (size_t)NW * wtab_n : 0);
     /* expanded [|nx|][|ny|][kz] copy for the coalesced x-pass lookup (power-of-two grids, <= 1 GB per slot) */
     const size_t wtab3_n = use_wtab ? window_table3_size(plan) : 0;
     const bool use_wtab3 = use_wtab && (nx & (nx - 1)) == 0 && nx >= 16 && wtab3_n * sizeof(float) <= ((size_t)1 << 30);
-    DevBuf<float> d_wtab3(use_wtab3 ? 2 * wtab3_n : 0);
+    DevBuf<float> d_wtab3(use_wtab3 ? (size_t)NW * wtab3_n : 0);
     g_stage.ensure(n_todo);
     if (n_todo > 0) {
         KeyInitArgs ka = {n_todo, d_keys};
@@ -764,11 +776,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R; km.fast = 1;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
             if (use_wtab) {
-                float *slot = d_wtab.p + (size_t)(j & 1) * wtab_n;
+                float *slot = d_wtab.p + (size_t)(j % NW) * wtab_n;
                 window_table_build(plan, c.hii_filter, km.R, dk0, slot);
                 km.wtab = slot; km.wtab_n = wtab_n;
                 if (use_wtab3) {
-                    float *slot3 = d_wtab3.p + (size_t)(j & 1) * wtab3_n;
+                    float *slot3 = d_wtab3.p + (size_t)(j % NW) * wtab3_n;
                     window_table_expand(plan, slot, slot3);
                     km.wtab3 = slot3;
                 }
@@ -777,7 +789,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         ZEpilogue epi;
         epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
         epi.minmax_keys = d_keys.p + 2 * k;
-        fft_c2r(plan, k_unfiltered, work[j & 1], km, epi);
+        fft_c2r(plan, k_unfiltered, work[j % NW], km, epi);
         d2h_async(g_stage.h_keys + 2 * k, d_keys.p + 2 * k, 2 * sizeof(int));
         dev_event_record(g_stage.events[k]);
     };
@@ -785,12 +797,13 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     FcollTable htab;
     double t_wait = 0, t_table = 0, t_launch = 0;
     const bool verbose = getenv("B200_TIMING") != nullptr;
-    if (n_mine > 0) enqueue_transform(0);
+    int next_enq = 0;
+    if (n_mine > 0) enqueue_transform(next_enq++);
     for (int j = 0; j < n_mine; j++) {
         const int k = mine[j];
         const RadiusSpec &rs = radii[todo[k]];
         double t0 = omp_get_wtime();
-        if (j + 1 < n_mine) enqueue_transform(j + 1);
+        while (next_enq < n_mine && next_enq <= j + ahead) enqueue_transform(next_enq++);
         double t1 = omp_get_wtime();
         dev_event_wait_host(g_stage.events[k]);
         double t2 = omp_get_wtime();
@@ -818,7 +831,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         const bool last = (k == n_todo - 1);
         float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : nullptr;
         if (last && io.nion && io.nion_written) *io.nion_written = true;
-        const float *filtered = reinterpret_cast<const float *>(work[j & 1]);
+        const float *filtered = reinterpret_cast<const float *>(work[j % NW]);
         SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
         sweep_smem_optin();
         if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
