@@ -9,19 +9,24 @@
  *
  *   density (host) --H2D--> r2c with clip / (1/N) fused          [prepare_box_for_filtering]
  *   for R from largest to smallest:
+ *     window table for this R (exact double formula per |n|^2, expanded to coalesced rows)
  *     c2r with W(kR) multiplied on load, clip + global min/max in the epilogue
  *                                                   [copy_filter_transform + clip_and_get_extrema]
  *     2 floats D2H -> host builds the 400-point f_coll(delta) table -> 1.6 KB H2D
  *                                                   [setup_integration_tables]
- *     sweep 1: table lookup per cell -> float f_coll grid + deterministic double block sums
+ *     sweep 1: grid sum of f_coll(delta) as deterministic double block sums (the f_coll grid itself
+ *              is only materialised for the last radius, where it is the unnormalised_nion output)
  *                                                               [calculate_fcoll_grid]
- *     sweep 2: mean fix, barrier test, flags / z_reion / partial ionisation
+ *     sweep 2: mean fix + barrier test re-evaluated from the filtered density -> ionised byte mask;
+ *              last radius: flags from the f_coll grid + partial ionisation of the other cells
  *                                                               [find_ionised_regions]
- *   temperatures of ionised cells, D2H of the outputs           [set_ionized_temperatures]
+ *   xH = 0 / z_reion from the mask, temperatures of ionised cells, D2H of the outputs
+ *                                                               [set_ionized_temperatures]
  *
  * The radius loop is software-pipelined: while the host waits for the two min/max keys of radius
- * k and integrates its table, the stream already filters and transforms radius k+1 into the
- * other work box, so the GPU does not idle on the host-side table build.
+ * k and integrates its table, the stream already filters and transforms the next radius (two at
+ * 256^3) into other work boxes, so the GPU does not idle on the host-side table build.
+ * Multi-GPU: the ladder can be partitioned by radius (IonPartition below).
  */
 #include "fft.h"
 #include "host_physics.h"

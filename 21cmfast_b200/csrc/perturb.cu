@@ -3,16 +3,22 @@
  * with cloud-in-cell onto the low-resolution grid, clip, and derive the velocity field
  * (reference PerturbedField.c:24-496 and move_grid_masses, map_mass.c:23-60,146-208).
  *
- * Scope: PERTURB_ON_HIGH_RES = False (the default).  LINEAR, ZELDOVICH and 2LPT algorithms.
+ * Scope: LINEAR, ZELDOVICH and 2LPT algorithms; PERTURB_ON_HIGH_RES off (default: the optimised path
+ * below) or on (perturb_core_hires).
  *
  * Deposit design: the reference adds 8 weighted contributions per hi-res particle into a double
  * grid with `omp atomic` (order, hence rounding, varies run to run).  Here every contribution is
  * converted to 2^-40 fixed point and accumulated in unsigned 64-bit integers: integer addition is
- * associative, so the deposit is bit-reproducible, and its quantisation (4.5e-13 per
- * contribution) is far below the float the sum is finally rounded to.  Each CTA owns a brick of
- * hi-res particles, accumulates into a shared-memory tile of the low-res grid (brick + halo) with
- * shared-memory atomics and flushes the tile once; contributions that land outside the tile go
- * straight to global atomics, so correctness never depends on the displacement size.
+ * associative, so the deposit is bit-reproducible (and can be split over GPUs and merged by an
+ * integer all-reduce, PerturbPartition), and its quantisation (4.5e-13 per contribution) is far
+ * below the float the sum is finally rounded to.
+ *   integer DIM / HII_DIM ratio F (the default 3): move_cic_grouped_kernel -- one thread per low-res
+ *     velocity cell contracts its F^3 particles into a 3x3x3 block: 27 reductions instead of 8 F^3;
+ *   otherwise: move_cic_kernel -- a CTA owns a brick of particles, accumulates into a shared-memory
+ *     tile of the low-res grid (brick + halo) and flushes it once; contributions outside the tile go
+ *     straight to global atomics, so correctness never depends on the displacement size.
+ * Host interface: with a cold IC cache the hi-res density travels in x-slabs on a copy stream and
+ * the deposit of slab k starts as soon as its copy has landed (PendingUpload).
  */
 #include "fft.h"
 #include "host_physics.h"

@@ -7,8 +7,11 @@
 One "step" = ComputePerturbedField + ComputeIonizedBox for one coeval box with the initial
 conditions already generated (ICs are outside the metric).
 
-b200 arm, per rank (one process per GPU, independent boxes -> weak scaling, no collective on the
-data path):
+Default workload = the configuration BASELINE.json's metric is quoted on: z = 8, HII_DIM = 512,
+DIM = 1536 (the reference's default 3x), BOX_LEN = 768 Mpc, R_BUBBLE_MAX = 40 -> 40 filter radii.
+
+b200 arm, per rank (one process per GPU; --partition boxes: independent boxes -> weak scaling, no
+collective on the data path; --partition radius: ONE box split over the GPUs, two collectives):
   value : steps with every input/output already resident in HBM (device-pointer entry points),
           timed with CUDA events on the library's stream, max over ranks.
   e2e   : the same steps through the reference-facing C-ABI (ComputePerturbedField /
