@@ -754,6 +754,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const size_t wtab3_n = use_wtab ? window_table3_size(plan) : 0;
     const bool use_wtab3 = use_wtab && (nx & (nx - 1)) == 0 && nx >= 16 && wtab3_n * sizeof(float) <= ((size_t)1 << 30);
     DevBuf<float> d_wtab3(use_wtab3 ? (size_t)NW * wtab3_n : 0);
+#ifndef B200_EMU
+    const bool overlap_tables = use_wtab && !(getenv("B200_TABLE_OVERLAP") && getenv("B200_TABLE_OVERLAP")[0] == '0');
+#else
+    const bool overlap_tables = false;
+#endif
     g_stage.ensure(n_todo);
     if (n_todo > 0) {
         KeyInitArgs ka = {n_todo, d_keys};
@@ -781,7 +786,15 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R; km.fast = 1;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
             if (use_wtab) {
+                /* the two small table kernels run on the auxiliary stream beside the main stream's
+                   passes of earlier radii; the slot is free once the x pass that read it NW radii
+                   ago has finished (event 64 + slot), the x pass of this radius waits for event j */
                 float *slot = d_wtab.p + (size_t)(j % NW) * wtab_n;
+                struct AuxGuard { bool on; ~AuxGuard() { if (on) rt_use_aux(false); } } guard{overlap_tables};
+                if (overlap_tables) {
+                    rt_use_aux(true);
+                    if (j >= NW) rt_stream_wait(64 + (j % NW));
+                }
                 window_table_build(plan, c.hii_filter, km.R, dk0, slot);
                 km.wtab = slot; km.wtab_n = wtab_n;
                 if (use_wtab3) {
@@ -789,12 +802,19 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
                     window_table_expand(plan, slot, slot3);
                     km.wtab3 = slot3;
                 }
+                if (overlap_tables) {
+                    rt_event_record(j % 64);
+                    rt_use_aux(false);
+                    guard.on = false;
+                    rt_stream_wait(j % 64);
+                }
             }
         }
         ZEpilogue epi;
         epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
         epi.minmax_keys = d_keys.p + 2 * k;
         fft_c2r(plan, k_unfiltered, work[j % NW], km, epi);
+        if (overlap_tables) rt_event_record(64 + (j % NW)); /* this radius' table slot is free again */
         d2h_async(g_stage.h_keys + 2 * k, d_keys.p + 2 * k, 2 * sizeof(int));
         dev_event_record(g_stage.events[k]);
     };

@@ -27,6 +27,9 @@ static std::map<void *, size_t> g_live;
 #ifndef B200_EMU
 cudaStream_t g_stream = nullptr;
 static cudaStream_t g_copy_stream = nullptr;
+static cudaStream_t g_main_stream = nullptr, g_aux_stream = nullptr;
+static cudaEvent_t g_rt_events[128];
+static bool g_rt_events_ready = false;
 static cudaEvent_t g_copy_events[64];
 static cudaEvent_t g_main_event = nullptr;
 static int g_device = -1;
@@ -54,6 +57,12 @@ extern "C" int b200_set_device(int device) {
             b200_release_device_cache();
             cudaStreamDestroy(g_stream);
             g_stream = nullptr;
+            if (g_rt_events_ready) {
+                cudaStreamDestroy(g_aux_stream);
+                g_aux_stream = nullptr;
+                for (int i = 0; i < 128; i++) cudaEventDestroy(g_rt_events[i]);
+                g_rt_events_ready = false;
+            }
             if (g_copy_stream) {
                 cudaStreamDestroy(g_copy_stream);
                 g_copy_stream = nullptr;
@@ -151,6 +160,29 @@ void copy_wait_main() {
     CUDA_CHECK(cudaStreamWaitEvent(g_copy_stream, g_main_event, 0));
 }
 void copy_stream_sync() { if (g_copy_stream) CUDA_CHECK(cudaStreamSynchronize(g_copy_stream)); }
+static void aux_init() {
+    rt_init();
+    if (g_rt_events_ready) return;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 128; i++) CUDA_CHECK(cudaEventCreateWithFlags(&g_rt_events[i], cudaEventDisableTiming));
+    g_rt_events_ready = true;
+}
+void rt_use_aux(bool on) {
+    aux_init();
+    if (on) {
+        if (g_stream != g_aux_stream) { g_main_stream = g_stream; g_stream = g_aux_stream; }
+    } else if (g_stream == g_aux_stream) {
+        g_stream = g_main_stream;
+    }
+}
+void rt_event_record(int slot) {
+    aux_init();
+    CUDA_CHECK(cudaEventRecord(g_rt_events[slot & 127], g_stream));
+}
+void rt_stream_wait(int slot) {
+    aux_init();
+    CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_rt_events[slot & 127], 0));
+}
 void *dev_event_create() {
     cudaEvent_t e;
     CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -258,6 +290,9 @@ void copy_event_record(int) {}
 void main_wait_copy_event(int) {}
 void copy_wait_main() {}
 void copy_stream_sync() {}
+void rt_use_aux(bool) {}
+void rt_event_record(int) {}
+void rt_stream_wait(int) {}
 void *dev_event_create() { return nullptr; }
 void dev_event_record(void *) {}
 void dev_event_wait_host(void *) {}

@@ -219,6 +219,13 @@ void copy_event_record(int slot);
 void main_wait_copy_event(int slot);
 void copy_wait_main();
 void copy_stream_sync();
+/* auxiliary compute stream: small independent kernels (the per-radius window tables) run beside the
+   main stream's big passes.  rt_use_aux(true) redirects B200_LAUNCH to the auxiliary stream until
+   rt_use_aux(false); rt_event_record(slot) records on the CURRENT stream, rt_stream_wait(slot) makes
+   the CURRENT stream wait for that record.  No-ops in the emulation build (everything is in order). */
+void rt_use_aux(bool on);
+void rt_event_record(int slot);
+void rt_stream_wait(int slot);
 void *dev_event_create();
 void dev_event_record(void *ev);
 void dev_event_wait_host(void *ev);
