@@ -222,3 +222,45 @@ def test_gaussians_from_raw_redraws_zero_words():
     assert np.allclose(got, exp, rtol=0, atol=1e-15)
     assert lib.b200_gaussians_from_raw_host(raw.ctypes.data_as(C.POINTER(C.c_uint)), 100, 1500,
                                             got.ctypes.data_as(C.POINTER(C.c_double))) == -1
+
+
+def test_bench_reference_arm_line_contract():
+    """bench.py --impl reference prints ONE JSON line with the keys the driver reads (metric, unit,
+    config identical to the b200 arm's, impl, cpu_baseline, e2e with zero copy bytes)."""
+    import json
+    import subprocess
+    import sys
+    if common.ref_backend() is None:
+        pytest.skip("needs oracle/_ref")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-hii-dim", "32"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("coeval cells/sec")
+    assert "HII_DIM=512 DIM=1536" in d["config"]["workload"] and "n_radii=40" in d["config"]["workload"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_bench_radius_count_matches_library():
+    """bench.py's n_radii() (used for the algorithmic-byte count) equals the ladder the library builds."""
+    import importlib.util
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("bench_mod", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    for hii, box, rmax in ((512, 768.0, 40.0), (256, 300.0, 15.0), (1024, 1000.0, 15.0), (64, 96.0, 15.0)):
+        inputs = common.make_inputs(hii=hii, dim=hii, box_len=box, R_BUBBLE_MAX=rmax)
+        emu.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+        out = (C.c_double * 8)()
+        emu.lib.b200_ionize_host_scalars.argtypes = [C.c_float, C.POINTER(C.c_double), C.c_int]
+        assert emu.lib.b200_ionize_host_scalars(C.c_float(8.0), out, 8) == 0
+        assert int(out[7]) == bench.n_radii(hii, box, rmax), (hii, box, rmax, out[7])
