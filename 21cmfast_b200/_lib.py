@@ -64,8 +64,10 @@ class Backend:
         lib.Broadcast_struct_global_all.restype = None
         lib.initialiseSigmaMInterpTable.argtypes = [C.c_float, C.c_float]
         for name in ("init_ps", "free_ps", "initialiseSigmaMInterpTable", "freeSigmaMInterpTable",
-                     "destruct_heat", "Free_cosmo_tables_global"):
+                     "destruct_heat", "Free_cosmo_tables_global", "init_MHR", "free_MHR"):
             getattr(lib, name).restype = None
+        lib.splined_recombination_rate.argtypes = [C.c_double, C.c_double]
+        lib.splined_recombination_rate.restype = C.c_double
         for name, args in (("dicke", [C.c_double]), ("sigma_z0", [C.c_double]),
                            ("dsigmasqdm_z0", [C.c_double]), ("power_in_k", [C.c_double])):
             f = getattr(lib, name)
@@ -88,9 +90,13 @@ class GlobalState:
         self.inputs = None
         self._keep = None
         self.inputs_are_broadcast = self.ps_inited = self.sigma_inited = self.heat_inited = False
+        self.recomb_inited = False
 
     def free(self):
         lib = self.backend.lib
+        if self.recomb_inited:
+            lib.free_MHR()
+            self.recomb_inited = False
         if self.heat_inited:
             lib.destruct_heat()
             self.heat_inited = False
@@ -104,13 +110,13 @@ class GlobalState:
             lib.Free_cosmo_tables_global()
             self.inputs_are_broadcast = False
 
-    def init(self, inputs, *, broadcast_inputs=False, ps=False, sigma=False, heat=False):
+    def init(self, inputs, *, broadcast_inputs=False, ps=False, sigma=False, heat=False, recomb=False):
         lib = self.backend.lib
         if self.inputs is None or self.inputs != inputs:
             self.free()
             self.inputs = inputs
-        if (broadcast_inputs or ps or sigma or heat) and not self.inputs_are_broadcast:
-            i = self.inputs
+        i = self.inputs
+        if (broadcast_inputs or ps or sigma or heat or recomb) and not self.inputs_are_broadcast:
             # keep the structs alive: the C side stores *pointers* (InputParameters.c:11-20)
             self._keep = (i.simulation_options.cstruct, i.matter_options.cstruct,
                           i.cosmo_params.cstruct, i.astro_params.cstruct,
@@ -126,6 +132,10 @@ class GlobalState:
                 and self.inputs.matter_options.USE_INTERPOLATION_TABLES != "no-interpolation"):
             lib.initialiseSigmaMInterpTable(5e2, 1e20)
             self.sigma_inited = True
+        if (recomb and not self.recomb_inited and i.astro_options.RECOMB_MODEL != "none"
+                and i.simulation_options.HII_DIM > 1):
+            lib.init_MHR()  # _global_initialization.py:147-159
+            self.recomb_inited = True
         if heat and not self.heat_inited:
             status = lib.init_heat()
             if status != 0:

@@ -164,6 +164,7 @@ class CubicSpline {
     bool ready() const { return !x_.empty(); }
     void clear() { x_.clear(); y_.clear(); c_.clear(); }
     double xmax() const { return x_.back(); }
+    const std::vector<double> &coeffs() const { return c_; } /* the c_i of y + t (b + t (c + t d)) */
   private:
     std::vector<double> x_, y_, c_;
 };

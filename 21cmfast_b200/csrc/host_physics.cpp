@@ -887,7 +887,7 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
 
 /* ------------------------------------------------------------------ IonizeBox host constants */
 void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
-    /* IonisationBox.c:125-227 (photon-conservation and recombination terms are out of scope) */
+    /* IonisationBox.c:125-227 (photon conservation is out of scope) */
     c->redshift = redshift;
     c->prev_redshift = prev_redshift;
     c->stored_redshift = redshift;
@@ -908,6 +908,13 @@ void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
     c->TK_nofluct = T_RECFAST(redshift);
     c->adia_TK_term = cT_approx(redshift);
     c->pixel_length = simulation_options_global->BOX_LEN / (double)simulation_options_global->HII_DIM;
+    /* the first snapshot takes its step from ZPRIME_STEP_FACTOR */
+    if (prev_redshift < 1) c->dz = (1. + redshift) * (simulation_options_global->ZPRIME_STEP_FACTOR - 1.);
+    else c->dz = prev_redshift - redshift;
+    c->fabs_dtdz = fabs(dtdz(redshift)) / 1e15; /* the rate table is in (1e15 s)^-1 */
+    c->gamma_prefactor = pow(1 + redshift, 2) * pc::cm_per_Mpc * pc::sigma_HI * astro_params_global->ALPHA_UVB /
+                         (astro_params_global->ALPHA_UVB + 2.75) * n_b0() * c->ion_eff_factor / 1.0e-12;
+    c->gamma_prefactor = c->gamma_prefactor / (c->sc.t_h * c->sc.t_star);
 }
 
 std::vector<RadiusSpec> setup_radii(const IonConsts &c) { /* IonisationBox.c:964-1006 */
@@ -979,6 +986,4 @@ double xion_RECFAST(float z) {
 }
 float cT_approx(float z) { return 0.58 - 0.006 * (z - 10.0); }
 
-extern "C" void init_MHR(void) {}
-extern "C" void free_MHR(void) {}
 extern "C" int CreateFFTWWisdoms(void) { return 0; }

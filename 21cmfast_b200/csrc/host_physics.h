@@ -80,6 +80,7 @@ struct IonConsts {
     double T_re, ion_eff_factor, ion_eff_factor_gl;
     double TK_nofluct, adia_TK_term;
     double M_min, lnMmin, lnMmax_gl, sigma_minmass, pixel_length;
+    double dz, fabs_dtdz, gamma_prefactor; /* recombination bookkeeping (IonisationBox.c:132-137,144,211-218) */
 };
 struct RadiusSpec {
     double R, M_max_R, ln_M_max_R, sigma_maxmass;

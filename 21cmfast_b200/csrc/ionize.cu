@@ -30,6 +30,7 @@
  */
 #include "fft.h"
 #include "host_physics.h"
+#include "host_recomb.h"
 
 #include <omp.h>
 #include <vector>
@@ -304,6 +305,15 @@ struct CritArgs {
     double n_cells, mean_f_coll, f_limit, ion_eff_factor;
     int mass_dep_zeta, R_index;
     double redshift, TK_nofluct, adia_TK_term, T_re;
+    /* recombinations (RECOMB_MODEL != none): the barrier becomes 1 + N_rec / (1 + delta_R) and the
+       first crossing records Gamma12 and the mean free path (IonisationBox.c:1084-1140) */
+    int recomb;              /* 0 none, 1 filtered N_rec grid (padded rows), 2 per-cell previous N_rec, 3 one global value */
+    const float *rec_grid;
+    double rec_scalar;
+    const float *filtered;   /* padded real rows of delta_R (curr_dens for R_index > 0) */
+    int nz, nzc;
+    float *G12, *mfp;
+    double R, gamma_prefactor;
 };
 
 DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { /* thermochem.c:58-63 */
@@ -320,6 +330,34 @@ DEV void ionise_cell(const CritArgs &a, long long idx, float fcoll, double mean_
     double curr_fcoll = mean_fix * (double)fcoll;
     if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
     if (curr_fcoll * a.ion_eff_factor > 1.0) {
+        a.mask[idx] = 1;
+    } else if (a.R_index == 0 && !a.mask[idx] && (a.xH[idx] > pc::TINY)) {
+        double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
+        if (a.Tk) {
+            const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
+            a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
+        }
+        if (res_xH < 0) res_xH = 0;
+        else if (res_xH > 1) res_xH = 1;
+        a.xH[idx] = (float)res_xH;
+    }
+}
+
+/* the same cell with recombinations in the barrier; runs at every radius of the ladder */
+DEV void ionise_cell_recomb(const CritArgs &a, long long idx, float fcoll, double mean_fix) {
+    double curr_fcoll = mean_fix * (double)fcoll;
+    if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
+    const long long row = idx / a.nz;
+    const long long idx_f = row * 2 * a.nzc + (idx - row * a.nz);
+    const double curr_dens = a.R_index == 0 ? (double)a.density[idx]
+                                            : (double)fmaxf(a.filtered[idx_f], (float)(-1. + pc::FRACT_FLOAT_ERR));
+    double rec = a.recomb == 1 ? (double)a.rec_grid[idx_f] : a.recomb == 2 ? (double)a.rec_grid[idx] : a.rec_scalar;
+    rec /= (1. + curr_dens);
+    if (curr_fcoll * a.ion_eff_factor > 1.0 + rec) {
+        if (!a.mask[idx] && (double)a.xH[idx] > pc::FRACT_FLOAT_ERR) { /* first (largest-R) crossing */
+            a.G12[idx] = (float)(a.R * (a.gamma_prefactor * curr_fcoll));
+            if (a.mfp) a.mfp[idx] = (float)a.R;
+        }
         a.mask[idx] = 1;
     } else if (a.R_index == 0 && !a.mask[idx] && (a.xH[idx] > pc::TINY)) {
         double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
@@ -354,7 +392,11 @@ __global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
         if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
     }
     const double mean_fix = a.mean_f_coll / grid_mean;
-    if ((a.n & 3) == 0) {
+    if (a.recomb) {
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n;
+             idx += (long long)gridDim.x * blockDim.x)
+            ionise_cell_recomb(a, idx, a.fcoll[idx], mean_fix);
+    } else if ((a.n & 3) == 0) {
         const long long n4 = a.n >> 2;
         const long long stride = (long long)gridDim.x * blockDim.x;
         const float4 *f4p = reinterpret_cast<const float4 *>(a.fcoll);
@@ -544,6 +586,71 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
     }
 }
 
+/* set_recombination_rates, inhomogeneous model (IonisationBox.c:1277-1341): per cell, the
+   PDF-integrated rate at the cell's effective redshift (1 + z) (1 + delta)^(1/3) - 1 and its own
+   Gamma12, evaluated from the host-built table (host_recomb.cpp): index-sampled in redshift, natural
+   cubic spline in ln(Gamma12) (splined_recombination_rate, recombinations.c:66-90). */
+struct RecombArgs {
+    long long n;
+    const float *density, *xH, *G12, *prev_rec; /* prev_rec null = zeros */
+    float *cum_rec;
+    const double *lnGamma, *y, *c; /* [NG], [NZ][NG], [NZ][NG] */
+    double lnGamma_max, one_plus_z, dt; /* dt = |dt/dz| dz in 1e15 s */
+    int *nonfinite;
+};
+DEV double recomb_rate_lookup(const RecombArgs &a, double z_eff, double gamma12) {
+    int z_ct = (int)(z_eff / RECOMB_DEL_Z + 0.5);
+    if (z_ct < 0) z_ct = 0;
+    else if (z_ct >= RECOMB_NZ) z_ct = RECOMB_NZ - 1;
+    double lnG = log(gamma12);
+    if (lnG < RECOMB_LNGAMMA_MIN) return 0;
+    if (lnG >= a.lnGamma_max) lnG = a.lnGamma_max - pc::FRACT_FLOAT_ERR;
+    int i = (int)((lnG - RECOMB_LNGAMMA_MIN) * 10.0);
+    if (i < 0) i = 0;
+    if (i > RECOMB_NG - 2) i = RECOMB_NG - 2;
+    while (i > 0 && a.lnGamma[i] > lnG) i--;
+    while (i < RECOMB_NG - 2 && a.lnGamma[i + 1] <= lnG) i++;
+    const double *y = a.y + (size_t)z_ct * RECOMB_NG, *c = a.c + (size_t)z_ct * RECOMB_NG;
+    const double dx = a.lnGamma[i + 1] - a.lnGamma[i], dy = y[i + 1] - y[i], t = lnG - a.lnGamma[i];
+    const double b = dy / dx - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
+    const double d = (c[i + 1] - c[i]) / (3.0 * dx);
+    return y[i] + t * (b + t * (c[i] + t * d));
+}
+__global__ void __launch_bounds__(256) recomb_update_kernel(RecombArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double curr_dens = 1.0 + (double)a.density[i];
+        const double z_eff = pow(curr_dens, 1.0 / 3.0) * a.one_plus_z;
+        const double dNrec = recomb_rate_lookup(a, z_eff - 1., (double)a.G12[i]) * a.dt * (1. - (double)a.xH[i]);
+        if (!isfinite(dNrec)) *a.nonfinite = 1;
+        a.cum_rec[i] = (float)((double)(a.prev_rec ? a.prev_rec[i] : 0.f) + dNrec);
+    }
+}
+
+/* box means of neutral_fraction and Gamma12 for the homogeneous model (IonisationBox.c:1594-1607):
+   deterministic double block sums, finished on the host */
+struct Mean2Args {
+    long long n;
+    const float *a, *b;
+    double *partial; /* [gridDim][2] */
+};
+__global__ void __launch_bounds__(256) mean2_kernel(Mean2Args a) {
+    __shared__ double ra[256], rb[256];
+    double sa = 0., sb = 0.;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        sa += (double)a.a[i];
+        sb += (double)a.b[i];
+    }
+    ra[threadIdx.x] = sa; rb[threadIdx.x] = sb;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { ra[threadIdx.x] += ra[threadIdx.x + s]; rb[threadIdx.x] += rb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { a.partial[2 * blockIdx.x] = ra[0]; a.partial[2 * blockIdx.x + 1] = rb[0]; }
+}
+
 struct FillArgs {
     long long n;
     float *p;
@@ -608,6 +715,12 @@ struct IonDeviceIO {
                                (their upload overlaps the radius ladder), or -1 */
     bool *nion_written = nullptr; /* out: the ladder stored a grid in `nion` (the reference leaves the
                                      caller's zero-initialised array untouched when it exits early) */
+    /* recombinations (RECOMB_MODEL != none) */
+    const float *prev_rec = nullptr;  /* device, N: previous cumulative recombinations (inhomogeneous), null = zeros */
+    double prev_rec_scalar = 0.;      /* the one global value of the homogeneous model */
+    float *G12 = nullptr, *mfp = nullptr, *cum_rec = nullptr; /* device, N; mfp optional; cum_rec inhomogeneous only */
+    double *cum_rec_scalar_out = nullptr; /* host: new global value (homogeneous) */
+    bool *rec_written = nullptr;      /* out: G12 / mfp / cumulative recombinations were updated */
 };
 
 /* pinned staging that outlives a call (cudaMallocHost is too slow to repeat per call) */
@@ -649,10 +762,21 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const MatterOptions *mo = matter_options_global;
     if (mo->SOURCE_MODEL != SRC_CONST_ION_EFF && mo->SOURCE_MODEL != SRC_E_INTEGRAL)
         b200_throw(B200_ValueError, "SOURCE_MODEL=%d: only CONST-ION-EFF and E-INTEGRAL are in scope", mo->SOURCE_MODEL);
-    if (ao->USE_TS_FLUCT || ao->RECOMB_MODEL != 0 || ao->USE_MINI_HALOS || ao->IONISE_ENTIRE_SPHERE ||
-        ao->PHOTON_CONS_TYPE != 0)
-        b200_throw(B200_ValueError, "USE_TS_FLUCT / RECOMB_MODEL / USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / "
+    if (ao->USE_TS_FLUCT || ao->USE_MINI_HALOS || ao->IONISE_ENTIRE_SPHERE || ao->PHOTON_CONS_TYPE != 0)
+        b200_throw(B200_ValueError, "USE_TS_FLUCT / USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / "
                                     "photon conservation are outside the scoped IonizeBox path");
+    /* recombinations: 1 homogeneous (one global N_rec), 2 inhomogeneous (per cell; filtered with the
+       density unless CELL_RECOMB) */
+    const int recomb = ao->RECOMB_MODEL;
+    const bool filter_rec = recomb != 0 && !ao->CELL_RECOMB;
+    if (recomb) {
+        if (recomb == 1 && filter_rec)
+            b200_throw(B200_ValueError, "RECOMB_MODEL=homogeneous needs CELL_RECOMB (there is no N_rec grid to filter)");
+        if (pt.phase >= 0) b200_throw(B200_ValueError, "the radius-parallel ladder is not built for RECOMB_MODEL != none");
+        if (!io.G12 || (recomb == 2 && !io.cum_rec))
+            b200_throw(B200_ValueError, "RECOMB_MODEL != none needs ionisation_rate_G12 and cumulative_recombinations");
+        if (!recomb_tables()) b200_throw(B200_TableEvaluationError, "RECOMB_MODEL != none needs init_MHR()");
+    }
     if (mo->USE_INTERPOLATION_TABLES != 2)
         b200_throw(B200_ValueError, "this build needs USE_INTERPOLATION_TABLES='hmf-interpolation'");
 
@@ -734,7 +858,15 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     float2 *work[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) { work_ring[i].alloc(plan->n_cplx()); work[i] = work_ring[i].p; }
     DevBuf<float> d_fcoll;
-    if (!io.nion) d_fcoll.alloc(N);
+    if (!io.nion || recomb) d_fcoll.alloc(N);
+    /* N_rec of the previous snapshot in k space and its filtered copies, one per work box */
+    const bool rec_grid_filtered = filter_rec && io.prev_rec;
+    DevBuf<float2> k_nrec, rec_ring[4];
+    float2 *work_rec[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (rec_grid_filtered) {
+        k_nrec.alloc(plan->n_cplx());
+        for (int i = 0; i < NW; i++) { rec_ring[i].alloc(plan->n_cplx()); work_rec[i] = rec_ring[i].p; }
+    }
     DevBuf<int> d_keys(2 * (size_t)(n_todo > 0 ? n_todo : 1));
     DevBuf<DevTable> d_tables((size_t)(n_todo > 0 ? n_todo : 1));
     const int sweep_blocks = grid_for((long long)nx * ny, 1);
@@ -771,6 +903,12 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     pro.clip = 1; pro.clip_lo = -1.f; pro.clip_hi = 1e6f;
     pro.post_scale = 1.f / (float)N;
     fft_r2c(plan, k_unfiltered, pro);
+    if (recomb && io.wait_slot >= 0) main_wait_copy_event(io.wait_slot); /* xH / G12 / N_rec are read at every radius */
+    if (rec_grid_filtered) {
+        ZPrologue pr = pro;
+        pr.src = io.prev_rec; pr.clip_lo = 0.f; pr.clip_hi = 1e20f;
+        fft_r2c(plan, k_nrec, pr);
+    }
 
     const double dk0 = 2.0 * M_PI / so->BOX_LEN;
     const double dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
@@ -814,6 +952,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
         epi.minmax_keys = d_keys.p + 2 * k;
         fft_c2r(plan, k_unfiltered, work[j % NW], km, epi);
+        if (rec_grid_filtered) { /* <N_rec> over the same window, floored at zero (IonisationBox.c:806-809) */
+            ZEpilogue er;
+            er.scale = 1.f; er.clip = 1; er.clip_lo = 0.f; er.clip_hi = 3.0e38f;
+            fft_c2r(plan, k_nrec, work_rec[j % NW], km, er);
+        }
         if (overlap_tables) rt_event_record(64 + (j % NW)); /* this radius' table slot is free again */
         d2h_async(g_stage.h_keys + 2 * k, d_keys.p + 2 * k, 2 * sizeof(int));
         dev_event_record(g_stage.events[k]);
@@ -854,7 +997,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
            other radius only needs the grid sum and the ionised flags, so its f_coll grid is never
            materialised */
         const bool last = (k == n_todo - 1);
-        float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : nullptr;
+        float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : (recomb ? d_fcoll.p : nullptr);
         if (last && io.nion && io.nion_written) *io.nion_written = true;
         const float *filtered = reinterpret_cast<const float *>(work[j % NW]);
         SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
@@ -862,7 +1005,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
         else B200_LAUNCH(fcoll_sum_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
 
-        if (!last) {
+        if (!last && !recomb) {
             CritDeltaArgs cd;
             memset(&cd, 0, sizeof(cd));
             cd.nx = nx; cd.ny = ny; cd.nz = nz; cd.nzc = plan->pitch;
@@ -883,6 +1026,14 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
             ca.R_index = rs.R_index; ca.redshift = c.redshift;
             ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
+            if (recomb) {
+                ca.recomb = rec_grid_filtered ? 1 : (recomb == 2 && io.prev_rec) ? 2 : 3;
+                ca.rec_grid = rec_grid_filtered ? reinterpret_cast<const float *>(work_rec[j % NW]) : io.prev_rec;
+                ca.rec_scalar = recomb == 1 ? io.prev_rec_scalar : 0.;
+                ca.filtered = filtered; ca.nz = nz; ca.nzc = plan->pitch;
+                ca.G12 = io.G12; ca.mfp = io.mfp;
+                ca.R = rs.R; ca.gamma_prefactor = c.gamma_prefactor;
+            }
             B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
         }
     }
@@ -906,6 +1057,39 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         g_stats.d2h -= (long long)sizeof(int);
         if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
     }
+    if (recomb == 2) { /* set_recombination_rates, inhomogeneous (IonisationBox.c:1277-1341) */
+        const RecombTables *rt = recomb_tables();
+        const size_t tn = (size_t)RECOMB_NZ * RECOMB_NG;
+        DevBuf<double> d_rr(2 * tn + RECOMB_NG);
+        h2d(d_rr.p, rt->y.data(), tn * sizeof(double));
+        h2d(d_rr.p + tn, rt->c.data(), tn * sizeof(double));
+        h2d(d_rr.p + 2 * tn, rt->lnGamma, RECOMB_NG * sizeof(double));
+        g_stats.h2d -= (long long)((2 * tn + RECOMB_NG) * sizeof(double));
+        RecombArgs ra = {N, io.density, io.xH, io.G12, io.prev_rec, io.cum_rec, d_rr.p + 2 * tn, d_rr.p, d_rr.p + tn,
+                         rt->lnGamma_max, 1. + c.stored_redshift, c.fabs_dtdz * c.dz, d_flag};
+        B200_LAUNCH(recomb_update_kernel, grid_for(N, 1024), 256, 0, ra);
+        int flag = 0;
+        d2h(&flag, d_flag, sizeof(int));
+        g_stats.d2h -= (long long)sizeof(int);
+        if (flag) b200_throw(B200_InfinityorNaNError, "recombinations returned an infinite or NaN value");
+    } else if (recomb == 1) { /* homogeneous (IonisationBox.c:1261-1276): one rate from the box means */
+        const int nb = grid_for(N, 1024);
+        DevBuf<double> d_p(2 * (size_t)nb);
+        Mean2Args ma = {N, io.xH, io.G12, d_p};
+        B200_LAUNCH(mean2_kernel, nb, 256, 0, ma);
+        std::vector<double> hp(2 * (size_t)nb);
+        d2h(hp.data(), d_p, hp.size() * sizeof(double));
+        g_stats.d2h -= (long long)(hp.size() * sizeof(double));
+        double sx = 0., sg = 0.;
+        for (int i = 0; i < nb; i++) { sx += hp[2 * i]; sg += hp[2 * i + 1]; }
+        const double global_xH = sx / (double)N;
+        const float global_G12 = (float)(sg / (double)N); /* a float in the reference */
+        const double dNrec = recomb_rate_host(c.stored_redshift, global_G12) * c.fabs_dtdz * c.dz * (1. - global_xH);
+        const double cum = io.prev_rec_scalar + dNrec;
+        if (!std::isfinite(cum)) b200_throw(B200_InfinityorNaNError, "non-finite cumulative recombinations");
+        if (io.cum_rec_scalar_out) *io.cum_rec_scalar_out = cum;
+    }
+    if (recomb && io.rec_written) *io.rec_written = true;
 }
 
 static void reset_stats() { g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0; }
@@ -945,10 +1129,45 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
             d_prev.alloc(N);
             h2d_copy_stream(d_prev, previous_ionize_box->z_reion, N * sizeof(float));
         }
+        /* recombinations: Gamma12 / mean free path keep the caller's values where no cell crosses the
+           barrier; the previous snapshot's cumulative recombinations are an input */
+        const int recomb = astro_options_global->RECOMB_MODEL;
+        DevBuf<float> d_G12, d_mfp, d_cum, d_prev_rec;
+        double cum_scalar = 0.;
+        bool rec_written = false;
+        if (recomb) {
+            if (!box->ionisation_rate_G12 || !box->cumulative_recombinations || !previous_ionize_box ||
+                !previous_ionize_box->cumulative_recombinations)
+                b200_throw(B200_ValueError, "ComputeIonizedBox: RECOMB_MODEL != none needs ionisation_rate_G12 and the "
+                                            "cumulative_recombinations of this and the previous box");
+            d_G12.alloc(N);
+            h2d_copy_stream(d_G12, box->ionisation_rate_G12, N * sizeof(float));
+            if (!matter_options_global->MINIMIZE_MEMORY && box->mean_free_path) {
+                d_mfp.alloc(N);
+                h2d_copy_stream(d_mfp, box->mean_free_path, N * sizeof(float));
+            }
+            if (recomb == 2) {
+                d_cum.alloc(N);
+                d_prev_rec.alloc(N);
+                h2d_copy_stream(d_prev_rec, previous_ionize_box->cumulative_recombinations, N * sizeof(float));
+            }
+        }
         copy_event_record(slot);
         bool nion_written = false;
         IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p, slot, &nion_written};
+        if (recomb) {
+            io.prev_rec = d_prev_rec.p;
+            io.prev_rec_scalar = recomb == 1 ? (double)previous_ionize_box->cumulative_recombinations[0] : 0.;
+            io.G12 = d_G12; io.mfp = d_mfp.p; io.cum_rec = d_cum.p;
+            io.cum_rec_scalar_out = &cum_scalar; io.rec_written = &rec_written;
+        }
         ionize_core(redshift, prev_redshift, io, box);
+        if (rec_written) {
+            d2h(box->ionisation_rate_G12, d_G12, N * sizeof(float));
+            if (d_mfp.p) d2h(box->mean_free_path, d_mfp, N * sizeof(float));
+            if (recomb == 2) d2h(box->cumulative_recombinations, d_cum, N * sizeof(float));
+            else box->cumulative_recombinations[0] = (float)cum_scalar;
+        }
 
         d2h(box->neutral_fraction, d_xH, N * sizeof(float));
         d2h(box->z_reion, d_zre, N * sizeof(float));

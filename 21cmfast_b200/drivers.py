@@ -53,11 +53,22 @@ def compute_ionization_field(*, perturbed_field: PerturbedField,
                              backend: Backend | None = None) -> IonizedBox:
     be = backend or get_backend()
     inputs = perturbed_field.inputs
-    if inputs.evolution_required or inputs.matter_options.lagrangian_source_grid:
+    ao = inputs.astro_options
+    if ao.USE_TS_FLUCT or ao.USE_MINI_HALOS or inputs.matter_options.lagrangian_source_grid:
         raise NotImplementedError(
-            "only the Eulerian, evolution-free IonizeBox path is in scope (SURVEY.md section 8)")
-    be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+            "only the Eulerian IonizeBox path without spin temperature / mini-halos is in scope "
+            "(SURVEY.md section 8)")
     redshift = perturbed_field.redshift
+    # previous-snapshot rules of the reference (single_field.py:773-791)
+    if redshift >= inputs.simulation_options.Z_HEAT_MAX:
+        previous_ionized_box = IonizedBox.initial(inputs)
+        previous_perturbed_field = PerturbedField.initial(inputs)
+    if inputs.evolution_required:
+        if previous_ionized_box is None:
+            raise ValueError("You need to provide a previous ionized box when redshift < Z_HEAT_MAX.")
+        if previous_perturbed_field is None:
+            raise ValueError("You need to provide a previous perturbed field when redshift < Z_HEAT_MAX.")
+    be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True, recomb=True)
     prev_pf = previous_perturbed_field or PerturbedField.initial(inputs)
     prev_ion = previous_ionized_box or IonizedBox.initial(inputs)
     ts, hb = TsBox.dummy(inputs), HaloBox.dummy(inputs)

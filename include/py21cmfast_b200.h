@@ -247,8 +247,10 @@ void initialiseSigmaMInterpTable(float M_Min, float M_Max);
 void freeSigmaMInterpTable(void);
 int init_heat(void);
 void destruct_heat(void);
-void init_MHR(void);          /* no-op: recombinations are outside the scoped path */
+void init_MHR(void);          /* recombination-rate tables (recombinations.c:92-122); needed when RECOMB_MODEL != none */
 void free_MHR(void);
+/* PDF-integrated recombination rate per baryon in (1e15 s)^-1 (recombinations.c:66-90); NaN before init_MHR() */
+double splined_recombination_rate(double z_eff, double gamma12_bg);
 int CreateFFTWWisdoms(void);  /* no-op: the FFT is the library's own sm_100a kernels */
 
 /* ---- scalar cosmology helpers the Python layer and tests call directly (:136-150) -------- */

@@ -118,6 +118,8 @@ def compare_ionized(test, ref):
     out = {"mask_mismatch": mism}
     for k, rv in ref.arrays().items():
         tv = test.arrays()[k]
+        if rv.size == 1:  # the homogeneous model's single cumulative_recombinations value: checked by its own test
+            continue
         if rv.shape != same.shape:
             rv, tv = rv[0], tv[0]
         e = rel_err(tv[same], rv[same]) if same.any() else 0.0

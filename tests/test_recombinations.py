@@ -1,0 +1,126 @@
+"""Recombinations and previous-snapshot evolution of the IonizeBox path
+against the compiled reference (oracle/_ref): RECOMB_MODEL = homogeneous / inhomogeneous, with the
+N_rec grid filtered per radius (CELL_RECOMB = False) or taken per cell, chained over three snapshots
+so that z_reion, Gamma12, the mean free path and the cumulative recombinations of one snapshot feed
+the next.  Also the rate table itself (init_MHR / splined_recombination_rate) as a known-answer test.
+CPU tier: host-emulated kernels; GPU tier: the CUDA library."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import common
+
+pkg = common.pkg
+
+REDSHIFTS = (9.0, 8.0, 7.0)
+CASES = {
+    "inhomogeneous_filtered": dict(model="inhomogeneous", cell=False, source="E-INTEGRAL"),
+    "inhomogeneous_cell": dict(model="inhomogeneous", cell=True, source="E-INTEGRAL"),
+    "homogeneous_cell": dict(model="homogeneous", cell=True, source="E-INTEGRAL"),
+    "inhomogeneous_filtered_const_zeta": dict(model="inhomogeneous", cell=False, source="CONST-ION-EFF"),
+}
+# the homogeneous model's one number comes from a float box sum in the reference (IonisationBox.c:1595-1607)
+TOL_GLOBAL_NREC = 1e-4
+
+
+def _inputs(model, cell, source, hii=32):
+    inp = common.make_inputs(hii=hii, dim=2 * hii, seed=77, source=source)
+    ao = dataclasses.replace(inp.astro_options, RECOMB_MODEL=model, CELL_RECOMB=cell)
+    return dataclasses.replace(inp, astro_options=ao)
+
+
+def _chain(be, inputs, ics, pfs):
+    prev_ib, prev_pf = pkg.IonizedBox.initial(inputs), pkg.PerturbedField.initial(inputs)
+    out = []
+    for pf in pfs:
+        ib = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, previous_ionized_box=prev_ib,
+                                          previous_perturbed_field=prev_pf, backend=be)
+        out.append(ib)
+        prev_ib, prev_pf = ib, pf
+    return out
+
+
+def _run_case(be, ref, name):
+    kw = CASES[name]
+    inputs = _inputs(**kw)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    pfs = [pkg.perturb_field(redshift=z, initial_conditions=ics, backend=ref) for z in REDSHIFTS]
+    got, want = _chain(be, inputs, ics, pfs), _chain(ref, inputs, ics, pfs)
+    for z, a, b in zip(REDSHIFTS, got, want):
+        stats = common.compare_ionized(a, b)
+        assert stats["mask_mismatch"] == 0, (name, z, stats)
+        # the first crossing is recorded at the same radius: the mean free path is one of the ladder's radii, bit for bit
+        assert np.array_equal(a.mean_free_path, b.mean_free_path), (name, z)
+        assert np.array_equal(a.z_reion, b.z_reion), (name, z)
+        for k, tol in (("ionisation_rate_G12", common.TOL_FIELD),
+                       ("cumulative_recombinations", TOL_GLOBAL_NREC if kw["model"] == "homogeneous" else common.TOL_FIELD)):
+            u, v = getattr(a, k), getattr(b, k)
+            assert u.shape == v.shape and np.isfinite(u).all(), (name, z, k)
+            err = np.abs(u - v).max() / max(np.abs(v).max(), 1e-30)
+            assert err <= tol, (name, z, k, err)
+    # the chain really evolved: reionisation redshifts of earlier snapshots survive, recombinations accumulate
+    last = got[-1]
+    assert set(np.unique(last.z_reion)) >= {-1.0, 9.0, 8.0, 7.0}
+    assert float(got[2].cumulative_recombinations.mean()) > float(got[1].cumulative_recombinations.mean()) > 0
+    assert float(last.ionisation_rate_G12.max()) > 0 and float(last.mean_free_path.max()) > 0
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_recombinations_emulated_vs_reference(name):
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    _run_case(emu, ref, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_recombinations_gpu_vs_reference(name):
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    _run_case(common.gpu_backend(), ref, name)
+
+
+def _rate_table_case(be, ref):
+    inputs = _inputs("inhomogeneous", False, "E-INTEGRAL", hii=16)
+    zs = np.array([-0.3, 0.0, 0.09, 0.11, 2.0, 5.37, 6.5, 8.0, 11.9, 13.0, 25.0, 59.8, 80.0])
+    gammas = np.exp(np.array([-12.0, -10.0, -9.95, -7.3, -2.0, -0.05, 0.0, 0.5, 3.1, 14.85, 14.9, 20.0]))
+    out = []
+    for b in (be, ref):
+        b.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True, recomb=True)
+        out.append(np.array([[b.lib.splined_recombination_rate(float(z), float(g)) for g in gammas] for z in zs]))
+    got, want = out
+    assert np.isfinite(want).all() and (want[:, 0] == 0).all() and (want[:, 3:] > 0).all()
+    assert np.allclose(got, want, rtol=1e-10, atol=0), np.abs(got / np.where(want == 0, 1, want) - 1).max()
+
+
+def test_recombination_rate_table_emulated_vs_reference():
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    _rate_table_case(emu, ref)
+
+
+@pytest.mark.gpu
+def test_recombination_rate_table_gpu_vs_reference():
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    _rate_table_case(common.gpu_backend(), ref)
+
+
+def test_recombinations_need_previous_boxes():
+    """single_field.py:779-787: with evolution, both previous boxes are required below Z_HEAT_MAX."""
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    inputs = _inputs("inhomogeneous", False, "E-INTEGRAL", hii=16)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+    pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+    with pytest.raises(ValueError):
+        pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
+    with pytest.raises(ValueError):
+        pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics,
+                                     previous_ionized_box=pkg.IonizedBox.initial(inputs), backend=emu)
