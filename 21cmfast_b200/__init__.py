@@ -12,7 +12,7 @@ from .drivers import (brightness_temperature, compute_initial_conditions,  # noq
 from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  # noqa: F401
                      MatterOptions, SimulationOptions)
 from .outputs import (BrightnessTemp, InitialConditions, IonizedBox,  # noqa: F401
-                      PerturbedField)
+                      PerturbedField, TsBox)
 from ._lib import Backend, BackendError, get_backend  # noqa: F401
 from .distributed import ionize_radius_parallel, perturb_slab_parallel  # noqa: F401
 

@@ -314,6 +314,11 @@ struct CritArgs {
     int nz, nzc;
     float *G12, *mfp;
     double R, gamma_prefactor;
+    /* spin-temperature inputs (USE_TS_FLUCT): the residual electron fraction x_e, filtered like the
+       density, lowers the barrier to (1 - x_e)(1 + rec) and is taken off the partial ionisations; the
+       neutral gas has the TsBox's temperature (IonisationBox.c:1100-1107,1165-1187) */
+    const float *xe_grid;    /* padded real rows of x_e at this radius, or null */
+    const float *Tk_neutral; /* unpadded, or null */
 };
 
 DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { /* thermochem.c:58-63 */
@@ -343,7 +348,7 @@ DEV void ionise_cell(const CritArgs &a, long long idx, float fcoll, double mean_
     }
 }
 
-/* the same cell with recombinations in the barrier; runs at every radius of the ladder */
+/* the same cell with recombinations and / or x_e in the barrier; runs at every radius of the ladder */
 DEV void ionise_cell_recomb(const CritArgs &a, long long idx, float fcoll, double mean_fix) {
     double curr_fcoll = mean_fix * (double)fcoll;
     if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
@@ -353,8 +358,9 @@ DEV void ionise_cell_recomb(const CritArgs &a, long long idx, float fcoll, doubl
                                             : (double)fmaxf(a.filtered[idx_f], (float)(-1. + pc::FRACT_FLOAT_ERR));
     double rec = a.recomb == 1 ? (double)a.rec_grid[idx_f] : a.recomb == 2 ? (double)a.rec_grid[idx] : a.rec_scalar;
     rec /= (1. + curr_dens);
-    if (curr_fcoll * a.ion_eff_factor > 1.0 + rec) {
-        if (!a.mask[idx] && (double)a.xH[idx] > pc::FRACT_FLOAT_ERR) { /* first (largest-R) crossing */
+    const double xe = a.xe_grid ? (double)a.xe_grid[idx_f] : 0.;
+    if (curr_fcoll * a.ion_eff_factor > (1. - xe) * (1.0 + rec)) {
+        if (a.recomb && !a.mask[idx] && (double)a.xH[idx] > pc::FRACT_FLOAT_ERR) { /* first (largest-R) crossing */
             a.G12[idx] = (float)(a.R * (a.gamma_prefactor * curr_fcoll));
             if (a.mfp) a.mfp[idx] = (float)a.R;
         }
@@ -362,9 +368,10 @@ DEV void ionise_cell_recomb(const CritArgs &a, long long idx, float fcoll, doubl
     } else if (a.R_index == 0 && !a.mask[idx] && (a.xH[idx] > pc::TINY)) {
         double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
         if (a.Tk) {
-            const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
+            const float T_HI = a.Tk_neutral ? a.Tk_neutral[idx] : (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
             a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
         }
+        res_xH -= xe;
         if (res_xH < 0) res_xH = 0;
         else if (res_xH > 1) res_xH = 1;
         a.xH[idx] = (float)res_xH;
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(256) ionise_kernel(CritArgs a) {
         if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
     }
     const double mean_fix = a.mean_f_coll / grid_mean;
-    if (a.recomb) {
+    if (a.recomb || a.xe_grid) {
         for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n;
              idx += (long long)gridDim.x * blockDim.x)
             ionise_cell_recomb(a, idx, a.fcoll[idx], mean_fix);
@@ -559,6 +566,7 @@ struct FinalArgs {
     int *nonfinite;
     double redshift, stored_redshift, T_re, TK_nofluct, adia_TK_term;
     double c_Tre17, c_z17; /* pow(T_re, 1.7), pow(1e4 (1 + z) / 4, 1.7) */
+    const float *Tk_neutral; /* USE_TS_FLUCT: the floor of the ionised gas temperature, else null */
 };
 /* materialise the flags (xH = 0, z_reion; IonisationBox.c:1142-1151) and set_ionized_temperatures
    (IonisationBox.c:1203-1256) in one pass */
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
             if (a.mask[i] && zre > 0) {
                 const float d = a.density[i];
                 tk = fully_ionized_temperature(zre, (float)a.stored_redshift, d, a.c_Tre17, a.c_z17);
-                const float thistk = a.TK_nofluct * (1 + a.adia_TK_term * d);
+                const float thistk = a.Tk_neutral ? a.Tk_neutral[i] : (float)(a.TK_nofluct * (1 + a.adia_TK_term * d));
                 if (tk < thistk) tk = thistk;
                 a.Tk[i] = tk;
             }
@@ -678,13 +686,19 @@ struct NeutralArgs {
     float *xH, *Tk;
     float xH_val;
     double TK_nofluct, adia_TK_term;
+    const float *xe, *Tk_neutral; /* USE_TS_FLUCT: x_HI = 1 - x_e and the TsBox's temperature, else null */
 };
-/* set_fully_neutral_box (IonisationBox.c:531-565), no-Ts branch */
+/* set_fully_neutral_box (IonisationBox.c:531-565) */
 __global__ void neutral_box_kernel(NeutralArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
          i += (long long)gridDim.x * blockDim.x) {
-        a.xH[i] = a.xH_val;
-        if (a.Tk) a.Tk[i] = a.TK_nofluct * (1.0 + a.adia_TK_term * a.density[i]);
+        if (a.xe) {
+            a.xH[i] = (float)(1. - (double)a.xe[i]);
+            if (a.Tk) a.Tk[i] = a.Tk_neutral[i];
+        } else {
+            a.xH[i] = a.xH_val;
+            if (a.Tk) a.Tk[i] = a.TK_nofluct * (1.0 + a.adia_TK_term * a.density[i]);
+        }
     }
 }
 
@@ -721,6 +735,8 @@ struct IonDeviceIO {
     float *G12 = nullptr, *mfp = nullptr, *cum_rec = nullptr; /* device, N; mfp optional; cum_rec inhomogeneous only */
     double *cum_rec_scalar_out = nullptr; /* host: new global value (homogeneous) */
     bool *rec_written = nullptr;      /* out: G12 / mfp / cumulative recombinations were updated */
+    /* spin-temperature inputs (USE_TS_FLUCT): device, N each */
+    const float *xe = nullptr, *Tk_neutral = nullptr;
 };
 
 /* pinned staging that outlives a call (cudaMallocHost is too slow to repeat per call) */
@@ -762,9 +778,16 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const MatterOptions *mo = matter_options_global;
     if (mo->SOURCE_MODEL != SRC_CONST_ION_EFF && mo->SOURCE_MODEL != SRC_E_INTEGRAL)
         b200_throw(B200_ValueError, "SOURCE_MODEL=%d: only CONST-ION-EFF and E-INTEGRAL are in scope", mo->SOURCE_MODEL);
-    if (ao->USE_TS_FLUCT || ao->USE_MINI_HALOS || ao->IONISE_ENTIRE_SPHERE || ao->PHOTON_CONS_TYPE != 0)
-        b200_throw(B200_ValueError, "USE_TS_FLUCT / USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / "
-                                    "photon conservation are outside the scoped IonizeBox path");
+    if (ao->USE_MINI_HALOS || ao->IONISE_ENTIRE_SPHERE || ao->PHOTON_CONS_TYPE != 0)
+        b200_throw(B200_ValueError, "USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / photon conservation are outside the "
+                                    "scoped IonizeBox path");
+    /* USE_TS_FLUCT: the caller's TsBox supplies x_e (filtered per radius) and the neutral-gas temperature */
+    const bool ts = ao->USE_TS_FLUCT;
+    if (ts) {
+        if (!io.xe || !io.Tk_neutral)
+            b200_throw(B200_ValueError, "USE_TS_FLUCT needs the TsBox's xray_ionised_fraction and kinetic_temp_neutral");
+        if (pt.phase >= 0) b200_throw(B200_ValueError, "the radius-parallel ladder is not built for USE_TS_FLUCT");
+    }
     /* recombinations: 1 homogeneous (one global N_rec), 2 inhomogeneous (per cell; filtered with the
        density unless CELL_RECOMB) */
     const int recomb = ao->RECOMB_MODEL;
@@ -822,7 +845,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         if (pt.phase == 0) { dev_zero(pt.mask, (size_t)N); dev_sync(); return; }
         if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
         { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
-        NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term};
+        NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term,
+                          ts ? io.xe : nullptr, ts ? io.Tk_neutral : nullptr};
         B200_LAUNCH(neutral_box_kernel, grid_for(N, 1024), 256, 0, na);
         return;
     }
@@ -858,7 +882,15 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     float2 *work[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) { work_ring[i].alloc(plan->n_cplx()); work[i] = work_ring[i].p; }
     DevBuf<float> d_fcoll;
-    if (!io.nion || recomb) d_fcoll.alloc(N);
+    const bool general = recomb != 0 || ts; /* per-cell barrier: the reference's arithmetic at every radius */
+    if (!io.nion || general) d_fcoll.alloc(N);
+    /* x_e in k space and its filtered copies, one per work box */
+    DevBuf<float2> k_xe, xe_ring[4];
+    float2 *work_xe[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (ts) {
+        k_xe.alloc(plan->n_cplx());
+        for (int i = 0; i < NW; i++) { xe_ring[i].alloc(plan->n_cplx()); work_xe[i] = xe_ring[i].p; }
+    }
     /* N_rec of the previous snapshot in k space and its filtered copies, one per work box */
     const bool rec_grid_filtered = filter_rec && io.prev_rec;
     DevBuf<float2> k_nrec, rec_ring[4];
@@ -903,7 +935,12 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     pro.clip = 1; pro.clip_lo = -1.f; pro.clip_hi = 1e6f;
     pro.post_scale = 1.f / (float)N;
     fft_r2c(plan, k_unfiltered, pro);
-    if (recomb && io.wait_slot >= 0) main_wait_copy_event(io.wait_slot); /* xH / G12 / N_rec are read at every radius */
+    if (general && io.wait_slot >= 0) main_wait_copy_event(io.wait_slot); /* xH / G12 / N_rec / x_e are read at every radius */
+    if (ts) { /* prepare_box_for_filtering(xray_ionised_fraction, 0, 1) (IonisationBox.c:1510-1513) */
+        ZPrologue px = pro;
+        px.src = io.xe; px.clip_lo = 0.f; px.clip_hi = 1.f;
+        fft_r2c(plan, k_xe, px);
+    }
     if (rec_grid_filtered) {
         ZPrologue pr = pro;
         pr.src = io.prev_rec; pr.clip_lo = 0.f; pr.clip_hi = 1e20f;
@@ -957,6 +994,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             er.scale = 1.f; er.clip = 1; er.clip_lo = 0.f; er.clip_hi = 3.0e38f;
             fft_c2r(plan, k_nrec, work_rec[j % NW], km, er);
         }
+        if (ts) { /* x_e over the same window, kept inside [0, 0.999] (IonisationBox.c:812-818) */
+            ZEpilogue ex;
+            ex.scale = 1.f; ex.clip = 1; ex.clip_lo = 0.f; ex.clip_hi = 0.999f;
+            fft_c2r(plan, k_xe, work_xe[j % NW], km, ex);
+        }
         if (overlap_tables) rt_event_record(64 + (j % NW)); /* this radius' table slot is free again */
         d2h_async(g_stage.h_keys + 2 * k, d_keys.p + 2 * k, 2 * sizeof(int));
         dev_event_record(g_stage.events[k]);
@@ -997,7 +1039,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
            other radius only needs the grid sum and the ionised flags, so its f_coll grid is never
            materialised */
         const bool last = (k == n_todo - 1);
-        float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : (recomb ? d_fcoll.p : nullptr);
+        float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : (general ? d_fcoll.p : nullptr);
         if (last && io.nion && io.nion_written) *io.nion_written = true;
         const float *filtered = reinterpret_cast<const float *>(work[j % NW]);
         SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
@@ -1005,7 +1047,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
         else B200_LAUNCH(fcoll_sum_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
 
-        if (!last && !recomb) {
+        if (!last && !general) {
             CritDeltaArgs cd;
             memset(&cd, 0, sizeof(cd));
             cd.nx = nx; cd.ny = ny; cd.nz = nz; cd.nzc = plan->pitch;
@@ -1026,11 +1068,14 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             ca.ion_eff_factor = c.ion_eff_factor; ca.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
             ca.R_index = rs.R_index; ca.redshift = c.redshift;
             ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
+            if (general) {
+                ca.filtered = filtered; ca.nz = nz; ca.nzc = plan->pitch;
+                if (ts) { ca.xe_grid = reinterpret_cast<const float *>(work_xe[j % NW]); ca.Tk_neutral = io.Tk_neutral; }
+            }
             if (recomb) {
                 ca.recomb = rec_grid_filtered ? 1 : (recomb == 2 && io.prev_rec) ? 2 : 3;
                 ca.rec_grid = rec_grid_filtered ? reinterpret_cast<const float *>(work_rec[j % NW]) : io.prev_rec;
                 ca.rec_scalar = recomb == 1 ? io.prev_rec_scalar : 0.;
-                ca.filtered = filtered; ca.nz = nz; ca.nzc = plan->pitch;
                 ca.G12 = io.G12; ca.mfp = io.mfp;
                 ca.R = rs.R; ca.gamma_prefactor = c.gamma_prefactor;
             }
@@ -1050,7 +1095,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
         FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
                         c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
-                        pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7)};
+                        pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), ts ? io.Tk_neutral : nullptr};
         B200_LAUNCH(finalize_kernel, grid_for(N, 1024), 256, 0, fa);
         int flag = 0;
         d2h(&flag, d_flag, sizeof(int)); /* also drains the stream before the work boxes are released */
@@ -1097,7 +1142,7 @@ static void reset_stats() { g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h =
 extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedField *perturbed_field,
                                  PerturbedField *previous_perturbed_field, IonizedBox *previous_ionize_box,
                                  TsBox *spin_temp, HaloBox *halos, InitialConditions *ini_boxes, IonizedBox *box) {
-    (void)previous_perturbed_field; (void)spin_temp; (void)halos; (void)ini_boxes;
+    (void)previous_perturbed_field; (void)halos; (void)ini_boxes;
     try {
         require_params(true);
         rt_init();
@@ -1109,11 +1154,15 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         if (!perturbed_field || !perturbed_field->density || !box || !box->neutral_fraction || !box->z_reion)
             b200_throw(B200_ValueError, "ComputeIonizedBox: required arrays are NULL");
 
+
         /* first snapshot: the reference writes z_reion = -1 into the *previous* box
            (setup_first_z_prevbox, IonisationBox.c:365-386) */
         const bool first = prev_redshift < 1;
         if (first && previous_ionize_box && previous_ionize_box->z_reion)
             for (long long i = 0; i < N; i++) previous_ionize_box->z_reion[i] = -1.0f;
+        const bool ts = astro_options_global->USE_TS_FLUCT;
+        if (ts && (!spin_temp || !spin_temp->xray_ionised_fraction || !spin_temp->kinetic_temp_neutral))
+            b200_throw(B200_ValueError, "ComputeIonizedBox: USE_TS_FLUCT needs a computed TsBox");
 
         DevBuf<float> d_density(N), d_xH(N), d_zre(N), d_prev, d_Tk, d_nion;
         h2d(d_density, perturbed_field->density, N * sizeof(float));
@@ -1152,9 +1201,16 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
                 h2d_copy_stream(d_prev_rec, previous_ionize_box->cumulative_recombinations, N * sizeof(float));
             }
         }
+        DevBuf<float> d_xe, d_Tkn;
+        if (ts) {
+            d_xe.alloc(N); d_Tkn.alloc(N);
+            h2d_copy_stream(d_xe, spin_temp->xray_ionised_fraction, N * sizeof(float));
+            h2d_copy_stream(d_Tkn, spin_temp->kinetic_temp_neutral, N * sizeof(float));
+        }
         copy_event_record(slot);
         bool nion_written = false;
         IonDeviceIO io = {d_density, d_prev.p, d_xH, d_zre, d_Tk.p, d_nion.p, slot, &nion_written};
+        io.xe = d_xe.p; io.Tk_neutral = d_Tkn.p;
         if (recomb) {
             io.prev_rec = d_prev_rec.p;
             io.prev_rec_scalar = recomb == 1 ? (double)previous_ionize_box->cumulative_recombinations[0] : 0.;

@@ -1,6 +1,6 @@
 /*
  * misc.cu -- test_filter (filtering.c:397-445) and ComputeBrightnessTemp
- * (BrightnessTemperatureBox.c:22-105, the no-spin-temperature branch).
+ * (BrightnessTemperatureBox.c:22-105; with USE_TS_FLUCT the caller's TsBox supplies the spin temperature).
  */
 #include "fft.h"
 #include "host_physics.h"
@@ -61,22 +61,36 @@ struct TbArgs {
     const float *density, *xH;
     float *tb;
     float const_factor;
+    const float *Ts; /* spin temperature (USE_TS_FLUCT) or null: saturated limit */
+    float *tau;      /* 21-cm optical depth output, with Ts only */
+    float redshift, T_rad;
+    int *nonfinite;
 };
 __global__ void brightness_kernel(TbArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
-         i += (long long)gridDim.x * blockDim.x)
-        a.tb[i] = a.const_factor * a.xH[i] * (1 + a.density[i]);
+         i += (long long)gridDim.x * blockDim.x) {
+        float tb = a.const_factor * a.xH[i] * (1 + a.density[i]);
+        if (a.Ts) {
+            /* prefactors -> optical depth (1000: K -> mK), then the full radiative-transfer form */
+            const float Ts = a.Ts[i];
+            tb *= (1. + a.redshift) / (1000. * Ts);
+            a.tau[i] = tb;
+            tb = (1. - exp(-(double)tb)) * 1000. * (Ts - a.T_rad) / (1. + a.redshift);
+        }
+        a.tb[i] = tb;
+        if (!isfinite(tb)) *a.nonfinite = 1;
+    }
 }
 
 extern "C" int ComputeBrightnessTemp(float redshift, TsBox *spin_temp, IonizedBox *ionized_box,
                                      PerturbedField *perturb_field, BrightnessTemp *box) {
-    (void)spin_temp;
     try {
         require_params(true);
         rt_init();
         g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0;
-        if (astro_options_global->USE_TS_FLUCT)
-            b200_throw(B200_ValueError, "USE_TS_FLUCT is outside the scoped path");
+        const bool ts = astro_options_global->USE_TS_FLUCT;
+        if (ts && (!spin_temp || !spin_temp->spin_temperature || !box->tau_21))
+            b200_throw(B200_ValueError, "ComputeBrightnessTemp: USE_TS_FLUCT needs the TsBox's spin_temperature and tau_21");
         const SimulationOptions *so = simulation_options_global;
         const CosmoParams *cp = cosmo_params_global;
         const long long N = (long long)so->HII_DIM * so->HII_DIM * hii_d_para();
@@ -86,9 +100,21 @@ extern "C" int ComputeBrightnessTemp(float redshift, TsBox *spin_temp, IonizedBo
         DevBuf<float> d_d(N), d_x(N), d_t(N);
         h2d(d_d, perturb_field->density, N * sizeof(float));
         h2d(d_x, ionized_box->neutral_fraction, N * sizeof(float));
-        TbArgs a = {N, d_d, d_x, d_t, const_factor};
+        DevBuf<float> d_ts, d_tau;
+        DevBuf<int> d_flag(1);
+        dev_zero(d_flag, sizeof(int));
+        if (ts) {
+            d_ts.alloc(N); d_tau.alloc(N);
+            h2d(d_ts, spin_temp->spin_temperature, N * sizeof(float));
+        }
+        const float T_rad = pc::T_cmb * (1 + redshift);
+        TbArgs a = {N, d_d, d_x, d_t, const_factor, d_ts.p, d_tau.p, redshift, T_rad, d_flag};
         B200_LAUNCH(brightness_kernel, dev_num_sms() * 4, 256, 0, a);
         d2h(box->brightness_temp, d_t, N * sizeof(float));
+        if (ts) d2h(box->tau_21, d_tau, N * sizeof(float));
+        int flag = 0;
+        d2h(&flag, d_flag, sizeof(int));
+        if (flag) b200_throw(B200_InfinityorNaNError, "brightness temperature is infinite or NaN");
     } catch (B200Error &e) {
         if (getenv("B200_VERBOSE") || e.code == B200_CUDAError)
             fprintf(stderr, "[21cmfast_b200] ComputeBrightnessTemp: %s\n", e.msg);

@@ -50,14 +50,16 @@ def compute_ionization_field(*, perturbed_field: PerturbedField,
                              initial_conditions: InitialConditions,
                              previous_perturbed_field: PerturbedField | None = None,
                              previous_ionized_box: IonizedBox | None = None,
+                             spin_temp: TsBox | None = None,
                              backend: Backend | None = None) -> IonizedBox:
     be = backend or get_backend()
     inputs = perturbed_field.inputs
     ao = inputs.astro_options
-    if ao.USE_TS_FLUCT or ao.USE_MINI_HALOS or inputs.matter_options.lagrangian_source_grid:
+    if ao.USE_MINI_HALOS or inputs.matter_options.lagrangian_source_grid:
         raise NotImplementedError(
-            "only the Eulerian IonizeBox path without spin temperature / mini-halos is in scope "
-            "(SURVEY.md section 8)")
+            "only the Eulerian IonizeBox path without mini-halos is in scope (SURVEY.md section 8)")
+    if ao.USE_TS_FLUCT and spin_temp is None:  # single_field.py:803-808
+        raise ValueError("You have USE_TS_FLUCT=True, but have not provided a spin_temp!")
     redshift = perturbed_field.redshift
     # previous-snapshot rules of the reference (single_field.py:773-791)
     if redshift >= inputs.simulation_options.Z_HEAT_MAX:
@@ -71,7 +73,7 @@ def compute_ionization_field(*, perturbed_field: PerturbedField,
     be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True, recomb=True)
     prev_pf = previous_perturbed_field or PerturbedField.initial(inputs)
     prev_ion = previous_ionized_box or IonizedBox.initial(inputs)
-    ts, hb = TsBox.dummy(inputs), HaloBox.dummy(inputs)
+    ts, hb = (spin_temp if ao.USE_TS_FLUCT else TsBox.dummy(inputs)), HaloBox.dummy(inputs)
     box = IonizedBox.new(inputs, redshift)
     _check(be.lib.ComputeIonizedBox(
         C.c_float(redshift), C.c_float(prev_pf.redshift), C.byref(perturbed_field.cstruct),
@@ -84,12 +86,15 @@ def compute_ionization_field(*, perturbed_field: PerturbedField,
 
 
 def brightness_temperature(*, ionized_box: IonizedBox, perturbed_field: PerturbedField,
+                           spin_temp: TsBox | None = None,
                            backend: Backend | None = None) -> BrightnessTemp:
     be = backend or get_backend()
     inputs = ionized_box.inputs
+    if inputs.astro_options.USE_TS_FLUCT and spin_temp is None:  # single_field.py brightness_temperature
+        raise ValueError("You have USE_TS_FLUCT=True, but have not provided a spin_temp!")
     be.state.init(inputs, broadcast_inputs=True)
     bt = BrightnessTemp.new(inputs, ionized_box.redshift)
-    ts = TsBox.dummy(inputs)
+    ts = spin_temp if inputs.astro_options.USE_TS_FLUCT else TsBox.dummy(inputs)
     _check(be.lib.ComputeBrightnessTemp(
         C.c_float(ionized_box.redshift), C.byref(ts.cstruct), C.byref(ionized_box.cstruct),
         C.byref(perturbed_field.cstruct), C.byref(bt.cstruct)), "ComputeBrightnessTemp")

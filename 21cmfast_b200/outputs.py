@@ -111,9 +111,25 @@ class TsBox(OutputStruct):
     _arrays = ("spin_temperature", "xray_ionised_fraction", "kinetic_temp_neutral", "J_21_LW")
     _scalars = ("Q_HI",)
 
+    def __init__(self, inputs, redshift=None, **kw):
+        super().__init__(inputs, **kw)
+        self.redshift = redshift
+
     @classmethod
     def dummy(cls, inputs):
         return cls(inputs)
+
+    @classmethod
+    def new(cls, inputs: InputParameters, redshift: float):
+        """Allocated arrays of a spin-temperature box (outputs.py ``TsBox.new``).  The spin-temperature
+        calculation itself is outside the scoped path: callers fill the arrays (from the reference, or
+        from a file) and pass the box to ``compute_ionization_field`` / ``brightness_temperature``."""
+        lo, _ = _shapes(inputs)
+        out = {k: np.zeros(lo, np.float32) for k in ("spin_temperature", "xray_ionised_fraction",
+                                                     "kinetic_temp_neutral")}
+        if inputs.astro_options.USE_MINI_HALOS:
+            out["J_21_LW"] = np.zeros(lo, np.float32)
+        return cls(inputs, redshift, **out)
 
 
 class HaloBox(OutputStruct):

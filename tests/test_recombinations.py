@@ -1,5 +1,7 @@
-"""Recombinations and previous-snapshot evolution of the IonizeBox path
-against the compiled reference (oracle/_ref): RECOMB_MODEL = homogeneous / inhomogeneous, with the
+"""Recombinations, x_e filtering and previous-snapshot evolution of the IonizeBox path (SURVEY.md
+section 8f, row 2) against the compiled reference (oracle/_ref): USE_TS_FLUCT with a caller-supplied
+TsBox (the spin-temperature calculation itself is out of scope: both sides get the same synthetic
+box), RECOMB_MODEL = homogeneous / inhomogeneous, with the
 N_rec grid filtered per radius (CELL_RECOMB = False) or taken per cell, chained over three snapshots
 so that z_reion, Gamma12, the mean free path and the cumulative recombinations of one snapshot feed
 the next.  Also the rate table itself (init_MHR / splined_recombination_rate) as a known-answer test.
@@ -19,23 +21,42 @@ CASES = {
     "inhomogeneous_cell": dict(model="inhomogeneous", cell=True, source="E-INTEGRAL"),
     "homogeneous_cell": dict(model="homogeneous", cell=True, source="E-INTEGRAL"),
     "inhomogeneous_filtered_const_zeta": dict(model="inhomogeneous", cell=False, source="CONST-ION-EFF"),
+    "ts_fluct": dict(model="none", cell=False, source="E-INTEGRAL", ts=True),
+    "ts_fluct_inhomogeneous_filtered": dict(model="inhomogeneous", cell=False, source="E-INTEGRAL", ts=True),
 }
 # the homogeneous model's one number comes from a float box sum in the reference (IonisationBox.c:1595-1607)
 TOL_GLOBAL_NREC = 1e-4
 
 
-def _inputs(model, cell, source, hii=32):
+def _inputs(model, cell, source, hii=32, ts=False):
     inp = common.make_inputs(hii=hii, dim=2 * hii, seed=77, source=source)
-    ao = dataclasses.replace(inp.astro_options, RECOMB_MODEL=model, CELL_RECOMB=cell)
+    ao = dataclasses.replace(inp.astro_options, RECOMB_MODEL=model, CELL_RECOMB=cell, USE_TS_FLUCT=ts)
     return dataclasses.replace(inp, astro_options=ao)
+
+
+def _synthetic_ts(inputs, pf):
+    """A TsBox with the right magnitudes and some structure: x_e of a few per cent following the density
+    (with excursions beyond [0, 1] so that the clips act), adiabatic-like neutral-gas temperature, and a
+    spin temperature between it and the CMB."""
+    ts = pkg.TsBox.new(inputs, pf.redshift)
+    rng = np.random.default_rng(int(pf.redshift * 100))
+    d = pf.density.astype(np.float64)
+    xe = 0.03 * (1 + d) + 0.02 * rng.standard_normal(d.shape)
+    xe[rng.random(d.shape) < 1e-3] = 1.2
+    ts.xray_ionised_fraction[...] = xe
+    tk = 40.0 * np.cbrt(np.clip(1 + d, 1e-3, None)) ** 2 * (1 + 0.1 * rng.random(d.shape))
+    ts.kinetic_temp_neutral[...] = tk
+    ts.spin_temperature[...] = 0.5 * (tk + 2.7255 * (1 + pf.redshift)) + 1.0
+    return ts
 
 
 def _chain(be, inputs, ics, pfs):
     prev_ib, prev_pf = pkg.IonizedBox.initial(inputs), pkg.PerturbedField.initial(inputs)
     out = []
     for pf in pfs:
+        ts = _synthetic_ts(inputs, pf) if inputs.astro_options.USE_TS_FLUCT else None
         ib = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, previous_ionized_box=prev_ib,
-                                          previous_perturbed_field=prev_pf, backend=be)
+                                          previous_perturbed_field=prev_pf, spin_temp=ts, backend=be)
         out.append(ib)
         prev_ib, prev_pf = ib, pf
     return out
@@ -55,6 +76,8 @@ def _run_case(be, ref, name):
         assert np.array_equal(a.z_reion, b.z_reion), (name, z)
         for k, tol in (("ionisation_rate_G12", common.TOL_FIELD),
                        ("cumulative_recombinations", TOL_GLOBAL_NREC if kw["model"] == "homogeneous" else common.TOL_FIELD)):
+            if kw["model"] == "none":
+                break
             u, v = getattr(a, k), getattr(b, k)
             assert u.shape == v.shape and np.isfinite(u).all(), (name, z, k)
             err = np.abs(u - v).max() / max(np.abs(v).max(), 1e-30)
@@ -62,8 +85,9 @@ def _run_case(be, ref, name):
     # the chain really evolved: reionisation redshifts of earlier snapshots survive, recombinations accumulate
     last = got[-1]
     assert set(np.unique(last.z_reion)) >= {-1.0, 9.0, 8.0, 7.0}
-    assert float(got[2].cumulative_recombinations.mean()) > float(got[1].cumulative_recombinations.mean()) > 0
-    assert float(last.ionisation_rate_G12.max()) > 0 and float(last.mean_free_path.max()) > 0
+    if kw["model"] != "none":
+        assert float(got[2].cumulative_recombinations.mean()) > float(got[1].cumulative_recombinations.mean()) > 0
+        assert float(last.ionisation_rate_G12.max()) > 0 and float(last.mean_free_path.max()) > 0
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -124,3 +148,45 @@ def test_recombinations_need_previous_boxes():
     with pytest.raises(ValueError):
         pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics,
                                      previous_ionized_box=pkg.IonizedBox.initial(inputs), backend=emu)
+
+
+def _ts_neutral_and_brightness_case(be, ref):
+    """USE_TS_FLUCT side branches: the fully neutral early exit (x_HI = 1 - x_e, T_k from the TsBox;
+    IonisationBox.c:531-549) and the brightness temperature with a finite spin temperature and the
+    21-cm optical depth (BrightnessTemperatureBox.c:73-82)."""
+    inputs = _inputs("none", False, "E-INTEGRAL", hii=24, ts=True)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    for z in (25.0, 8.0):
+        pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=ref)
+        ts = _synthetic_ts(inputs, pf)
+        kw = dict(perturbed_field=pf, initial_conditions=ics, previous_ionized_box=pkg.IonizedBox.initial(inputs),
+                  previous_perturbed_field=pkg.PerturbedField.initial(inputs), spin_temp=ts)
+        a, b = pkg.compute_ionization_field(backend=be, **kw), pkg.compute_ionization_field(backend=ref, **kw)
+        assert common.compare_ionized(a, b)["mask_mismatch"] == 0
+        if z == 25.0:  # nothing ionised: the box is the TsBox's own x_e and temperature, bit for bit
+            assert np.array_equal(a.neutral_fraction, b.neutral_fraction)
+            assert np.array_equal(a.kinetic_temperature, ts.kinetic_temp_neutral)
+        ta = pkg.brightness_temperature(ionized_box=b, perturbed_field=pf, spin_temp=ts, backend=be)
+        tb = pkg.brightness_temperature(ionized_box=b, perturbed_field=pf, spin_temp=ts, backend=ref)
+        for k in ("brightness_temp", "tau_21"):
+            u, v = getattr(ta, k), getattr(tb, k)
+            assert np.abs(v).max() > 0 and np.abs(u - v).max() <= 2e-6 * np.abs(v).max(), (z, k)
+    with pytest.raises(ValueError):
+        pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics,
+                                     previous_ionized_box=pkg.IonizedBox.initial(inputs),
+                                     previous_perturbed_field=pkg.PerturbedField.initial(inputs), backend=be)
+
+
+def test_ts_fluct_neutral_box_and_brightness_emulated_vs_reference():
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    _ts_neutral_and_brightness_case(emu, ref)
+
+
+@pytest.mark.gpu
+def test_ts_fluct_neutral_box_and_brightness_gpu_vs_reference():
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    _ts_neutral_and_brightness_case(common.gpu_backend(), ref)
