@@ -338,3 +338,8 @@ extern "C" int b200_host_gaussian_stream(unsigned long mt_seed, long long n, dou
 extern "C" long long b200_gaussians_from_raw_host(const unsigned int *raw, long long n_raw, long long want, double *out) {
     return gaussians_from_raw_host(raw, n_raw, want, out);
 }
+
+/* test hook: the x-plane range of thread t under the reference's static OpenMP schedule */
+extern "C" void b200_omp_static_range(int n, int n_threads, int t, int *begin, int *end) {
+    hostnum::omp_static_range(n, n_threads, t, begin, end);
+}

@@ -135,6 +135,120 @@ double Mt19937::ugaussian() {
     return y * std::sqrt(-2.0 * std::log(r2) / r2);
 }
 
+/* ---- the other four per-thread generator types (rng.c:57-83) ---- */
+namespace {
+inline unsigned long lcg69069(unsigned long n) { return (69069UL * n) & 0xffffffffUL; }
+/* (a x) mod m without overflow by Schrage's decomposition m = a q + r */
+inline long schrage(long a, long q, long r, long x) { const long h = x / q; return a * (x - h * q) - h * r; }
+}  // namespace
+
+uint32_t ThreadRng::next_taus() {
+    auto step = [](uint32_t s, int a, int b, uint32_t c, int d) -> uint32_t { return ((s & c) << d) ^ (((s << a) ^ s) >> b); };
+    taus_[0] = step(taus_[0], 13, 19, 4294967294U, 12);
+    taus_[1] = step(taus_[1], 2, 25, 4294967288U, 4);
+    taus_[2] = step(taus_[2], 3, 11, 4294967280U, 17);
+    return taus_[0] ^ taus_[1] ^ taus_[2];
+}
+uint32_t ThreadRng::next_gfsr4() {
+    const int M = 16383;
+    ring_pos_ = (ring_pos_ + 1) & M;
+    const uint32_t v = ring_[(ring_pos_ + M + 1 - 471) & M] ^ ring_[(ring_pos_ + M + 1 - 1586) & M] ^
+                       ring_[(ring_pos_ + M + 1 - 6988) & M] ^ ring_[(ring_pos_ + M + 1 - 9689) & M];
+    ring_[ring_pos_] = v;
+    return v;
+}
+unsigned long ThreadRng::next_cmrg() {
+    const long m1 = 2147483647, m2 = 2145483479;
+    long *x = lag_, *y = lag_ + 3;
+    long p3 = schrage(183326, 11714, 2883, x[2]), p2 = schrage(63308, 33921, 12979, x[1]);
+    if (p3 < 0) p3 += m1;
+    if (p2 < 0) p2 += m1;
+    x[2] = x[1]; x[1] = x[0]; x[0] = p2 - p3;
+    if (x[0] < 0) x[0] += m1;
+    long q3 = schrage(539608, 3976, 2071, y[2]), q1 = schrage(86098, 24919, 7417, y[0]);
+    if (q3 < 0) q3 += m2;
+    if (q1 < 0) q1 += m2;
+    y[2] = y[1]; y[1] = y[0]; y[0] = q1 - q3;
+    if (y[0] < 0) y[0] += m2;
+    return (unsigned long)(x[0] < y[0] ? x[0] - y[0] + m1 : x[0] - y[0]);
+}
+unsigned long ThreadRng::next_mrg() {
+    const long m = 2147483647;
+    long *x = lag_;
+    long p5 = schrage(104480, 20554, 1727, x[4]), p1 = schrage(107374182, 20, 7, x[0]);
+    if (p5 > 0) p5 -= m;
+    if (p1 < 0) p1 += m;
+    x[4] = x[3]; x[3] = x[2]; x[2] = x[1]; x[1] = x[0];
+    x[0] = p1 + p5;
+    if (x[0] < 0) x[0] += m;
+    return (unsigned long)x[0];
+}
+ThreadRng::ThreadRng(int thread_index, unsigned long s) : kind_(thread_index % 5), mt_(0) {
+    switch (kind_) {
+    case 0:
+        mt_.seed(s);
+        break;
+    case 1: { /* every word is assembled from the top bits of 32 LCG steps; 32 words are then forced independent */
+        if (s == 0) s = 4357;
+        ring_.assign(16384, 0);
+        for (auto &w : ring_) {
+            uint32_t t = 0;
+            for (uint32_t bit = 0x80000000U; bit; bit >>= 1) {
+                s = lcg69069(s);
+                if (s & 0x80000000UL) t |= bit;
+            }
+            w = t;
+        }
+        uint32_t msb = 0x80000000U, mask = 0xffffffffU;
+        for (int i = 0; i < 32; i++, mask >>= 1, msb >>= 1) ring_[7 + 3 * i] = (ring_[7 + 3 * i] & mask) | msb;
+        ring_pos_ = 32;
+        break;
+    }
+    case 2: {
+        const long m1 = 2147483647, m2 = 2145483479;
+        if (s == 0) s = 1;
+        for (int i = 0; i < 6; i++) { s = lcg69069(s); lag_[i] = (long)(s % (unsigned long)(i < 3 ? m1 : m2)); }
+        for (int i = 0; i < 7; i++) next_cmrg();
+        break;
+    }
+    case 3: {
+        if (s == 0) s = 1;
+        for (int i = 0; i < 5; i++) { s = lcg69069(s); lag_[i] = (long)(s % 2147483647UL); }
+        for (int i = 0; i < 6; i++) next_mrg();
+        break;
+    }
+    default: {
+        if (s == 0) s = 1;
+        const uint32_t floor_[3] = {2, 8, 16};
+        unsigned long v = s;
+        for (int i = 0; i < 3; i++) {
+            v = lcg69069(v);
+            if (v < floor_[i]) v += floor_[i];
+            taus_[i] = (uint32_t)v;
+        }
+        for (int i = 0; i < 6; i++) next_taus();
+    }
+    }
+}
+double ThreadRng::uniform() {
+    switch (kind_) {
+    case 0: return mt_.uniform();
+    case 1: return next_gfsr4() / 4294967296.0;
+    case 2: return next_cmrg() / 2147483647.0;
+    case 3: return next_mrg() / 2147483647.0;
+    default: return next_taus() / 4294967296.0;
+    }
+}
+double ThreadRng::ugaussian() {
+    double x, y, r2;
+    do {
+        x = -1 + 2 * uniform_pos();
+        y = -1 + 2 * uniform_pos();
+        r2 = x * x + y * y;
+    } while (r2 > 1.0 || r2 == 0);
+    return y * std::sqrt(-2.0 * std::log(r2) / r2);
+}
+
 unsigned int derive_thread_seeds(unsigned long long seed, int n_threads, unsigned int *out) {
     /* rng.c:31-54: choose n_threads of the integers 0..INT_MAX/16-1 by sequential selection
        (an integer i is taken when (n-i) U < k-j), then Fisher-Yates shuffle the picks.  The big

@@ -187,6 +187,37 @@ class Mt19937 {
     int mti_;
 };
 
+/* The generator each OpenMP thread of the reference owns: thread t gets type t mod 5 of
+   {mt19937, gfsr4, cmrg, mrg, taus2} (rng.c:57-83), seeded and scaled to doubles as GSL does
+   (gfsr4: Ziff 1998 four-tap shift register; cmrg: L'Ecuyer 1996; mrg: L'Ecuyer, Blouin & Couture
+   1993; taus2: L'Ecuyer 1999 with the corrected seeding).  Used for seed parity with N_THREADS > 1. */
+class ThreadRng {
+  public:
+    ThreadRng(int thread_index, unsigned long seed);
+    double uniform();
+    double uniform_pos() { double x; do { x = uniform(); } while (x == 0); return x; }
+    double ugaussian(); /* polar Box-Muller, gsl_ran_ugaussian */
+  private:
+    int kind_;
+    Mt19937 mt_;
+    std::vector<uint32_t> ring_; /* gfsr4: 2^14 words */
+    int ring_pos_ = 0;
+    long lag_[6] = {0, 0, 0, 0, 0, 0}; /* cmrg: x1..x3, y1..y3; mrg: x1..x5 */
+    uint32_t taus_[3] = {0, 0, 0};
+    unsigned long next_cmrg();
+    unsigned long next_mrg();
+    uint32_t next_taus();
+    uint32_t next_gfsr4();
+};
+
+/* [begin, end) of the iterations 0..n-1 that thread t of n_threads runs under the static schedule of
+   `#pragma omp for` (libgomp: the first n % n_threads threads take one extra iteration) */
+inline void omp_static_range(int n, int n_threads, int t, int *begin, int *end) {
+    const int q = n / n_threads, r = n % n_threads;
+    *begin = t < r ? t * (q + 1) : r * (q + 1) + (t - r) * q;
+    *end = *begin + (t < r ? q + 1 : q);
+}
+
 /* the seed the reference derives for thread 0 from the user seed (rng.c:31-54 with N_THREADS=1):
    sequential selection of 1 of INT_MAX/16 integers, then a (trivial) shuffle */
 unsigned int derive_thread_seeds(unsigned long long seed, int n_threads, unsigned int *out);

@@ -306,6 +306,9 @@ int b200_ComputeIonizedBox_device_part(float redshift, float prev_redshift,
 int b200_gsl_gaussian_stream(unsigned long mt_seed, long long n1, long long n2, double *host_out);
 int b200_host_gaussian_stream(unsigned long mt_seed, long long n, double *host_out);
 long long b200_gaussians_from_raw_host(const unsigned int *raw, long long n_raw, long long want, double *out);
+/* x-plane range [begin, end) of thread t of n_threads under the static schedule of sample_ic_modes
+   (InitialConditions.c:103-134); test hook for the N_THREADS > 1 seed-parity path */
+void b200_omp_static_range(int n, int n_threads, int t, int *begin, int *end);
 
 #ifdef __cplusplus
 }
