@@ -8,7 +8,8 @@ wrapper/driver layer for that path.  The directory name starts with a digit, so 
 ``importlib.import_module("21cmfast_b200")``.
 """
 from .drivers import (brightness_temperature, compute_initial_conditions,  # noqa: F401
-                      compute_ionization_field, perturb_field, run_coeval)
+                      compute_ionization_field, get_logspaced_redshifts, perturb_field,
+                      run_coeval)
 from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  # noqa: F401
                      MatterOptions, SimulationOptions)
 from .outputs import (BrightnessTemp, InitialConditions, IonizedBox,  # noqa: F401

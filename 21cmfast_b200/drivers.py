@@ -2,13 +2,16 @@
 
 ``compute_initial_conditions`` (single_field.py:38-113), ``perturb_field`` (:116-156),
 ``compute_ionization_field`` (:714-840), ``brightness_temperature`` and a minimal ``run_coeval``
-(coeval.py:521-697, evolution-free configs only).  Each call initialises the backend's global
+(coeval.py:521-697: independent redshifts, or the scrolled evolution over node redshifts that
+``RECOMB_MODEL`` needs).  Each call initialises the backend's global
 state exactly as ``@init_c_state`` does in the reference and then calls the C-ABI entry point
 with numpy-owned host buffers.
 """
 from __future__ import annotations
 
 import ctypes as C
+
+import numpy as np
 
 from ._lib import Backend, BackendError, get_backend
 from .inputs import InputParameters
@@ -102,13 +105,51 @@ def brightness_temperature(*, ionized_box: IonizedBox, perturbed_field: Perturbe
     return bt
 
 
-def run_coeval(*, out_redshifts, inputs: InputParameters, initial_conditions=None,
+def get_logspaced_redshifts(min_redshift: float, z_step_factor: float, max_redshift: float):
+    """Log-spaced evolution nodes, highest first (wrapper/inputs.py:1774-1789)."""
+    z = 10 ** np.arange(np.log10(1 + min_redshift), np.log10((1 + max_redshift) * z_step_factor),
+                        np.log10(z_step_factor)) - 1
+    return tuple(float(v) for v in z[::-1])
+
+
+def run_coeval(*, out_redshifts=None, inputs: InputParameters, initial_conditions=None,
                backend: Backend | None = None):
-    """ICs once, then perturb + ionize (+ T_b) per redshift; returns a list of dicts."""
+    """ICs once, then perturb + ionize + T_b per redshift; returns a list of dicts, one per output
+    redshift, highest first (drivers/coeval.py:530-700 without caching / halos / spin temperature).
+
+    Without evolution every output redshift is independent.  With evolution (``RECOMB_MODEL`` set) the
+    boxes are scrolled from the highest node down: the previous ionized box and perturbed field passed
+    to each step are those of the last *node* redshift (``inputs.node_redshifts``, or log-spaced nodes
+    from the lowest output redshift up to ``Z_HEAT_MAX`` in steps of ``ZPRIME_STEP_FACTOR``); output
+    redshifts between nodes are computed from the node above them but do not feed the evolution
+    (coeval.py:505-512)."""
+    if out_redshifts is None:
+        out_redshifts = inputs.node_redshifts
+    outs = [float(out_redshifts)] if isinstance(out_redshifts, (int, float)) else [float(z) for z in out_redshifts]
+    if not outs:
+        raise ValueError("out_redshifts must be given if inputs has no node redshifts")
+    if inputs.astro_options.USE_TS_FLUCT:
+        raise NotImplementedError("run_coeval with USE_TS_FLUCT needs the spin-temperature calculation, which is "
+                                  "outside the scoped path; pass a TsBox to compute_ionization_field instead")
     ics = initial_conditions or compute_initial_conditions(inputs=inputs, backend=backend)
     out = []
-    for z in ([out_redshifts] if isinstance(out_redshifts, (int, float)) else out_redshifts):
+    if not inputs.evolution_required:
+        for z in sorted(outs, reverse=True):
+            pf = perturb_field(redshift=z, initial_conditions=ics, backend=backend)
+            ib = compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=backend)
+            bt = brightness_temperature(ionized_box=ib, perturbed_field=pf, backend=backend)
+            out.append({"redshift": z, "perturbed_field": pf, "ionized_box": ib, "brightness_temp": bt})
+        return out
+    so = inputs.simulation_options
+    nodes = tuple(inputs.node_redshifts) or get_logspaced_redshifts(min(outs), so.ZPRIME_STEP_FACTOR, so.Z_HEAT_MAX)
+    prev_pf, prev_ib = PerturbedField.initial(inputs), IonizedBox.initial(inputs)
+    for z in sorted(set(nodes) | set(outs), reverse=True):
         pf = perturb_field(redshift=z, initial_conditions=ics, backend=backend)
-        ib = compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=backend)
-        out.append({"redshift": z, "perturbed_field": pf, "ionized_box": ib})
+        ib = compute_ionization_field(perturbed_field=pf, initial_conditions=ics, previous_perturbed_field=prev_pf,
+                                      previous_ionized_box=prev_ib, backend=backend)
+        if z in outs:
+            bt = brightness_temperature(ionized_box=ib, perturbed_field=pf, backend=backend)
+            out.append({"redshift": z, "perturbed_field": pf, "ionized_box": ib, "brightness_temp": bt})
+        if z in nodes:
+            prev_pf, prev_ib = pf, ib
     return out

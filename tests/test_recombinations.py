@@ -190,3 +190,32 @@ def test_ts_fluct_neutral_box_and_brightness_gpu_vs_reference():
     if ref is None:
         pytest.skip("oracle/_ref not present on this box")
     _ts_neutral_and_brightness_case(common.gpu_backend(), ref)
+
+
+def test_run_coeval_scrolls_the_evolution_over_node_redshifts():
+    """run_coeval with RECOMB_MODEL set: the chain over the node redshifts equals the explicit chain of
+    single-field calls, and an output redshift between two nodes is computed from the node above it
+    without feeding the evolution (coeval.py:505-512)."""
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    base = _inputs("inhomogeneous", False, "E-INTEGRAL", hii=16)
+    inputs = dataclasses.replace(base, node_redshifts=REDSHIFTS)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+    pfs = [pkg.perturb_field(redshift=z, initial_conditions=ics, backend=emu) for z in REDSHIFTS]
+    want = _chain(emu, inputs, ics, pfs)
+    got = pkg.run_coeval(inputs=inputs, initial_conditions=ics, backend=emu)
+    assert [c["redshift"] for c in got] == list(REDSHIFTS)
+    for c, w in zip(got, want):
+        for k in ("neutral_fraction", "z_reion", "ionisation_rate_G12", "cumulative_recombinations"):
+            assert np.array_equal(getattr(c["ionized_box"], k), getattr(w, k)), (c["redshift"], k)
+        assert np.isfinite(c["brightness_temp"].brightness_temp).all()
+    mixed = pkg.run_coeval(out_redshifts=(8.5, 7.0), inputs=inputs, initial_conditions=ics, backend=emu)
+    assert [c["redshift"] for c in mixed] == [8.5, 7.0]
+    assert np.array_equal(mixed[1]["ionized_box"].cumulative_recombinations, want[2].cumulative_recombinations)
+    z85 = mixed[0]["ionized_box"]
+    assert set(np.unique(z85.z_reion)) <= {-1.0, 9.0, 8.5}
+    # default nodes: log-spaced from the lowest output up to Z_HEAT_MAX
+    nodes = pkg.get_logspaced_redshifts(7.0, 1.02, 35.0)
+    assert abs(nodes[-1] - 7.0) < 1e-9 and nodes[0] >= 35.0 and all(a > b for a, b in zip(nodes, nodes[1:]))
+    assert abs((1 + nodes[0]) / (1 + nodes[1]) - 1.02) < 1e-9
