@@ -24,6 +24,11 @@ CASES = {
     "ts_fluct": dict(model="none", cell=False, source="E-INTEGRAL", ts=True),
     "ts_fluct_inhomogeneous_filtered": dict(model="inhomogeneous", cell=False, source="E-INTEGRAL", ts=True),
 }
+GOLDEN_CHAIN_CASES = ("inhomogeneous_filtered", "homogeneous_cell", "ts_fluct_inhomogeneous_filtered")
+GOLDEN_FIELDS = ("neutral_fraction", "z_reion", "ionisation_rate_G12", "mean_free_path", "cumulative_recombinations",
+                 "kinetic_temperature")
+RATE_Z = np.array([-0.3, 0.0, 0.09, 0.11, 2.0, 5.37, 6.5, 8.0, 11.9, 13.0, 25.0, 59.8, 80.0])
+RATE_GAMMA = np.exp(np.array([-12.0, -10.0, -9.95, -7.3, -2.0, -0.05, 0.0, 0.5, 3.1, 14.85, 14.9, 20.0]))
 # the homogeneous model's one number comes from a float box sum in the reference (IonisationBox.c:1595-1607)
 TOL_GLOBAL_NREC = 1e-4
 
@@ -109,8 +114,7 @@ def test_recombinations_gpu_vs_reference(name):
 
 def _rate_table_case(be, ref):
     inputs = _inputs("inhomogeneous", False, "E-INTEGRAL", hii=16)
-    zs = np.array([-0.3, 0.0, 0.09, 0.11, 2.0, 5.37, 6.5, 8.0, 11.9, 13.0, 25.0, 59.8, 80.0])
-    gammas = np.exp(np.array([-12.0, -10.0, -9.95, -7.3, -2.0, -0.05, 0.0, 0.5, 3.1, 14.85, 14.9, 20.0]))
+    zs, gammas = RATE_Z, RATE_GAMMA
     out = []
     for b in (be, ref):
         b.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True, recomb=True)
@@ -219,3 +223,42 @@ def test_run_coeval_scrolls_the_evolution_over_node_redshifts():
     nodes = pkg.get_logspaced_redshifts(7.0, 1.02, 35.0)
     assert abs(nodes[-1] - 7.0) < 1e-9 and nodes[0] >= 35.0 and all(a > b for a, b in zip(nodes, nodes[1:]))
     assert abs((1 + nodes[0]) / (1 + nodes[1]) - 1.02) < 1e-9
+
+
+# ---- committed fixtures (tests/golden/recomb.npz, generator tests/golden/make_golden_recomb.py): these
+# ---- run wherever the repository is, with or without oracle/_ref
+def _golden():
+    return np.load(common.GOLDEN / "recomb.npz")
+
+
+def test_shipped_library_rate_table_matches_golden():
+    """init_MHR / splined_recombination_rate are host code: the shipped CUDA library computes them
+    without a GPU, and they equal what the compiled reference produced (75 000 adaptive integrals, three
+    parameter splines, 300 rate splines)."""
+    from test_host_logic import _host_backend
+    be = _host_backend()
+    g = _golden()
+    inputs = _inputs("inhomogeneous", False, "E-INTEGRAL", hii=16)
+    be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True, recomb=True)
+    got = np.array([[be.lib.splined_recombination_rate(float(z), float(gm)) for gm in g["rate_gamma"]] for z in g["rate_z"]])
+    assert np.allclose(got, g["rate"], rtol=1e-10, atol=0)
+    be.state.free()
+    assert np.isnan(be.lib.splined_recombination_rate(8.0, 1.0))  # freed tables fail loudly, not silently
+
+
+@pytest.mark.parametrize("name", GOLDEN_CHAIN_CASES)
+def test_emulated_chain_reproduces_golden(name):
+    emu = common.emu_backend()
+    if emu is None:
+        pytest.skip("tests/_emu not built")
+    g = _golden()
+    inputs = _inputs(hii=16, **CASES[name])
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+    pfs = [pkg.perturb_field(redshift=z, initial_conditions=ics, backend=emu) for z in REDSHIFTS]
+    for z, ib in zip(REDSHIFTS, _chain(emu, inputs, ics, pfs)):
+        for k in GOLDEN_FIELDS:
+            u, v = getattr(ib, k), g[f"{name}_{int(z)}_{k}"]
+            if k == "neutral_fraction":
+                assert np.array_equal(u == 0, v == 0), (name, z)
+            tol = TOL_GLOBAL_NREC if v.size == 1 else 5 * common.TOL_FIELD  # ICs and density are recomputed here too
+            assert np.abs(u - v).max() <= tol * max(np.abs(v).max(), 1e-30), (name, z, k)
