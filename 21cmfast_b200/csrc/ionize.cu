@@ -319,6 +319,9 @@ struct CritArgs {
        neutral gas has the TsBox's temperature (IonisationBox.c:1100-1107,1165-1187) */
     const float *xe_grid;    /* padded real rows of x_e at this radius, or null */
     const float *Tk_neutral; /* unpadded, or null */
+    /* IONISE_ENTIRE_SPHERE: cells already painted by a sphere of an earlier radius (their x_HI is 0:
+       no partial ionisation), or null */
+    const unsigned char *paint;
 };
 
 DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { /* thermochem.c:58-63 */
@@ -336,7 +339,7 @@ DEV void ionise_cell(const CritArgs &a, long long idx, float fcoll, double mean_
     if (a.mass_dep_zeta && curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
     if (curr_fcoll * a.ion_eff_factor > 1.0) {
         a.mask[idx] = 1;
-    } else if (a.R_index == 0 && !a.mask[idx] && (a.xH[idx] > pc::TINY)) {
+    } else if (a.R_index == 0 && !a.mask[idx] && !(a.paint && a.paint[idx]) && (a.xH[idx] > pc::TINY)) {
         double res_xH = 1. - curr_fcoll * a.ion_eff_factor;
         if (a.Tk) {
             const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
@@ -567,6 +570,7 @@ struct FinalArgs {
     double redshift, stored_redshift, T_re, TK_nofluct, adia_TK_term;
     double c_Tre17, c_z17; /* pow(T_re, 1.7), pow(1e4 (1 + z) / 4, 1.7) */
     const float *Tk_neutral; /* USE_TS_FLUCT: the floor of the ionised gas temperature, else null */
+    const unsigned char *paint; /* IONISE_ENTIRE_SPHERE: cells inside a painted sphere (x_HI = 0 only), else null */
 };
 /* materialise the flags (xH = 0, z_reion; IonisationBox.c:1142-1151) and set_ionized_temperatures
    (IonisationBox.c:1203-1256) in one pass */
@@ -578,6 +582,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
             const float pz = a.prev_zre ? a.prev_zre[i] : -1.f;
             zre = (pz < 0) ? (float)a.redshift : pz;
             a.xH[i] = 0.f;
+        } else if (a.paint && a.paint[i]) {
+            a.xH[i] = 0.f; /* inside a sphere: ionised, but only the sphere's centre records z_reion and T_k */
         }
         a.z_reion[i] = zre;
         if (a.Tk) {
@@ -657,6 +663,76 @@ __global__ void __launch_bounds__(256) mean2_kernel(Mean2Args a) {
         __syncthreads();
     }
     if (threadIdx.x == 0) { a.partial[2 * blockIdx.x] = ra[0]; a.partial[2 * blockIdx.x + 1] = rb[0]; }
+}
+
+/* IONISE_ENTIRE_SPHERE (update_in_sphere / check_region, bubble_helper_progs.c:263-413): every cell
+   whose periodic distance to a centre flagged at this radius is below R (in cells of the x axis) is
+   ionised.  The reference scatters a sphere from every flagged centre; here the set is the exact
+   squared Euclidean distance transform of the centre flags, built separably -- nearest flagged cell
+   along z, then the lower envelope of d_z^2 + dy^2 along y, then of that + dx^2 along x -- and
+   thresholded with the reference's float comparison.  Offsets beyond ceil(R) cannot decide a cell, so
+   every pass scans a window of 2 ceil(R) + 1 cells (at most the whole periodic axis). */
+struct SphereArgs {
+    int nx, ny, nz, h;            /* h = min(ceil(R), n/2) per axis is applied in the kernel */
+    const unsigned char *centre;  /* flags of this radius */
+    unsigned short *dz;           /* pass z out: distance to the nearest flagged cell of the row, capped */
+    unsigned int *d2;             /* pass y out: min d_z^2 + dy^2, capped */
+    unsigned char *paint, *mask;  /* pass x: paint |= (Rsq > d^2); mask |= centre */
+    float Rsq;
+};
+constexpr unsigned int SPHERE_FAR = 0x3fffffffu;
+__global__ void __launch_bounds__(256) sphere_z_kernel(SphereArgs a) {
+    const long long n = (long long)a.nx * a.ny * a.nz;
+    const int h = a.h < a.nz / 2 ? a.h : a.nz / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / a.nz;
+        const int z = (int)(i - row * a.nz);
+        const unsigned char *c = a.centre + row * a.nz;
+        int best = 0xffff;
+        for (int d = 0; d <= h; d++) {
+            int zp = z + d; if (zp >= a.nz) zp -= a.nz;
+            int zm = z - d; if (zm < 0) zm += a.nz;
+            if (c[zp] | c[zm]) { best = d; break; }
+        }
+        a.dz[i] = (unsigned short)best;
+    }
+}
+__global__ void __launch_bounds__(256) sphere_y_kernel(SphereArgs a) {
+    const long long n = (long long)a.nx * a.ny * a.nz;
+    const int h = a.h < a.ny / 2 ? a.h : a.ny / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % a.nz);
+        const long long xy = i / a.nz;
+        const int y = (int)(xy % a.ny);
+        const long long x = xy / a.ny;
+        unsigned int best = SPHERE_FAR;
+        for (int d = -h; d <= h; d++) {
+            int yy = y + d; if (yy >= a.ny) yy -= a.ny; else if (yy < 0) yy += a.ny;
+            const unsigned int dz = a.dz[(x * a.ny + yy) * a.nz + z];
+            if (dz != 0xffffu) {
+                const unsigned int v = dz * dz + (unsigned int)(d * d);
+                if (v < best) best = v;
+            }
+        }
+        a.d2[i] = best;
+    }
+}
+__global__ void __launch_bounds__(256) sphere_x_kernel(SphereArgs a) {
+    const long long n = (long long)a.nx * a.ny * a.nz;
+    const long long plane = (long long)a.ny * a.nz;
+    const int h = a.h < a.nx / 2 ? a.h : a.nx / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i / plane);
+        const long long yz = i - (long long)x * plane;
+        unsigned int best = SPHERE_FAR;
+        for (int d = -h; d <= h; d++) {
+            int xx = x + d; if (xx >= a.nx) xx -= a.nx; else if (xx < 0) xx += a.nx;
+            const unsigned int v = a.d2[(long long)xx * plane + yz];
+            if (v != SPHERE_FAR && v + (unsigned int)(d * d) < best) best = v + (unsigned int)(d * d);
+        }
+        if (best != SPHERE_FAR && a.Rsq > (float)best) a.paint[i] = 1;
+        if (a.centre[i]) a.mask[i] = 1;
+    }
 }
 
 struct FillArgs {
@@ -778,9 +854,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const MatterOptions *mo = matter_options_global;
     if (mo->SOURCE_MODEL != SRC_CONST_ION_EFF && mo->SOURCE_MODEL != SRC_E_INTEGRAL)
         b200_throw(B200_ValueError, "SOURCE_MODEL=%d: only CONST-ION-EFF and E-INTEGRAL are in scope", mo->SOURCE_MODEL);
-    if (ao->USE_MINI_HALOS || ao->IONISE_ENTIRE_SPHERE || ao->PHOTON_CONS_TYPE != 0)
-        b200_throw(B200_ValueError, "USE_MINI_HALOS / IONISE_ENTIRE_SPHERE / photon conservation are outside the "
-                                    "scoped IonizeBox path");
+    if (ao->USE_MINI_HALOS || ao->PHOTON_CONS_TYPE != 0)
+        b200_throw(B200_ValueError, "USE_MINI_HALOS / photon conservation are outside the scoped IonizeBox path");
     /* USE_TS_FLUCT: the caller's TsBox supplies x_e (filtered per radius) and the neutral-gas temperature */
     const bool ts = ao->USE_TS_FLUCT;
     if (ts) {
@@ -909,6 +984,36 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     unsigned char *d_mask = pt.mask;
     if (pt.phase < 0) { own_mask.alloc((size_t)N); d_mask = own_mask; }
     if (pt.phase <= 0) dev_zero(d_mask, (size_t)N); /* phase 1 continues on the merged mask */
+    /* IONISE_ENTIRE_SPHERE: the flags of each radius are kept apart (d_centre), dilated by the radius'
+       sphere into d_paint and merged into d_mask (the centres, which alone record z_reion and T_k) */
+    const bool sphere = ao->IONISE_ENTIRE_SPHERE;
+    auto sphere_radius_cells = [&](double R) { return (float)(R / so->BOX_LEN) * (float)so->HII_DIM; };
+    if (sphere) {
+        if (general || pt.phase >= 0)
+            b200_throw(B200_ValueError, "IONISE_ENTIRE_SPHERE is built for the plain ladder only (no recombinations, "
+                                        "spin temperature or radius partition: the reference's result then depends "
+                                        "on its cell visiting order)");
+        /* at the unfiltered radius the partial ionisations of the same sweep would depend on the visiting
+           order unless the sphere is the centre cell alone */
+        if (n_todo > 0 && radii[todo.back()].R_index == 0) {
+            const float rc = sphere_radius_cells(radii[todo.back()].R);
+            if ((float)pow((double)rc, 2) > 1.0f)
+                b200_throw(B200_ValueError, "IONISE_ENTIRE_SPHERE with R_BUBBLE_MIN above one cell is order-dependent "
+                                            "in the reference and not built");
+        }
+    }
+    DevBuf<unsigned char> d_centre(sphere ? (size_t)N : 0), d_paint(sphere ? (size_t)N : 0);
+    DevBuf<unsigned short> d_sdz(sphere ? (size_t)N : 0);
+    DevBuf<unsigned int> d_sd2(sphere ? (size_t)N : 0);
+    if (sphere) dev_zero(d_paint, (size_t)N);
+    auto paint_spheres = [&](double R) {
+        const float rc = sphere_radius_cells(R);
+        SphereArgs sa = {nx, ny, nz, (int)ceil((double)rc), d_centre, d_sdz, d_sd2, d_paint, d_mask, (float)pow((double)rc, 2)};
+        const int nb = grid_for(N, 256);
+        B200_LAUNCH(sphere_z_kernel, nb, 256, 0, sa);
+        B200_LAUNCH(sphere_y_kernel, nb, 256, 0, sa);
+        B200_LAUNCH(sphere_x_kernel, nb, 256, 0, sa);
+    };
     /* window tables over |n|^2 (cubic boxes, top-hat / gaussian): one slot per work box, stream-ordered reuse */
     const bool cubic = nx == ny && ny == nz && so->NON_CUBIC_FACTOR == 1.0f;
     const bool use_wtab = cubic && (c.hii_filter == 0 || c.hii_filter == 2);
@@ -1053,10 +1158,12 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             cd.nx = nx; cd.ny = ny; cd.nz = nz; cd.nzc = plan->pitch;
             cd.filtered = filtered; cd.table = d_tables.p + k;
             cd.partial = d_partial; cd.n_partial = sweep_blocks; cd.mask = d_mask;
+            if (sphere) { dev_zero(d_centre, (size_t)N); cd.mask = d_centre; }
             cd.n_cells = (double)N; cd.mean_f_coll = box->mean_f_coll; cd.f_limit = f_limit;
             cd.ion_eff_factor = c.ion_eff_factor; cd.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
             if (htab.log_valued) B200_LAUNCH(ionise_delta_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
             else B200_LAUNCH(ionise_delta_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
+            if (sphere) paint_spheres(rs.R);
         } else {
             if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
             CritArgs ca;
@@ -1079,7 +1186,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
                 ca.G12 = io.G12; ca.mfp = io.mfp;
                 ca.R = rs.R; ca.gamma_prefactor = c.gamma_prefactor;
             }
+            const bool dilate_last = sphere && rs.R_index != 0; /* at R_index 0 the sphere is the centre cell itself */
+            if (sphere) ca.paint = d_paint;
+            if (dilate_last) { dev_zero(d_centre, (size_t)N); ca.mask = d_centre; }
             B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
+            if (dilate_last) paint_spheres(rs.R);
         }
     }
 
@@ -1095,7 +1206,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
         FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
                         c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
-                        pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), ts ? io.Tk_neutral : nullptr};
+                        pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), ts ? io.Tk_neutral : nullptr,
+                        sphere ? d_paint.p : nullptr};
         B200_LAUNCH(finalize_kernel, grid_for(N, 1024), 256, 0, fa);
         int flag = 0;
         d2h(&flag, d_flag, sizeof(int)); /* also drains the stream before the work boxes are released */

@@ -96,7 +96,7 @@ def _unsupported_cases(be):
         ao = dataclasses.replace(base.astro_options, **kw)
         return dataclasses.replace(base, astro_options=ao)
 
-    for kw in (dict(USE_TS_FLUCT=True), dict(RECOMB_MODEL="homogeneous"), dict(IONISE_ENTIRE_SPHERE=True)):
+    for kw in (dict(USE_TS_FLUCT=True), dict(RECOMB_MODEL="homogeneous"), dict(PHOTON_CONS_TYPE="z-photoncons")):
         inp = with_opts(**kw)
         be.state.init(inp, broadcast_inputs=True, ps=True, sigma=True, heat=True)
         box = pkg.IonizedBox.new(inp, 8.0)
