@@ -622,7 +622,7 @@ static double integrate_qag(double lo, double hi, const MFParams &p, int which) 
 
 #define NGL_INT 100
 static double xi_GL[NGL_INT + 1], wi_GL[NGL_INT + 1], GL_limit[2] = {0, 0};
-void initialise_GL(double lnM_Min, double lnM_Max) { /* hmf.c:699-706 */
+extern "C" void initialise_GL(double lnM_Min, double lnM_Max) { /* hmf.c:699-706 */
     if (lnM_Min == GL_limit[0] && lnM_Max == GL_limit[1]) return;
     hostnum::gauss_legendre(lnM_Min, lnM_Max, NGL_INT, xi_GL, wi_GL);
     GL_limit[0] = lnM_Min;
@@ -987,3 +987,18 @@ double xion_RECFAST(float z) {
 float cT_approx(float z) { return 0.58 - 0.006 * (z - 10.0); }
 
 extern "C" int CreateFFTWWisdoms(void) { return 0; }
+
+/* integral_wrappers.c:18-24: sigma(M) and d sigma^2/dM from the interpolation table for an array of masses */
+extern "C" void get_sigma(int n_masses, double *mass_values, double *sigma_out, double *dsigmasqdm_out) {
+    for (int i = 0; i < n_masses; i++) {
+        try {
+            sigma_out[i] = EvaluateSigma(log(mass_values[i]));
+            dsigmasqdm_out[i] = EvaluatedSigmasqdm(log(mass_values[i]));
+        } catch (B200Error &e) { /* table not initialised / out of range: NaN, never an exception across the C boundary */
+            fprintf(stderr, "[21cmfast_b200] get_sigma: %s\n", e.msg);
+            sigma_out[i] = dsigmasqdm_out[i] = std::nan("");
+        }
+    }
+}
+/* read by the reference's coeval driver (coeval.py:686); photon conservation is not built */
+extern "C" { bool photon_cons_allocated = false; }

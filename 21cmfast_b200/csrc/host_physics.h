@@ -61,7 +61,7 @@ double Fcoll_General(double z, double lnMmin, double lnMmax);
 double Nion_ConditionalM(double growthf, double lnM1, double lnM2, double lnM_cond, double sigma2,
                          double delta2, double Mturn, const ScalingConstants *sc, int method);
 double FgtrM_bias_fast(float growthf, float del_bias, float sig_small, float sig_large);
-void initialise_GL(double lnM_Min, double lnM_Max);
+extern "C" void initialise_GL(double lnM_Min, double lnM_Max); /* also part of the reference's cffi surface */
 
 /* heating_helper_progs.c:94-197 */
 double T_RECFAST(float z);

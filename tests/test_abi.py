@@ -7,6 +7,7 @@ import subprocess
 import tempfile
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 import common
@@ -99,3 +100,71 @@ def test_library_loads_without_gpu_and_product_has_no_fallback():
     for py in (ROOT / "21cmfast_b200").glob("*.py"):
         t = py.read_text()
         assert "from oracle" not in t and "import oracle" not in t and "_emu" not in t, py
+
+
+def _reference_prototypes():
+    ref = Path("/root/reference/src/py21cmfast/src/_functionprototypes_wrapper.h")
+    if not ref.exists():
+        pytest.skip("reference tree not present on this box")
+    text = re.sub(r"/\*.*?\*/", "", ref.read_text(), flags=re.S)
+    text = re.sub(r"//.*", "", text)
+    return {re.search(r"(\w+)\s*\(", p).group(1): " ".join(p.split()) for p in text.split(";") if "(" in p}
+
+
+def test_library_is_a_complete_link_target_for_the_reference_cffi_surface():
+    """Every function and global the reference's cdef names (_functionprototypes_wrapper.h,
+    _inputparams_wrapper.h) is exported, so the API-mode cffi build links against the library alone
+    (SURVEY.md section 8b); the header declares the same prototypes."""
+    if not LIB.exists():
+        pytest.skip("CUDA library not built")
+    protos = _reference_prototypes()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(LIB)], check=True, capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    assert not [n for n in protos if n not in exported]
+    assert "photon_cons_allocated" in exported
+    declared = set(_declared_functions())
+    assert not [n for n in protos if n not in declared], [n for n in protos if n not in declared]
+
+
+def test_unscoped_symbols_fail_loudly(capfd):
+    """Outside the scoped path nothing computes: status 3 / NaN and a message, never a silent CPU result."""
+    import ctypes as C
+    pkg = common.pkg
+    if not LIB.exists():
+        pytest.skip("CUDA library not built")
+    lib = pkg.Backend().lib
+    lib.InitialisePhotonCons.restype = C.c_int
+    assert lib.InitialisePhotonCons() == 3
+    lib.ComputeZstart_PhotonCons.restype = C.c_int
+    assert lib.ComputeZstart_PhotonCons(None) == 3
+    lib.expected_nhalo.restype = C.c_double
+    lib.expected_nhalo.argtypes = [C.c_double]
+    assert np.isnan(lib.expected_nhalo(8.0))
+    lib.ComputeTau.restype = C.c_float
+    assert np.isnan(lib.ComputeTau(0, None, None, C.c_float(3.0)))
+    assert C.c_bool.in_dll(lib, "photon_cons_allocated").value is False
+    err = capfd.readouterr().err
+    assert "InitialisePhotonCons is outside the scoped hot path" in err and "expected_nhalo" in err
+
+
+def test_get_sigma_matches_reference():
+    import ctypes as C
+    pkg = common.pkg
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    inputs = common.make_inputs()
+    masses = np.logspace(5.5, 15.5, 41)
+    res = []
+    for be in (emu, ref):
+        be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True)
+        s, d = np.zeros_like(masses), np.zeros_like(masses)
+        fn = be.lib.get_sigma
+        fn.restype = None
+        fn.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        fn(len(masses), dp(masses), dp(s), dp(d))
+        res.append((s, d))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-10)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-10)
+    assert (np.diff(res[0][0]) < 0).all()
