@@ -262,3 +262,21 @@ def test_emulated_chain_reproduces_golden(name):
                 assert np.array_equal(u == 0, v == 0), (name, z)
             tol = TOL_GLOBAL_NREC if v.size == 1 else 5 * common.TOL_FIELD  # ICs and density are recomputed here too
             assert np.abs(u - v).max() <= tol * max(np.abs(v).max(), 1e-30), (name, z, k)
+
+
+def test_ragged_noncubic_grid_with_recombinations_and_ts_emulated():
+    """The reference's awkward test sizes (35 cells, non-cubic z extent 42: mixed-radix transforms, rows that
+    are not a multiple of four) through the general route -- filtered N_rec and x_e together."""
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    inp = common.make_inputs(hii=35, dim=70, seed=3)
+    ao = dataclasses.replace(inp.astro_options, RECOMB_MODEL="inhomogeneous", CELL_RECOMB=False, USE_TS_FLUCT=True)
+    so = dataclasses.replace(inp.simulation_options, NON_CUBIC_FACTOR=1.2)
+    inp = dataclasses.replace(inp, astro_options=ao, simulation_options=so)
+    ics = pkg.compute_initial_conditions(inputs=inp, backend=ref)
+    pfs = [pkg.perturb_field(redshift=z, initial_conditions=ics, backend=ref) for z in (9.0, 7.5)]
+    for a, b in zip(_chain(emu, inp, ics, pfs), _chain(ref, inp, ics, pfs)):
+        assert a.neutral_fraction.shape == (35, 35, 42)
+        assert common.compare_ionized(a, b)["mask_mismatch"] == 0
+        assert np.array_equal(a.mean_free_path, b.mean_free_path)

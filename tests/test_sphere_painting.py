@@ -83,3 +83,19 @@ def test_sphere_painting_refuses_order_dependent_configurations():
                                      previous_ionized_box=pkg.IonizedBox.initial(rec),
                                      previous_perturbed_field=pkg.PerturbedField.initial(rec), backend=emu)
     assert e.value.code == 3
+
+
+def test_sphere_painting_ragged_noncubic_emulated():
+    """35 x 35 x 42 cells: the sphere's radius is in x-cells while z wraps with its own length
+    (update_in_sphere's dimensions / dimensions_ncf), on mixed-radix transforms."""
+    emu, ref = common.emu_backend(), common.ref_backend()
+    if emu is None or ref is None:
+        pytest.skip("needs tests/_emu and oracle/_ref")
+    inputs = _inputs("E-INTEGRAL", 35, 1.2)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=ref)
+    got = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
+    want = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=ref)
+    assert got.neutral_fraction.shape == (35, 35, 42)
+    assert np.array_equal(got.neutral_fraction == 0, want.neutral_fraction == 0)
+    assert np.array_equal(got.z_reion, want.z_reion)
