@@ -14,7 +14,7 @@
  * at T = 1e4 K; it is interpolated by a natural cubic spline along ln(Gamma12) only, the redshift is
  * index-sampled.  The 75 000 adaptive integrals are independent: they run over all host threads.
  * Values and spline coefficients are kept on the host (homogeneous model, one evaluation per
- * snapshot) and handed to ionize.cu for the per-cell evaluation of the inhomogeneous model.
+ * snapshot); ionize.cu uploads them (1.2 MB) for the per-cell evaluation of the inhomogeneous model.
  */
 #include "host_recomb.h"
 
@@ -176,7 +176,6 @@ extern "C" void init_MHR(void) {
         }
         if (status && getenv("B200_VERBOSE"))
             fprintf(stderr, "[21cmfast_b200] init_MHR: an adaptive integral returned status %d\n", status);
-        g_rr.version++;
         g_ready = true;
     } catch (B200Error &e) {
         fprintf(stderr, "[21cmfast_b200] init_MHR: %s\n", e.msg);

@@ -12,7 +12,6 @@ struct RecombTables {
     double lnGamma[RECOMB_NG];
     double lnGamma_max;
     std::vector<double> y, c; /* [RECOMB_NZ][RECOMB_NG]: rate (1e-15 s^-1) and natural-spline c coefficients */
-    int version = 0;          /* bumped by every init_MHR(): the device copy is refreshed when it changes */
 };
 
 /* null until init_MHR() has run */
