@@ -668,6 +668,95 @@ double Nion_General(double z, double lnMmin, double lnMmax, double Mturn, const 
         return integrate_qag(lnMmin, lnMmax, p, 1);
     });
 }
+/* ---- INTEGRATION_METHOD_ATOMIC = GAMMA-APPROX (Munoz et al. 2022, appendix B; hmf.c:728-892) ----
+   sigma(M) is taken as a triple power law around two pivot masses and the turnover as a sharp cut, which
+   turns the conditional Press-Schechter integral of M^(alpha_star + alpha_esc) into differences of
+   upper incomplete gamma functions Gamma(1/2 + beta, nu/2). */
+static double expint_e1(double x) { /* E1(x) = Gamma(0, x) */
+    if (x <= 1.0) {
+        double sum = 0, term = 1;
+        for (int k = 1; k < 60; k++) { term *= -x / k; sum -= term / k; }
+        return -0.5772156649015328606 - log(x) + sum;
+    }
+    double b = x + 1.0, c = 1e300, d = 1.0 / b, h = d;
+    for (int i = 1; i < 200; i++) { /* modified Lentz */
+        const double an = -1.0 * i * i;
+        b += 2.0; d = 1.0 / (an * d + b); c = b + an / c;
+        const double del = c * d; h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return h * exp(-x);
+}
+static double upper_gamma_pos(double a, double x) { /* Gamma(a, x), a > 0 */
+    if (x <= 0) return tgamma(a);
+    if (x < a + 1.0) { /* series of the lower function */
+        double ap = a, sum = 1.0 / a, del = sum;
+        for (int n = 0; n < 500; n++) { ap += 1; del *= x / ap; sum += del; if (fabs(del) < fabs(sum) * 1e-16) break; }
+        return tgamma(a) - sum * exp(-x + a * log(x));
+    }
+    double b = x + 1.0 - a, c = 1e300, d = 1.0 / b, h = d; /* continued fraction */
+    for (int i = 1; i < 500; i++) {
+        const double an = -i * (i - a);
+        b += 2.0; d = an * d + b; if (fabs(d) < 1e-300) d = 1e-300;
+        c = b + an / c; if (fabs(c) < 1e-300) c = 1e-300;
+        d = 1.0 / d; const double del = d * c; h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return exp(-x + a * log(x)) * h;
+}
+static double upper_gamma(double a, double x) { /* any real a (gsl_sf_gamma_inc at hmf.c:733) */
+    if (a > 0) return upper_gamma_pos(a, x);
+    if (x <= 0) return INFINITY;
+    /* start in (0, 1] (E1 for an integer a) and recur down: Gamma(a, x) = (Gamma(a + 1, x) - x^a e^-x) / a */
+    const double fa = a - floor(a);
+    double g, acur;
+    if (fa == 0.0) { g = expint_e1(x); acur = 0.0; }
+    else { g = upper_gamma_pos(fa, x); acur = fa; }
+    while (acur > a + 0.5) {
+        acur -= 1.0;
+        g = (g - pow(x, acur) * exp(-x)) / acur;
+    }
+    return g;
+}
+static double fcoll_approx(double numin, double beta) { /* int nu^beta exp(-nu/2) / sqrt(nu) dnu from numin */
+    return upper_gamma(0.5 + beta, 0.5 * numin) * pow(2, 0.5 + beta) * pow(2.0 * M_PI, -0.5);
+}
+static double fcoll_approx_condition(double numin, double nucondition, double beta) {
+    return (fcoll_approx(numin, beta) - fcoll_approx(nucondition, beta)) + fcoll_approx(nucondition, 0.) * pow(nucondition, beta);
+}
+static double nion_conditional_gamma_approx(double lnM_lo, double lnM_hi, const MFParams &p) {
+    /* MFIntegral_Approx for the conditional N_ion integral (gamma_type = -3) */
+    const double M_PIVOT1 = 1.5e9, M_PIVOT2 = 5.3e5, A1 = 9.0, A2 = 13.6, A3 = 21.0; /* hmf.c:97-101 */
+    const double delta = p.delta, sigma_c = p.sigma_cond;
+    double lo = lnM_lo;
+    const double lnMturn = log(p.Mturn);
+    if (lnMturn > lo) lo = lnMturn; /* sharp lower cut at the turnover */
+    if (lo >= lnM_hi || EvaluateSigma(lo) <= sigma_c) return 0.;
+    const double index_base = p.alpha_star + p.alpha_esc;
+    const double delta_arg = pow((pc::delta_c_sph - delta) / p.growthf, 2);
+    const double beta1 = index_base * A1 * 0.5, beta2 = index_base * A2 * 0.5, beta3 = index_base * A3 * 0.5;
+    const double s1 = EvaluateSigma(log(M_PIVOT1)), s2 = EvaluateSigma(log(M_PIVOT2)), slo = EvaluateSigma(lo);
+    const double nu_pivot1_umf = delta_arg / (s1 * s1), nu_pivot2_umf = delta_arg / (s2 * s2);
+    const double nu_condition = delta_arg / (sigma_c * sigma_c);
+    const double nu_pivot1 = delta_arg / (s1 * s1 - sigma_c * sigma_c), nu_pivot2 = delta_arg / (s2 * s2 - sigma_c * sigma_c);
+    const double nu_lo = delta_arg / (slo * slo - sigma_c * sigma_c);
+    if (nu_lo >= nu_condition) return fcoll_approx(nu_lo, 0.); /* flat part of sigma(nu): an erfc */
+    double fcoll = 0.;
+    if (nu_lo >= nu_pivot1) {
+        fcoll += fcoll_approx_condition(nu_lo, nu_condition, beta1) * pow(nu_pivot1_umf, -beta1);
+    } else {
+        fcoll += fcoll_approx_condition(nu_pivot1, nu_condition, beta1) * pow(nu_pivot1_umf, -beta1);
+        if (nu_lo > nu_pivot2) {
+            fcoll += (fcoll_approx(nu_lo, beta2) - fcoll_approx(nu_pivot1, beta2)) * pow(nu_pivot1_umf, -beta2);
+        } else {
+            fcoll += (fcoll_approx(nu_pivot2, beta2) - fcoll_approx(nu_pivot1, beta2)) * pow(nu_pivot1_umf, -beta2);
+            fcoll += (fcoll_approx(nu_lo, beta3) - fcoll_approx(nu_pivot2, beta3)) * pow(nu_pivot2_umf, -beta3);
+        }
+    }
+    if (fcoll <= 0.0) fcoll = 1e-40;
+    return fcoll;
+}
+
 double Nion_ConditionalM(double growthf, double lnM1, double lnM2, double lnM_cond, double sigma2,
                          double delta2, double Mturn, const ScalingConstants *sc, int method) {
     /* hmf.c:1106-1140 */
@@ -683,7 +772,8 @@ double Nion_ConditionalM(double growthf, double lnM1, double lnM2, double lnM_co
     /* IntegratedNdM, hmf.c:896-905: Gauss-Legendre degrades near the barrier -> QAG above 1.2 */
     if (method == INTEG_QAG || (method == INTEG_GL && delta2 > 1.2)) return integrate_qag(lnM1, lnM2, p, 2);
     if (method == INTEG_GL) return integrate_gl(lnM1, lnM2, p);
-    b200_throw(B200_ValueError, "integration method %d (GAMMA-APPROX) is outside the scoped path", method);
+    if (method == INTEG_GAMMA) return nion_conditional_gamma_approx(lnM1, lnM2, p);
+    b200_throw(B200_ValueError, "invalid integration method %d", method);
 }
 
 /* ------------------------------------------------------------------ constant-zeta collapse fraction */

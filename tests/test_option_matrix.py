@@ -15,6 +15,9 @@ CASES = {
     "hmf_ps": dict(matter=dict(HMF="PS")),
     "hmf_ps_const_zeta": dict(matter=dict(HMF="PS", SOURCE_MODEL="CONST-ION-EFF")),
     "qag_integrals": dict(aopt=dict(INTEGRATION_METHOD_ATOMIC="GSL-QAG")),
+    "gamma_approx_integrals": dict(aopt=dict(INTEGRATION_METHOD_ATOMIC="GAMMA-APPROX")),
+    "gamma_approx_steeper_scaling": dict(aopt=dict(INTEGRATION_METHOD_ATOMIC="GAMMA-APPROX"),
+                                         astro=dict(ALPHA_STAR=0.3, ALPHA_ESC=-0.1)),
     "minimize_memory": dict(matter=dict(MINIMIZE_MEMORY=True)),
     "gaussian_filter_const_zeta": dict(matter=dict(SOURCE_MODEL="CONST-ION-EFF"), aopt=dict(HII_FILTER="gaussian")),
     "sharp_k_zeldovich": dict(matter=dict(PERTURB_ALGORITHM="ZELDOVICH"), aopt=dict(HII_FILTER="sharp-k")),
@@ -67,8 +70,14 @@ def test_option_matrix_emulated_vs_reference(name):
     _run_case(emu, ref, name)
 
 
+# GAMMA-APPROX only changes the host-built 400-point table (same g++-compiled host code in both builds): it is
+# checked on the CPU tier; its GPU variant joins this list once it has run on a B200 (the round's GPU budget
+# was spent when it was added)
+GPU_CASES = [c for c in CASES if not c.startswith("gamma_approx")]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", GPU_CASES)
 def test_option_matrix_gpu_vs_reference(name):
     ref = common.ref_backend()
     if ref is None:
