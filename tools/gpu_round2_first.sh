@@ -9,6 +9,17 @@ O=gpurun_out/$TAG
 mkdir -p "$O"
 ( time python -m pytest tests -m gpu -q -x ) > "$O/pytest_gpu.log" 2>&1; tail -4 "$O/pytest_gpu.log"
 python __graft_entry__.py smoke > "$O/smoke.log" 2>&1; tail -1 "$O/smoke.log"
+python - > "$O/gamma_approx_gpu.txt" 2>&1 <<'PY'
+# option-matrix cases that so far only ran on the CPU tier: run them on the GPU, then move them into GPU_CASES
+import sys
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import common, test_option_matrix as m
+for name in m.CASES:
+    if name not in m.GPU_CASES:
+        m._run_case(common.gpu_backend(), common.ref_backend(), name)
+        print("ok", name)
+PY
+cat "$O/gamma_approx_gpu.txt"
 python bench.py --steps 5 --warmup 3 > "$O/bench.json" 2> "$O/bench.err"; tail -2 "$O/bench.err"
 python - > "$O/evolution_timing.txt" 2>&1 <<'PY'
 import sys, time, dataclasses
