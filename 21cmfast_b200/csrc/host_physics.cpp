@@ -517,7 +517,7 @@ extern "C" double get_delta_crit(int HMF, double sigma, double growthf) { /* hmf
     return pc::delta_c_sph;
 }
 
-static double umf(double growthf, double lnM, int HMF) { /* hmf.c:553-580 */
+static double umf(double growthf, double lnM, int HMF, double z) { /* hmf.c:553-580 */
     double sigma = EvaluateSigma(lnM), dsigmadm = EvaluatedSigmasqdm(lnM);
     if (HMF == HMF_PS) { /* hmf.c:345-355 */
         sigma = sigma * growthf;
@@ -539,7 +539,21 @@ static double umf(double growthf, double lnM, int HMF) { /* hmf.c:553-580 */
         const double dfdnu = 0.519 * pow(nu, 0.582) * exp(-0.469 * nu * nu);
         return dfdnu * fabs(dsdm) * sigma_inv;
     }
-    b200_throw(B200_ValueError, "HMF=%d is outside the scoped path (PS, ST, DELOS supported)", HMF);
+    if (HMF == HMF_WATSON || HMF == HMF_WATSON_Z) { /* Watson et al. 2013 FOF fits, hmf.c:370-417 */
+        sigma = sigma * growthf;
+        dsigmadm = dsigmadm * (growthf * growthf / (2. * sigma));
+        double A = 0.282, alpha = 2.163, beta = 1.406, gamma = 1.210;
+        if (HMF == HMF_WATSON_Z) { /* their eqs. 12-15: the fit parameters follow Omega_m(z) */
+            const double Om_z = CP->OMm * pow(1. + z, 3.) / (CP->OMl + CP->OMm * pow(1. + z, 3.) + CP->OMr * pow(1. + z, 4.));
+            A = Om_z * (0.990 * pow(1. + z, -3.216) + 0.074);
+            alpha = Om_z * (5.907 * pow(1. + z, -3.058) + 2.349);
+            beta = Om_z * (3.136 * pow(1. + z, -3.599) + 2.344);
+            gamma = 1.318;
+        }
+        const double f_sigma = A * (pow(beta / sigma, alpha) + 1.) * exp(-gamma / (sigma * sigma));
+        return -(dsigmadm / sigma) * f_sigma;
+    }
+    b200_throw(B200_ValueError, "HMF=%d is outside the scoped path (PS, ST, WATSON, WATSON-Z, DELOS supported)", HMF);
 }
 
 static double st_taylor_factor(double sig, double sig_cond, double growthf, double *zeroth) {
@@ -588,6 +602,7 @@ static double cmf(double growthf, double lnM, double delta_cond, double sigma_co
 }
 
 struct MFParams {
+    double redshift; /* only the z-dependent Watson fit reads it */
     double growthf;
     int HMF;
     double sigma_cond, delta;
@@ -609,8 +624,8 @@ static double integrate_qag(double lo, double hi, const MFParams &p, int which) 
     double res, err;
     auto f = [&](double lnM) {
         switch (which) {
-            case 0: return exp(lnM) * umf(p.growthf, lnM, p.HMF);                /* u_fcoll */
-            case 1: return nion_fraction(lnM, p) * umf(p.growthf, lnM, p.HMF);  /* u_nion  */
+            case 0: return exp(lnM) * umf(p.growthf, lnM, p.HMF, p.redshift);                /* u_fcoll */
+            case 1: return nion_fraction(lnM, p) * umf(p.growthf, lnM, p.HMF, p.redshift);  /* u_nion  */
             default:
                 return nion_fraction(lnM, p) * cmf(p.growthf, lnM, p.delta, p.sigma_cond, p.HMF);
         }
@@ -658,6 +673,7 @@ double Fcoll_General(double z, double lnMmin, double lnMmax) { /* hmf.c:945-953 
     const double args[3] = {z, lnMmin, lnMmax};
     return memoised(2, true, args, 3, [&] {
         MFParams p = mf_params(dicke(z), 0., nullptr);
+        p.redshift = z;
         return integrate_qag(lnMmin, lnMmax, p, 0);
     });
 }
@@ -665,6 +681,7 @@ double Nion_General(double z, double lnMmin, double lnMmax, double Mturn, const 
     const double args[4] = {z, lnMmin, lnMmax, Mturn}; /* sc derives from astro params (in the key) */
     return memoised(3, true, args, 4, [&] {
         MFParams p = mf_params(dicke(z), Mturn, sc); /* hmf.c:955-971 */
+        p.redshift = z;
         return integrate_qag(lnMmin, lnMmax, p, 1);
     });
 }
