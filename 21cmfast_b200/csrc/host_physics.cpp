@@ -553,7 +553,28 @@ static double umf(double growthf, double lnM, int HMF, double z) { /* hmf.c:553-
         const double f_sigma = A * (pow(beta / sigma, alpha) + 1.) * exp(-gamma / (sigma * sigma));
         return -(dsigmadm / sigma) * f_sigma;
     }
-    b200_throw(B200_ValueError, "HMF=%d is outside the scoped path (PS, ST, WATSON, WATSON-Z, DELOS supported)", HMF);
+    if (HMF == HMF_REED07) { /* Reed et al. 2007 (astro-ph/0607150) fit with its n_eff term, hmf.c:156-163,419-439 */
+        const double neff = -3. * (2. * (-exp(lnM) * dsigmadm / (2. * sigma * sigma)) + 1.);
+        const double sigma_z = sigma * growthf;
+        dsigmadm = dsigmadm * (growthf * growthf / (2. * sigma_z));
+        const double nu = pc::delta_c_sph / sigma_z, lnsigma = -log(sigma_z);
+        const double G1 = exp(-pow(lnsigma - 0.4, 2) / (2. * 0.6 * 0.6)), G2 = exp(-pow(lnsigma - 0.75, 2) / (2. * 0.2 * 0.2));
+        const double ac = 0.764 / 1.08;
+        const double f_sigma = 0.3222 * sqrt(2. * ac / M_PI) * (1. + pow(1. / (ac * nu * nu), 0.3) + 0.6 * G1 + 0.4 * G2) * nu *
+                               exp(-1.08 * ac * nu * nu / 2. - 0.03 * pow(nu, 0.6) / pow(neff + 3., 2));
+        return -(dsigmadm / sigma_z) * f_sigma;
+    }
+    if (HMF == HMF_YUNG24) { /* Yung et al. 2024 (arXiv:2304.04348): Watson form, parameters quadratic in z; hmf.c:441-459 */
+        const double sigma_z = sigma * growthf;
+        dsigmadm = dsigmadm * (growthf * growthf / (2. * sigma_z));
+        const double A_z = 0.13765772 + -0.01003821 * z + 0.00102964 * z * z;
+        const double a_z = 1.06641384 + 0.02475576 * z + -0.00283342 * z * z;
+        const double b_z = 4.86693806 + 0.09212356 * z + -0.01426283 * z * z;
+        const double c_z = 1.19837952 + -0.00142967 * z + -0.00033074 * z * z;
+        const double f_sigma = A_z * (pow(sigma_z / b_z, -a_z) + 1.) * exp(-c_z / (sigma_z * sigma_z));
+        return -(dsigmadm / sigma_z) * f_sigma;
+    }
+    b200_throw(B200_ValueError, "invalid HMF %d", HMF);
 }
 
 static double st_taylor_factor(double sig, double sig_cond, double growthf, double *zeroth) {

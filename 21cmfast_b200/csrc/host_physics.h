@@ -20,7 +20,7 @@ constexpr double M_MIN_INTEGRAL = 1e5, M_MAX_INTEGRAL = 1e16;
 }  // namespace pc
 
 /* enum values of InputParameters.h:9-57 */
-enum { HMF_PS = 0, HMF_ST = 1, HMF_WATSON = 2, HMF_WATSON_Z = 3, HMF_DELOS = 4 };
+enum { HMF_PS = 0, HMF_ST = 1, HMF_WATSON = 2, HMF_WATSON_Z = 3, HMF_DELOS = 4, HMF_REED07 = 5, HMF_YUNG24 = 6 };
 enum { FILTER_TOPHAT = 0, FILTER_SHARP_K = 1, FILTER_GAUSSIAN = 2 };
 enum { PERTURB_LINEAR = 0, PERTURB_ZELDOVICH = 1, PERTURB_2LPT = 2 };
 enum { SRC_CONST_ION_EFF = 0, SRC_E_INTEGRAL = 1 };
