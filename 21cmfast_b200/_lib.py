@@ -74,6 +74,15 @@ class Backend:
             f.argtypes, f.restype = args, C.c_double
         self.config = _abi.ConfigSettingsStruct.in_dll(lib, "config_settings")
         self.state = GlobalState(self)
+        self._table_path = None
+
+    def ensure_table_path(self):
+        """Point ``config_settings.external_table_path`` at the packaged RECFAST table unless the
+        caller already chose a directory with ``set_table_path`` (the reference sets it from
+        ``py21cmfast/_cfg.py:61-70`` at import time)."""
+        if self._table_path is None:
+            from ._data import default_table_dir
+            self.set_table_path(default_table_dir())
 
     def set_table_path(self, path):
         self._table_path = os.fsencode(str(path))
@@ -137,6 +146,7 @@ class GlobalState:
             lib.init_MHR()  # _global_initialization.py:147-159
             self.recomb_inited = True
         if heat and not self.heat_inited:
+            self.backend.ensure_table_path()
             status = lib.init_heat()
             if status != 0:
                 raise BackendError(status, "init_heat")

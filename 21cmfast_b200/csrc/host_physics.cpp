@@ -104,8 +104,12 @@ double box_volume() { /* VOLUME macro, indexing.h:39-43 (float products, as in C
  * their arguments; a coeval run asks for the same ~70 values at every call, each one an adaptive
  * quadrature.  Results are memoised under a key that hashes the *contents* of the input structs
  * (Python may re-use a pointer for new values), the function id and the argument bits. */
+#include <mutex>
 #include <unordered_map>
 static std::unordered_map<unsigned long long, double> g_memo;
+static std::mutex g_memo_lock;             /* two host threads may call the library at once */
+static unsigned long long g_sigma_epoch = 0; /* bumped whenever the sigma(M) table is (re)built or freed: the
+                                                memoised integrals read it when USE_INTERPOLATION_TABLES is on */
 static unsigned long long fnv(const void *p, size_t n, unsigned long long h) {
     const unsigned char *b = (const unsigned char *)p;
     for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ULL;
@@ -127,9 +131,14 @@ template <typename F> static double memoised(int fn_id, bool astro, const double
     unsigned long long h = params_signature(astro);
     h = fnv(&fn_id, sizeof(int), h);
     h = fnv(args, sizeof(double) * nargs, h);
-    auto it = g_memo.find(h);
-    if (it != g_memo.end()) return it->second;
-    const double v = compute();
+    h = fnv(&g_sigma_epoch, sizeof(g_sigma_epoch), h);
+    {
+        std::lock_guard<std::mutex> guard(g_memo_lock);
+        auto it = g_memo.find(h);
+        if (it != g_memo.end()) return it->second;
+    }
+    const double v = compute(); /* outside the lock: it may recurse into other memoised scalars */
+    std::lock_guard<std::mutex> guard(g_memo_lock);
     if (g_memo.size() > 100000) g_memo.clear();
     g_memo[h] = v;
     return v;
@@ -427,11 +436,12 @@ extern "C" void initialiseSigmaMInterpTable(float M_min, float M_max) {
         }
         if (fail) b200_throw(B200_TableGenerationError, "sigma(M) table has non-finite entries");
         st.ready = true;
+        g_sigma_epoch++;
     } catch (B200Error &e) {
         fprintf(stderr, "[21cmfast_b200] initialiseSigmaMInterpTable failed: %s\n", e.msg);
     }
 }
-extern "C" void freeSigmaMInterpTable(void) { st.ready = false; }
+extern "C" void freeSigmaMInterpTable(void) { st.ready = false; g_sigma_epoch++; }
 
 double EvaluateSigma(double lnM) { /* interp_tables.c:1171-1177 */
     if (MO->USE_INTERPOLATION_TABLES != 0) {
@@ -623,7 +633,7 @@ static double cmf(double growthf, double lnM, double delta_cond, double sigma_co
 }
 
 struct MFParams {
-    double redshift; /* only the z-dependent Watson fit reads it */
+    double redshift; /* read by the z-dependent fits (WATSON-Z, YUNG24) */
     double growthf;
     int HMF;
     double sigma_cond, delta;
@@ -742,9 +752,25 @@ static double upper_gamma_pos(double a, double x) { /* Gamma(a, x), a > 0 */
     }
     return exp(-x + a * log(x)) * h;
 }
+/* Legendre continued fraction of Gamma(a, x) by modified Lentz: converges for every real a when x > 0
+   (slowly below x ~ 1/4, where the recurrence is used instead, as gsl_sf_gamma_inc does) */
+static double upper_gamma_cf(double a, double x) {
+    double b = x + 1.0 - a, c = 1e300, d = 1.0 / b, h = d;
+    for (int i = 1; i < 5000; i++) {
+        const double an = -i * (i - a);
+        b += 2.0; d = an * d + b; if (fabs(d) < 1e-300) d = 1e-300;
+        c = b + an / c; if (fabs(c) < 1e-300) c = 1e-300;
+        d = 1.0 / d; const double del = d * c; h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return exp(-x + a * log(x)) * h;
+}
 static double upper_gamma(double a, double x) { /* any real a (gsl_sf_gamma_inc at hmf.c:733) */
     if (a > 0) return upper_gamma_pos(a, x);
     if (x <= 0) return INFINITY;
+    /* the downward recurrence from (0, 1] cancels catastrophically for large x (rel. error 3.5e-4 at
+       a = -4.75, x = 300): the continued fraction is exact there */
+    if (x > 0.25) return a == 0.0 ? expint_e1(x) : upper_gamma_cf(a, x);
     /* start in (0, 1] (E1 for an integer a) and recur down: Gamma(a, x) = (Gamma(a + 1, x) - x^a e^-x) / a */
     const double fa = a - floor(a);
     double g, acur;
@@ -756,6 +782,7 @@ static double upper_gamma(double a, double x) { /* any real a (gsl_sf_gamma_inc 
     }
     return g;
 }
+extern "C" double b200_upper_gamma(double a, double x) { return upper_gamma(a, x); } /* test hook */
 static double fcoll_approx(double numin, double beta) { /* int nu^beta exp(-nu/2) / sqrt(nu) dnu from numin */
     return upper_gamma(0.5 + beta, 0.5 * numin) * pow(2, 0.5 + beta) * pow(2.0 * M_PI, -0.5);
 }

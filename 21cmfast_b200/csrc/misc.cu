@@ -56,6 +56,52 @@ extern "C" int test_filter(float *input_box, double R, double R_param, double R_
     return 0;
 }
 
+/* Measurement hook for bench.py's library-baseline leg: the library's own
+   3-D transforms of an n^3 box timed alone with CUDA events on the library's stream -- r2c, plain
+   c2r, and c2r with the per-radius window on load exactly as the ionisation ladder runs it (window
+   table + expansion included).  Mean milliseconds per transform over `iters` repetitions; the box
+   holds whatever the allocator returned (the FFT's time does not depend on the data). */
+extern "C" int b200_fft_probe(int n, int iters, double box_len, double *ms_r2c, double *ms_c2r, double *ms_c2r_window) {
+    try {
+        rt_init();
+        if (n < 16 || iters < 1) b200_throw(B200_ValueError, "b200_fft_probe: bad arguments");
+        Fft3D *plan = fft_plan(n, n, n);
+        DevBuf<float2> kbox(plan->n_cplx()), work(plan->n_cplx());
+        dev_zero(kbox, plan->n_cplx() * sizeof(float2));
+        dev_zero(work, plan->n_cplx() * sizeof(float2));
+        const bool pow2 = (n & (n - 1)) == 0;
+        DevBuf<float> wtab((size_t)window_table_size(plan)), wtab3(pow2 ? window_table3_size(plan) : 0);
+        const double dk = 2.0 * M_PI / box_len;
+        KMul km;
+        km.kind = KMUL_FILTER; km.filter_type = 0; km.R = (float)(box_len / 40.0); km.fast = 1;
+        km.dk[0] = km.dk[1] = km.dk[2] = dk;
+        ZPrologue pro;
+        pro.post_scale = 1.f / ((float)n * n * n);
+        ZEpilogue epi;
+        epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
+        DevTimer t;
+        for (int w = 0; w < 2; w++) { fft_r2c(plan, work, pro); fft_c2r(plan, kbox, work, KMul(), epi); } /* warm-up */
+        t.start();
+        for (int i = 0; i < iters; i++) fft_r2c(plan, work, pro);
+        if (ms_r2c) *ms_r2c = t.stop_ms() / iters;
+        t.start();
+        for (int i = 0; i < iters; i++) fft_c2r(plan, kbox, work, KMul(), epi);
+        if (ms_c2r) *ms_c2r = t.stop_ms() / iters;
+        t.start();
+        for (int i = 0; i < iters; i++) {
+            window_table_build(plan, 0, km.R, dk, wtab);
+            km.wtab = wtab; km.wtab_n = window_table_size(plan);
+            if (pow2) { window_table_expand(plan, wtab, wtab3); km.wtab3 = wtab3; }
+            fft_c2r(plan, kbox, work, km, epi);
+        }
+        if (ms_c2r_window) *ms_c2r_window = t.stop_ms() / iters;
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_fft_probe: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
 struct TbArgs {
     long long n;
     const float *density, *xH;

@@ -41,7 +41,23 @@ void ics_cache_drop() {
     g_ics.hires.release();
     for (int a = 0; a < 3; a++) { g_ics.v[a].release(); g_ics.v2[a].release(); }
 }
-/* cheap content signature: 4096 evenly spaced words + length (guards against a reused pointer) */
+/* The cache is OPT-IN (b200_ics_cache(1) or B200_ICS_CACHE=1): the reference reads the caller's
+   arrays on every call, so by default so does this library.  When enabled, the caller promises not
+   to modify the IC arrays in place between calls (or to call b200_ics_cache_invalidate() after
+   doing so): a hit is decided by the host pointers, the grid sizes and a signature of ~4096
+   sampled words per array, which guards against a reused allocation, not against a sparse edit.
+   A full-content hash would cost as much host time as the upload it saves (14.5 GB at DIM=1536). */
+static int g_ics_cache_on = -1; /* -1: follow the environment */
+extern "C" void b200_ics_cache(int enable) {
+    g_ics_cache_on = enable ? 1 : 0;
+    if (!enable) ics_cache_drop();
+}
+extern "C" void b200_ics_cache_invalidate(void) { g_ics.valid = false; }
+static bool ics_cache_enabled() {
+    if (g_ics_cache_on >= 0) return g_ics_cache_on == 1;
+    const char *ce = getenv("B200_ICS_CACHE");
+    return ce && ce[0] == '1';
+}
 static unsigned long long sample_signature(const float *p, size_t n) {
     if (!p) return 0;
     unsigned long long h = 1469598103934665603ULL ^ n;
@@ -712,13 +728,12 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
         const int nuse = linear ? 1 : (lpt2 ? 7 : 4);
         for (int i = 0; i < nuse; i++)
             if (!hv[i]) b200_throw(B200_ValueError, "ComputePerturbedField: a required IC array is NULL");
-        /* keep the initial conditions resident between calls (perturb_field is called once per
-           redshift on the same ICs); B200_ICS_CACHE=0 forces a fresh upload every call */
-        const char *ce = getenv("B200_ICS_CACHE");
-        const bool use_cache = !(ce && ce[0] == '0');
+        /* opt-in: keep the initial conditions resident between calls (perturb_field is called once
+           per redshift on the same ICs), see b200_ics_cache() above; default = upload every call */
+        const bool use_cache = ics_cache_enabled();
         bool hit = use_cache && g_ics.valid && g_ics.dim == so->DIM && g_ics.hii == so->HII_DIM;
         unsigned long long sig[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < nuse; i++) {
+        for (int i = 0; i < nuse && use_cache; i++) {
             sig[i] = sample_signature(hv[i], hn[i]);
             if (hit && (g_ics.host[i] != hv[i] || g_ics.sig[i] != sig[i])) hit = false;
         }

@@ -132,6 +132,31 @@ def run_coeval(*, out_redshifts=None, inputs: InputParameters, initial_condition
         raise NotImplementedError("run_coeval with USE_TS_FLUCT needs the spin-temperature calculation, which is "
                                   "outside the scoped path; pass a TsBox to compute_ionization_field instead")
     ics = initial_conditions or compute_initial_conditions(inputs=inputs, backend=backend)
+    with _resident_ics(backend or get_backend()):
+        return _run_coeval(outs, inputs, ics, backend)
+
+
+class _resident_ics:
+    """Keep the initial conditions in HBM for the duration of a driver loop that owns them (nothing
+    mutates ``ics`` inside the loop): one upload instead of one per redshift.  The cache is opt-in in
+    the library (``b200_ics_cache``); other backends (the compiled reference) have no such symbol."""
+
+    def __init__(self, backend):
+        self.fn = getattr(backend.lib, "b200_ics_cache", None) if hasattr(backend.lib, "b200_ics_cache") else None
+        if self.fn is not None:
+            self.fn.argtypes, self.fn.restype = [C.c_int], None
+
+    def __enter__(self):
+        if self.fn is not None:
+            self.fn(1)
+
+    def __exit__(self, *exc):
+        if self.fn is not None:
+            self.fn(0)
+        return False
+
+
+def _run_coeval(outs, inputs, ics, backend):
     out = []
     if not inputs.evolution_required:
         for z in sorted(outs, reverse=True):

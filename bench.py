@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--ref-hii-dim", type=int, default=256, help="bounded CPU sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-yardstick", action="store_true", help="skip the cuFFT library-baseline leg")
     ap.add_argument("--partition", default="boxes", choices=["boxes", "radius"],
                     help="N > 1: 'boxes' = one independent coeval box per GPU (weak scaling, no collective); "
                          "'radius' = ONE box: particle deposit split by x-slab + all-reduce(SUM) of the fixed-point "
@@ -141,8 +142,113 @@ def pinned_like(torch, arr):
     return t, a
 
 
+def reference_ics(args, ref, pkg, common, ncpu):
+    """Initial conditions for the reference arm, made by the reference itself (outside the timed
+    region).  Its IC generator needs ~15 single-threaded FFTs of DIM^3: about half an hour at
+    DIM=1536.  The workload's ICs are therefore the reference's own ICs of the half-size box (same
+    cell size, HII_DIM/2, DIM/2, BOX_LEN/2) replicated 2x2x2: an exactly periodic field of the
+    workload's shape with the same densities, velocities and displacements in cell units."""
+    hii, dim, box_len = workload(args)
+    t = 2 if (hii >= 256 and hii % 2 == 0 and dim % 2 == 0) else 1
+    small = common.make_inputs(hii=hii // t, dim=dim // t, box_len=box_len / t, source=args.source,
+                               n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
+    s_ics = pkg.compute_initial_conditions(inputs=small, backend=ref)
+    full = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source, n_threads=ncpu,
+                              R_BUBBLE_MAX=args.r_bubble_max)
+    if t == 1:
+        return full, s_ics, small, s_ics, "the reference's own ComputeInitialConditions"
+    ics = pkg.InitialConditions(full)
+    for k in ("hires_density", "lowres_density", "lowres_vx", "lowres_vy", "lowres_vz",
+              "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"):
+        a = getattr(s_ics, k)
+        if a is not None:
+            setattr(ics, k, np.ascontiguousarray(np.tile(a, (t, t, t))))
+    ics.is_computed = True
+    how = (f"the reference's own ComputeInitialConditions at HII_DIM={hii // t} DIM={dim // t} "
+           f"BOX_LEN={box_len / t:g}, replicated {t}x{t}x{t} (periodic) to the workload's grid")
+    return full, ics, small, s_ics, how
+
+
+def with_threads(inputs, n):
+    """the same inputs with another N_THREADS (the reference sets omp_set_num_threads from it)"""
+    return inputs.evolve_input_structs(N_THREADS=int(n))
+
+
+def cufft_yardstick(torch, lib, hii, box_len, iters=10):
+    """SURVEY.md section 8d "library baseline": the transforms of one filter radius done by cuFFT
+    (in-place padded r2c / c2r plans through the CUDA toolkit's libcufft, called with ctypes) plus
+    the separate passes a cuFFT-based sweep needs around them (window multiply, clip, min/max -- plain
+    torch ops), next to the library's own transforms timed alone (b200_fft_probe).  cuFFT is the
+    measured baseline here, never the product path."""
+    out = {}
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    lib.b200_fft_probe.argtypes = [C.c_int, C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 3
+    if lib.b200_fft_probe(hii, iters, float(box_len), C.byref(a), C.byref(b), C.byref(c)) == 0:
+        out.update({"own_r2c_ms": a.value, "own_c2r_ms": b.value, "own_c2r_window_clip_minmax_ms": c.value})
+    cands = [os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cufft", "lib", "libcufft.so.11"),
+             "/usr/local/cuda/lib64/libcufft.so.11", "libcufft.so.11", "libcufft.so"]
+    cufft = None
+    for cand in cands:
+        try:
+            cufft = C.CDLL(cand)
+            break
+        except OSError:
+            continue
+    if cufft is None:
+        out["cufft"] = "libcufft not found"
+        return out
+    nzc = hii // 2 + 1
+    box = torch.zeros((hii, hii, 2 * nzc), dtype=torch.float32, device="cuda")
+    box[:, :, :hii].normal_()
+    win = torch.rand((hii, hii, nzc), dtype=torch.float32, device="cuda")
+    kview = torch.view_as_complex(box.view(hii, hii, nzc, 2))
+    plans = {}
+    for name, typ in (("r2c", 0x2A), ("c2r", 0x2C)):
+        h = C.c_int()
+        if cufft.cufftPlan3d(C.byref(h), hii, hii, hii, typ) != 0:
+            out["cufft"] = "cufftPlan3d failed"
+            return out
+        cufft.cufftSetStream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        plans[name] = h
+    ptr = C.c_void_p(box.data_ptr())
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out["cufft_r2c_ms"] = timed(lambda: cufft.cufftExecR2C(plans["r2c"], ptr, ptr))
+    out["cufft_c2r_ms"] = timed(lambda: cufft.cufftExecC2R(plans["c2r"], ptr, ptr))
+
+    def sweep():
+        kview.mul_(win)                                  # filter_box
+        cufft.cufftExecC2R(plans["c2r"], ptr, ptr)        # dft_c2r_cube
+        real = box[:, :, :hii]
+        torch.aminmax(real)                               # clip_and_get_extrema
+        real.clamp_(-1.0, 1e6)
+    out["cufft_c2r_window_clip_minmax_ms"] = timed(sweep)
+    for h in plans.values():
+        cufft.cufftDestroy(h)
+    out["note"] = ("per 3-D transform of one HII_DIM^3 box, CUDA events; own = this library's Stockham passes "
+                   "(window, clip and min/max fused into them); cufft = in-place cufftExecR2C/C2R + torch "
+                   "elementwise passes for the window, clip and extrema")
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation (oracle/_ref) on this host."""
+    """--impl reference: the reference's own CPU implementation (oracle/_ref) of the SAME workload
+    (config.workload) on this host's cores.  One step = ComputePerturbedField + ComputeIonizedBox
+    of the full-size box.  A step takes of the order of a minute, so the run is time-boxed
+    (BENCH_REF_BUDGET_S, default 240 s of stepping): `steps`/`warmup` echo the request,
+    `steps_timed`/`warmup_run` say what was actually run; ms_per_step is the mean of the timed
+    steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,36 +256,65 @@ def run_reference(args):
     pkg = common.pkg
     ref = common.ref_backend()
     ncpu = os.cpu_count() or 1
-    hii, dim, box_len = workload(args, args.ref_hii_dim)
-    full_hii, full_dim, full_box = workload(args)
+    hii, dim, box_len = workload(args)
+    z = float(args.redshift)
     base = {"impl": "reference", "metric": "coeval cells/sec (perturb+ionize, one redshift)",
             "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"perturb_field+ionize_box z={float(args.redshift)} HII_DIM={full_hii} "
-                                   f"DIM={full_dim} BOX_LEN={full_box:g} {args.source} "
-                                   f"n_radii={n_radii(full_hii, full_box, args.r_bubble_max)}"}}
+            "config": {"workload": f"perturb_field+ionize_box z={z} HII_DIM={hii} "
+                                   f"DIM={dim} BOX_LEN={box_len:g} {args.source} "
+                                   f"n_radii={n_radii(hii, box_len, args.r_bubble_max)}"}}
     if ref is None:
         print(json.dumps({**base, "unavailable": "oracle/_ref/libref21cmfast.so not present"}))
         return
-    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source,
-                                n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
-    # the reference arm is the reference end to end: its own IC generator too (outside the timed region)
-    ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
-    times = []
-    for i in range(args.warmup + args.steps):
+    t_ic = time.perf_counter()
+    inputs, ics, small, s_ics, ics_how = reference_ics(args, ref, pkg, common, ncpu)
+    t_ic = time.perf_counter() - t_ic
+
+    def step(inp, boxes):
+        boxes.inputs = inp
         t0 = time.perf_counter()
-        pf = pkg.perturb_field(redshift=args.redshift, initial_conditions=ics, backend=ref)
-        pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=ref)
-        if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    ms = 1e3 * float(np.mean(times))
+        pf = pkg.perturb_field(redshift=z, initial_conditions=boxes, backend=ref)
+        t1 = time.perf_counter()
+        ib = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=boxes, backend=ref)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, float(ib.neutral_fraction.mean())
+
+    # thread count: the reference's docs advise few threads (joss-paper/paper.md:261); time one
+    # half-size step with 4 threads and with every core, keep the faster setting
+    threads, thread_note = ncpu, {}
+    if ncpu > 4 and small is not inputs:
+        for n in (4, ncpu):
+            a, b, _ = step(with_threads(small, n), s_ics)
+            thread_note[str(n)] = round(a + b, 3)
+        threads = min(thread_note, key=thread_note.get)
+        threads = int(threads)
+    inputs = with_threads(inputs, threads)
+    del s_ics
+
+    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "240"))
+    want = args.warmup + args.steps
+    done, t_start = [], time.perf_counter()
+    while len(done) < want:
+        done.append(step(inputs, ics))
+        spent = time.perf_counter() - t_start
+        if spent + 1.05 * (done[-1][0] + done[-1][1]) > budget:
+            break
+    # the first step counts as warm-up whenever more than one step fitted into the budget
+    n_warm = min(args.warmup, max(0, len(done) - 1), 1 if len(done) < want else args.warmup)
+    timed = done[n_warm:]
+    ms = 1e3 * float(np.mean([a + b for a, b, _ in timed]))
     value = hii**3 / (ms / 1e3)
-    sample = (f"HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g} (same cell size and physics as the "
-              f"HII_DIM={full_hii} workload), N_THREADS={ncpu}; FFT back-end = MKL-DFTI shim, "
-              f"single-threaded as in the reference (dft.c), not FFTW")
+    sample = (f"the full workload: HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g}, N_THREADS={threads} "
+              f"({ncpu} cores; calibration step seconds by thread count: {thread_note}); {len(timed)} timed "
+              f"step(s) after {n_warm} warm-up inside a {budget:g} s budget; perturb "
+              f"{np.mean([a for a, _, _ in timed]):.1f} s + ionize {np.mean([b for _, b, _ in timed]):.1f} s; "
+              f"FFT back-end = MKL-DFTI shim, single-threaded as in the reference (dft.c), not FFTW; "
+              f"ICs = {ics_how} ({t_ic:.0f} s, outside the timed region)")
     print(json.dumps({**base, "value": value, "ms_per_step": ms,
-                      "cpu_baseline": {"value": value, "unit": "cells/s", "cores": ncpu,
+                      "steps_timed": len(timed), "warmup_run": n_warm, "global_xH": timed[-1][2],
+                      "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads,
                                        "kind": "reference", "sample": sample},
                       "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,
                               "d2h_bytes_per_step": 0}}))
@@ -319,7 +454,7 @@ def main():
     # ---------------- end-to-end leg through the C-ABI with pinned host buffers ----------------
     e2e = None
     if not args.no_e2e and not radius_mode:
-        os.environ["B200_ICS_CACHE"] = "0"  # every step uploads its initial conditions
+        os.environ["B200_ICS_CACHE"] = "0"  # (the library default) every step uploads its initial conditions
         keep = []
         h_ics = pkg.InitialConditions(inputs)
         for k in names_ic:
@@ -374,6 +509,11 @@ def main():
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms_step, ms_perturb, ms_ionize, e2e_s, t_wall = [float(x) for x in vals.tolist()]
 
+    yardstick = None
+    if rank == 0 and world == 1 and not args.no_yardstick:
+        torch.cuda.synchronize()
+        yardstick = cufft_yardstick(torch, lib, hii, box_len)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref = common.ref_backend()
@@ -397,7 +537,7 @@ def main():
     if rank == 0:
         peak, peak_kind = measured_peak()
         pitch = ((hii // 2 + 1) + 7) // 8 * 8
-        Nk = hii * hii * pitch
+        Nk = hii * hii * (hii // 2 + 1)  # algorithmic = unpadded modes (the row pitch is an internal choice)
         alg = {  # algorithmic bytes per launch
             "fft_strided_pow2_kernel": 16 * Nk, "fft_strided_kernel": 16 * Nk,
             "fft_c2r_z_pow2_kernel": 8 * Nk + 4 * N, "fft_c2r_z_kernel": 8 * Nk + 4 * N,
@@ -442,6 +582,7 @@ def main():
                               "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "kernel_profile_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu_baseline,
+            "cufft_yardstick": yardstick,
         }
         if e2e:
             out["e2e"] = {"value": world * N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(e2e[1]),

@@ -316,6 +316,13 @@ double minimum_source_mass(double redshift, bool xray);
 int b200_set_device(int device);
 /* Drop every cached device buffer (initial conditions kept resident between calls, FFT plans). */
 void b200_release_device_cache(void);
+/* Device-resident initial conditions across ComputePerturbedField calls.  OFF by default: like the
+   reference (PerturbedField.c:389-496 reads boxes->hires_density on every call) the library uploads
+   the caller's arrays each time.  b200_ics_cache(1) (or B200_ICS_CACHE=1) keeps them in HBM between
+   calls on the same InitialConditions; the caller then promises not to modify those arrays in place
+   without calling b200_ics_cache_invalidate().  b200_ics_cache(0) switches it off and frees the copy. */
+void b200_ics_cache(int enable);
+void b200_ics_cache_invalidate(void);
 /* Counters for the last Compute* call: kernels launched, H2D and D2H bytes, device milliseconds
    (CUDA events on the library's stream). Any pointer may be NULL. */
 void b200_last_call_stats(long long *kernel_launches, long long *h2d_bytes, long long *d2h_bytes,
@@ -355,6 +362,12 @@ int b200_ComputeIonizedBox_device_part(float redshift, float prev_redshift,
 int b200_gsl_gaussian_stream(unsigned long mt_seed, long long n1, long long n2, double *host_out);
 int b200_host_gaussian_stream(unsigned long mt_seed, long long n, double *host_out);
 long long b200_gaussians_from_raw_host(const unsigned int *raw, long long n_raw, long long want, double *out);
+/* Measurement hook (bench.py's cuFFT yardstick leg): mean device milliseconds of
+   the library's own n^3 r2c, c2r and c2r-with-window transforms over `iters` repetitions. */
+int b200_fft_probe(int n, int iters, double box_len, double *ms_r2c, double *ms_c2r, double *ms_c2r_window);
+/* upper incomplete gamma function Gamma(a, x) for any real a as used by the GAMMA-APPROX integrals
+   (gsl_sf_gamma_inc at hmf.c:733); test hook for the known-answer test against mpmath */
+double b200_upper_gamma(double a, double x);
 /* x-plane range [begin, end) of thread t of n_threads under the static schedule of sample_ic_modes
    (InitialConditions.c:103-134); test hook for the N_THREADS > 1 seed-parity path */
 void b200_omp_static_range(int n, int n_threads, int t, int *begin, int *end);

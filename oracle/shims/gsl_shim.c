@@ -731,20 +731,32 @@ static double gamma_inc_pos(double a, double x) { /* a > 0: Gamma(a,x) */
         return exp(-x + a * log(x)) * h;
     }
 }
+/* Legendre continued fraction (modified Lentz), any real a, x > 0: what GSL's gamma_inc_CF evaluates */
+static double gamma_inc_cf(double a, double x) {
+    double b = x + 1.0 - a, c = 1e300, d = 1.0 / b, h = d;
+    for (int i = 1; i < 5000; i++) {
+        const double an = -i * (i - a);
+        b += 2.0; d = an * d + b; if (fabs(d) < 1e-300) d = 1e-300;
+        c = b + an / c; if (fabs(c) < 1e-300) c = 1e-300;
+        d = 1.0 / d; { const double del = d * c; h *= del; if (fabs(del - 1.0) < 1e-16) break; }
+    }
+    return exp(-x + a * log(x)) * h;
+}
 double gsl_sf_gamma_inc(const double a, const double x) {
     if (a > 0) return gamma_inc_pos(a, x);
     if (x <= 0) return INFINITY;
-    /* recur upward from a0 in (0,1] (or E1 for a0 = 0): G(a,x) = (G(a+1,x) - x^a e^-x)/a */
-    double fa = a - floor(a);
-    int steps = (int)(floor(a) < 0 ? -floor(a) : 0);
-    double g, acur;
-    if (fa == 0.0) { g = expint_E1(x); acur = 0.0; }
-    else { g = gamma_inc_pos(fa, x); acur = fa; }
-    while (acur > a + 0.5) {
-        acur -= 1.0;
-        g = (g - pow(x, acur) * exp(-x)) / acur;
-        steps--;
+    /* GSL (specfunc/gamma_inc.c, gsl_sf_gamma_inc_e): continued fraction for x > 0.25, downward
+       recurrence from (0,1] below it (the recurrence cancels catastrophically for large x) */
+    if (x > 0.25) return a == 0.0 ? expint_E1(x) : gamma_inc_cf(a, x);
+    {
+        double fa = a - floor(a);
+        double g, acur;
+        if (fa == 0.0) { g = expint_E1(x); acur = 0.0; }
+        else { g = gamma_inc_pos(fa, x); acur = fa; }
+        while (acur > a + 0.5) {
+            acur -= 1.0;
+            g = (g - pow(x, acur) * exp(-x)) / acur;
+        }
+        return g;
     }
-    (void)steps;
-    return g;
 }

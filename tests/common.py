@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import importlib
 import os
-import tempfile
 from pathlib import Path
 
 import numpy as np
@@ -38,23 +37,14 @@ def make_inputs(hii=32, dim=None, box_len=None, source="E-INTEGRAL", hii_filter=
     )
 
 
-_tmp_table_dir = None
-
-
 def table_dir() -> Path:
-    """Directory holding recfast_LCDM.dat (what config_settings.external_table_path points at)."""
-    global _tmp_table_dir
+    """Directory holding recfast_LCDM.dat (what config_settings.external_table_path points at): the
+    reference's own data directory where it is present, else the table packaged with the product."""
     for p in (os.environ.get("PY21CMFAST_DATA"), ROOT / "oracle" / "_ref" / "data",
               "/root/reference/src/py21cmfast/_data"):
         if p and Path(p, "recfast_LCDM.dat").exists():
             return Path(p)
-    if _tmp_table_dir is None:  # rebuild the table file from the committed golden columns
-        g = np.load(GOLDEN / "recfast_table.npz")
-        _tmp_table_dir = Path(tempfile.mkdtemp(prefix="b200_tables_"))
-        with open(_tmp_table_dir / "recfast_LCDM.dat", "w") as f:
-            for z, xe, c3, tk in zip(g["z"], g["xe"], g["col3"], g["tk"]):
-                f.write(f"{z:8.2f}   {xe:.5E}    {c3:.5E}    {tk:.5E}\n")
-    return _tmp_table_dir
+    return importlib.import_module("21cmfast_b200._data").default_table_dir()
 
 
 def ref_backend():

@@ -196,3 +196,96 @@ def test_full_size_properties(gpu):
     assert np.abs(fab - fa - fb).max() < 5e-6 * np.abs(fab).max() + 1e-6   # linearity
     assert abs(fa.sum() - a.astype(np.float64).sum()) < 1e-3 * hii**1.5      # DC mode is kept
     assert fa.std() < a.std()                                                # smoothing
+
+
+# ---------------------------------------------------------------------------------------------
+# Parity at the sizes the benchmark runs (BASELINE.json configs C2 and C3 / the bench default)
+# ---------------------------------------------------------------------------------------------
+def _ref_threads(inputs):
+    import os
+    return inputs.evolve_input_structs(N_THREADS=os.cpu_count() or 1)
+
+
+def _perturb_ionize_vs_reference(gpu, ref, inputs, ics, z):
+    """the same host ICs through both shared libraries; returns the comparison statistics"""
+    pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=gpu)
+    ics.inputs = _ref_threads(inputs)
+    r_pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=ref)
+    e_pf = common.compare_struct(pf, r_pf, tols={"velocity_z": common.TOL_VELOCITY})
+    r_ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=ics, backend=ref)
+    ics.inputs = inputs
+    r_pf.inputs = inputs
+    ib = pkg.compute_ionization_field(perturbed_field=r_pf, initial_conditions=ics, backend=gpu)
+    stats = common.compare_ionized(ib, r_ib)
+    assert stats["mask_mismatch"] == 0, stats
+    assert 0.05 < float(r_ib.neutral_fraction.mean()) < 0.95  # a partially ionised box: the ladder did work
+    return e_pf, stats
+
+
+def test_config_c2_vs_reference(gpu):
+    """BASELINE.json config C2 exactly: perturb_field + ionize_box, z = 8, HII_DIM = 256, DIM = 768,
+    BOX_LEN = 300 Mpc (32 filter radii), GPU-made ICs (exact GSL stream) fed to both libraries."""
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    inputs = common.make_inputs(hii=256, dim=768, box_len=300.0)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=gpu)
+    e_pf, stats = _perturb_ionize_vs_reference(gpu, ref, inputs, ics, 8.0)
+    print("C2 parity:", e_pf, stats)
+
+
+def test_bench_workload_512_vs_reference(gpu, monkeypatch):
+    """The workload bench.py times (BASELINE config C3's grid): HII_DIM = 512, DIM = 1536, BOX_LEN = 768,
+    R_BUBBLE_MAX = 40 -> 40 filter radii, E-INTEGRAL, on the library's DEFAULT path (F = 3 grouped deposit
+    behind the pipelined upload, tabulated window rows, single-precision flag sweep, transform run-ahead)
+    against the compiled reference: ionised mask bit-exact, fields within TOL_FIELD."""
+    import psutil
+    ref = common.ref_backend()
+    if ref is None:
+        pytest.skip("oracle/_ref not present on this box")
+    dim = 1536 if psutil.virtual_memory().available > 90 * 2**30 else 1024
+    monkeypatch.setenv("B200_IC_RNG", "device")          # Philox field: the ICs are inputs here, not under test
+    monkeypatch.setenv("B200_SKIP_SCRATCH_OUTPUTS", "1")  # no 3 x DIM^3 scratch boxes on the host
+    inputs = common.make_inputs(hii=512, dim=dim, box_len=768.0, R_BUBBLE_MAX=40.0)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=gpu)
+    e_pf, stats = _perturb_ionize_vs_reference(gpu, ref, inputs, ics, 8.0)
+    print(f"512 / DIM={dim} parity:", e_pf, stats)
+
+
+@pytest.mark.parametrize("hii,dim,source", [(64, 128, "E-INTEGRAL"), (128, 384, "CONST-ION-EFF")])
+def test_device_entry_points_equal_host_entry(gpu, hii, dim, source):
+    """b200_ComputePerturbedField_device / b200_ComputeIonizedBox_device (what bench.py's `value` leg
+    calls, device pointers) are bit-identical to the reference-facing host-pointer entry points."""
+    import torch
+    from importlib import import_module
+    _abi = import_module("21cmfast_b200._abi")
+    inputs = common.make_inputs(hii=hii, dim=dim, source=source)
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=gpu)
+    pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=gpu)
+    ib = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=gpu)
+    lib = gpu.lib
+    dev = torch.device("cuda", 0)
+    names_ic = ["hires_density", "lowres_density", "lowres_vx", "lowres_vy", "lowres_vz",
+                "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+    d_ic = {k: torch.from_numpy(getattr(ics, k)).to(dev) for k in names_ic}
+    d_pf = {k: torch.zeros((hii,) * 3, dtype=torch.float32, device=dev) for k in ("density", "velocity_z")}
+    d_ib = {k: torch.zeros((hii,) * 3, dtype=torch.float32, device=dev)
+            for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion")}
+    d_ib["neutral_fraction"].fill_(1.0)
+    s_ic, s_pf, s_ib = _abi.InitialConditionsStruct(), _abi.PerturbedFieldStruct(), _abi.IonizedBoxStruct()
+    for s, d in ((s_ic, d_ic), (s_pf, d_pf), (s_ib, d_ib)):
+        for k, t in d.items():
+            setattr(s, k, C.cast(t.data_ptr(), _abi.c_float_p))
+    lib.b200_ComputePerturbedField_device.argtypes = [C.c_float, C.POINTER(_abi.InitialConditionsStruct),
+                                                      C.POINTER(_abi.PerturbedFieldStruct)]
+    lib.b200_ComputeIonizedBox_device.argtypes = [C.c_float, C.c_float, C.POINTER(_abi.PerturbedFieldStruct),
+                                                  C.POINTER(_abi.IonizedBoxStruct)]
+    torch.cuda.synchronize()
+    gpu.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+    assert lib.b200_ComputePerturbedField_device(C.c_float(8.0), C.byref(s_ic), C.byref(s_pf)) == 0
+    assert lib.b200_ComputeIonizedBox_device(C.c_float(8.0), C.c_float(-1.0), C.byref(s_pf), C.byref(s_ib)) == 0
+    for k, t in d_pf.items():
+        assert np.array_equal(t.cpu().numpy(), getattr(pf, k)), k
+    for k, t in d_ib.items():
+        assert np.array_equal(t.cpu().numpy(), getattr(ib, k).reshape(t.shape)), k
+    assert s_ib.mean_f_coll == ib.mean_f_coll

@@ -77,11 +77,7 @@ def test_option_matrix_emulated_vs_reference(name):
     _run_case(emu, ref, name)
 
 
-# GAMMA-APPROX and the Watson / Delos mass functions only change host-built scalars and the 400-point table
-# (the same g++-compiled host code in both builds): they are checked on the CPU tier; their GPU variants join
-# this list once they have run on a B200 (the round's GPU budget was spent when they were added)
-CPU_TIER_ONLY = ("gamma_approx_integrals", "gamma_approx_steeper_scaling", "hmf_watson", "hmf_watson_z", "hmf_delos", "hmf_reed07", "hmf_yung24")
-GPU_CASES = [c for c in CASES if c not in CPU_TIER_ONLY]
+GPU_CASES = list(CASES)
 
 
 @pytest.mark.gpu
