@@ -15,6 +15,6 @@ from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  #
 from .outputs import (BrightnessTemp, InitialConditions, IonizedBox,  # noqa: F401
                       PerturbedField, TsBox)
 from ._lib import Backend, BackendError, get_backend  # noqa: F401
-from .distributed import ionize_radius_parallel, perturb_slab_parallel  # noqa: F401
+from .distributed import SlabGroup, ionize_radius_parallel, perturb_slab_parallel  # noqa: F401
 
 __version__ = "0.1.0"

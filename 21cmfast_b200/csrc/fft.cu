@@ -1,5 +1,6 @@
 /* fft.cu -- batched shared-memory Stockham FFTs and the 3-D r2c / c2r drivers (see fft.h). */
 #include "fft.h"
+#include "dist.h"
 
 #include <map>
 #include <tuple>
@@ -208,7 +209,18 @@ struct StridedArgs {
     const float *wtab;
     const float *wtab3;      /* expanded [|nx|][|ny|][pitch] form of wtab, or null */
     long long w3_xstride;    /* (ny/2+1) * pitch */
+    int y_off;               /* slab-decomposed boxes: global y index of the first local (y, kz) row */
+    /* slab-decomposed transforms: the store stage IS the all-to-all transpose.  Point i of a line goes
+       to rank i / sc_nl, at sc_base[rank] + (i % sc_nl) * sc_line_stride + group * sc_group_stride + col
+       (sc_base[r] is rank r's receive buffer as mapped here: a peer pointer over NVLink, see dist.h) */
+    int sc_on, sc_nl;
+    float2 *sc_base[8];
+    long long sc_line_stride, sc_group_stride;
 };
+DEV float2 *scatter_dst(const StridedArgs &a, int i, long long group, int col) {
+    const int r = i / a.sc_nl;
+    return a.sc_base[r] + ((long long)(i - r * a.sc_nl) * a.sc_line_stride + group * a.sc_group_stride + col);
+}
 
 /* index_to_k (indexing.h:116-120): double wavenumber of a grid index */
 DEV double kd_of_index(int n, int dim, double dk) {
@@ -219,7 +231,8 @@ DEV double kd_of_index(int n, int dim, double dk) {
 /* k-space multipliers of the x-pass load stage: derivative operator first (rounded to float),
    then the window -- see KMul in fft.h.  (i = x index, col = flattened (y, kz) with row pitch) */
 DEV float2 apply_kmul(float2 v, int i, int col, const StridedArgs &a) {
-    const int iy = col / a.pitch, iz = col - iy * a.pitch;
+    const int iyl = col / a.pitch, iz = col - iyl * a.pitch;
+    const int iy = iyl + a.y_off;
     if (iz >= a.nzc) return v; /* pad column */
     if (a.op != KOP_NONE) {
         if (i == 0 && iy == 0 && iz == 0) {
@@ -294,7 +307,8 @@ __global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restri
         if (col < a.ncols) {
             float2 v = res[i * a.Tp + c];
             if (a.scale != 1.f) { v.x *= a.scale; v.y *= a.scale; }
-            dst[gbase + (long long)i * a.line_stride + col] = v;
+            if (a.sc_on) *scatter_dst(a, i, blockIdx.y, col) = v;
+            else dst[gbase + (long long)i * a.line_stride + col] = v;
         }
     }
 }
@@ -495,11 +509,22 @@ static bool pow2_c2r_z(const float2 *, float *, const ZArgs &) { return false; }
 static bool pow2_r2c_z(const float *, float2 *, const ZArgs &) { return false; }
 #endif
 
+struct Scatter {
+    int nl = 0;               /* line points per destination rank */
+    float2 *base[8];
+    long long line_stride = 0, group_stride = 0;
+};
 static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long long line_stride,
                         int ncols, long long group_stride, int ngroups, int sign, float scale,
-                        const KMul *km, const Fft3D *p3) {
+                        const KMul *km, const Fft3D *p3, int y_off = 0, const Scatter *sc = nullptr) {
     StridedArgs a;
     memset(&a, 0, sizeof(a));
+    a.y_off = y_off;
+    if (sc) {
+        a.sc_on = 1; a.sc_nl = sc->nl;
+        for (int r = 0; r < 8; r++) a.sc_base[r] = sc->base[r];
+        a.sc_line_stride = sc->line_stride; a.sc_group_stride = sc->group_stride;
+    }
     a.n = p1.n; a.line_stride = line_stride; a.ncols = ncols; a.group_stride = group_stride;
     a.T = pick_tile(p1.n, 8); a.Tp = a.T + 1; a.sign = sign; a.scale = scale;
     a.f = p1.f; a.tw = p1.tw;
@@ -596,9 +621,95 @@ void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {
     run_strided(p->px, box, box, (long long)ny * pitch, ny * pitch, 0, 1, -1, pro.post_scale, nullptr, p);
 }
 
+/* ------------------------------------------------------------------ slab-decomposed transforms
+ * One box over P ranks (replaces dft_r2c_cube / dft_c2r_cube, dft.c:18-72, for a
+ * box that is split over GPUs).  Real space and the y/z passes live on x-slabs [nxl][ny][...]; k space
+ * lives transposed, on y-slabs [nx][nyl][pitch], where the x pass (and every k-space multiplier) is
+ * local.  The all-to-all between the two layouts is not a separate step: the pass in front of it
+ * stores every point of a line straight into the owning rank's receive buffer (Scatter), local HBM for
+ * the own block, NVLink peer stores for the others, and ONE stream-ordered barrier makes the blocks
+ * visible.  Two receive buffers alternate, so the barrier of transform i also licenses the reuse of the
+ * buffer of transform i - 1 (every rank has finished reading it before it arrives).  Per-line arithmetic is
+ * that of the single-GPU kernels: the result is bit-identical to the undistributed transform. */
+FftSlab fft_slab_setup(Fft3D *plan) {
+    dist_require();
+    FftSlab s;
+    s.plan = plan;
+    s.P = g_dist.world; s.rank = g_dist.rank;
+    if (plan->nx % s.P || plan->ny % s.P)
+        b200_throw(B200_ValueError, "slab FFT: HII_DIM = %d must be a multiple of the number of ranks (%d)", plan->nx, s.P);
+    s.nxl = plan->nx / s.P; s.nyl = plan->ny / s.P;
+    s.x0 = s.rank * s.nxl; s.y0 = s.rank * s.nyl;
+    for (int b = 0; b < 2; b++) s.recv[b] = (float2 *)dist_alloc(s.n_cplx() * sizeof(float2));
+    return s;
+}
+
+void fft_r2c_slab(FftSlab *s, float2 *kT, float2 *tmp, const ZPrologue &pro) {
+    Fft3D *p = s->plan;
+    const int ny = p->ny, nx = p->nx, pitch = p->pitch;
+    /* z: the rank's real rows -> complex rows, x-slab layout */
+    ZArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = p->nz; a.nzc = p->nzc; a.pitch = pitch; a.nrows = s->nxl * ny;
+    a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
+    a.f = p->pz.f; a.tw = p->pz.tw;
+    a.scale = 1.f; a.premul = pro.premul; a.clip = pro.clip;
+    a.clip_lo = pro.clip_lo; a.clip_hi = pro.clip_hi;
+    const float *src = pro.src ? pro.src : reinterpret_cast<const float *>(tmp);
+    a.real_row_stride = pro.src ? pro.src_row_stride : 2LL * pitch;
+    if (!pow2_r2c_z(src, tmp, a)) {
+        const int nblocks = (a.nrows + a.L - 1) / a.L;
+        size_t smem = tile_smem(a.n, a.L);
+        allow_smem(fft_r2c_z_kernel, smem);
+        B200_LAUNCH(fft_r2c_z_kernel, dim3(nblocks), 256, smem, src, tmp, a);
+    }
+    /* y: lines over kz per local x plane; point y goes to rank y / nyl at [x0 + xl][y % nyl][kz] */
+    float2 *recv = s->recv[g_dist.transforms & 1];
+    g_dist.transforms++;
+    Scatter sc;
+    sc.nl = s->nyl; sc.line_stride = pitch; sc.group_stride = (long long)s->nyl * pitch;
+    for (int r = 0; r < 8; r++) sc.base[r] = r < s->P ? dist_peer(recv, r) + (long long)s->x0 * s->nyl * pitch : nullptr;
+    run_strided(p->py, tmp, tmp, pitch, pitch, (long long)ny * pitch, s->nxl, -1, 1.f, nullptr, p, 0, &sc);
+    dist_barrier();
+    /* x: lines over the local (y, kz) columns, out of the receive buffer into the caller's k-space box */
+    run_strided(p->px, recv, kT, (long long)s->nyl * pitch, s->nyl * pitch, 0, 1, -1, pro.post_scale, nullptr, p, s->y0);
+    (void)nx;
+}
+
+void fft_c2r_slab(FftSlab *s, const float2 *kT, float2 *work, const KMul &km, const ZEpilogue &epi) {
+    Fft3D *p = s->plan;
+    const int ny = p->ny, pitch = p->pitch;
+    /* x (multipliers on the load): point x goes to rank x / nxl at [x % nxl][y0 + yl][kz] */
+    float2 *recv = s->recv[g_dist.transforms & 1];
+    g_dist.transforms++;
+    Scatter sc;
+    sc.nl = s->nxl; sc.line_stride = (long long)ny * pitch; sc.group_stride = 0;
+    for (int r = 0; r < 8; r++) sc.base[r] = r < s->P ? dist_peer(recv, r) + (long long)s->y0 * pitch : nullptr;
+    run_strided(p->px, kT, nullptr, (long long)s->nyl * pitch, s->nyl * pitch, 0, 1, +1, 1.f, &km, p, s->y0, &sc);
+    dist_barrier();
+    /* y: per local x plane, receive buffer -> work box */
+    run_strided(p->py, recv, work, pitch, pitch, (long long)ny * pitch, s->nxl, +1, 1.f, nullptr, p);
+    /* z: complex rows -> real rows with the epilogue */
+    ZArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = p->nz; a.nzc = p->nzc; a.pitch = pitch; a.nrows = s->nxl * ny;
+    a.L = pick_tile(p->nz, 8); a.Tp = a.L + 1;
+    a.f = p->pz.f; a.tw = p->pz.tw;
+    a.scale = epi.scale; a.clip = epi.clip; a.clip_lo = epi.clip_lo; a.clip_hi = epi.clip_hi;
+    float *dst = epi.dst ? epi.dst : reinterpret_cast<float *>(work);
+    a.real_row_stride = epi.dst ? epi.dst_row_stride : 2LL * pitch;
+    a.minmax_keys = epi.minmax_keys;
+    if (pow2_c2r_z(work, dst, a)) return;
+    const int nblocks = (a.nrows + a.L - 1) / a.L;
+    size_t smem = tile_smem(a.n, a.L);
+    allow_smem(fft_c2r_z_kernel, smem);
+    B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, work, dst, a);
+}
+
 /* ------------------------------------------------------------------ in-place k-space window */
 struct KWinArgs {
     int nx, ny, nz, nzc, pitch;
+    int nyl, y_off; /* rows held locally per x and the global y index of the first one (slab layout) */
     int type;
     float R;
     double R_param, r_const, dkx, dky, dkz;
@@ -606,9 +717,9 @@ struct KWinArgs {
 };
 /* filter_box (filtering.c:308-394) as a separate pass: box *= W(k R), rounded to float */
 __global__ void kspace_window_kernel(KWinArgs a) {
-    const long long rows = (long long)a.nx * a.ny;
+    const long long rows = (long long)a.nx * a.nyl;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int ix = (int)(row / a.ny), iy = (int)(row - (long long)ix * a.ny);
+        const int ix = (int)(row / a.nyl), iy = (int)(row - (long long)ix * a.nyl) + a.y_off;
         const float kx = kf_of_index(ix, a.nx, a.dkx), ky = kf_of_index(iy, a.ny, a.dky);
         for (int iz = threadIdx.x; iz < a.nzc; iz += blockDim.x) {
             const float kz = (float)((double)iz * a.dkz);
@@ -620,10 +731,11 @@ __global__ void kspace_window_kernel(KWinArgs a) {
         }
     }
 }
-void fft_apply_window(Fft3D *p, float2 *box, const KMul &km) {
-    KWinArgs a = {p->nx, p->ny, p->nz, p->nzc, p->pitch, km.filter_type, km.R, km.R_param, km.r_const,
+void fft_apply_window(Fft3D *p, float2 *box, const KMul &km, int nyl, int y_off) {
+    if (nyl <= 0) { nyl = p->ny; y_off = 0; }
+    KWinArgs a = {p->nx, p->ny, p->nz, p->nzc, p->pitch, nyl, y_off, km.filter_type, km.R, km.R_param, km.r_const,
                   km.dk[0], km.dk[1], km.dk[2], box};
-    const long long rows = (long long)p->nx * p->ny;
+    const long long rows = (long long)p->nx * nyl;
     const int cap = dev_num_sms() * 16;
     B200_LAUNCH(kspace_window_kernel, (int)(rows < cap ? rows : cap), 128, 0, a);
 }

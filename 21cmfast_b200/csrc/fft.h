@@ -96,12 +96,28 @@ void window_table_build(const Fft3D *p, int type, float R, double dk, float *out
 size_t window_table3_size(const Fft3D *p);
 void window_table_expand(const Fft3D *p, const float *tab, float *out3);
 
-/* box *= W(kR) in place (the exact double window of filter_box, rounded to float per mode) */
-void fft_apply_window(Fft3D *p, float2 *box, const KMul &km);
+/* box *= W(kR) in place (the exact double window of filter_box, rounded to float per mode); with
+   nyl > 0 the box is a transposed k-space slab [nx][nyl][pitch] whose first row is global y = y_off */
+void fft_apply_window(Fft3D *p, float2 *box, const KMul &km, int nyl = 0, int y_off = 0);
 /* forward: real (padded or pro.src) -> complex in `box` */
 void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro);
 /* inverse: complex `src` -> real in `work` (src may equal work); optional k-space multiplier */
 void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZEpilogue &epi);
+
+/* Slab-decomposed transforms of ONE box over the ranks of dist.h (see fft.cu): real space and work
+   boxes are x-slabs [nxl][ny][...], k space is the transposed y-slab [nx][nyl][pitch]. */
+struct FftSlab {
+    Fft3D *plan = nullptr;
+    int P = 1, rank = 0, nxl = 0, nyl = 0, x0 = 0, y0 = 0;
+    float2 *recv[2] = {nullptr, nullptr}; /* symmetric receive buffers of the transpose */
+    size_t n_cplx() const { return (size_t)nxl * plan->ny * plan->pitch; } /* = nx * nyl * pitch */
+    size_t n_real() const { return (size_t)nxl * plan->ny * plan->nz; }
+};
+FftSlab fft_slab_setup(Fft3D *plan);
+/* real x-slab (pro.src, or padded in tmp) -> transposed k-space slab kT; tmp is an x-slab work box */
+void fft_r2c_slab(FftSlab *s, float2 *kT, float2 *tmp, const ZPrologue &pro);
+/* transposed k-space slab -> real x-slab in `work` (or epi.dst); multipliers ride on the x-pass load */
+void fft_c2r_slab(FftSlab *s, const float2 *kT, float2 *work, const KMul &km, const ZEpilogue &epi);
 
 /* Restatement of the reference's window functions (filtering.c:18-117) with the arithmetic
    types of the -Ofast x86-64 build of filter_box (filtering.c:331-381): |k|^2 is accumulated in

@@ -299,7 +299,8 @@ template <int N, int TL> DEV void stage_window(float *Wbuf, const StridedArgs &a
             const int ax = e / CH, j = e - ax * CH;
             const int col = col0 + 4 * j;
             if (col < a.ncols) {
-                const int iy = col / a.pitch, iz = col - iy * a.pitch;
+                const int iyl = col / a.pitch, iz = col - iyl * a.pitch;
+                const int iy = iyl + a.y_off;
                 const int ay = (iy > a.ny / 2) ? a.ny - iy : iy;
                 cp_async_16(Wbuf + ax * TL + 4 * j, a.wtab3 + ((long long)ax * a.w3_xstride + (long long)ay * a.pitch + iz));
             }
@@ -307,7 +308,7 @@ template <int N, int TL> DEV void stage_window(float *Wbuf, const StridedArgs &a
     }
     cp_async_commit();
 }
-template <int N, int SIGN, int MODE>
+template <int N, int SIGN, int MODE, bool SCATTER>
 __global__ void __launch_bounds__(Pow2Cfg<N>::THREADS, Pow2Cfg<N>::MIN_CTAS)
 fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst, StridedArgs a, int tiles_per_group,
                         int ntiles) {
@@ -378,45 +379,65 @@ fft_strided_pow2_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst
         }
         fft_line_regs<N, SIGN, TilePolicy<TL>, MODE == PM_WTAB>(v, t, pol, twS);
         if (live) {
-            float2 *q = dst + base;
-            if (a.scale != 1.f) {
+            if constexpr (SCATTER) {
+                /* the transpose of the slab FFT: point t + m STEP of the line belongs to rank
+                   (t + m STEP) / sc_nl; the TL lanes of a tile row write one contiguous segment
+                   of that rank's receive buffer (local HBM or a peer's over NVLink) */
 #pragma unroll
-                for (int m = 0; m < 8; m++) q[m * rs] = pk_scale(v[m], a.scale);
+                for (int m = 0; m < 8; m++) {
+                    float2 *q = scatter_dst(a, t + m * STEP, g, col);
+                    *q = (a.scale != 1.f) ? pk_scale(v[m], a.scale) : v[m];
+                }
             } else {
+                float2 *q = dst + base;
+                if (a.scale != 1.f) {
 #pragma unroll
-                for (int m = 0; m < 8; m++) q[m * rs] = v[m];
+                    for (int m = 0; m < 8; m++) q[m * rs] = pk_scale(v[m], a.scale);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 8; m++) q[m * rs] = v[m];
+                }
             }
         }
         if (Pow2Sync<N>::NEED_TAIL_SYNC) __syncthreads();
     }
 }
 
-template <int N, int MODE> static void launch_strided_pow2_mode(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
+template <int N, int SIGN, int MODE, bool SCATTER>
+static void launch_strided_pow2_inst(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
     using P = Pow2Plan<N>;
     constexpr int TL = Pow2Cfg<N>::TL;
     const size_t smem = (size_t)2 * N * TL * sizeof(float2) + (size_t)P::TW_TOTAL * sizeof(float4) +
                         (MODE == PM_WTAB ? (size_t)2 * (N / 2 + 1) * TL * sizeof(float) : 0);
     const int tiles_per_group = (a.ncols + TL - 1) / TL;
     const long long ntiles = (long long)tiles_per_group * ngroups;
-    auto kf = &fft_strided_pow2_kernel<N, -1, MODE>;
-    auto ki = &fft_strided_pow2_kernel<N, 1, MODE>;
+    auto k = &fft_strided_pow2_kernel<N, SIGN, MODE, SCATTER>;
     /* persistent grid: exactly the CTAs that are resident at once */
-    allow_smem(kf, smem);
-    allow_smem(ki, smem);
+    allow_smem(k, smem);
     static int per_sm = 0;
     if (per_sm == 0) {
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ki, Pow2Cfg<N>::THREADS, smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, Pow2Cfg<N>::THREADS, smem));
         if (per_sm < 1) per_sm = 1;
     }
     long long grid = (long long)dev_num_sms() * per_sm;
     if (grid > ntiles) grid = ntiles;
-    if (a.sign < 0) {
-        B200_LAUNCH_T("fft_strided_pow2_kernel", kf, dim3((unsigned)grid), Pow2Cfg<N>::THREADS, smem, src, dst, a,
-                      tiles_per_group, (int)ntiles);
-    } else {
-        B200_LAUNCH_T("fft_strided_pow2_kernel", ki, dim3((unsigned)grid), Pow2Cfg<N>::THREADS, smem, src, dst, a,
-                      tiles_per_group, (int)ntiles);
+    B200_LAUNCH_T(SCATTER ? "fft_strided_pow2_scatter_kernel" : "fft_strided_pow2_kernel", k, dim3((unsigned)grid),
+                  Pow2Cfg<N>::THREADS, smem, src, dst, a, tiles_per_group, (int)ntiles);
+}
+template <int N, int MODE> static void launch_strided_pow2_mode(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
+    if (a.sc_on) {
+        /* scatter stores exist for the passes the slab transforms use: the forward y pass (plain)
+           and the inverse x pass (any multiplier) */
+        if (a.sign < 0) {
+            if constexpr (MODE == PM_PLAIN) launch_strided_pow2_inst<N, -1, PM_PLAIN, true>(src, dst, a, ngroups);
+            else b200_throw(B200_ValueError, "slab FFT: no forward scatter pass with a k-space multiplier");
+        } else {
+            launch_strided_pow2_inst<N, 1, MODE, true>(src, dst, a, ngroups);
+        }
+        return;
     }
+    if (a.sign < 0) launch_strided_pow2_inst<N, -1, MODE, false>(src, dst, a, ngroups);
+    else launch_strided_pow2_inst<N, 1, MODE, false>(src, dst, a, ngroups);
 }
 template <int N> static void launch_strided_pow2(const float2 *src, float2 *dst, const StridedArgs &a, int ngroups) {
     const bool has_kmul = a.kmul != KMUL_NONE || a.op != KOP_NONE;

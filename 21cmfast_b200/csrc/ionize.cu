@@ -29,6 +29,7 @@
  * Multi-GPU: the ladder can be partitioned by radius (IonPartition below).
  */
 #include "fft.h"
+#include "dist.h"
 #include "host_physics.h"
 #include "host_recomb.h"
 
@@ -48,9 +49,16 @@ struct SweepArgs {
     int nx, ny, nz, nzc;
     const float *filtered;   /* padded real rows, already clipped to [-1, 1e6] */
     const DevTable *table;
-    double *partial;         /* [gridDim.x] block sums */
+    double *partial;         /* [ceil(nx ny / chunk_rows)] sums of consecutive row chunks */
     float *fcoll;            /* unpadded f_coll grid of this radius, or null (sum only) */
+    int chunk_rows;          /* rows per chunk: divides ny, so that chunks never straddle an x plane */
 };
+
+/* The grid sum is reduced in a FIXED tree that depends on the box shape only -- chunk sums (a CTA's
+   deterministic reduction over chunk_rows consecutive rows), then per-x-plane sums of the chunk sums in
+   order (plane_sum_kernel), then the fixed-order sum over the planes that every CTA of the flag sweep
+   re-adds -- so the mean fix is bit-identical for any grid size and for any split of the box into
+   x-slabs over GPUs. */
 
 /* Shared-memory copy of the radius' table in the forms the sweeps use.
  *
@@ -236,6 +244,74 @@ DEV void for_each_chunk(const float *filtered, long long nrows, int nz, int pitc
 #endif
 }
 
+/* The same visit order restricted to chunks of `CH` consecutive rows: CTA b owns chunks b, b + grid, ...
+   and end_chunk(chunk) is called by every thread of the CTA after the last cell of a chunk (it may hold
+   barriers).  The cp.async ring keeps running across chunk boundaries. */
+template <class R, class F1, class F2, class F3>
+DEV void for_each_chunk_blocked(const float *filtered, long long nrows, int nz, int pitch, int CH, float4 *ring, F1 &&fast,
+                                F2 &&finish, F3 &&end_chunk) {
+    const int q = nz >> 2;
+    const long long rstride = 2LL * pitch;
+    const long long nchunks = (nrows + CH - 1) / CH;
+#ifndef B200_EMU
+    if (blockDim.x == 256 && q <= 256 && (256 % q) == 0 && (CH % (4 * (256 / q))) == 0) {
+        const int rows_per_step = 256 / q;
+        const int r = threadIdx.x / q, zc = threadIdx.x - r * q;
+        const int step_rows = 4 * rows_per_step;
+        const int ipc = CH / step_rows; /* iterations per chunk */
+        auto issue = [&](long long row0, int slot) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                long long row = row0 + r + (long long)u * rows_per_step;
+                if (row >= nrows) row = nrows - 1; /* harmless duplicate, discarded below */
+                cp_async_16(&ring[(slot * 4 + u) * 256 + threadIdx.x], filtered + row * rstride + 4 * zc);
+            }
+            cp_async_commit();
+        };
+        long long chunk = blockIdx.x, next_chunk = blockIdx.x;
+        int it_in = 0, next_it = 0; /* position of the current / the prefetched iteration inside its chunk */
+        auto advance = [&](long long &c, int &i) { if (++i == ipc) { i = 0; c += gridDim.x; } };
+        if (chunk < nchunks) { issue(chunk * CH, 0); advance(next_chunk, next_it); }
+        for (int it = 0; chunk < nchunks; it++) {
+            if (next_chunk < nchunks) issue(next_chunk * CH + (long long)next_it * step_rows, (it + 1) & 1);
+            else cp_async_commit(); /* keep one group per iteration so that wait_group 1 is uniform */
+            advance(next_chunk, next_it);
+            cp_async_wait_group<1>();
+            const long long row0 = chunk * CH + (long long)it_in * step_rows;
+            float4 d4[4];
+            R res[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) d4[u] = ring[((it & 1) * 4 + u) * 256 + threadIdx.x];
+#pragma unroll
+            for (int u = 0; u < 4; u++) res[u] = fast(d4[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long row = row0 + r + (long long)u * rows_per_step;
+                if (row < nrows) finish(res[u], d4[u], row, zc);
+            }
+            const long long done = chunk;
+            advance(chunk, it_in);
+            if (it_in == 0) end_chunk(done);
+        }
+        cp_async_wait_all();
+        return;
+    }
+#else
+    (void)ring;
+#endif
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long r0 = chunk * CH, r1 = (r0 + CH < nrows) ? r0 + CH : nrows;
+        const long long nch = (r1 - r0) * q;
+        for (long long id = threadIdx.x; id < nch; id += blockDim.x) {
+            const long long row = r0 + id / q;
+            const int zc = (int)(id - (row - r0) * q);
+            const float4 d = *reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc);
+            finish(fast(d), d, row, zc);
+        }
+        end_chunk(chunk);
+    }
+}
+
 /* sweep 1: sum of f_coll over the grid as deterministic double block sums (calculate_fcoll_grid,
    IonisationBox.c:773-962).  With a.fcoll set (last radius: the grid is the unnormalised_nion
    output) every cell takes the reference arithmetic and the float grid is written. */
@@ -246,13 +322,26 @@ template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(Swee
     sweep_table_load(&st, a.table, rep, LOG);
     __syncthreads();
     const long long nrows = (long long)a.nx * a.ny;
+    const int CH = a.chunk_rows;
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
     const SweepConstsF kf = sweep_consts(&st, dens_floor);
     double acc = 0.;
+    /* deterministic CTA reduction of the chunk's thread sums -> partial[chunk] */
+    auto end_chunk = [&](long long chunk) {
+        red[threadIdx.x] = acc;
+        acc = 0.;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) a.partial[chunk] = red[0];
+        __syncthreads();
+    };
     if ((a.nz & 3) == 0 && !a.fcoll) {
         struct SumRes { float sum; bool steep; };
-        for_each_chunk<SumRes>(
-            a.filtered, nrows, a.nz, a.nzc, reinterpret_cast<float4 *>(rep + N_DENS_INTERP * SWEEP_REP),
+        for_each_chunk_blocked<SumRes>(
+            a.filtered, nrows, a.nz, a.nzc, CH, reinterpret_cast<float4 *>(rep + N_DENS_INTERP * SWEEP_REP),
             [&](const float4 &d) -> SumRes {
                 SumRes r;
                 r.steep = false;
@@ -267,36 +356,49 @@ template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(Swee
                            (fcoll_exact(fmaxf(d.z, dens_floor), &st) + fcoll_exact(fmaxf(d.w, dens_floor), &st));
                 else
                     acc += (double)r.sum;
-            });
+            },
+            end_chunk);
     } else {
-        for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-            const float *src = a.filtered + row * 2 * a.nzc;
-            for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
-                if (a.fcoll) {
-                    const double f = fcoll_exact(fmaxf(src[z], dens_floor), &st);
-                    acc += f;
-                    a.fcoll[row * a.nz + z] = (float)f;
-                } else {
-                    bool steep = false;
-                    const float f = fcoll_fast2<LOG>(make_float2(src[z], src[z]), &st, kf, steep).x;
-                    acc += steep ? fcoll_exact(fmaxf(src[z], dens_floor), &st) : (double)f;
+        const long long nchunks = (nrows + CH - 1) / CH;
+        for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+            const long long r0 = chunk * CH, r1 = (r0 + CH < nrows) ? r0 + CH : nrows;
+            for (long long row = r0; row < r1; row++) {
+                const float *src = a.filtered + row * 2 * a.nzc;
+                for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
+                    if (a.fcoll) {
+                        const double f = fcoll_exact(fmaxf(src[z], dens_floor), &st);
+                        acc += f;
+                        a.fcoll[row * a.nz + z] = (float)f;
+                    } else {
+                        bool steep = false;
+                        const float f = fcoll_fast2<LOG>(make_float2(src[z], src[z]), &st, kf, steep).x;
+                        acc += steep ? fcoll_exact(fmaxf(src[z], dens_floor), &st) : (double)f;
+                    }
                 }
             }
+            end_chunk(chunk);
         }
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
+}
+
+/* second level of the fixed reduction tree: plane[x] = sum of the chunk sums of x-plane x, in order */
+struct PlaneSumArgs {
+    int nx, chunks_per_plane;
+    const double *partial;
+    double *plane;
+};
+__global__ void plane_sum_kernel(PlaneSumArgs a) {
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.nx; x += gridDim.x * blockDim.x) {
+        double acc = 0.;
+        for (int c = 0; c < a.chunks_per_plane; c++) acc += a.partial[(long long)x * a.chunks_per_plane + c];
+        a.plane[x] = acc;
     }
-    if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
 }
 
 struct CritArgs {
     long long n;
     const float *fcoll;      /* f_coll grid written by sweep 1 */
-    const double *partial;   /* block sums of sweep 1 */
+    const double *partial;   /* x-plane sums of sweep 1 (plane_sum_kernel), all planes of the box */
     int n_partial;
     const float *density;    /* unfiltered perturbed density, unpadded */
     const float *prev_zre;   /* previous box z_reion or null (= all -1) */
@@ -440,7 +542,7 @@ struct CritDeltaArgs {
     int nx, ny, nz, nzc;
     const float *filtered;   /* padded real rows of this radius (the sweep-1 input) */
     const DevTable *table;
-    const double *partial;   /* block sums of sweep 1 */
+    const double *partial;   /* x-plane sums of sweep 1 (plane_sum_kernel), all planes of the box */
     int n_partial;
     unsigned char *mask;     /* 1 = ionised at some radius so far */
     double n_cells, mean_f_coll, f_limit, ion_eff_factor;
@@ -845,7 +947,39 @@ static IonStaging g_stage;
 struct IonPartition {
     int part = 0, nparts = 1, phase = -1;
     unsigned char *mask = nullptr;
+    /* slab = true: the box is split into x-slabs over the ranks of dist.h (every array of the call is
+       this rank's slab [nxl][ny][nz]); the transforms are the slab-decomposed ones of fft.cu, the
+       per-radius extrema and plane sums are combined by dist_barrier_minmax / dist_barrier_gather.
+       Same arithmetic per cell and the same reduction tree: bit-identical to the single-GPU ladder. */
+    bool slab = false;
 };
+
+/* rows per chunk of the sum sweep: a multiple of the fast path's rows per iteration where that
+   divides ny (so that the cp.async ring applies), grown to >= 32 rows; else the largest divisor of ny <= 32 */
+static int sweep_chunk_rows(int ny, int nz) {
+    int step_rows = 0;
+    if ((nz & 3) == 0) {
+        const int q = nz >> 2;
+        if (q <= 256 && 256 % q == 0) step_rows = 4 * (256 / q);
+    }
+    if (step_rows && ny % step_rows == 0) {
+        int ch = step_rows;
+        while (ch < 32 && ny % (2 * ch) == 0) ch *= 2;
+        return ch;
+    }
+    int ch = 1;
+    for (int d = 1; d <= 32 && d <= ny; d++)
+        if (ny % d == 0) ch = d;
+    return ch;
+}
+/* CTAs of the sum sweep: the largest divisor of the chunk count that is resident at once (no tail) */
+static int sweep_grid(long long nchunks) {
+    const long long cap = (long long)dev_num_sms() * 8;
+    if (nchunks <= cap) return (int)(nchunks > 0 ? nchunks : 1);
+    for (long long g = cap; g >= cap / 2; g--)
+        if (nchunks % g == 0) return (int)g;
+    return (int)cap;
+}
 
 static void ionize_core(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box,
                         const IonPartition &pt = IonPartition()) {
@@ -861,7 +995,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     if (ts) {
         if (!io.xe || !io.Tk_neutral)
             b200_throw(B200_ValueError, "USE_TS_FLUCT needs the TsBox's xray_ionised_fraction and kinetic_temp_neutral");
-        if (pt.phase >= 0) b200_throw(B200_ValueError, "the radius-parallel ladder is not built for USE_TS_FLUCT");
+        if (pt.phase >= 0 || pt.slab) b200_throw(B200_ValueError, "the multi-GPU ladders are not built for USE_TS_FLUCT");
     }
     /* recombinations: 1 homogeneous (one global N_rec), 2 inhomogeneous (per cell; filtered with the
        density unless CELL_RECOMB) */
@@ -870,7 +1004,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     if (recomb) {
         if (recomb == 1 && filter_rec)
             b200_throw(B200_ValueError, "RECOMB_MODEL=homogeneous needs CELL_RECOMB (there is no N_rec grid to filter)");
-        if (pt.phase >= 0) b200_throw(B200_ValueError, "the radius-parallel ladder is not built for RECOMB_MODEL != none");
+        if (pt.phase >= 0 || pt.slab) b200_throw(B200_ValueError, "the multi-GPU ladders are not built for RECOMB_MODEL != none");
         if (!io.G12 || (recomb == 2 && !io.cum_rec))
             b200_throw(B200_ValueError, "RECOMB_MODEL != none needs ionisation_rate_G12 and cumulative_recombinations");
         if (!recomb_tables()) b200_throw(B200_TableEvaluationError, "RECOMB_MODEL != none needs init_MHR()");
@@ -882,9 +1016,19 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     IonConsts c;
     set_ionbox_constants(redshift, prev_redshift, &c);
     const int nx = so->HII_DIM, ny = so->HII_DIM, nz = hii_d_para();
-    const long long N = (long long)nx * ny * nz;
+    const long long N = (long long)nx * ny * nz; /* cells of the whole box */
     Fft3D *plan = fft_plan(nx, ny, nz);
-
+    /* slab decomposition: this call owns x-planes [x0, x0 + nxl) */
+    FftSlab slab;
+    const bool sl = pt.slab;
+    if (sl) {
+        if (pt.phase >= 0) b200_throw(B200_ValueError, "slab and radius partitions do not combine");
+        dist_reset();
+        slab = fft_slab_setup(plan);
+    }
+    const int nxl = sl ? slab.nxl : nx;
+    const long long NL = (long long)nxl * ny * nz; /* cells of this call's arrays */
+    const size_t kbox_n = sl ? slab.n_cplx() : plan->n_cplx();
 
     std::vector<RadiusSpec> radii = setup_radii(c);
     const int n_radii = (int)radii.size();
@@ -919,10 +1063,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     if (exp_global_hii < HII_ROUND_ERR) {
         if (pt.phase == 0) { dev_zero(pt.mask, (size_t)N); dev_sync(); return; }
         if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
-        { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
-        NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term,
+        { FillArgs f = {NL, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(NL, 1024), 256, 0, f); }
+        NeutralArgs na = {NL, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term,
                           ts ? io.xe : nullptr, ts ? io.Tk_neutral : nullptr};
-        B200_LAUNCH(neutral_box_kernel, grid_for(N, 1024), 256, 0, na);
+        B200_LAUNCH(neutral_box_kernel, grid_for(NL, 1024), 256, 0, na);
+        if (sl) { dist_barrier(); dist_check(); }
         return;
     }
 
@@ -948,17 +1093,17 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
        radius) two ahead is measurably better (12.0 -> 11.3 ms per step), at 128^3 and below the
        host is the serial resource and running further ahead only delays the sweeps (7.2 -> 7.5 ms).
        B200_IONIZE_AHEAD = 1..3 overrides. */
-    const size_t work_bytes = plan->n_cplx() * sizeof(float2);
+    const size_t work_bytes = kbox_n * sizeof(float2);
     int ahead = (work_bytes >= ((size_t)32 << 20) && work_bytes <= ((size_t)256 << 20)) ? 2 : 1;
     if (const char *e = getenv("B200_IONIZE_AHEAD")) { ahead = atoi(e); if (ahead < 1) ahead = 1; if (ahead > 3) ahead = 3; }
     const int NW = ahead + 1;
-    DevBuf<float2> k_unfiltered(plan->n_cplx());
+    DevBuf<float2> k_unfiltered(kbox_n);
     DevBuf<float2> work_ring[4];
     float2 *work[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) { work_ring[i].alloc(plan->n_cplx()); work[i] = work_ring[i].p; }
+    for (int i = 0; i < NW; i++) { work_ring[i].alloc(kbox_n); work[i] = work_ring[i].p; }
     DevBuf<float> d_fcoll;
     const bool general = recomb != 0 || ts; /* per-cell barrier: the reference's arithmetic at every radius */
-    if (!io.nion || general) d_fcoll.alloc(N);
+    if (!io.nion || general) d_fcoll.alloc(NL);
     /* x_e in k space and its filtered copies, one per work box */
     DevBuf<float2> k_xe, xe_ring[4];
     float2 *work_xe[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -976,20 +1121,33 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     }
     DevBuf<int> d_keys(2 * (size_t)(n_todo > 0 ? n_todo : 1));
     DevBuf<DevTable> d_tables((size_t)(n_todo > 0 ? n_todo : 1));
-    const int sweep_blocks = grid_for((long long)nx * ny, 1);
-    DevBuf<double> d_partial(sweep_blocks);
+    /* fixed reduction tree of the grid sum: chunk sums -> x-plane sums -> sum over all planes of the box */
+    const int chunk_rows = sweep_chunk_rows(ny, nz);
+    const int chunks_per_plane = ny / chunk_rows;
+    const long long nchunks = (long long)nxl * chunks_per_plane;
+    const int sum_blocks = sweep_grid(nchunks);
+    const int sweep_blocks = grid_for((long long)nxl * ny, 1);
+    DevBuf<double> d_partial((size_t)nchunks);
+    DevBuf<double> d_plane((size_t)nx);
+    /* slab mode: this rank's extrema keys and plane sums are published in the symmetric heap, one slot per radius */
+    int *keys_sym = nullptr;
+    double *plane_sym = nullptr;
+    if (sl) {
+        keys_sym = (int *)dist_alloc(sizeof(int) * 2 * 64);
+        plane_sym = (double *)dist_alloc(sizeof(double) * 64 * (size_t)nxl);
+    }
     DevBuf<int> d_flag(1);
     dev_zero(d_flag, sizeof(int));
     DevBuf<unsigned char> own_mask;
     unsigned char *d_mask = pt.mask;
-    if (pt.phase < 0) { own_mask.alloc((size_t)N); d_mask = own_mask; }
-    if (pt.phase <= 0) dev_zero(d_mask, (size_t)N); /* phase 1 continues on the merged mask */
+    if (pt.phase < 0) { own_mask.alloc((size_t)NL); d_mask = own_mask; }
+    if (pt.phase <= 0) dev_zero(d_mask, (size_t)NL); /* phase 1 continues on the merged mask */
     /* IONISE_ENTIRE_SPHERE: the flags of each radius are kept apart (d_centre), dilated by the radius'
        sphere into d_paint and merged into d_mask (the centres, which alone record z_reion and T_k) */
     const bool sphere = ao->IONISE_ENTIRE_SPHERE;
     auto sphere_radius_cells = [&](double R) { return (float)(R / so->BOX_LEN) * (float)so->HII_DIM; };
     if (sphere) {
-        if (general || pt.phase >= 0)
+        if (general || pt.phase >= 0 || sl)
             b200_throw(B200_ValueError, "IONISE_ENTIRE_SPHERE is built for the plain ladder only (no recombinations, "
                                         "spin temperature or radius partition: the reference's result then depends "
                                         "on its cell visiting order)");
@@ -1030,7 +1188,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 #endif
     g_stage.ensure(n_todo);
     if (n_todo > 0) {
-        KeyInitArgs ka = {n_todo, d_keys};
+        KeyInitArgs ka = {n_todo, sl ? keys_sym : d_keys.p};
         B200_LAUNCH(minmax_key_init_kernel, 1, 64, 0, ka);
     }
 
@@ -1039,7 +1197,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     pro.src = io.density; pro.src_row_stride = nz; pro.premul = 1.f;
     pro.clip = 1; pro.clip_lo = -1.f; pro.clip_hi = 1e6f;
     pro.post_scale = 1.f / (float)N;
-    fft_r2c(plan, k_unfiltered, pro);
+    if (sl) fft_r2c_slab(&slab, k_unfiltered, work[0], pro);
+    else fft_r2c(plan, k_unfiltered, pro);
     if (general && io.wait_slot >= 0) main_wait_copy_event(io.wait_slot); /* xH / G12 / N_rec / x_e are read at every radius */
     if (ts) { /* prepare_box_for_filtering(xray_ionised_fraction, 0, 1) (IonisationBox.c:1510-1513) */
         ZPrologue px = pro;
@@ -1092,8 +1251,13 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         }
         ZEpilogue epi;
         epi.scale = 1.f; epi.clip = 1; epi.clip_lo = -1.f; epi.clip_hi = 1e6f;
-        epi.minmax_keys = d_keys.p + 2 * k;
-        fft_c2r(plan, k_unfiltered, work[j % NW], km, epi);
+        epi.minmax_keys = (sl ? keys_sym : d_keys.p) + 2 * k;
+        if (sl) {
+            fft_c2r_slab(&slab, k_unfiltered, work[j % NW], km, epi);
+            dist_barrier_minmax(keys_sym + 2 * k, d_keys.p + 2 * k); /* extrema of the whole box on every rank */
+        } else {
+            fft_c2r(plan, k_unfiltered, work[j % NW], km, epi);
+        }
         if (rec_grid_filtered) { /* <N_rec> over the same window, floored at zero (IonisationBox.c:806-809) */
             ZEpilogue er;
             er.scale = 1.f; er.clip = 1; er.clip_lo = 0.f; er.clip_hi = 3.0e38f;
@@ -1147,17 +1311,23 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : (general ? d_fcoll.p : nullptr);
         if (last && io.nion && io.nion_written) *io.nion_written = true;
         const float *filtered = reinterpret_cast<const float *>(work[j % NW]);
-        SweepArgs sa = {nx, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc};
+        SweepArgs sa = {nxl, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc, chunk_rows};
         sweep_smem_optin();
-        if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
-        else B200_LAUNCH(fcoll_sum_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, sa);
+        if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sum_blocks, 256, SWEEP_REP_BYTES, sa);
+        else B200_LAUNCH(fcoll_sum_kernel<false>, sum_blocks, 256, SWEEP_REP_BYTES, sa);
+        {
+            PlaneSumArgs ps = {nxl, chunks_per_plane, d_partial, sl ? plane_sym + (size_t)k * nxl : d_plane.p};
+            B200_LAUNCH(plane_sum_kernel, (nxl + 127) / 128, 128, 0, ps);
+            if (sl) dist_barrier_gather(reinterpret_cast<const unsigned long long *>(plane_sym + (size_t)k * nxl),
+                                        reinterpret_cast<unsigned long long *>(d_plane.p), nxl);
+        }
 
         if (!last && !general) {
             CritDeltaArgs cd;
             memset(&cd, 0, sizeof(cd));
-            cd.nx = nx; cd.ny = ny; cd.nz = nz; cd.nzc = plan->pitch;
+            cd.nx = nxl; cd.ny = ny; cd.nz = nz; cd.nzc = plan->pitch;
             cd.filtered = filtered; cd.table = d_tables.p + k;
-            cd.partial = d_partial; cd.n_partial = sweep_blocks; cd.mask = d_mask;
+            cd.partial = d_plane; cd.n_partial = nx; cd.mask = d_mask;
             if (sphere) { dev_zero(d_centre, (size_t)N); cd.mask = d_centre; }
             cd.n_cells = (double)N; cd.mean_f_coll = box->mean_f_coll; cd.f_limit = f_limit;
             cd.ion_eff_factor = c.ion_eff_factor; cd.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
@@ -1168,7 +1338,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
             CritArgs ca;
             memset(&ca, 0, sizeof(ca));
-            ca.n = N; ca.fcoll = fc; ca.partial = d_partial; ca.n_partial = sweep_blocks;
+            ca.n = NL; ca.fcoll = fc; ca.partial = d_plane; ca.n_partial = nx;
             ca.density = io.density; ca.prev_zre = io.prev_zre;
             ca.mask = d_mask; ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
             ca.n_cells = (double)N; ca.mean_f_coll = box->mean_f_coll; ca.f_limit = f_limit;
@@ -1189,7 +1359,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             const bool dilate_last = sphere && rs.R_index != 0; /* at R_index 0 the sphere is the centre cell itself */
             if (sphere) ca.paint = d_paint;
             if (dilate_last) { dev_zero(d_centre, (size_t)N); ca.mask = d_centre; }
-            B200_LAUNCH(ionise_kernel, grid_for(N, 1024), 256, 0, ca);
+            B200_LAUNCH(ionise_kernel, grid_for(NL, 1024), 256, 0, ca);
             if (dilate_last) paint_spheres(rs.R);
         }
     }
@@ -1204,14 +1374,16 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     {
         if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
         const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
-        FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
+        FinalArgs fa = {NL, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
                         c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
                         pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), ts ? io.Tk_neutral : nullptr,
                         sphere ? d_paint.p : nullptr};
-        B200_LAUNCH(finalize_kernel, grid_for(N, 1024), 256, 0, fa);
+        B200_LAUNCH(finalize_kernel, grid_for(NL, 1024), 256, 0, fa);
+        if (sl) dist_barrier(); /* no rank leaves (and reuses the symmetric heap) before every rank is done */
         int flag = 0;
         d2h(&flag, d_flag, sizeof(int)); /* also drains the stream before the work boxes are released */
         g_stats.d2h -= (long long)sizeof(int);
+        if (sl) dist_check();
         if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
     }
     if (recomb == 2) { /* set_recombination_rates, inhomogeneous (IonisationBox.c:1277-1341) */
@@ -1392,6 +1564,31 @@ extern "C" int b200_ComputeIonizedBox_device_part(float redshift, float prev_red
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
         fprintf(stderr, "[21cmfast_b200] b200_ComputeIonizedBox_device_part: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+/* Slab-decomposed variant ("slab FFT"): ONE box over the ranks connected with
+   b200_dist_init / b200_dist_connect.  The structs hold DEVICE pointers to this rank's x-slab
+   [HII_DIM / P][HII_DIM][HII_D_PARA] of every array; the result is this rank's slab of the outputs,
+   bit-identical to the same planes of the single-GPU box. */
+extern "C" int b200_ComputeIonizedBox_slab(float redshift, float prev_redshift, PerturbedField *d_pf, IonizedBox *d_box) {
+    try {
+        require_params(true);
+        rt_init();
+        reset_stats();
+        dist_require();
+        DevTimer timer;
+        timer.start();
+        IonDeviceIO io = {d_pf->density, nullptr, d_box->neutral_fraction, d_box->z_reion, d_box->kinetic_temperature,
+                          d_box->unnormalised_nion};
+        IonPartition pt;
+        pt.slab = true;
+        ionize_core(redshift, prev_redshift, io, d_box, pt);
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ComputeIonizedBox_slab: %s\n", e.msg);
         return e.code;
     }
     return 0;

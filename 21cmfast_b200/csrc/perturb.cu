@@ -21,6 +21,7 @@
  * the deposit of slab k starts as soon as its copy has landed (PendingUpload).
  */
 #include "fft.h"
+#include "dist.h"
 #include "host_physics.h"
 
 #include <vector>
@@ -86,6 +87,12 @@ struct MoveArgs {
     int tile0[3];   /* low-res cells covered by a brick (without halo) */
     int halo;
     int tiles[3];   /* bricks per axis */
+    /* slab-decomposed deposit (move_cic_grouped_kernel<.., SLAB = true>): this rank holds the velocity
+       cells of x-planes [vel_x0, vel_x0 + vn[0]) (vn[0] = local planes), the hi-res planes starting at the
+       (unwrapped) global plane dens_x0, and an accumulator window of out_nxl planes whose first one is the
+       (unwrapped) global plane out_x0 = x0 - halo; mass leaving the window raises *overflow */
+    int vel_x0, dens_x0, out_x0, out_nxl;
+    int *overflow;
 };
 
 /* single periodic wrap without a branch, for indices known to lie in [-n, 2n) */
@@ -209,7 +216,7 @@ DEV long long to_fixed(float v) { return llrintf(v * (float)FIXED_SCALE); }
    in single precision: each of the 27 sums carries ~1e-7 relative error, which averages to
    < 6e-8 of the cell total (itself rounded to float32 afterwards), at a third of the instruction
    cost of the double contraction (B200_CIC_DOUBLE=1 selects T = double). */
-template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kernel(GroupArgs g) {
+template <int F, typename T, bool SLAB> __global__ void __launch_bounds__(128, 4) move_cic_grouped_kernel(GroupArgs g) {
     const MoveArgs &a = g.m;
     const int nzg = a.vn[2], nyg = a.vn[1], nxg = a.vn[0];
     const long long ngroups = (long long)nxg * nyg * nzg;
@@ -220,7 +227,7 @@ template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_
          p += (long long)gridDim.x * blockDim.x) {
         const int cz = (int)(p % nzg);
         const int cy = (int)((p / nzg) % nyg);
-        const int cx = (int)(p / ((long long)nzg * nyg));
+        const int cx = (int)(p / ((long long)nzg * nyg)) + (SLAB ? a.vel_x0 : 0); /* global x of the velocity cell */
         double disp[3];
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) {
@@ -246,7 +253,7 @@ template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_
             int hx[F], hy[F], hz[F];
 #pragma unroll
             for (int t = 0; t < F; t++) {
-                hx[t] = wrap_once(isx + t, a.dn[0]);
+                hx[t] = SLAB ? isx + t - a.dens_x0 : wrap_once(isx + t, a.dn[0]); /* slab: index into the rank's own planes */
                 hy[t] = wrap_once(isy + t, a.dn[1]);
                 hz[t] = wrap_once(isz + t, a.dn[2]);
             }
@@ -284,7 +291,7 @@ template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_
         }
         /* x contraction one output plane at a time (rolled loop keeps the kernel inside the
            instruction cache), 9 fixed-point 64-bit reductions per plane straight into L2 */
-        const bool inside = Bx >= 0 && By >= 0 && Bz >= 0 && Bx + 2 < a.on[0] && By + 2 < a.on[1] && Bz + 2 < a.on[2];
+        const bool inside = (SLAB || (Bx >= 0 && Bx + 2 < a.on[0])) && By >= 0 && Bz >= 0 && By + 2 < a.on[1] && Bz + 2 < a.on[2];
 #pragma unroll 1
         for (int aa = 0; aa < 3; aa++) {
             T A[3][3];
@@ -296,7 +303,13 @@ template <int F, typename T> __global__ void __launch_bounds__(128, 4) move_cic_
 #pragma unroll
                 for (int i = 0; i < 9; i++) (&A[0][0])[i] += wx * (&Cy[t0][0][0])[i];
             }
-            const int gx = inside ? Bx + aa : wrap_index(Bx + aa, a.on[0]);
+            int gx;
+            if (SLAB) { /* plane of the rank's accumulator window (interior + halo), no wrap */
+                gx = Bx + aa - a.out_x0;
+                if (gx < 0 || gx >= a.out_nxl) { *a.overflow = 1; continue; }
+            } else {
+                gx = inside ? Bx + aa : wrap_index(Bx + aa, a.on[0]);
+            }
             unsigned long long *plane = a.acc + (long long)gx * out_sx;
 #pragma unroll
             for (int b = 0; b < 3; b++) {
@@ -325,12 +338,67 @@ template <int F> static void launch_grouped(const MoveArgs &a, long long p_begin
     if (blocks > cap) blocks = cap;
     static int dbl = -1;
     if (dbl < 0) { const char *e = getenv("B200_CIC_DOUBLE"); dbl = (e && e[0] == '1') ? 1 : 0; }
-    if (dbl) {
-        auto kp = &move_cic_grouped_kernel<F, double>;
+    if (a.overflow) { /* slab-decomposed deposit */
+        if (dbl) {
+            auto kp = &move_cic_grouped_kernel<F, double, true>;
+            B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
+        } else {
+            auto kp = &move_cic_grouped_kernel<F, float, true>;
+            B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
+        }
+    } else if (dbl) {
+        auto kp = &move_cic_grouped_kernel<F, double, false>;
         B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
     } else {
-        auto kp = &move_cic_grouped_kernel<F, float>;
+        auto kp = &move_cic_grouped_kernel<F, float, false>;
         B200_LAUNCH_T("move_cic_grouped_kernel", kp, (int)blocks, 128, 0, g);
+    }
+}
+
+/* largest |x displacement| of the rank's velocity cells, in output cells, as an order key */
+struct MaxDispArgs {
+    long long n;
+    const float *vx, *vx2;
+    double vdf, vdf2, ratio_out;
+    int *keys; /* [1] = max key */
+};
+__global__ void max_disp_kernel(MaxDispArgs a) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        double d = (double)a.vx[i] * a.vdf;
+        if (a.vx2) d -= (double)a.vx2[i] * a.vdf2;
+        const float f = (float)fabs(d * a.ratio_out);
+        m = f > m ? f : m;
+    }
+    atomic_max_i32(&a.keys[1], float_order_key(float_as_int_bits(m)));
+}
+
+struct AccSlabArgs {
+    int nxl, halo;
+    long long plane; /* ny * nz */
+    int ny, nz, nzc;
+    const unsigned long long *acc, *left, *right; /* own window, and the windows of the ranks below / above (peer memory) */
+    float *padded;
+    double mass_factor;
+};
+/* halo exchange + normalise_delta_grid: the mass that this rank's neighbours deposited into their halo
+   planes is pulled over NVLink and added to the rank's own planes -- integer sums, so the total is
+   bit-identical to the single-GPU accumulator */
+__global__ void acc_to_delta_slab_kernel(AccSlabArgs a) {
+    const long long nrows = (long long)a.nxl * a.ny;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int xl = (int)(row / a.ny);
+        const long long yz0 = (row - (long long)xl * a.ny) * a.nz;
+        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) {
+            unsigned long long q = a.acc[(long long)(a.halo + xl) * a.plane + yz0 + z];
+            if (xl < a.halo) q += a.left[(long long)(a.nxl + a.halo + xl) * a.plane + yz0 + z];
+            if (xl >= a.nxl - a.halo) q += a.right[(long long)(xl - (a.nxl - a.halo)) * a.plane + yz0 + z];
+            const double m = (double)(long long)q * (1.0 / FIXED_SCALE);
+            float v = (float)m;
+            v = (float)((double)v * a.mass_factor);
+            v = v - 1.0f;
+            a.padded[row * 2 * a.nzc + z] = v;
+        }
     }
 }
 
@@ -698,6 +766,138 @@ static void perturb_core(float redshift_f, const PerturbDeviceIO &io, const Pend
     }
 }
 
+/* ONE box over the ranks of dist.h, every stage on x-slabs (SURVEY.md section 8e, rows "PerturbField
+   move+CIC" and "slab FFT"): the rank deposits the particles of its own velocity cells into an
+   accumulator window of its planes plus `halo` planes on either side (the halo is sized from the largest
+   x displacement of the box), pulls its neighbours' halo planes over NVLink while normalising
+   (acc_to_delta_slab_kernel), and runs the density / velocity transforms slab-decomposed.  The IC
+   arrays of io are the rank's slabs: velocity boxes [nxl][ny][nz], hi-res density F nxl planes starting
+   at global plane F x0 - F/2 (periodic).  Bit-identical to perturb_core on the whole box. */
+static void perturb_core_slab(float redshift_f, const PerturbDeviceIO &io) {
+    const SimulationOptions *so = simulation_options_global;
+    const MatterOptions *mo = matter_options_global;
+    dist_require();
+    if (mo->PERTURB_ON_HIGH_RES || mo->PERTURB_ALGORITHM == PERTURB_LINEAR)
+        b200_throw(B200_ValueError, "the slab-decomposed perturbed field needs PERTURB_ALGORITHM = ZELDOVICH or 2LPT on the low-res grid");
+    const double redshift = redshift_f;
+    const int hn[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
+    const int dn[3] = {so->DIM, so->DIM, d_para()};
+    const long long N = (long long)hn[0] * hn[1] * hn[2];
+    const long long M = (long long)dn[0] * dn[1] * dn[2];
+    const int F = dn[0] / hn[0];
+    if (!(F * hn[0] == dn[0] && F * hn[1] == dn[1] && F * hn[2] == dn[2] && F >= 1 && F <= 4))
+        b200_throw(B200_ValueError, "the slab-decomposed deposit needs an integer DIM / HII_DIM ratio <= 4");
+    Fft3D *plan = fft_plan(hn[0], hn[1], hn[2]);
+    dist_reset();
+    FftSlab slab = fft_slab_setup(plan);
+    const int nxl = slab.nxl, x0 = slab.x0, P = slab.P;
+    const long long plane = (long long)hn[1] * hn[2];
+    DevBuf<float2> kT(slab.n_cplx()), work(slab.n_cplx());
+    float *padded = reinterpret_cast<float *>(work.p);
+
+    const double growth = dicke(redshift);
+    MoveArgs a;
+    memset(&a, 0, sizeof(a));
+    const double boxlen = so->BOX_LEN, boxlen_z = boxlen * so->NON_CUBIC_FACTOR;
+    const double box_size[3] = {boxlen, boxlen, boxlen_z};
+    const double init_growth = dicke(so->INITIAL_REDSHIFT);
+    const double d2 = -(3.0 / 7.0) * growth * growth, d2i = -(3.0 / 7.0) * init_growth * init_growth;
+    for (int ax = 0; ax < 3; ax++) {
+        a.dn[ax] = dn[ax]; a.vn[ax] = hn[ax]; a.on[ax] = hn[ax];
+        a.v[ax] = io.v[ax];
+        a.v2[ax] = (mo->PERTURB_ALGORITHM == PERTURB_2LPT) ? io.v2[ax] : nullptr;
+        a.vdf[ax] = (growth - init_growth) / box_size[ax] * dn[ax];
+        a.vdf2[ax] = (d2 - d2i) / box_size[ax] * dn[ax];
+    }
+    a.vn[0] = nxl; /* local velocity planes */
+    a.dens = io.hires_density;
+    a.ratio_vel = (double)hn[0] / (double)dn[0];
+    a.ratio_out = (double)hn[0] / (double)dn[0];
+    a.init_growth = init_growth;
+
+    /* halo width from the largest x displacement of the whole box */
+    int *keys_sym = (int *)dist_alloc(2 * sizeof(int));
+    DevBuf<int> d_keys(2), d_over(1);
+    dev_zero(d_over, sizeof(int));
+    {
+        const int init[2] = {2147483647, -2147483647 - 1};
+        h2d(keys_sym, init, sizeof(init));
+        g_stats.h2d -= (long long)sizeof(init);
+        MaxDispArgs ma = {(long long)nxl * plane, a.v[0], a.v2[0], a.vdf[0], a.vdf2[0], a.ratio_out, keys_sym};
+        B200_LAUNCH(max_disp_kernel, dev_num_sms() * 4, 256, 0, ma);
+        dist_barrier_minmax(keys_sym, d_keys);
+    }
+    int hkeys[2];
+    d2h(hkeys, d_keys, sizeof(hkeys));
+    g_stats.d2h -= (long long)sizeof(hkeys);
+    const double max_disp = (double)float_from_order_key(hkeys[1]);
+    int halo = (int)ceil(max_disp) + 2;
+    if (const char *e = getenv("B200_SLAB_HALO")) halo = atoi(e);
+    if (halo < 1) halo = 1;
+    if (halo > nxl)
+        b200_throw(B200_ValueError, "slab deposit: displacements of %.1f cells exceed the slab thickness %d (use fewer ranks)", max_disp, nxl);
+
+    a.vel_x0 = x0;
+    a.dens_x0 = F * x0 - F / 2;
+    a.out_x0 = x0 - halo;
+    a.out_nxl = nxl + 2 * halo;
+    a.overflow = d_over;
+    const size_t acc_n = (size_t)a.out_nxl * plane;
+    unsigned long long *acc = (unsigned long long *)dist_alloc(acc_n * sizeof(unsigned long long));
+    dev_zero(acc, acc_n * sizeof(unsigned long long));
+    a.acc = acc;
+    const long long ngroups = (long long)nxl * plane;
+    if (F == 1) launch_grouped<1>(a, 0, ngroups);
+    else if (F == 2) launch_grouped<2>(a, 0, ngroups);
+    else if (F == 3) launch_grouped<3>(a, 0, ngroups);
+    else launch_grouped<4>(a, 0, ngroups);
+    dist_barrier(); /* every rank's deposit has landed before the halos are pulled */
+    {
+        const int row_blocks = (int)((long long)nxl * hn[1] < 4096 ? (long long)nxl * hn[1] : 4096);
+        AccSlabArgs ca = {nxl, halo, plane, hn[1], hn[2], plan->pitch, acc,
+                          dist_peer(acc, (slab.rank + P - 1) % P), dist_peer(acc, (slab.rank + 1) % P), padded,
+                          (double)N / (double)M};
+        B200_LAUNCH(acc_to_delta_slab_kernel, row_blocks, 256, 0, ca);
+    }
+
+    /* smooth_and_clip_density, PerturbedField.c:212-282 */
+    ZPrologue pro;
+    fft_r2c_slab(&slab, kT, work, pro);
+    KMul km;
+    const double dk0 = 2.0 * M_PI / so->BOX_LEN, dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
+    km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
+    if (mo->SMOOTH_EVOLVED_DENSITY_FIELD) {
+        KMul ks = km;
+        ks.kind = KMUL_FILTER; ks.filter_type = 2;
+        ks.R = (float)(so->DENSITY_SMOOTH_RADIUS * so->BOX_LEN / (float)so->HII_DIM);
+        fft_apply_window(plan, kT, ks, slab.nyl, slab.y0);
+    }
+    ZEpilogue epi;
+    epi.scale = 1.f / (float)N;
+    epi.clip = 1; epi.clip_lo = (float)(-1.0 + pc::FRACT_FLOAT_ERR); epi.clip_hi = 3.0e38f;
+    epi.dst = io.density; epi.dst_row_stride = hn[2];
+    fft_c2r_slab(&slab, kT, work, KMul(), epi);
+
+    /* compute_perturbed_velocities, PerturbedField.c:284-387 */
+    if (so->HII_DIM > 1) {
+        const double dDdt_over_D = ddickedt(redshift) / dicke(redshift);
+        for (int ax = 0; ax < 3; ax++) {
+            if (!io.vel[ax]) continue;
+            KMul kv = km;
+            kv.op = KOP_VELOCITY_F; kv.axis_a = ax; kv.op_factor = dDdt_over_D / (double)N;
+            ZEpilogue ev;
+            ev.dst = io.vel[ax]; ev.dst_row_stride = hn[2];
+            fft_c2r_slab(&slab, kT, work, kv, ev);
+        }
+    }
+    dist_barrier(); /* no rank leaves (and reuses the symmetric heap) before every rank is done */
+    int over = 0;
+    d2h(&over, d_over, sizeof(int));
+    g_stats.d2h -= (long long)sizeof(int);
+    dist_check();
+    if (over) b200_throw(B200_ValueError, "slab deposit: mass left the halo of %d planes (B200_SLAB_HALO too small)", halo);
+}
+
 static void reset_stats() { g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0; }
 
 extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, PerturbedField *pf) {
@@ -834,6 +1034,26 @@ extern "C" int b200_ComputePerturbedField_device(float redshift, InitialConditio
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
         fprintf(stderr, "[21cmfast_b200] b200_ComputePerturbedField_device: %s\n", e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+/* Slab-decomposed variant: DEVICE pointers to this rank's slabs (see perturb_core_slab); ranks connected
+   with b200_dist_init / b200_dist_connect. */
+extern "C" int b200_ComputePerturbedField_slab(float redshift, InitialConditions *d_boxes, PerturbedField *d_pf) {
+    try {
+        require_params(false);
+        rt_init();
+        reset_stats();
+        DevTimer timer;
+        timer.start();
+        PerturbDeviceIO io;
+        fill_device_io(io, d_boxes, d_pf);
+        perturb_core_slab(redshift, io);
+        g_stats.ms = timer.stop_ms();
+    } catch (B200Error &e) {
+        fprintf(stderr, "[21cmfast_b200] b200_ComputePerturbedField_slab: %s\n", e.msg);
         return e.code;
     }
     return 0;

@@ -76,8 +76,7 @@ def ionize_radius_parallel(*, redshift: float, density, inputs, backend, group=N
         st = lib.b200_ComputeIonizedBox_device_part(
             C.c_float(redshift), C.c_float(-1.0), C.byref(s_pf), C.byref(s_ib),
             C.c_void_p(mask.data_ptr()), rank, world, phase)
-        if st != 0:
-            raise BackendError(st, f"b200_ComputeIonizedBox_device_part(phase={phase})")
+        _agree(st, f"b200_ComputeIonizedBox_device_part(phase={phase})", group)
 
     call(0)
     if world > 1:
@@ -129,8 +128,7 @@ def perturb_slab_parallel(*, redshift: float, ics: dict, inputs, backend, group=
     def call(phase):
         st = lib.b200_ComputePerturbedField_device_part(
             C.c_float(redshift), C.byref(s_ic), C.byref(s_pf), C.c_void_p(acc.data_ptr()), rank, world, phase)
-        if st != 0:
-            raise BackendError(st, f"b200_ComputePerturbedField_device_part(phase={phase})")
+        _agree(st, f"b200_ComputePerturbedField_device_part(phase={phase})", group)
 
     call(0)
     if world > 1:
@@ -139,3 +137,134 @@ def perturb_slab_parallel(*, redshift: float, ics: dict, inputs, backend, group=
             torch.cuda.synchronize(dev)
     call(1)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Slab decomposition: ONE box, every stage on x-slabs, transposes / halos over peer memory
+# ---------------------------------------------------------------------------------------------
+def _agree(status: int, where: str, group=None):
+    """Raise on EVERY rank when any rank failed (a lone raise would leave the others in a collective)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor([int(status)], dtype=torch.int32)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        status = int(t.item())
+    if status != 0:
+        raise BackendError(status, where)
+
+
+class SlabGroup:
+    """The ranks of ``torch.distributed`` as one slab-decomposed box (``include/py21cmfast_b200.h``,
+    "ONE box over the GPUs of a node").
+
+    Construction allocates the library's symmetric heap on this rank's device, exchanges the 64-byte
+    peer-memory handles through ``torch.distributed`` (the only use of it on this path) and maps the
+    peers.  Afterwards ``perturb`` / ``ionize`` are plain library calls: the all-to-all transposes of
+    the FFTs, the halo exchange of the deposit and the per-radius scalar reductions all happen inside
+    the library's kernels over NVLink.
+    """
+
+    def __init__(self, *, inputs, backend, group=None, heap_bytes: int | None = None):
+        import torch.distributed as dist
+        self.backend, self.inputs, self.group = backend, inputs, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        so = inputs.simulation_options
+        hii, hz = so.HII_DIM, so.HII_D_PARA
+        if hii % self.world:
+            raise ValueError(f"HII_DIM={hii} must be a multiple of the number of ranks ({self.world})")
+        self.nxl = hii // self.world
+        self.x0 = self.rank * self.nxl
+        self.F = so.dim // hii
+        if heap_bytes is None:
+            pitch = ((hz // 2 + 1) + 7) // 8 * 8
+            halo = min(self.nxl, 24)
+            heap_bytes = (2 * 8 * self.nxl * hii * pitch + 8 * (self.nxl + 2 * halo) * hii * hz + (16 << 20))
+        lib = backend.lib
+        lib.b200_dist_init.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
+        lib.b200_dist_connect.argtypes = [C.c_void_p]
+        lib.b200_ComputePerturbedField_slab.argtypes = [
+            C.c_float, C.POINTER(_abi.InitialConditionsStruct), C.POINTER(_abi.PerturbedFieldStruct)]
+        lib.b200_ComputeIonizedBox_slab.argtypes = [
+            C.c_float, C.c_float, C.POINTER(_abi.PerturbedFieldStruct), C.POINTER(_abi.IonizedBoxStruct)]
+        handle = C.create_string_buffer(64)
+        st = lib.b200_dist_init(self.rank, self.world, C.c_ulonglong(heap_bytes), handle)
+        _agree(st, "b200_dist_init", group)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle.raw, group=group)
+        else:
+            handles = [handle.raw]
+        blob = C.create_string_buffer(b"".join(handles), 64 * self.world)
+        st = lib.b200_dist_connect(blob)
+        _agree(st, "b200_dist_connect", group)
+        self.open = True
+
+    def close(self):
+        if self.open:
+            self.backend.lib.b200_dist_shutdown()
+            self.open = False
+
+    # -- slab views of whole-box arrays (host-side helpers for tests / feeders) ------------------
+    def lowres_slab(self, a):
+        return a[self.x0:self.x0 + self.nxl]
+
+    def hires_slab(self, a):
+        """the F * nxl hi-res planes the rank's velocity cells read: from F x0 - F // 2, periodic"""
+        import numpy as np
+        n = a.shape[0]
+        idx = (np.arange(self.F * self.nxl) + self.F * self.x0 - self.F // 2) % n
+        if isinstance(a, np.ndarray):
+            return np.ascontiguousarray(a[idx])
+        import torch
+        return a[torch.as_tensor(idx, device=a.device)].contiguous()
+
+    def perturb(self, *, redshift: float, ics_slab: dict):
+        """ics_slab: device tensors of this rank's slabs (``hires_density`` from ``hires_slab``, the low-res
+        velocity boxes from ``lowres_slab``).  Returns ``dict(density, velocity_z)`` slabs."""
+        import torch
+        be = self.backend
+        be.state.init(self.inputs, broadcast_inputs=True)
+        ref = ics_slab["lowres_vx"]
+        dev, shape = ref.device, tuple(ref.shape)
+        out = {"density": torch.zeros(shape, dtype=torch.float32, device=dev),
+               "velocity_z": torch.zeros(shape, dtype=torch.float32, device=dev)}
+        s_ic = _abi.InitialConditionsStruct()
+        for k, t in ics_slab.items():
+            assert t.is_contiguous()
+            setattr(s_ic, k, _ptr(t))
+        s_pf = _abi.PerturbedFieldStruct()
+        for k, t in out.items():
+            setattr(s_pf, k, _ptr(t))
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        st = be.lib.b200_ComputePerturbedField_slab(C.c_float(redshift), C.byref(s_ic), C.byref(s_pf))
+        _agree(st, "b200_ComputePerturbedField_slab", self.group)
+        return out
+
+    def ionize(self, *, redshift: float, density_slab, want_nion: bool = True):
+        """density_slab: this rank's x-slab of the perturbed density (device tensor).  Returns the slabs of
+        ``neutral_fraction``, ``z_reion``, ``kinetic_temperature`` (, ``unnormalised_nion``) and ``mean_f_coll``."""
+        import torch
+        be = self.backend
+        be.state.init(self.inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+        dev, shape = density_slab.device, tuple(density_slab.shape)
+        out = {"neutral_fraction": torch.ones(shape, dtype=torch.float32, device=dev),
+               "z_reion": torch.zeros(shape, dtype=torch.float32, device=dev),
+               "kinetic_temperature": torch.zeros(shape, dtype=torch.float32, device=dev)}
+        if want_nion:
+            out["unnormalised_nion"] = torch.zeros(shape, dtype=torch.float32, device=dev)
+        s_pf = _abi.PerturbedFieldStruct()
+        s_pf.density = _ptr(density_slab)
+        s_ib = _abi.IonizedBoxStruct()
+        for k, t in out.items():
+            setattr(s_ib, k, _ptr(t))
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        st = be.lib.b200_ComputeIonizedBox_slab(C.c_float(redshift), C.c_float(-1.0), C.byref(s_pf), C.byref(s_ib))
+        _agree(st, "b200_ComputeIonizedBox_slab", self.group)
+        out["mean_f_coll"] = float(s_ib.mean_f_coll)
+        return out

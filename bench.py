@@ -58,11 +58,14 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-yardstick", action="store_true", help="skip the cuFFT library-baseline leg")
-    ap.add_argument("--partition", default="boxes", choices=["boxes", "radius"],
-                    help="N > 1: 'boxes' = one independent coeval box per GPU (weak scaling, no collective); "
-                         "'radius' = ONE box: particle deposit split by x-slab + all-reduce(SUM) of the fixed-point "
-                         "accumulator, filter radii split over the GPUs + all-reduce(MAX) of the ionised mask, both "
-                         "over NCCL (strong scaling)")
+    ap.add_argument("--partition", default="boxes", choices=["boxes", "radius", "slab"],
+                    help="N > 1: 'boxes' = one independent coeval box per GPU (weak scaling, no collective; the line "
+                         "also carries a `strong` record with both one-box partitions); 'slab' = ONE box on x-slabs: "
+                         "slab-decomposed FFTs whose transposes are peer stores over NVLink, slab-local deposit with a "
+                         "halo pull (strong scaling); 'radius' = ONE box: deposit by x-slab + all-reduce(SUM) of the "
+                         "accumulator, filter radii split over the GPUs + all-reduce(MAX) of the mask over NCCL")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1, partition boxes: skip the one-box strong legs")
+    ap.add_argument("--strong-steps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -346,7 +349,8 @@ def main():
 
     ncpu = max(1, (os.cpu_count() or 1) // max(1, world))
     hii, dim, box_len = workload(args)
-    radius_mode = args.partition == "radius" and world > 1
+    radius_mode = args.partition in ("radius", "slab") and world > 1  # ONE box over all ranks
+    slab_mode = args.partition == "slab" and world > 1
     inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source,
                                 seed=1234 + (0 if radius_mode else rank),
                                 n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
@@ -394,23 +398,48 @@ def main():
     lib.b200_ComputeIonizedBox_device.argtypes = [C.c_float, C.c_float, C.POINTER(_abi.PerturbedFieldStruct),
                                                   C.POINTER(_abi.IonizedBoxStruct)]
 
-    def radius_step():
-        """one box on all ranks: slab-parallel deposit + all-reduce(SUM), radius-parallel ionize +
-        all-reduce(MAX); host clock around device syncs (library stream + NCCL on torch's stream)"""
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ppf = pkg.perturb_slab_parallel(redshift=z, ics=d_ic_part, inputs=inputs, backend=be)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        out = pkg.ionize_radius_parallel(redshift=z, density=ppf["density"], inputs=inputs, backend=be)
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        d_ib["neutral_fraction"].copy_(out["neutral_fraction"])
-        return 1e3 * (t1 - t0), 1e3 * (t2 - t1), 4
+    def make_radius_step(ic_part, inp):
+        def radius_step():
+            """one box on all ranks: slab-parallel deposit + all-reduce(SUM), radius-parallel ionize +
+            all-reduce(MAX); host clock around device syncs (library stream + NCCL on torch's stream)"""
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ppf = pkg.perturb_slab_parallel(redshift=z, ics=ic_part, inputs=inp, backend=be)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            out = pkg.ionize_radius_parallel(redshift=z, density=ppf["density"], inputs=inp, backend=be)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            return 1e3 * (t1 - t0), 1e3 * (t2 - t1), 4, float(out["neutral_fraction"].double().sum().item())
+        return radius_step
+
+    def make_slab_step(ic_full, inp):
+        """one box on x-slabs (library stream only: transposes, halo pull and scalar reductions are peer
+        loads / stores inside the library's kernels); device milliseconds of the two library calls"""
+        grp = pkg.SlabGroup(inputs=inp, backend=be)
+        sl = {k: grp.lowres_slab(v).contiguous() for k, v in ic_full.items() if k.startswith("lowres_v")}
+        sl["hires_density"] = grp.hires_slab(ic_full["hires_density"])
+
+        def slab_step():
+            ppf = grp.perturb(redshift=z, ics_slab=sl)
+            l1, _, _, ms1 = stats()
+            out = grp.ionize(redshift=z, density_slab=ppf["density"])
+            l2, _, _, ms2 = stats()
+            return ms1, ms2, l1 + l2, float(out["neutral_fraction"].double().sum().item())
+        return slab_step, grp
+
+    strong_step, slab_group = None, None
+    if slab_mode:
+        strong_step, slab_group = make_slab_step(d_ic_part, inputs)
+    elif radius_mode:
+        strong_step = make_radius_step(d_ic_part, inputs)
+    strong_xh = [0.0]
 
     def device_step():
         if radius_mode:
-            return radius_step()
+            m1, m2, ln, xs = strong_step()
+            strong_xh[0] = xs
+            return m1, m2, ln
         d_ib["neutral_fraction"].fill_(1.0)
         d_ib["kinetic_temperature"].zero_()
         torch.cuda.synchronize()
@@ -449,7 +478,13 @@ def main():
     ms_perturb = float(np.mean([p[0] for p in per]))
     ms_ionize = float(np.mean([p[1] for p in per]))
     ms_step = ms_perturb + ms_ionize
-    xh_dev = float(d_ib["neutral_fraction"].mean().item())
+    if radius_mode:
+        xs = torch.tensor([strong_xh[0]], dtype=torch.float64, device=dev)
+        if slab_mode:
+            dist.all_reduce(xs)  # every rank holds a slab; the radius partition leaves the whole box everywhere
+        xh_dev = float(xs.item()) / N
+    else:
+        xh_dev = float(d_ib["neutral_fraction"].mean().item())
 
     # ---------------- end-to-end leg through the C-ABI with pinned host buffers ----------------
     e2e = None
@@ -501,6 +536,58 @@ def main():
         assert abs(xh_host - xh_dev) < 1e-6, (xh_host, xh_dev)
         e2e = (e2e_s, h2d_b, d2h_b)
         os.environ.pop("B200_ICS_CACHE")
+
+    # ---------------- ONE box over all GPUs (strong scaling), reported beside the replica value ----------------
+    strong = None
+    if world > 1 and not radius_mode and not args.no_strong:
+        strong = {}
+        del d_ic_part
+        if rank != 0:  # every rank needs rank 0's box (seed 1234)
+            d_ic.clear()
+            torch.cuda.empty_cache()
+            cin = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source, seed=1234,
+                                     n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
+            cics = pkg.compute_initial_conditions(inputs=cin, backend=be)
+            d_c = {k: torch.from_numpy(getattr(cics, k)).to(dev) for k in names_ic if k != "lowres_density"}
+            del cics
+        else:
+            cin = inputs
+            d_c = {k: v for k, v in d_ic.items() if k != "lowres_density"}
+        be.state.init(cin, broadcast_inputs=True, ps=True, sigma=True, heat=True)
+        xh0 = torch.tensor([xh_dev], dtype=torch.float64, device=dev)
+        dist.broadcast(xh0, 0)  # the single-GPU answer for the same box
+        for name in ("slab", "radius"):
+            try:
+                if name == "slab":
+                    step, grp = make_slab_step(d_c, cin)
+                else:
+                    step, grp = make_radius_step(d_c, cin), None
+                for _ in range(2):
+                    step()
+                barrier()
+                t0 = time.perf_counter()
+                rec = [step() for _ in range(args.strong_steps)]
+                barrier()
+                wall = (time.perf_counter() - t0) / args.strong_steps
+                v = torch.tensor([np.mean([r[0] for r in rec]), np.mean([r[1] for r in rec]), wall, rec[-1][3]],
+                                 dtype=torch.float64, device=dev)
+                vmax = v.clone()
+                dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+                xs = v[3:4].clone()
+                if name == "slab":
+                    dist.all_reduce(xs)
+                ms_s = float(vmax[0] + vmax[1])
+                strong[name] = {"ms_per_step": ms_s, "ms_perturb": float(vmax[0]), "ms_ionize": float(vmax[1]),
+                                "wall_ms_per_step": 1e3 * float(vmax[2]), "value": N / (ms_s * 1e-3), "unit": "cells/s",
+                                "scaling": "strong", "steps": args.strong_steps,
+                                "global_xH": float(xs.item()) / N,
+                                "matches_single_gpu_xH": bool(abs(float(xs.item()) / N - float(xh0.item())) < 1e-7),
+                                "speedup_vs_one_gpu": ms_step / ms_s}
+                if grp is not None:
+                    grp.close()
+            except Exception as e:  # a strong leg must never cost the replica line
+                strong[name] = {"error": repr(e)[:300]}
+                break
 
     # ---------------- reduce over ranks (max time) ----------------
     vals = torch.tensor([ms_step, ms_perturb, ms_ionize, e2e[0] if e2e else 0.0, t_wall], device=dev,
@@ -570,7 +657,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"perturb_field+ionize_box z={z} HII_DIM={hii} DIM={dim} BOX_LEN={box_len:g} "
                                    f"{args.source} n_radii={nrad}",
-                       "parallelism": (f"one box over {world} GPUs: x-slab deposit + all-reduce(SUM), radii split + "
+                       "parallelism": (f"one box over {world} GPUs on x-slabs: slab-decomposed FFTs (transposes = peer "
+                                       f"stores over NVLink), slab deposit + halo pull") if slab_mode else
+                                      (f"one box over {world} GPUs: x-slab deposit + all-reduce(SUM), radii split + "
                                        f"all-reduce(MAX) of the mask") if radius_mode else
                                       f"{world} independent coeval boxes (one per GPU)",
                        "l2": f"inputs larger than L2 (every pass streams a {4 * N / 1e6:.0f} MB box; L2 is 126 MB)",
@@ -578,11 +667,14 @@ def main():
                        "wall_ms_per_step": 1e3 * t_wall / args.steps},
             "clocks": clk, "gpu_launches": launches,
             "roofline": roofline,
+            # one box over `world` GPUs is measured against world x the per-GPU peak
             "step_roofline": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
-                              "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                              "peak": peak * (world if radius_mode else 1), "unit": "GB/s",
+                              "frac": step_bytes / (ms_step * 1e-3) / 1e9 / (peak * (world if radius_mode else 1))},
             "kernel_profile_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu_baseline,
             "cufft_yardstick": yardstick,
+            "strong": strong,
         }
         if e2e:
             out["e2e"] = {"value": world * N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(e2e[1]),

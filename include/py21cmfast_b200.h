@@ -355,6 +355,29 @@ int b200_ComputeIonizedBox_device_part(float redshift, float prev_redshift,
                                        PerturbedField *d_perturbed_field, IonizedBox *d_box,
                                        unsigned char *d_mask, int part, int nparts, int phase);
 
+/* ---- ONE box over the GPUs of a node, slab-decomposed (replaces dft_r2c_cube /
+   dft_c2r_cube, dft.c:18-72, and move_grid_masses, map_mass.c:146-208, for a box split over GPUs) ------
+   One process per GPU.  b200_dist_init allocates this rank's symmetric heap (peer-mapped device memory:
+   the transposes of the slab FFT and the halo exchange of the deposit are kernel stores / loads on peer
+   pointers over NVLink, ordered by a barrier kernel on the library's stream -- no NCCL call) and returns
+   a 64-byte handle; the caller exchanges the handles of all ranks by any means (torch.distributed in
+   21cmfast_b200/distributed.py) and passes the concatenation, in rank order, to b200_dist_connect.
+   HII_DIM must be a multiple of `world` (<= 8). */
+int b200_dist_init(int rank, int world, unsigned long long heap_bytes, void *handle_out_64_bytes);
+int b200_dist_connect(const void *handles_world_times_64_bytes);
+int b200_dist_shutdown(void);
+int b200_dist_rank(void);
+int b200_dist_world(void);
+int b200_dist_barrier(void);
+/* Slab entry points: the structs hold DEVICE pointers to this rank's x-slab of every array, planes
+   [rank, rank + 1) * HII_DIM / world: low-res boxes [HII_DIM / world][HII_DIM][HII_D_PARA]; hires_density
+   the F * HII_DIM / world hi-res planes that start at global plane F * x0 - F / 2 (periodic), F = DIM /
+   HII_DIM integer <= 4.  Outputs are the rank's slab of the result, bit-identical to the same planes of the
+   single-GPU box (same per-line FFT arithmetic, integer deposit sums, fixed reduction tree of the grid
+   sum).  ZELDOVICH / 2LPT on the low-res grid; ionisation without recombinations / spin temperature. */
+int b200_ComputePerturbedField_slab(float redshift, InitialConditions *d_boxes_slab, PerturbedField *d_pf_slab);
+int b200_ComputeIonizedBox_slab(float redshift, float prev_redshift, PerturbedField *d_pf_slab, IonizedBox *d_box_slab);
+
 /* Test hooks for the random stream of sample_ic_modes (InitialConditions.c:103-139; rng.c:31-90):
    n1 then n2 values of gsl_ran_ugaussian on gsl_rng_mt19937 seeded with mt_seed, produced by the
    device pipeline (csrc/gslrng.cu) resp. by the sequential host generator; and the sequential
