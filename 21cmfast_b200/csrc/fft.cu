@@ -755,15 +755,19 @@ struct WExpandArgs {
     int nax, nay, pitch, nzc;
     const float *tab;
     float *out;
+    int ay0, ay1; /* rows |ny| in [ay0, ay1] only (a y-slab of a slab-decomposed box reads no others) */
 };
 __global__ void window_expand_kernel(WExpandArgs a) {
     /* the table is symmetric in (ax, ay) for a cubic box: gather each row once, write it twice */
-    const bool sym = a.nax == a.nay;
-    const long long rows = (long long)a.nax * a.nay;
-    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int ax = (int)(row / a.nay), ay = (int)(row - (long long)ax * a.nay);
+    const bool whole = a.ay0 == 0 && a.ay1 == a.nay - 1;
+    const bool sym = whole && a.nax == a.nay;
+    const int nsel = a.ay1 - a.ay0 + 1;
+    const long long rows = (long long)a.nax * nsel;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int ax = (int)(r / nsel), ay = a.ay0 + (int)(r - (long long)ax * nsel);
         if (sym && ax > ay) continue;
         const int n2 = ax * ax + ay * ay;
+        const long long row = (long long)ax * a.nay + ay;
         const long long mirror = (long long)ay * a.nay + ax;
         for (int iz = threadIdx.x; iz < a.pitch; iz += blockDim.x) {
             const float w = iz < a.nzc ? ldg(&a.tab[n2 + iz * iz]) : 1.0f;
@@ -773,9 +777,18 @@ __global__ void window_expand_kernel(WExpandArgs a) {
     }
 }
 size_t window_table3_size(const Fft3D *p) { return (size_t)(p->nx / 2 + 1) * (p->ny / 2 + 1) * p->pitch; }
-void window_table_expand(const Fft3D *p, const float *tab, float *out3) {
-    WExpandArgs a = {p->nx / 2 + 1, p->ny / 2 + 1, p->pitch, p->nzc, tab, out3};
-    const long long rows = (long long)a.nax * a.nay;
+void window_table_expand(const Fft3D *p, const float *tab, float *out3, int y_lo, int y_hi) {
+    WExpandArgs a = {p->nx / 2 + 1, p->ny / 2 + 1, p->pitch, p->nzc, tab, out3, 0, p->ny / 2};
+    if (y_hi >= y_lo) { /* |ny| range of the global rows y_lo .. y_hi */
+        int lo = p->ny, hi = 0;
+        for (int y = y_lo; y <= y_hi; y++) {
+            const int ay = (y > p->ny / 2) ? p->ny - y : y;
+            lo = ay < lo ? ay : lo;
+            hi = ay > hi ? ay : hi;
+        }
+        a.ay0 = lo; a.ay1 = hi;
+    }
+    const long long rows = (long long)a.nax * (a.ay1 - a.ay0 + 1);
     const int cap = dev_num_sms() * 16;
     B200_LAUNCH(window_expand_kernel, (int)(rows < cap ? rows : cap), 256, 0, a);
 }

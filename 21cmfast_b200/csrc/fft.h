@@ -94,7 +94,8 @@ int window_table_size(const Fft3D *p);
 void window_table_build(const Fft3D *p, int type, float R, double dk, float *out);
 /* expanded form for the power-of-two x pass: out3[(ax * (ny/2+1) + ay) * pitch + kz] = tab[ax^2 + ay^2 + kz^2] */
 size_t window_table3_size(const Fft3D *p);
-void window_table_expand(const Fft3D *p, const float *tab, float *out3);
+/* y_lo <= y_hi: only the rows a y-slab [y_lo, y_hi] of the box reads are filled */
+void window_table_expand(const Fft3D *p, const float *tab, float *out3, int y_lo = 0, int y_hi = -1);
 
 /* box *= W(kR) in place (the exact double window of filter_box, rounded to float per mode); with
    nyl > 0 the box is a transposed k-space slab [nx][nyl][pitch] whose first row is global y = y_off */

@@ -34,6 +34,8 @@
 #include "host_recomb.h"
 
 #include <omp.h>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 #define HII_ROUND_ERR (1e-5)
@@ -52,7 +54,52 @@ struct SweepArgs {
     double *partial;         /* [ceil(nx ny / chunk_rows)] sums of consecutive row chunks */
     float *fcoll;            /* unpadded f_coll grid of this radius, or null (sum only) */
     int chunk_rows;          /* rows per chunk: divides ny, so that chunks never straddle an x plane */
+    /* speculative flags (fcoll_sum_kernel<LOG, true>), see SpecState */
+    struct SpecState *spec;
+    int j;                   /* index of this radius among the radii of the call */
+    double ion_eff_factor;
+    unsigned char *mask;
+    uint2 *queue;            /* gridDim.x private segments of qcap (cell index, density bits) pairs, one per CTA */
+    unsigned int qcap;
+    unsigned int *qcounts;   /* [gridDim.x] cells each CTA wanted to queue (> qcap: its segment overflowed) */
 };
+
+/* ONE sweep per radius instead of two.  The ionised flag of a cell is mean_fix f_coll(delta) zeta > 1, and
+   mean_fix = <f_coll> / (grid mean of f_coll) is only known after the whole grid has been summed -- which is why
+   the reference (and ionise_delta_kernel) walk the filtered grid a second time.  The mean fix, however,
+   drifts by well under a per cent from one radius of the ladder to the next.  The sum sweep therefore
+   classifies every cell against a BRACKET of the mean fix predicted from the two previous radii
+   (geometric extrapolation, +- SPEC_EPS): cells that are ionised for every mean fix inside the bracket
+   are flagged at once, cells that are neutral for every mean fix inside it are skipped, and the few cells
+   in between are queued (4-byte cell indices; every CTA fills a private segment of the queue behind a
+   shared-memory counter -- one global counter serialised the sweep: 0.95 ms per radius against 0.19).  Once
+   the grid sum exists, spec_resolve_kernel checks that the
+   true mean fix lies inside the bracket and decides the queued cells with the reference arithmetic.  If the
+   prediction ever fails, flags may already be wrong: the kernel raises `failed` and the host re-runs the
+   ladder of this call without speculation (never observed; the check is what makes the shortcut exact).
+   A queue that overflows only costs that radius a full flag sweep (spec_fallback). */
+#define SPEC_EPS 0.02
+#define SPEC_MAX_RADII 64
+struct SpecState {
+    double eps;                      /* half width of the bracket (SPEC_EPS; B200_SPEC_EPS overrides it for tests) */
+    double mean_fix[SPEC_MAX_RADII]; /* true mean fix of every radius processed so far in this call */
+    unsigned int qcount[SPEC_MAX_RADII];   /* queued cells of the radius, all segments */
+    unsigned int overflow[SPEC_MAX_RADII]; /* a segment of the radius was too small: full flag sweep instead */
+    int failed;
+};
+struct SpecBracket {
+    double gain_lo, gain_hi; /* mean_fix zeta at the ends of the bracket */
+};
+DEV SpecBracket spec_bracket(const SpecState *sp, int j, double ion_eff_factor) {
+    const double p1 = sp->mean_fix[j - 1], p2 = sp->mean_fix[j - 2];
+    double ratio = p1 / p2;
+    if (!(ratio > 0.5 && ratio < 2.0)) ratio = 1.0;
+    const double pred = p1 * ratio;
+    SpecBracket b;
+    b.gain_lo = pred * (1.0 - sp->eps) * ion_eff_factor;
+    b.gain_hi = pred * (1.0 + sp->eps) * ion_eff_factor;
+    return b;
+}
 
 /* The grid sum is reduced in a FIXED tree that depends on the box shape only -- chunk sums (a CTA's
    deterministic reduction over chunk_rows consecutive rows), then per-x-plane sums of the chunk sums in
@@ -315,47 +362,137 @@ DEV void for_each_chunk_blocked(const float *filtered, long long nrows, int nz, 
 /* sweep 1: sum of f_coll over the grid as deterministic double block sums (calculate_fcoll_grid,
    IonisationBox.c:773-962).  With a.fcoll set (last radius: the grid is the unnormalised_nion
    output) every cell takes the reference arithmetic and the float grid is written. */
-template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
+template <bool LOG, bool SPEC> __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     __shared__ SweepTable st;
-    __shared__ double red[256];
+    __shared__ double red[8];
+    __shared__ unsigned int q_n;
     DYN_SMEM(float2, rep);
     sweep_table_load(&st, a.table, rep, LOG);
+    __shared__ int s_first_hi, s_last_lo;
+    __shared__ float s_d_lo, s_d_hi;
+    if (SPEC && threadIdx.x == 0) { q_n = 0; s_first_hi = N_DENS_INTERP; s_last_lo = -1; }
     __syncthreads();
+    /* The flag test of the reference, (float) f_coll(delta) mean_fix zeta > 1, follows the table, which grows
+       with the density (up to a few unordered nodes, below), so the bracket of the mean fix becomes a bracket
+       [d_lo, d_hi] of the filtered density itself: ionised for every mean fix inside the bracket above d_hi,
+       neutral for every one below d_lo.  Two compares per cell instead of a second table evaluation.  The
+       crossings are solved on the interpolant of the reference path (fcoll_exact) with a margin of 1e-5 in
+       (log) f_coll -- two orders above its rounding -- and rounded outwards. */
+    float d_lo = 0.f, d_hi = 0.f;
+    if (SPEC) {
+        const SpecBracket br = spec_bracket(a.spec, a.j, a.ion_eff_factor);
+        const double v_hi = LOG ? -log(br.gain_lo) + 1e-5 : (1.0 / br.gain_lo) * (1.0 + 1e-5);
+        const double v_lo = LOG ? -log(br.gain_hi) - 1e-5 : (1.0 / br.gain_hi) * (1.0 - 1e-5);
+        /* the table need not be ordered (the reference's integrals switch method at delta = 1.2 and collapse to
+           one halo of the condition mass near delta_crit): d_hi lies in the bin after the LAST node below v_hi --
+           every node above it, hence the interpolant, is >= v_hi -- and d_lo in the bin before the FIRST node
+           above v_lo; what is unordered in between simply falls inside [d_lo, d_hi] and is queued */
+        for (int i = threadIdx.x; i < N_DENS_INTERP; i += blockDim.x) {
+            const double y = (double)st.y[i];
+            if (y < v_hi) atomic_max_i32(&s_last_lo, i);   /* reused: last node below v_hi */
+            if (y > v_lo) atomic_min_i32(&s_first_hi, i);  /* reused: first node above v_lo */
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float inf = 3.0e38f;
+            float lo, hi;
+            const int a_hi = s_last_lo, b_lo = s_first_hi;
+            if (a_hi < 0) hi = -inf;                          /* every node ionises for sure */
+            else if (a_hi >= N_DENS_INTERP - 1) hi = inf;     /* no cell can be ionised for sure */
+            else {
+                const double y0 = (double)st.y[a_hi], y1 = (double)st.y[a_hi + 1];
+                const double x = st.x_min + st.x_width * ((double)a_hi + (v_hi - y0) / (y1 - y0));
+                hi = (float)x;
+                hi += fabsf(hi) * 2.4e-7f + 1e-30f; /* outwards by two units in the last place */
+            }
+            if (b_lo >= N_DENS_INTERP) lo = inf;              /* every node is neutral for sure */
+            else if (b_lo == 0) lo = -inf;
+            else {
+                const double y0 = (double)st.y[b_lo - 1], y1 = (double)st.y[b_lo];
+                const double x = st.x_min + st.x_width * ((double)(b_lo - 1) + (v_lo - y0) / (y1 - y0));
+                lo = (float)x;
+                lo -= fabsf(lo) * 2.4e-7f + 1e-30f;
+            }
+            if (!(lo <= hi)) { lo = -inf; hi = inf; } /* cannot happen for v_lo < v_hi; then every cell goes to the queue */
+            s_d_lo = lo; s_d_hi = hi;
+        }
+        __syncthreads();
+        d_lo = s_d_lo; d_hi = s_d_hi;
+    }
+    /* four cells: bits 0..3 = ionised for sure, bits 4..7 = inside the bracket */
+    auto classify4 = [&](const float4 &d) -> unsigned {
+        const unsigned s = (d.x > d_hi ? 1u : 0u) | (d.y > d_hi ? 2u : 0u) | (d.z > d_hi ? 4u : 0u) | (d.w > d_hi ? 8u : 0u);
+        const unsigned n = (d.x < d_lo ? 1u : 0u) | (d.y < d_lo ? 2u : 0u) | (d.z < d_lo ? 4u : 0u) | (d.w < d_lo ? 8u : 0u);
+        return s | ((~(s | n) & 15u) << 4);
+    };
+    uint2 *const seg = SPEC ? a.queue + (size_t)blockIdx.x * a.qcap : nullptr;
+    auto push_cells = [&](unsigned bits, unsigned int cell, const float4 &d) { /* bits 0..3: cells cell + i, with their densities */
+        const unsigned n = (unsigned)__builtin_popcount(bits);
+        const unsigned at = atomic_fetch_add_u32(&q_n, n);
+        const float dv[4] = {d.x, d.y, d.z, d.w};
+        unsigned k = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (bits & (1u << i)) {
+                if (at + k < a.qcap) seg[at + k] = make_uint2(cell + i, (unsigned int)float_as_int_bits(dv[i]));
+                k++;
+            }
+    };
+    /* flags of four cells = one 32-bit OR into the byte mask (a fire-and-forget reduction: no branches, and the
+       flags of earlier radii in the same word stay) */
+    auto set_sure = [&](unsigned m4, unsigned int cell) {
+        atomic_or_u32(reinterpret_cast<unsigned int *>(a.mask + cell), (m4 * 0x00204081u) & 0x01010101u);
+    };
     const long long nrows = (long long)a.nx * a.ny;
     const int CH = a.chunk_rows;
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
     const SweepConstsF kf = sweep_consts(&st, dens_floor);
     double acc = 0.;
-    /* deterministic CTA reduction of the chunk's thread sums -> partial[chunk] */
+    /* deterministic CTA reduction of the chunk's thread sums -> partial[chunk]: butterfly over the
+       lanes of each warp (every lane ends with the same bits), then the warp sums in warp order */
     auto end_chunk = [&](long long chunk) {
-        red[threadIdx.x] = acc;
-        acc = 0.;
+#ifndef B200_EMU
+        double v = acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
         __syncthreads();
-        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-            __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+            a.partial[chunk] = t;
         }
-        if (threadIdx.x == 0) a.partial[chunk] = red[0];
         __syncthreads();
+#else
+        a.partial[chunk] = acc;
+#endif
+        acc = 0.;
     };
     if ((a.nz & 3) == 0 && !a.fcoll) {
-        struct SumRes { float sum; bool steep; };
+        struct SumRes { float sum; bool steep; unsigned code; };
         for_each_chunk_blocked<SumRes>(
             a.filtered, nrows, a.nz, a.nzc, CH, reinterpret_cast<float4 *>(rep + N_DENS_INTERP * SWEEP_REP),
             [&](const float4 &d) -> SumRes {
                 SumRes r;
                 r.steep = false;
+                r.code = 0;
                 const float2 f = f2_add(fcoll_fast2<LOG>(make_float2(d.x, d.y), &st, kf, r.steep),
                                         fcoll_fast2<LOG>(make_float2(d.z, d.w), &st, kf, r.steep));
                 r.sum = f.x + f.y;
+                if (SPEC) r.code = classify4(d);
                 return r;
             },
-            [&](const SumRes &r, const float4 &d, long long, int) {
+            [&](const SumRes &r, const float4 &d, long long row, int zc) {
                 if (r.steep) /* a steep bin somewhere in the chunk: reference arithmetic for its cells */
                     acc += (fcoll_exact(fmaxf(d.x, dens_floor), &st) + fcoll_exact(fmaxf(d.y, dens_floor), &st)) +
                            (fcoll_exact(fmaxf(d.z, dens_floor), &st) + fcoll_exact(fmaxf(d.w, dens_floor), &st));
                 else
                     acc += (double)r.sum;
+                if (SPEC && r.code) {
+                    const unsigned int cell = (unsigned int)row * (unsigned int)a.nz + 4u * (unsigned int)zc; /* NL < 2^32 */
+                    if (r.code & 15u) set_sure(r.code & 15u, cell);
+                    if (r.code & 0xf0u) push_cells(r.code >> 4, cell, d);
+                }
             },
             end_chunk);
     } else {
@@ -379,6 +516,10 @@ template <bool LOG> __global__ void __launch_bounds__(256) fcoll_sum_kernel(Swee
             end_chunk(chunk);
         }
     }
+    if (SPEC) {
+        __syncthreads();
+        if (threadIdx.x == 0) a.qcounts[blockIdx.x] = q_n;
+    }
 }
 
 /* second level of the fixed reduction tree: plane[x] = sum of the chunk sums of x-plane x, in order */
@@ -389,8 +530,17 @@ struct PlaneSumArgs {
 };
 __global__ void plane_sum_kernel(PlaneSumArgs a) {
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.nx; x += gridDim.x * blockDim.x) {
+        const double *p = a.partial + (long long)x * a.chunks_per_plane;
         double acc = 0.;
-        for (int c = 0; c < a.chunks_per_plane; c++) acc += a.partial[(long long)x * a.chunks_per_plane + c];
+        int c = 0;
+        for (; c + 8 <= a.chunks_per_plane; c += 8) { /* eight loads in flight, added in order */
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = p[c + u];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc += v[u];
+        }
+        for (; c < a.chunks_per_plane; c++) acc += p[c];
         a.plane[x] = acc;
     }
 }
@@ -547,6 +697,15 @@ struct CritDeltaArgs {
     unsigned char *mask;     /* 1 = ionised at some radius so far */
     double n_cells, mean_f_coll, f_limit, ion_eff_factor;
     int mass_dep_zeta;
+    /* speculation bookkeeping: the true mean fix of radius j is recorded in spec->mean_fix[j]; with
+       only_if_overflow the kernel is the fallback of a speculative radius and returns at once unless that
+       radius' queue overflowed; with resolve it decides the queued cells instead of walking the grid */
+    SpecState *spec;
+    int j, only_if_overflow;
+    const uint2 *queue;         /* n_seg segments of qcap (cell, density) pairs, qcounts[s] of them wanted by segment s */
+    const unsigned int *qcounts;
+    unsigned int qcap;
+    int n_seg;
 };
 /* sweep 2 for every radius but the last one processed: only the flag "f_coll zeta > 1" is needed
    (find_ionised_regions, IonisationBox.c:1040-1151, centre-cell method), so the f_coll grid is never
@@ -576,6 +735,13 @@ template <bool LOG> __global__ void __launch_bounds__(256) ionise_delta_kernel(C
     }
     const double mean_fix = a.mean_f_coll / grid_mean;
     const double gain = mean_fix * a.ion_eff_factor;
+    if (a.spec) {
+        if (a.only_if_overflow) {
+            if (!a.spec->overflow[a.j]) return; /* the queue held every bracket cell: nothing to do */
+        } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.spec->mean_fix[a.j] = mean_fix;
+        }
+    }
     const bool floor_ionises = a.mass_dep_zeta && (a.f_limit * a.ion_eff_factor > 1.0);
     /* threshold in the table's own units: log f_coll or f_coll */
     const float thr = LOG ? (float)(-log(gain)) : (float)(1.0 / gain);
@@ -637,6 +803,56 @@ template <bool LOG> __global__ void __launch_bounds__(256) ionise_delta_kernel(C
                 const bool ion = (res & 16u) ? exact(src[z]) : (res & 1u) != 0;
                 if (ion) a.mask[row * a.nz + z] = 1;
             }
+        }
+    }
+}
+
+/* second half of a speculative radius: check the bracket against the true mean fix, then the queued cells */
+__global__ void __launch_bounds__(256) spec_resolve_kernel(CritDeltaArgs a) {
+    __shared__ SweepTable st;
+    __shared__ double red[256];
+    DYN_SMEM(float2, rep);
+    sweep_table_load(&st, a.table, rep, false);
+    double acc = 0.;
+    for (int i = threadIdx.x; i < a.n_partial; i += blockDim.x) acc += a.partial[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    double grid_mean = red[0] / a.n_cells;
+    if (a.mass_dep_zeta) {
+        if (grid_mean <= a.f_limit) grid_mean = a.f_limit;
+    } else {
+        if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
+    }
+    const double mean_fix = a.mean_f_coll / grid_mean;
+    const double gain = mean_fix * a.ion_eff_factor;
+    const SpecBracket br = spec_bracket(a.spec, a.j, a.ion_eff_factor);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.spec->mean_fix[a.j] = mean_fix;
+        if (!(gain >= br.gain_lo && gain <= br.gain_hi)) a.spec->failed = 1;
+    }
+    if (!(gain >= br.gain_lo && gain <= br.gain_hi)) return;
+    const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
+    /* a segment that overflowed sends the whole radius to the fallback sweep; flags set here meanwhile are
+       ones that sweep would set as well */
+    for (int sg = blockIdx.x; sg < a.n_seg; sg += gridDim.x) {
+        unsigned int n = a.qcounts[sg];
+        if (threadIdx.x == 0) {
+            atomic_fetch_add_u32(&a.spec->qcount[a.j], n);
+            if (n > a.qcap) a.spec->overflow[a.j] = 1;
+        }
+        if (n > a.qcap) n = a.qcap;
+        const uint2 *seg = a.queue + (size_t)sg * a.qcap;
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint2 e = seg[i];
+            const unsigned int cell = e.x;
+            const float dens = int_bits_as_float((int)e.y);
+            double curr = mean_fix * (double)(float)fcoll_exact(fmaxf(dens, dens_floor), &st);
+            if (a.mass_dep_zeta && curr < a.f_limit) curr = a.f_limit;
+            if (curr * a.ion_eff_factor > 1.0) a.mask[cell] = 1;
         }
     }
 }
@@ -886,8 +1102,11 @@ static void sweep_smem_optin() {
     static bool done = false;
     if (done) return;
     const int bytes = (int)SWEEP_REP_BYTES;
-    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(fcoll_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CUDA_CHECK(cudaFuncSetAttribute(ionise_delta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CUDA_CHECK(cudaFuncSetAttribute(ionise_delta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     done = true;
@@ -1238,7 +1457,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
                 km.wtab = slot; km.wtab_n = wtab_n;
                 if (use_wtab3) {
                     float *slot3 = d_wtab3.p + (size_t)(j % NW) * wtab3_n;
-                    window_table_expand(plan, slot, slot3);
+                    if (sl) window_table_expand(plan, slot, slot3, slab.y0, slab.y0 + slab.nyl - 1);
+                    else window_table_expand(plan, slot, slot3);
                     km.wtab3 = slot3;
                 }
                 if (overlap_tables) {
@@ -1273,9 +1493,37 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         dev_event_record(g_stage.events[k]);
     };
 
+    /* speculative single-sweep radii (SpecState): plain ladder on one GPU or on slabs, never with a per-cell
+       barrier, sphere painting or a floor that ionises everything; B200_SPEC=0 switches it off */
+    bool use_spec = !general && !sphere && pt.phase < 0 && (nz & 3) == 0 && NL < ((long long)1 << 32) && n_mine > 3 &&
+                    !(c.mass_dep_zeta && f_limit * c.ion_eff_factor > 1.0) &&
+                    !(getenv("B200_SPEC") && getenv("B200_SPEC")[0] == '0');
+    DevBuf<SpecState> d_spec(1);
+    /* a private queue segment per CTA of the sum sweep, a sixteenth of the CTA's cells (a per cent or two of the
+       cells sit inside the bracket) */
+    unsigned int qcap = use_spec ? (unsigned int)((NL / 16) / sum_blocks > 256 ? (NL / 16) / sum_blocks : 256) : 0;
+    if (use_spec && getenv("B200_SPEC_QCAP")) qcap = (unsigned int)atoi(getenv("B200_SPEC_QCAP")); /* tests: force overflows */
+    DevBuf<uint2> d_queue((size_t)qcap * (use_spec ? sum_blocks : 0));
+    DevBuf<unsigned int> d_qcounts(use_spec ? sum_blocks : 0);
+
     FcollTable htab;
     double t_wait = 0, t_table = 0, t_launch = 0;
     const bool verbose = getenv("B200_TIMING") != nullptr;
+    for (int attempt = 0; attempt < 2; attempt++) {
+    bool restart = false;
+    dev_zero(d_spec, sizeof(SpecState));
+    if (use_spec) {
+        const double eps = getenv("B200_SPEC_EPS") ? atof(getenv("B200_SPEC_EPS")) : SPEC_EPS;
+        h2d(d_spec.p, &eps, sizeof(double));
+        g_stats.h2d -= (long long)sizeof(double);
+    }
+    if (attempt > 0) { /* the prediction of the mean fix failed somewhere: the same ladder, two sweeps per radius */
+        use_spec = false;
+        if (pt.phase <= 0) dev_zero(d_mask, (size_t)NL);
+        KeyInitArgs ka = {n_todo, sl ? keys_sym : d_keys.p};
+        B200_LAUNCH(minmax_key_init_kernel, 1, 64, 0, ka);
+        if (verbose) fprintf(stderr, "[21cmfast_b200] ionize: mean-fix prediction left its bracket, ladder re-run without speculation\n");
+    }
     int next_enq = 0;
     if (n_mine > 0) enqueue_transform(next_enq++);
     for (int j = 0; j < n_mine; j++) {
@@ -1311,13 +1559,31 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         float *fc = last ? (io.nion ? io.nion : d_fcoll.p) : (general ? d_fcoll.p : nullptr);
         if (last && io.nion && io.nion_written) *io.nion_written = true;
         const float *filtered = reinterpret_cast<const float *>(work[j % NW]);
-        SweepArgs sa = {nxl, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc, chunk_rows};
+        if (last && use_spec && j >= 3) {
+            /* every speculative radius has been resolved once the stream has drained: a failed prediction
+               must be known before the last radius turns the mask into the outputs */
+            SpecState hs;
+            d2h(&hs, d_spec, sizeof(SpecState));
+            g_stats.d2h -= (long long)sizeof(SpecState);
+            if (verbose) {
+                fprintf(stderr, "[21cmfast_b200] ionize speculation: mean fix / queued cells per radius:");
+                for (int q = 0; q < j; q++) fprintf(stderr, " %.6f/%u", hs.mean_fix[q], hs.qcount[q]);
+                fprintf(stderr, " (queue: %d segments of %u)\n", sum_blocks, qcap);
+            }
+            if (hs.failed) { restart = true; break; }
+        }
+        const bool spec_j = use_spec && j >= 2 && !last;
+        SweepArgs sa = {nxl, ny, nz, plan->pitch, filtered, d_tables.p + k, d_partial, fc, chunk_rows,
+                        d_spec.p, j, c.ion_eff_factor, d_mask, d_queue.p, qcap, d_qcounts.p};
         sweep_smem_optin();
-        if (htab.log_valued) B200_LAUNCH(fcoll_sum_kernel<true>, sum_blocks, 256, SWEEP_REP_BYTES, sa);
-        else B200_LAUNCH(fcoll_sum_kernel<false>, sum_blocks, 256, SWEEP_REP_BYTES, sa);
+        {
+            auto ks = spec_j ? (htab.log_valued ? &fcoll_sum_kernel<true, true> : &fcoll_sum_kernel<false, true>)
+                             : (htab.log_valued ? &fcoll_sum_kernel<true, false> : &fcoll_sum_kernel<false, false>);
+            B200_LAUNCH_T(spec_j ? "fcoll_sum_classify_kernel" : "fcoll_sum_kernel", ks, sum_blocks, 256, SWEEP_REP_BYTES, sa);
+        }
         {
             PlaneSumArgs ps = {nxl, chunks_per_plane, d_partial, sl ? plane_sym + (size_t)k * nxl : d_plane.p};
-            B200_LAUNCH(plane_sum_kernel, (nxl + 127) / 128, 128, 0, ps);
+            B200_LAUNCH(plane_sum_kernel, (nxl + 31) / 32, 32, 0, ps);
             if (sl) dist_barrier_gather(reinterpret_cast<const unsigned long long *>(plane_sym + (size_t)k * nxl),
                                         reinterpret_cast<unsigned long long *>(d_plane.p), nxl);
         }
@@ -1331,6 +1597,11 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             if (sphere) { dev_zero(d_centre, (size_t)N); cd.mask = d_centre; }
             cd.n_cells = (double)N; cd.mean_f_coll = box->mean_f_coll; cd.f_limit = f_limit;
             cd.ion_eff_factor = c.ion_eff_factor; cd.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
+            if (use_spec) { cd.spec = d_spec.p; cd.j = j; cd.queue = d_queue.p; cd.qcounts = d_qcounts.p; cd.qcap = qcap; cd.n_seg = sum_blocks; }
+            if (spec_j) { /* queued cells, then (only if the queue overflowed) the full flag sweep */
+                B200_LAUNCH(spec_resolve_kernel, dev_num_sms() * 2, 256, SWEEP_REP_BYTES, cd);
+                cd.only_if_overflow = 1;
+            }
             if (htab.log_valued) B200_LAUNCH(ionise_delta_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
             else B200_LAUNCH(ionise_delta_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
             if (sphere) paint_spheres(rs.R);
@@ -1362,6 +1633,8 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             B200_LAUNCH(ionise_kernel, grid_for(NL, 1024), 256, 0, ca);
             if (dilate_last) paint_spheres(rs.R);
         }
+    }
+    if (!restart) break;
     }
 
     if (verbose)
@@ -1423,6 +1696,22 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
 
 static void reset_stats() { g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0; g_stats.ms = 0; }
 
+/* fills a host array with one value on a few helper threads while the caller goes on (the radius ladder
+   leaves the host cores idle); joined when the object leaves scope, on the error path as well.  The
+   single-threaded loop it replaces cost 55 ms per call at 512^3 -- more than the whole ladder. */
+struct HostFill {
+    std::vector<std::thread> workers;
+    void start(float *p, long long n, float value, int nthreads = 4) {
+        for (int t = 0; t < nthreads; t++) {
+            const long long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            workers.emplace_back([=] { std::fill(p + lo, p + hi, value); });
+        }
+    }
+    ~HostFill() {
+        for (auto &w : workers) w.join();
+    }
+};
+
 extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedField *perturbed_field,
                                  PerturbedField *previous_perturbed_field, IonizedBox *previous_ionize_box,
                                  TsBox *spin_temp, HaloBox *halos, InitialConditions *ini_boxes, IonizedBox *box) {
@@ -1442,8 +1731,9 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         /* first snapshot: the reference writes z_reion = -1 into the *previous* box
            (setup_first_z_prevbox, IonisationBox.c:365-386) */
         const bool first = prev_redshift < 1;
+        HostFill prev_fill;
         if (first && previous_ionize_box && previous_ionize_box->z_reion)
-            for (long long i = 0; i < N; i++) previous_ionize_box->z_reion[i] = -1.0f;
+            prev_fill.start(previous_ionize_box->z_reion, N, -1.0f);
         const bool ts = astro_options_global->USE_TS_FLUCT;
         if (ts && (!spin_temp || !spin_temp->xray_ionised_fraction || !spin_temp->kinetic_temp_neutral))
             b200_throw(B200_ValueError, "ComputeIonizedBox: USE_TS_FLUCT needs a computed TsBox");

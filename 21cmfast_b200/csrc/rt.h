@@ -88,10 +88,13 @@ void prof_end(int slot);
 #define DEV __device__ __forceinline__
 template <typename T> DEV T ldg(const T *p) { return __ldg(p); }
 DEV void atomic_add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+DEV unsigned int atomic_fetch_add_u32(unsigned int *p, unsigned int v) { return atomicAdd(p, v); }
+DEV void atomic_or_u32(unsigned int *p, unsigned int v) { atomicOr(p, v); }
 DEV void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 DEV void atomic_min_i32(int *p, int v) { atomicMin(p, v); }
 DEV void atomic_max_i32(int *p, int v) { atomicMax(p, v); }
 DEV int float_as_int_bits(float f) { return __float_as_int(f); }
+DEV float int_bits_as_float(int i) { return __int_as_float(i); }
 /* asynchronous 16-byte global -> shared copies (LDGSTS): in-flight loads that hold no registers */
 DEV void cp_async_16(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -121,6 +124,8 @@ struct dim3 {
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
+struct uint2 { unsigned int x, y; };
+static inline uint2 make_uint2(unsigned int a, unsigned int b) { uint2 r = {a, b}; return r; }
 static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r; }
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r = {a, b, c, d}; return r; }
 extern thread_local uint3e blockIdx;
@@ -150,6 +155,8 @@ inline void atomic_add_f64(double *p, double v) {
 #pragma omp atomic
     *p += v;
 }
+inline unsigned int atomic_fetch_add_u32(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void atomic_or_u32(unsigned int *p, unsigned int v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void atomic_min_i32(int *p, int v) {
 #pragma omp critical(b200_minmax)
     { if (v < *p) *p = v; }
@@ -159,6 +166,7 @@ inline void atomic_max_i32(int *p, int v) {
     { if (v > *p) *p = v; }
 }
 inline int float_as_int_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float int_bits_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline float2 f2_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 inline float2 f2_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 inline float2 f2_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }

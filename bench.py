@@ -508,12 +508,15 @@ def main():
                 setattr(obj, k, a)
         ppf, ts, hb = pkg.PerturbedField(inputs, -1.0), pkg.outputs.TsBox.dummy(inputs), pkg.outputs.HaloBox.dummy(inputs)
 
+        e2e_split = []  # seconds inside ComputePerturbedField, per step
+
         def host_step():
             h_ib.neutral_fraction[...] = 1.0
             h_ib.kinetic_temperature[...] = 0.0
             t0 = time.perf_counter()
             st = lib.ComputePerturbedField(C.c_float(z), C.byref(h_ics.cstruct), C.byref(h_pf.cstruct))
             assert st == 0, st
+            e2e_split.append(time.perf_counter() - t0)
             _, hb1, db1, _ = stats()
             st = lib.ComputeIonizedBox(C.c_float(z), C.c_float(-1.0), C.byref(h_pf.cstruct), C.byref(ppf.cstruct),
                                        C.byref(h_prev.cstruct), C.byref(ts.cstruct), C.byref(hb.cstruct),
@@ -534,7 +537,20 @@ def main():
         e2e_s = float(np.mean(tt))
         xh_host = float(h_ib.neutral_fraction.mean())
         assert abs(xh_host - xh_dev) < 1e-6, (xh_host, xh_dev)
-        e2e = (e2e_s, h2d_b, d2h_b)
+        # what the link itself does: one 2 GiB pinned copy each way on torch's stream (the e2e floor is
+        # h2d_bytes / this rate when the two directions overlap perfectly)
+        big = torch.empty(1 << 29, dtype=torch.float32, pin_memory=True)
+        dbig = torch.empty(1 << 29, dtype=torch.float32, device=dev)
+        link = {}
+        for name, (dst, src) in (("h2d", (dbig, big)), ("d2h", (big, dbig))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            link[name + "_GBps"] = big.numel() * 4 / (time.perf_counter() - t0) / 1e9
+        del big, dbig
+        e2e = (e2e_s, h2d_b, d2h_b, float(np.mean(e2e_split[-args.steps:])), link)
         os.environ.pop("B200_ICS_CACHE")
 
     # ---------------- ONE box over all GPUs (strong scaling), reported beside the replica value ----------------
@@ -678,7 +694,9 @@ def main():
         }
         if e2e:
             out["e2e"] = {"value": world * N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(e2e[1]),
-                          "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": 1e3 * e2e_s}
+                          "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": 1e3 * e2e_s,
+                          "ms_perturb_call": 1e3 * e2e[3], "ms_ionize_call": 1e3 * (e2e_s - e2e[3]),
+                          "pinned_copy_yardstick": e2e[4]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
