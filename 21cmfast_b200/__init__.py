@@ -7,12 +7,12 @@ is the C-ABI shared library ``csrc/lib21cmfast_b200.so`` (hand-written CUDA + C 
 wrapper/driver layer for that path.  The directory name starts with a digit, so import it with
 ``importlib.import_module("21cmfast_b200")``.
 """
-from .drivers import (brightness_temperature, compute_initial_conditions,  # noqa: F401
+from .drivers import (brightness_temperature, compute_halobox, compute_initial_conditions,  # noqa: F401
                       compute_ionization_field, get_logspaced_redshifts, perturb_field,
                       run_coeval)
 from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  # noqa: F401
                      MatterOptions, SimulationOptions)
-from .outputs import (BrightnessTemp, InitialConditions, IonizedBox,  # noqa: F401
+from .outputs import (BrightnessTemp, HaloBox, InitialConditions, IonizedBox,  # noqa: F401
                       PerturbedField, TsBox)
 from ._lib import Backend, BackendError, get_backend  # noqa: F401
 from .distributed import SlabGroup, ionize_radius_parallel, perturb_slab_parallel  # noqa: F401

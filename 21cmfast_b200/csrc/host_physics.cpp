@@ -1040,6 +1040,38 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
     if (err_code) b200_throw(err_code, "conditional Nion table generation failed");
 }
 
+void build_cond_table(FcollTable *t, double redshift, double min_dens, double max_dens, double Mmin,
+                      double Mmax, double Mcond, const ScalingConstants *sc, int method, double log_floor,
+                      int n_threads) {
+    const double growthf = dicke(redshift);
+    const double lnMmin = log(Mmin), lnMmax = log(Mmax), lnMcond = log(Mcond);
+    const double sigma2 = EvaluateSigma(lnMcond);
+    t->x_min = min_dens;
+    t->x_width = (max_dens - min_dens) / (N_DENS_INTERP - 1.);
+    t->log_valued = 1;
+    int err_code = 0;
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 1)
+    for (int i = 0; i < N_DENS_INTERP; i++) {
+        try {
+            const double dens = min_dens + (float)i / ((float)N_DENS_INTERP - 1.) * (max_dens - min_dens);
+            float y = log(Nion_ConditionalM(growthf, lnMmin, lnMmax, lnMcond, sigma2, dens, sc->mturn_a_nofb, sc, method));
+            if (y < log_floor) y = log_floor;
+            t->y[i] = y;
+            if (!std::isfinite(y)) err_code = B200_TableGenerationError;
+        } catch (B200Error &e) { err_code = e.code; }
+    }
+    if (err_code) b200_throw(err_code, "conditional table generation failed");
+}
+
+ScalingConstants evolve_scaling_constants_sfr(const ScalingConstants *sc) {
+    ScalingConstants s = *sc;
+    s.fesc_10 = 1.;
+    s.alpha_esc = 0.;
+    s.Mlim_Fesc = 0.;
+    return s;
+}
+
 /* ------------------------------------------------------------------ IonizeBox host constants */
 void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
     /* IonisationBox.c:125-227 (photon conservation is out of scope) */
@@ -1056,6 +1088,10 @@ void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
     else
         c->ion_eff_factor_gl = astro_params_global->HII_EFF_FACTOR;
     c->ion_eff_factor = c->ion_eff_factor_gl;
+    /* the halo fields already carry f_star, f_esc and the photon yield (IonisationBox.c:170-178) */
+    c->lagrangian = matter_options_global->SOURCE_MODEL >= SRC_L_INTEGRAL;
+    if (c->lagrangian) c->ion_eff_factor = 1.;
+    c->mfp_meandens = 25.483241248322766 / cosmo_params_global->hlittle;
     c->M_min = minimum_source_mass(redshift, false);
     c->lnMmin = log(c->M_min);
     c->lnMmax_gl = log(pc::M_MAX_INTEGRAL);
@@ -1069,13 +1105,16 @@ void set_ionbox_constants(double redshift, double prev_redshift, IonConsts *c) {
     c->fabs_dtdz = fabs(dtdz(redshift)) / 1e15; /* the rate table is in (1e15 s)^-1 */
     c->gamma_prefactor = pow(1 + redshift, 2) * pc::cm_per_Mpc * pc::sigma_HI * astro_params_global->ALPHA_UVB /
                          (astro_params_global->ALPHA_UVB + 2.75) * n_b0() * c->ion_eff_factor / 1.0e-12;
-    c->gamma_prefactor = c->gamma_prefactor / (c->sc.t_h * c->sc.t_star);
+    if (c->lagrangian) c->gamma_prefactor /= rho_crit() * cosmo_params_global->OMb;
+    else c->gamma_prefactor = c->gamma_prefactor / (c->sc.t_h * c->sc.t_star);
 }
 
 std::vector<RadiusSpec> setup_radii(const IonConsts &c) { /* IonisationBox.c:964-1006 */
     const AstroParams *ap = astro_params_global;
     const double maximum_radius = fmin(ap->R_BUBBLE_MAX, pc::l_factor * simulation_options_global->BOX_LEN);
-    const double minimum_radius = fmax(ap->R_BUBBLE_MIN, pc::l_factor * c.pixel_length);
+    double cell_length_factor = pc::l_factor;
+    if (c.lagrangian && !astro_options_global->IONISE_ENTIRE_SPHERE && c.pixel_length < 1) cell_length_factor = 1.;
+    const double minimum_radius = fmax(ap->R_BUBBLE_MIN, cell_length_factor * c.pixel_length);
     int n_radii = (int)(log(maximum_radius / minimum_radius) / log(ap->DELTA_R_HII_FACTOR) + 1);
     std::vector<RadiusSpec> r;
     for (int i = 0; i < n_radii; i++) {

@@ -23,7 +23,7 @@ constexpr double M_MIN_INTEGRAL = 1e5, M_MAX_INTEGRAL = 1e16;
 enum { HMF_PS = 0, HMF_ST = 1, HMF_WATSON = 2, HMF_WATSON_Z = 3, HMF_DELOS = 4, HMF_REED07 = 5, HMF_YUNG24 = 6 };
 enum { FILTER_TOPHAT = 0, FILTER_SHARP_K = 1, FILTER_GAUSSIAN = 2 };
 enum { PERTURB_LINEAR = 0, PERTURB_ZELDOVICH = 1, PERTURB_2LPT = 2 };
-enum { SRC_CONST_ION_EFF = 0, SRC_E_INTEGRAL = 1 };
+enum { SRC_CONST_ION_EFF = 0, SRC_E_INTEGRAL = 1, SRC_L_INTEGRAL = 2 };
 enum { INTEG_QAG = 0, INTEG_GL = 1, INTEG_GAMMA = 2 };
 
 /* parameter access with a loud failure if Broadcast_struct_global_* was never called */
@@ -81,6 +81,8 @@ struct IonConsts {
     double TK_nofluct, adia_TK_term;
     double M_min, lnMmin, lnMmax_gl, sigma_minmass, pixel_length;
     double dz, fabs_dtdz, gamma_prefactor; /* recombination bookkeeping (IonisationBox.c:132-137,144,211-218) */
+    bool lagrangian;      /* source grids come from a HaloBox (IonisationBox.c:151-153,172-178) */
+    double mfp_meandens;  /* mean free path of the exponential filter, Mpc (IonisationBox.c:191) */
 };
 struct RadiusSpec {
     double R, M_max_R, ln_M_max_R, sigma_maxmass;
@@ -102,3 +104,11 @@ void build_fgtrm_table(FcollTable *t, double min_dens, double max_dens, double g
 void build_nion_table(FcollTable *t, double redshift, double min_dens, double max_dens,
                       double Mmin, double Mmax, const ScalingConstants *sc, int method,
                       int n_threads);
+/* the same table for a condition mass that is not the upper limit (the Lagrangian cell of the halo
+   boxes): initialise_Nion_Conditional_spline / initialise_SFRD_Conditional_table without mini-halos
+   (interp_tables.c:291-408, :415-495); log_floor = -40 resp. -50 */
+void build_cond_table(FcollTable *t, double redshift, double min_dens, double max_dens, double Mmin,
+                      double Mmax, double Mcond, const ScalingConstants *sc, int method, double log_floor,
+                      int n_threads);
+/* scaling_relations.c:122-131: the star-formation integrals are the N_ion integrals without f_esc */
+ScalingConstants evolve_scaling_constants_sfr(const ScalingConstants *sc);

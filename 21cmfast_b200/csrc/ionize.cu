@@ -574,6 +574,11 @@ struct CritArgs {
     /* IONISE_ENTIRE_SPHERE: cells already painted by a sphere of an earlier radius (their x_HI is 0:
        no partial ionisation), or null */
     const unsigned char *paint;
+    /* Lagrangian source grids (SOURCE_MODEL = L-INTEGRAL): the filtered photon-output grid of the HaloBox replaces
+       f_coll, divided by the local baryon density (IonisationBox.c:1054-1066); sfr_grid feeds Gamma12 (:1126-1132) */
+    const float *stars_grid; /* padded real rows, or null */
+    const float *sfr_grid;   /* padded real rows, or null */
+    double rho_baryon;       /* RHOcrit * OMb */
 };
 
 DEV float partially_ionized_temperature(float T_HI, float res_xH, float T_re) { /* thermochem.c:58-63 */
@@ -631,6 +636,64 @@ DEV void ionise_cell_recomb(const CritArgs &a, long long idx, float fcoll, doubl
         else if (res_xH > 1) res_xH = 1;
         a.xH[idx] = (float)res_xH;
     }
+}
+
+/* the same cell when the sources are a HaloBox grid: no mean fix, ion_eff_factor = 1, the photon output per
+   baryon of the (filtered) cell against 1 + recombinations */
+DEV void ionise_cell_lagrangian(const CritArgs &a, long long idx) {
+    const long long row = idx / a.nz;
+    const long long idx_f = row * 2 * a.nzc + (idx - row * a.nz);
+    const double curr_dens = a.R_index == 0 ? (double)a.density[idx]
+                                            : (double)fmaxf(a.filtered[idx_f], (float)(-1. + pc::FRACT_FLOAT_ERR));
+    double curr_fcoll = (double)fmaxf(a.stars_grid[idx_f], 0.0f);
+    curr_fcoll *= 1 / (a.rho_baryon * (1 + curr_dens));
+    if (curr_fcoll < a.f_limit) curr_fcoll = a.f_limit;
+    double rec = 0.;
+    if (a.recomb) {
+        rec = a.recomb == 1 ? (double)fmaxf(a.rec_grid[idx_f], 0.0f) : a.recomb == 2 ? (double)a.rec_grid[idx] : a.rec_scalar;
+        rec /= (1. + curr_dens);
+    }
+    if (curr_fcoll > (1.0 + rec)) {
+        if (a.recomb && !a.mask[idx] && (double)a.xH[idx] > pc::FRACT_FLOAT_ERR) { /* first (largest-R) crossing */
+            a.G12[idx] = (float)(a.R * a.gamma_prefactor / (1 + curr_dens) * (double)fmaxf(a.sfr_grid[idx_f], 0.0f));
+            if (a.mfp) a.mfp[idx] = (float)a.R;
+        }
+        a.mask[idx] = 1;
+    } else if (a.R_index == 0 && !a.mask[idx] && (a.xH[idx] > pc::TINY)) {
+        double res_xH = 1. - curr_fcoll;
+        if (a.Tk) {
+            const float T_HI = (float)(a.TK_nofluct * (1 + a.adia_TK_term * a.density[idx]));
+            a.Tk[idx] = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.T_re);
+        }
+        if (res_xH < 0) res_xH = 0;
+        else if (res_xH > 1) res_xH = 1;
+        a.xH[idx] = (float)res_xH;
+    }
+}
+__global__ void __launch_bounds__(256) ionise_lagrangian_kernel(CritArgs a) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n; idx += (long long)gridDim.x * blockDim.x)
+        ionise_cell_lagrangian(a, idx);
+}
+/* deterministic block sums of a padded real grid clipped at zero (the grid mean the reference reports as
+   mean_f_coll for Lagrangian sources, IonisationBox.c:1623-1628) */
+struct RowSumArgs {
+    long long nrows;
+    int nz, nzc;
+    const float *grid;
+    double *partial; /* [gridDim.x] */
+};
+__global__ void __launch_bounds__(256) clipped_sum_kernel(RowSumArgs a) {
+    __shared__ double red[256];
+    double acc = 0.;
+    for (long long row = blockIdx.x; row < a.nrows; row += gridDim.x)
+        for (int z = threadIdx.x; z < a.nz; z += blockDim.x) acc += (double)fmaxf(a.grid[row * 2 * a.nzc + z], 0.0f);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
 }
 
 /* sweep 2: find_ionised_regions (IonisationBox.c:1008-1201) */
@@ -1134,6 +1197,9 @@ struct IonDeviceIO {
     bool *rec_written = nullptr;      /* out: G12 / mfp / cumulative recombinations were updated */
     /* spin-temperature inputs (USE_TS_FLUCT): device, N each */
     const float *xe = nullptr, *Tk_neutral = nullptr;
+    /* Lagrangian source grids (HaloBox): device, N each; whalo_sfr only with recombinations */
+    const float *halo_nion = nullptr, *halo_wsfr = nullptr;
+    double log10_Mcrit_ACG_ave = 0., log10_Mcrit_MCG_ave = 0.;
 };
 
 /* pinned staging that outlives a call (cudaMallocHost is too slow to repeat per call) */
@@ -1198,6 +1264,42 @@ static int sweep_grid(long long nchunks) {
     for (long long g = cap; g >= cap / 2; g--)
         if (nchunks % g == 0) return (int)g;
     return (int)cap;
+}
+
+/* set_recombination_rates (IonisationBox.c:1258-1342) after the ladder */
+static void recomb_update(int recomb, const IonDeviceIO &io, const IonConsts &c, long long N, int *d_flag) {
+    if (recomb == 2) { /* set_recombination_rates, inhomogeneous (IonisationBox.c:1277-1341) */
+        const RecombTables *rt = recomb_tables();
+        const size_t tn = (size_t)RECOMB_NZ * RECOMB_NG;
+        DevBuf<double> d_rr(2 * tn + RECOMB_NG);
+        h2d(d_rr.p, rt->y.data(), tn * sizeof(double));
+        h2d(d_rr.p + tn, rt->c.data(), tn * sizeof(double));
+        h2d(d_rr.p + 2 * tn, rt->lnGamma, RECOMB_NG * sizeof(double));
+        g_stats.h2d -= (long long)((2 * tn + RECOMB_NG) * sizeof(double));
+        RecombArgs ra = {N, io.density, io.xH, io.G12, io.prev_rec, io.cum_rec, d_rr.p + 2 * tn, d_rr.p, d_rr.p + tn,
+                         rt->lnGamma_max, 1. + c.stored_redshift, c.fabs_dtdz * c.dz, d_flag};
+        B200_LAUNCH(recomb_update_kernel, grid_for(N, 1024), 256, 0, ra);
+        int flag = 0;
+        d2h(&flag, d_flag, sizeof(int));
+        g_stats.d2h -= (long long)sizeof(int);
+        if (flag) b200_throw(B200_InfinityorNaNError, "recombinations returned an infinite or NaN value");
+    } else if (recomb == 1) { /* homogeneous (IonisationBox.c:1261-1276): one rate from the box means */
+        const int nb = grid_for(N, 1024);
+        DevBuf<double> d_p(2 * (size_t)nb);
+        Mean2Args ma = {N, io.xH, io.G12, d_p};
+        B200_LAUNCH(mean2_kernel, nb, 256, 0, ma);
+        std::vector<double> hp(2 * (size_t)nb);
+        d2h(hp.data(), d_p, hp.size() * sizeof(double));
+        g_stats.d2h -= (long long)(hp.size() * sizeof(double));
+        double sx = 0., sg = 0.;
+        for (int i = 0; i < nb; i++) { sx += hp[2 * i]; sg += hp[2 * i + 1]; }
+        const double global_xH = sx / (double)N;
+        const float global_G12 = (float)(sg / (double)N); /* a float in the reference */
+        const double dNrec = recomb_rate_host(c.stored_redshift, global_G12) * c.fabs_dtdz * c.dz * (1. - global_xH);
+        const double cum = io.prev_rec_scalar + dNrec;
+        if (!std::isfinite(cum)) b200_throw(B200_InfinityorNaNError, "non-finite cumulative recombinations");
+        if (io.cum_rec_scalar_out) *io.cum_rec_scalar_out = cum;
+    }
 }
 
 static void ionize_core(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box,
@@ -1659,38 +1761,161 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         if (sl) dist_check();
         if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
     }
-    if (recomb == 2) { /* set_recombination_rates, inhomogeneous (IonisationBox.c:1277-1341) */
-        const RecombTables *rt = recomb_tables();
-        const size_t tn = (size_t)RECOMB_NZ * RECOMB_NG;
-        DevBuf<double> d_rr(2 * tn + RECOMB_NG);
-        h2d(d_rr.p, rt->y.data(), tn * sizeof(double));
-        h2d(d_rr.p + tn, rt->c.data(), tn * sizeof(double));
-        h2d(d_rr.p + 2 * tn, rt->lnGamma, RECOMB_NG * sizeof(double));
-        g_stats.h2d -= (long long)((2 * tn + RECOMB_NG) * sizeof(double));
-        RecombArgs ra = {N, io.density, io.xH, io.G12, io.prev_rec, io.cum_rec, d_rr.p + 2 * tn, d_rr.p, d_rr.p + tn,
-                         rt->lnGamma_max, 1. + c.stored_redshift, c.fabs_dtdz * c.dz, d_flag};
-        B200_LAUNCH(recomb_update_kernel, grid_for(N, 1024), 256, 0, ra);
+    recomb_update(recomb, io, c, N, d_flag);
+    if (recomb && io.rec_written) *io.rec_written = true;
+}
+
+/* The radius ladder on Lagrangian source grids (SOURCE_MODEL = L-INTEGRAL; the `lagrangian_source_grids`
+   branches of IonisationBox.c:587-593,615-621,636-642,819-835,1054-1066,1126-1132,1425-1430,1482-1488,1623-1628).
+   The HaloBox already holds the ionising photons emitted per cell, so no per-radius table, extrema or mean fix
+   exist: every radius is filter + c2r of the density (window HII_FILTER) and of the photon grid (the
+   exponential mean-free-path window with USE_EXP_FILTER) and one criterion sweep, all enqueued without a
+   host round trip. */
+static void ionize_core_lagrangian(float redshift_f, float prev_redshift_f, const IonDeviceIO &io, IonizedBox *box) {
+    const SimulationOptions *so = simulation_options_global;
+    const AstroOptions *ao = astro_options_global;
+    const MatterOptions *mo = matter_options_global;
+    if (ao->USE_MINI_HALOS || ao->PHOTON_CONS_TYPE != 0 || ao->USE_TS_FLUCT || ao->IONISE_ENTIRE_SPHERE)
+        b200_throw(B200_ValueError, "L-INTEGRAL ladder: mini-halos, photon conservation, USE_TS_FLUCT and IONISE_ENTIRE_SPHERE are not built");
+    if (!io.halo_nion) b200_throw(B200_ValueError, "SOURCE_MODEL = L-INTEGRAL needs a computed HaloBox (n_ion)");
+    const int recomb = ao->RECOMB_MODEL;
+    const bool filter_rec = recomb != 0 && !ao->CELL_RECOMB;
+    if (recomb) {
+        if (recomb == 1 && filter_rec)
+            b200_throw(B200_ValueError, "RECOMB_MODEL=homogeneous needs CELL_RECOMB (there is no N_rec grid to filter)");
+        if (!io.G12 || (recomb == 2 && !io.cum_rec) || !io.halo_wsfr)
+            b200_throw(B200_ValueError, "RECOMB_MODEL != none needs ionisation_rate_G12, cumulative_recombinations and the HaloBox's whalo_sfr");
+        if (!recomb_tables()) b200_throw(B200_TableEvaluationError, "RECOMB_MODEL != none needs init_MHR()");
+    }
+    if (mo->USE_INTERPOLATION_TABLES != 2)
+        b200_throw(B200_ValueError, "this build needs USE_INTERPOLATION_TABLES='hmf-interpolation'");
+    const double redshift = redshift_f, prev_redshift = prev_redshift_f;
+    IonConsts c;
+    set_ionbox_constants(redshift, prev_redshift, &c);
+    const int nx = so->HII_DIM, ny = so->HII_DIM, nz = hii_d_para();
+    const long long N = (long long)nx * ny * nz;
+    Fft3D *plan = fft_plan(nx, ny, nz);
+    std::vector<RadiusSpec> radii = setup_radii(c);
+    const int n_radii = (int)radii.size();
+
+    box->log10_Mturnover_ave = io.log10_Mcrit_ACG_ave;
+    box->log10_Mturnover_MINI_ave = io.log10_Mcrit_MCG_ave;
+    const double Mturn_avg = pow(10., io.log10_Mcrit_ACG_ave);
+    if (ao->INTEGRATION_METHOD_ATOMIC == INTEG_GL) initialise_GL(c.lnMmin, c.lnMmax_gl);
+    box->mean_f_coll = Nion_General(redshift, c.lnMmin, c.lnMmax_gl, Mturn_avg, &c.sc);
+    const double f_limit = Nion_General(so->Z_HEAT_MAX, c.lnMmin, c.lnMmax_gl, Mturn_avg, &c.sc);
+    box->mean_f_coll_MINI = 0.;
+    if (!std::isfinite(box->mean_f_coll) || box->mean_f_coll < 0)
+        b200_throw(B200_InfinityorNaNError, "Mean collapse fraction is invalid");
+    if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
+    if (box->mean_f_coll * c.ion_eff_factor_gl < HII_ROUND_ERR) {
+        { FillArgs f = {N, io.z_reion, -1.0f}; B200_LAUNCH(fill_kernel, grid_for(N, 1024), 256, 0, f); }
+        NeutralArgs na = {N, io.density, io.xH, io.Tk, (float)(1. - xion_RECFAST(redshift)), c.TK_nofluct, c.adia_TK_term, nullptr, nullptr};
+        B200_LAUNCH(neutral_box_kernel, grid_for(N, 1024), 256, 0, na);
+        return;
+    }
+    std::vector<int> todo;
+    for (int R_ct = n_radii; R_ct--;) {
+        if (c.M_min > RtoM(radii[R_ct].R)) break;
+        todo.push_back(R_ct);
+    }
+    const int n_todo = (int)todo.size();
+    const bool complete = n_todo > 0 && todo.back() == 0; /* the loop reached R_index 0 */
+
+    const size_t kn = plan->n_cplx();
+    DevBuf<float2> k_dens(kn), k_stars(kn), k_sfr(recomb ? kn : 0), k_nrec;
+    DevBuf<float2> w_dens(kn), w_stars(kn), w_sfr(recomb ? kn : 0), w_nrec;
+    DevBuf<unsigned char> d_mask((size_t)N);
+    dev_zero(d_mask, (size_t)N);
+    DevBuf<int> d_flag(1);
+    dev_zero(d_flag, sizeof(int));
+    /* prepare_box_for_filtering (IonisationBox.c:1478-1488,1515-1518) */
+    ZPrologue pro;
+    pro.src = io.density; pro.src_row_stride = nz; pro.premul = 1.f;
+    pro.clip = 1; pro.clip_lo = -1.f; pro.clip_hi = 1e6f;
+    pro.post_scale = 1.f / (float)N;
+    fft_r2c(plan, k_dens, pro);
+    ZPrologue ps = pro;
+    ps.src = io.halo_nion; ps.clip_lo = 0.f; ps.clip_hi = 1e20f;
+    fft_r2c(plan, k_stars, ps);
+    if (recomb) { ZPrologue pf = ps; pf.src = io.halo_wsfr; fft_r2c(plan, k_sfr, pf); }
+    const bool rec_grid_filtered = filter_rec && io.prev_rec;
+    if (rec_grid_filtered) {
+        k_nrec.alloc(kn); w_nrec.alloc(kn);
+        ZPrologue pr = ps; pr.src = io.prev_rec;
+        fft_r2c(plan, k_nrec, pr);
+    }
+    const double dk0 = 2.0 * M_PI / so->BOX_LEN, dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
+    const int filter_hf = ao->USE_EXP_FILTER ? 3 : c.hii_filter;
+    for (int k = 0; k < n_todo; k++) {
+        const RadiusSpec &rs = radii[todo[k]];
+        KMul km, kh; /* density / N_rec window, halo-field window */
+        if (rs.R_index > 0) {
+            km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R;
+            km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
+            kh = km;
+            kh.filter_type = filter_hf;
+            if (filter_hf == 3) { /* filter_box(.., 3, R, mfp, 0.) with float arguments (filtering.c:308,330) */
+                kh.R_param = (double)(float)c.mfp_meandens;
+                const float q = -(float)rs.R / (float)c.mfp_meandens; /* the quotient of two floats: the window's
+                                                                        cancellation amplifies its rounding to 1e-4 */
+                kh.r_const = exp((double)q);
+            }
+        }
+        ZEpilogue e0; /* the clips of calculate_fcoll_grid are applied where the sweeps read the grids */
+        e0.scale = 1.f;
+        fft_c2r(plan, k_dens, w_dens, km, e0);
+        fft_c2r(plan, k_stars, w_stars, kh, e0);
+        if (recomb) fft_c2r(plan, k_sfr, w_sfr, kh, e0);
+        if (rec_grid_filtered) fft_c2r(plan, k_nrec, w_nrec, km, e0);
+        CritArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.n = N; ca.density = io.density; ca.prev_zre = io.prev_zre;
+        ca.mask = d_mask; ca.xH = io.xH; ca.z_reion = io.z_reion; ca.Tk = io.Tk;
+        ca.f_limit = f_limit; ca.ion_eff_factor = 1.; ca.mass_dep_zeta = 1;
+        ca.R_index = rs.R_index; ca.redshift = c.redshift;
+        ca.TK_nofluct = c.TK_nofluct; ca.adia_TK_term = c.adia_TK_term; ca.T_re = c.T_re;
+        ca.filtered = reinterpret_cast<const float *>(w_dens.p); ca.nz = nz; ca.nzc = plan->pitch;
+        ca.stars_grid = reinterpret_cast<const float *>(w_stars.p);
+        ca.rho_baryon = rho_crit() * cosmo_params_global->OMb;
+        if (recomb) {
+            ca.recomb = rec_grid_filtered ? 1 : (recomb == 2 && io.prev_rec) ? 2 : 3;
+            ca.rec_grid = rec_grid_filtered ? reinterpret_cast<const float *>(w_nrec.p) : io.prev_rec;
+            ca.rec_scalar = recomb == 1 ? io.prev_rec_scalar : 0.;
+            ca.sfr_grid = reinterpret_cast<const float *>(w_sfr.p);
+            ca.G12 = io.G12; ca.mfp = io.mfp;
+            ca.R = rs.R; ca.gamma_prefactor = c.gamma_prefactor;
+        }
+        B200_LAUNCH(ionise_lagrangian_kernel, grid_for(N, 1024), 256, 0, ca);
+    }
+    /* the output's mean_f_coll is the grid mean of the last radius (no mean fix to report), floored like the
+       reference's (IonisationBox.c:1566-1570,1623-1628); a ladder cut short leaves the global value */
+    if (complete) {
+        const int nb = grid_for((long long)nx * ny, 1);
+        DevBuf<double> d_p((size_t)nb);
+        RowSumArgs sa = {(long long)nx * ny, nz, plan->pitch, reinterpret_cast<const float *>(w_stars.p), d_p};
+        B200_LAUNCH(clipped_sum_kernel, nb, 256, 0, sa);
+        std::vector<double> hp((size_t)nb);
+        d2h(hp.data(), d_p, hp.size() * sizeof(double));
+        g_stats.d2h -= (long long)(hp.size() * sizeof(double));
+        double sum = 0.;
+        for (int i = 0; i < nb; i++) sum += hp[i];
+        double grid_mean = sum / (double)N;
+        if (grid_mean <= f_limit) grid_mean = f_limit;
+        box->mean_f_coll = grid_mean;
+    }
+    {
+        const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
+        FinalArgs fa = {N, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
+                        c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
+                        pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), nullptr, nullptr};
+        B200_LAUNCH(finalize_kernel, grid_for(N, 1024), 256, 0, fa);
         int flag = 0;
         d2h(&flag, d_flag, sizeof(int));
         g_stats.d2h -= (long long)sizeof(int);
-        if (flag) b200_throw(B200_InfinityorNaNError, "recombinations returned an infinite or NaN value");
-    } else if (recomb == 1) { /* homogeneous (IonisationBox.c:1261-1276): one rate from the box means */
-        const int nb = grid_for(N, 1024);
-        DevBuf<double> d_p(2 * (size_t)nb);
-        Mean2Args ma = {N, io.xH, io.G12, d_p};
-        B200_LAUNCH(mean2_kernel, nb, 256, 0, ma);
-        std::vector<double> hp(2 * (size_t)nb);
-        d2h(hp.data(), d_p, hp.size() * sizeof(double));
-        g_stats.d2h -= (long long)(hp.size() * sizeof(double));
-        double sx = 0., sg = 0.;
-        for (int i = 0; i < nb; i++) { sx += hp[2 * i]; sg += hp[2 * i + 1]; }
-        const double global_xH = sx / (double)N;
-        const float global_G12 = (float)(sg / (double)N); /* a float in the reference */
-        const double dNrec = recomb_rate_host(c.stored_redshift, global_G12) * c.fabs_dtdz * c.dz * (1. - global_xH);
-        const double cum = io.prev_rec_scalar + dNrec;
-        if (!std::isfinite(cum)) b200_throw(B200_InfinityorNaNError, "non-finite cumulative recombinations");
-        if (io.cum_rec_scalar_out) *io.cum_rec_scalar_out = cum;
+        if (flag) b200_throw(B200_InfinityorNaNError, "Tk after full ionisation is infinite or NaN");
     }
+    recomb_update(recomb, io, c, N, d_flag);
     if (recomb && io.rec_written) *io.rec_written = true;
 }
 
@@ -1715,7 +1940,7 @@ struct HostFill {
 extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedField *perturbed_field,
                                  PerturbedField *previous_perturbed_field, IonizedBox *previous_ionize_box,
                                  TsBox *spin_temp, HaloBox *halos, InitialConditions *ini_boxes, IonizedBox *box) {
-    (void)previous_perturbed_field; (void)halos; (void)ini_boxes;
+    (void)previous_perturbed_field; (void)ini_boxes;
     try {
         require_params(true);
         rt_init();
@@ -1726,6 +1951,9 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         const long long N = (long long)so->HII_DIM * so->HII_DIM * hii_d_para();
         if (!perturbed_field || !perturbed_field->density || !box || !box->neutral_fraction || !box->z_reion)
             b200_throw(B200_ValueError, "ComputeIonizedBox: required arrays are NULL");
+        const bool lagrangian = matter_options_global->SOURCE_MODEL == SRC_L_INTEGRAL;
+        if (lagrangian && (!halos || !halos->n_ion))
+            b200_throw(B200_ValueError, "ComputeIonizedBox: SOURCE_MODEL = L-INTEGRAL needs a computed HaloBox");
 
 
         /* first snapshot: the reference writes z_reion = -1 into the *previous* box
@@ -1747,7 +1975,7 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         h2d_copy_stream(d_xH, box->neutral_fraction, N * sizeof(float));
         const bool want_Tk = !matter_options_global->MINIMIZE_MEMORY && box->kinetic_temperature;
         if (want_Tk) { d_Tk.alloc(N); h2d_copy_stream(d_Tk, box->kinetic_temperature, N * sizeof(float)); }
-        if (box->unnormalised_nion) d_nion.alloc(N);
+        if (box->unnormalised_nion && !lagrangian) d_nion.alloc(N);
         if (!first && previous_ionize_box && previous_ionize_box->z_reion) {
             d_prev.alloc(N);
             h2d_copy_stream(d_prev, previous_ionize_box->z_reion, N * sizeof(float));
@@ -1791,7 +2019,23 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
             io.G12 = d_G12; io.mfp = d_mfp.p; io.cum_rec = d_cum.p;
             io.cum_rec_scalar_out = &cum_scalar; io.rec_written = &rec_written;
         }
-        ionize_core(redshift, prev_redshift, io, box);
+        DevBuf<float> d_hnion, d_hwsfr;
+        if (lagrangian) { /* HaloBox grids: read by the first transforms of the ladder */
+            d_hnion.alloc(N);
+            h2d(d_hnion, halos->n_ion, N * sizeof(float));
+            io.halo_nion = d_hnion;
+            if (recomb) {
+                if (!halos->whalo_sfr) b200_throw(B200_ValueError, "ComputeIonizedBox: RECOMB_MODEL != none needs the HaloBox's whalo_sfr");
+                d_hwsfr.alloc(N);
+                h2d(d_hwsfr, halos->whalo_sfr, N * sizeof(float));
+                io.halo_wsfr = d_hwsfr;
+            }
+            io.log10_Mcrit_ACG_ave = halos->log10_Mcrit_ACG_ave;
+            io.log10_Mcrit_MCG_ave = halos->log10_Mcrit_MCG_ave;
+            ionize_core_lagrangian(redshift, prev_redshift, io, box);
+        } else {
+            ionize_core(redshift, prev_redshift, io, box);
+        }
         if (rec_written) {
             d2h(box->ionisation_rate_G12, d_G12, N * sizeof(float));
             if (d_mfp.p) d2h(box->mean_free_path, d_mfp, N * sizeof(float));

@@ -40,7 +40,10 @@ extern "C" int test_filter(float *input_box, double R, double R_param, double R_
         fft_r2c(plan, kbox, pro);
         KMul km;
         km.kind = KMUL_FILTER; km.filter_type = filter_flag; km.R = (float)R; km.R_param = (float)R_param;
-        if (filter_flag == 3) km.r_const = exp(-(double)(float)R / (double)(float)R_param);
+        if (filter_flag == 3) { /* filter_box: exp(-R / R_param) with the quotient of two floats (filtering.c:320-322) */
+            const float q = -(float)R / (float)R_param;
+            km.r_const = exp((double)q);
+        }
         km.dk[0] = 2.0 * M_PI / so->BOX_LEN; km.dk[1] = km.dk[0];
         km.dk[2] = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
         ZEpilogue epi;

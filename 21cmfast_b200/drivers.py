@@ -49,18 +49,52 @@ def perturb_field(*, redshift: float, initial_conditions: InitialConditions,
     return pf
 
 
+class _HaloCatalogStruct(C.Structure):
+    """``HaloCatalog.dummy()``: no sampled halos (``_outputstructs_wrapper.h:30-45``); L-INTEGRAL never reads it."""
+    _fields_ = [("n_halos", C.c_ulonglong), ("buffer_size", C.c_ulonglong), ("halo_masses", C.c_void_p),
+                ("halo_coords", C.c_void_p), ("star_rng", C.c_void_p), ("sfr_rng", C.c_void_p), ("xray_rng", C.c_void_p)]
+
+
+def compute_halobox(*, redshift: float, initial_conditions: InitialConditions,
+                    previous_spin_temp: TsBox | None = None, previous_ionize_box: IonizedBox | None = None,
+                    backend: Backend | None = None) -> HaloBox:
+    """``compute_halo_grid`` (single_field.py:297-380) for ``SOURCE_MODEL='L-INTEGRAL'``: the photon-output and
+    star-formation grids integrated over the conditional mass function of every Lagrangian cell and moved to
+    Eulerian space with the perturbed field's displacements.  Sampled halo catalogues are out of scope."""
+    be = backend or get_backend()
+    inputs = initial_conditions.inputs
+    if inputs.matter_options.SOURCE_MODEL != "L-INTEGRAL":
+        raise NotImplementedError("only SOURCE_MODEL='L-INTEGRAL' builds a HaloBox here (no halo sampler)")
+    be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True)
+    hb = HaloBox.new(inputs, redshift)
+    cat = _HaloCatalogStruct()
+    ts = previous_spin_temp or TsBox.dummy(inputs)
+    prev = previous_ionize_box or IonizedBox(inputs, -1.0)
+    fn = be.lib.ComputeHaloBox
+    fn.restype = C.c_int
+    _check(fn(C.c_double(redshift), C.byref(initial_conditions.cstruct), C.byref(cat), C.byref(ts.cstruct),
+              C.byref(prev.cstruct), C.byref(hb.cstruct)), "ComputeHaloBox")
+    hb.pull_scalars()
+    hb.is_computed = True
+    return hb
+
+
 def compute_ionization_field(*, perturbed_field: PerturbedField,
                              initial_conditions: InitialConditions,
                              previous_perturbed_field: PerturbedField | None = None,
                              previous_ionized_box: IonizedBox | None = None,
                              spin_temp: TsBox | None = None,
+                             halobox: HaloBox | None = None,
                              backend: Backend | None = None) -> IonizedBox:
     be = backend or get_backend()
     inputs = perturbed_field.inputs
     ao = inputs.astro_options
-    if ao.USE_MINI_HALOS or inputs.matter_options.lagrangian_source_grid:
+    lagrangian = inputs.matter_options.lagrangian_source_grid
+    if ao.USE_MINI_HALOS or (lagrangian and inputs.matter_options.SOURCE_MODEL != "L-INTEGRAL"):
         raise NotImplementedError(
-            "only the Eulerian IonizeBox path without mini-halos is in scope (SURVEY.md section 8)")
+            "mini-halos and the halo-sampler source models are outside the scoped IonizeBox path (SURVEY.md section 8)")
+    if lagrangian and halobox is None:  # single_field.py:796-801
+        raise ValueError("SOURCE_MODEL requires a halobox, but none was provided")
     if ao.USE_TS_FLUCT and spin_temp is None:  # single_field.py:803-808
         raise ValueError("You have USE_TS_FLUCT=True, but have not provided a spin_temp!")
     redshift = perturbed_field.redshift
@@ -76,7 +110,7 @@ def compute_ionization_field(*, perturbed_field: PerturbedField,
     be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True, recomb=True)
     prev_pf = previous_perturbed_field or PerturbedField.initial(inputs)
     prev_ion = previous_ionized_box or IonizedBox.initial(inputs)
-    ts, hb = (spin_temp if ao.USE_TS_FLUCT else TsBox.dummy(inputs)), HaloBox.dummy(inputs)
+    ts, hb = (spin_temp if ao.USE_TS_FLUCT else TsBox.dummy(inputs)), (halobox if lagrangian else HaloBox.dummy(inputs))
     box = IonizedBox.new(inputs, redshift)
     _check(be.lib.ComputeIonizedBox(
         C.c_float(redshift), C.c_float(prev_pf.redshift), C.byref(perturbed_field.cstruct),
@@ -158,10 +192,15 @@ class _resident_ics:
 
 def _run_coeval(outs, inputs, ics, backend):
     out = []
+    lagrangian = inputs.matter_options.lagrangian_source_grid
+
+    def halobox(z):  # coeval.py:783-800: the source grids of this redshift (L-INTEGRAL: no halo catalogue)
+        return compute_halobox(redshift=z, initial_conditions=ics, backend=backend) if lagrangian else None
+
     if not inputs.evolution_required:
         for z in sorted(outs, reverse=True):
             pf = perturb_field(redshift=z, initial_conditions=ics, backend=backend)
-            ib = compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=backend)
+            ib = compute_ionization_field(perturbed_field=pf, initial_conditions=ics, halobox=halobox(z), backend=backend)
             bt = brightness_temperature(ionized_box=ib, perturbed_field=pf, backend=backend)
             out.append({"redshift": z, "perturbed_field": pf, "ionized_box": ib, "brightness_temp": bt})
         return out
@@ -171,7 +210,7 @@ def _run_coeval(outs, inputs, ics, backend):
     for z in sorted(set(nodes) | set(outs), reverse=True):
         pf = perturb_field(redshift=z, initial_conditions=ics, backend=backend)
         ib = compute_ionization_field(perturbed_field=pf, initial_conditions=ics, previous_perturbed_field=prev_pf,
-                                      previous_ionized_box=prev_ib, backend=backend)
+                                      previous_ionized_box=prev_ib, halobox=halobox(z), backend=backend)
         if z in outs:
             bt = brightness_temperature(ionized_box=ib, perturbed_field=pf, backend=backend)
             out.append({"redshift": z, "perturbed_field": pf, "ionized_box": ib, "brightness_temp": bt})

@@ -137,9 +137,23 @@ class HaloBox(OutputStruct):
     _arrays = tuple(n for n, t in _abi.HaloBoxStruct._fields_ if t is _abi.c_float_p)
     _scalars = ("log10_Mcrit_ACG_ave", "log10_Mcrit_MCG_ave")
 
+    def __init__(self, inputs, redshift=None, **kw):
+        super().__init__(inputs, **kw)
+        self.redshift = redshift
+
     @classmethod
     def dummy(cls, inputs):
         return cls(inputs)
+
+    @classmethod
+    def new(cls, inputs: InputParameters, redshift: float):
+        """Arrays of ``HaloBox.new`` (outputs.py:1095-1135) for the options in scope: the photon-output and
+        star-formation grids, plus the escape-weighted star formation with recombinations."""
+        lo, _ = _shapes(inputs)
+        out = {"halo_sfr": np.zeros(lo, np.float32), "n_ion": np.zeros(lo, np.float32)}
+        if inputs.astro_options.RECOMB_MODEL != "none":
+            out["whalo_sfr"] = np.zeros(lo, np.float32)
+        return cls(inputs, redshift, **out)
 
 
 class IonizedBox(OutputStruct):
