@@ -272,10 +272,76 @@ static double tf_other(double k, int which) { /* cosmology.c:75-127 */
                "POWER_SPECTRUM=%d (CLASS tables) is outside the scoped path; use EH", which);
 }
 
+/* CLASS transfer tables (transfer_function_CLASS, cosmology.c:130-213): natural cubic splines (gsl_interp_cspline)
+   through the caller's T(k) samples of the matter density at z = 0 and, with V_CB_MODEL = FLUCTS, of the
+   dark-matter/baryon relative velocity at kinematic decoupling; above the last sample the density follows
+   Eisenstein & Hu scaled to the last sample, the velocity a log-log line through the last two. */
+static struct {
+    bool ready = false, has_vcb = false;
+    std::vector<double> k, Tm, Tv;
+    hostnum::CubicSpline dens, vcb;
+    double eh_ratio_at_kmax = 0.;
+    double *d_nodes = nullptr; /* device copy for the IC kernels: k, Tm, c_m, Tv, c_v (n each) */
+} g_class;
+static void class_free() {
+    if (g_class.d_nodes) dev_free(g_class.d_nodes);
+    g_class.d_nodes = nullptr;
+    g_class.ready = false;
+}
+static void class_init() {
+    const Table1D *td = cosmo_tables_global->transfer_density;
+    if (!td || td->size < 3 || !td->x_values || !td->y_values)
+        b200_throw(B200_ValueError, "POWER_SPECTRUM=CLASS needs cosmo_tables.transfer_density (k, T) samples");
+    class_free();
+    g_class.k.assign(td->x_values, td->x_values + td->size);
+    g_class.Tm.assign(td->y_values, td->y_values + td->size);
+    g_class.dens.init(g_class.k, g_class.Tm);
+    const double kmax = g_class.k.back();
+    g_class.eh_ratio_at_kmax = g_class.Tm.back() / kmax / kmax / tf_EH(kmax);
+    g_class.has_vcb = MO->V_CB_MODEL == 2;
+    if (g_class.has_vcb) {
+        const Table1D *tv = cosmo_tables_global->transfer_vcb;
+        if (!tv || tv->size != td->size || !tv->y_values)
+            b200_throw(B200_ValueError, "V_CB_MODEL=FLUCTS needs cosmo_tables.transfer_vcb on the k samples of transfer_density");
+        g_class.Tv.assign(tv->y_values, tv->y_values + tv->size);
+        g_class.vcb.init(g_class.k, g_class.Tv);
+    }
+    g_class.ready = true;
+}
+static double tf_class(double k, int dv) {
+    const size_t n = g_class.k.size();
+    if (k > g_class.k[n - 1]) {
+        if (dv == 0) return g_class.eh_ratio_at_kmax * tf_EH(k) * k * k;
+        const std::vector<double> &Tv = g_class.Tv, &kc = g_class.k;
+        return exp(log(Tv[n - 1]) + (log(Tv[n - 1]) - log(Tv[n - 2])) / (log(kc[n - 1]) - log(kc[n - 2])) * (log(k) - log(kc[n - 1])));
+    }
+    return dv == 0 ? g_class.dens.eval(k) : g_class.vcb.eval(k);
+}
+/* average relative-velocity suppression of the matter power (cosmology.c:27-29,295-300) */
+static const double KP_VCB_PM = 300.0, A_VCB_PM = 0.24, SIGMAK_VCB_PM = 0.9;
+
 extern "C" double power_in_k(double k) { /* cosmology.c:278-303 */
     if (k == 0.) return 0.;
-    double T = (MO->POWER_SPECTRUM == 0) ? tf_EH(k) : tf_other(k, MO->POWER_SPECTRUM);
-    T *= k * k; /* non-CLASS transfer functions tend to 1 at k->0 */
+    double T;
+    if (MO->POWER_SPECTRUM == 5) {
+        T = tf_class(k, 0); /* CLASS convention: T = delta / zeta, no k^2 */
+    } else {
+        T = (MO->POWER_SPECTRUM == 0) ? tf_EH(k) : tf_other(k, MO->POWER_SPECTRUM);
+        T *= k * k; /* non-CLASS transfer functions tend to 1 at k->0 */
+    }
+    const double primordial = cosmo_tables_global->ps_norm * pow(k / 0.05, CP->POWER_INDEX - 1.);
+    double p = cc.sigma_norm * primordial * T * T / pow(k, 3);
+    if (MO->POWER_SPECTRUM == 5 && MO->V_CB_MODEL != 0)
+        p *= 1.0 - A_VCB_PM * exp(-pow(log(k / KP_VCB_PM), 2.0) / (2.0 * SIGMAK_VCB_PM * SIGMAK_VCB_PM));
+    return p;
+}
+extern "C" double power_in_vcb(double k) { /* cosmology.c:310-332 */
+    if (MO->POWER_SPECTRUM != 5 || !g_class.ready || !g_class.has_vcb) {
+        fprintf(stderr, "[21cmfast_b200] power_in_vcb needs POWER_SPECTRUM=CLASS and V_CB_MODEL=FLUCTS\n");
+        return std::nan("");
+    }
+    if (k == 0.) return 0.;
+    const double T = tf_class(k, 1);
     const double primordial = cosmo_tables_global->ps_norm * pow(k / 0.05, CP->POWER_INDEX - 1.);
     return cc.sigma_norm * primordial * T * T / pow(k, 3);
 }
@@ -337,8 +403,6 @@ extern "C" double dsigmasqdm_z0(double M) { /* cosmology.c:421-456 */
 static void init_ps_impl() { /* cosmology.c:459-557 */
     require_params(false);
     if (!cosmo_tables_global) b200_throw(B200_ValueError, "cosmo tables were never broadcast");
-    if (MO->POWER_SPECTRUM == 5)
-        b200_throw(B200_ValueError, "POWER_SPECTRUM=CLASS is outside the scoped path; use EH");
     cc.omhh = CP->OMm * CP->hlittle * CP->hlittle;
     cc.theta_cmb = pc::T_cmb / 2.7;
     cc.f_nu = fmax(CP->OMn / CP->OMm, 1e-10);
@@ -367,6 +431,7 @@ static void init_ps_impl() { /* cosmology.c:459-557 */
         cc.alpha_nu = alpha_nu;
         cc.beta_c = 1.0 / (1.0 - 0.949 * f_nub);
     }
+    if (MO->POWER_SPECTRUM == 5) class_init(); /* after TFset_parameters: E&H extrapolates the tables (cosmology.c:515-524) */
     if (cosmo_tables_global->USE_SIGMA_8) {
         const double Radius_8 = 8.0 / CP->hlittle;
         cc.sigma_norm = 1;
@@ -382,16 +447,41 @@ extern "C" void init_ps(void) {
         fprintf(stderr, "[21cmfast_b200] init_ps failed: %s\n", e.msg);
     }
 }
-extern "C" void free_ps(void) { cc.ready = false; }
+extern "C" void free_ps(void) { cc.ready = false; class_free(); }
 
 /* constants the device-side power spectrum (ics.cu) needs */
 struct PsConsts {
     int which;
     double sound_horizon, alpha_nu, beta_c, omhh, f_nu, theta_cmb, sigma_norm;
     double ps_norm, n_s, h, OMm, OMb;
+    /* CLASS tables: n spline nodes each (device pointers), see g_class */
+    int n_class, vcb_suppression;
+    const double *ck, *cTm, *cCm, *cTv, *cCv;
+    double eh_ratio_at_kmax;
 };
 void ps_export_consts(PsConsts *o) {
     if (!cc.ready) init_ps_impl();
+    o->n_class = 0; o->vcb_suppression = 0;
+    o->ck = o->cTm = o->cCm = o->cTv = o->cCv = nullptr;
+    o->eh_ratio_at_kmax = 0.;
+    if (MO->POWER_SPECTRUM == 5) {
+        const size_t n = g_class.k.size();
+        if (!g_class.d_nodes) {
+            std::vector<double> h(5 * n, 0.0);
+            for (size_t i = 0; i < n; i++) {
+                h[i] = g_class.k[i]; h[n + i] = g_class.Tm[i]; h[2 * n + i] = g_class.dens.coeffs()[i];
+                if (g_class.has_vcb) { h[3 * n + i] = g_class.Tv[i]; h[4 * n + i] = g_class.vcb.coeffs()[i]; }
+            }
+            g_class.d_nodes = (double *)dev_alloc(5 * n * sizeof(double));
+            h2d(g_class.d_nodes, h.data(), 5 * n * sizeof(double));
+            dev_sync();
+        }
+        o->n_class = (int)n;
+        o->ck = g_class.d_nodes; o->cTm = o->ck + n; o->cCm = o->ck + 2 * n;
+        o->cTv = g_class.has_vcb ? o->ck + 3 * n : nullptr; o->cCv = g_class.has_vcb ? o->ck + 4 * n : nullptr;
+        o->eh_ratio_at_kmax = g_class.eh_ratio_at_kmax;
+        o->vcb_suppression = MO->V_CB_MODEL != 0;
+    }
     o->which = MO->POWER_SPECTRUM;
     o->sound_horizon = cc.sound_horizon; o->alpha_nu = cc.alpha_nu; o->beta_c = cc.beta_c;
     o->omhh = cc.omhh; o->f_nu = cc.f_nu; o->theta_cmb = cc.theta_cmb; o->sigma_norm = cc.sigma_norm;

@@ -324,22 +324,46 @@ class AstroParams(_InputStruct):
         return d
 
 
-@dataclass(frozen=True)
+@dataclass(frozen=True, eq=False)
 class CosmoTables:
-    """Derived tables (inputs.py:358-382).  CLASS transfer tables are out of scope: EH only."""
+    """Derived tables (inputs.py:358-382).  With ``POWER_SPECTRUM='CLASS'`` the reference fills
+    ``transfer_density`` / ``transfer_vcb`` by running ``classy`` (inputs.py:1864-1966); that package is not
+    part of this build, so the caller passes the ``(k [1/Mpc], T(k))`` samples (k = 0 first, as the reference
+    prepends it) -- from a classy run elsewhere, a file, or any tabulated transfer function."""
 
     ps_norm: float
     USE_SIGMA_8: bool = True
     V_CB_AVG: float = V_CB_AVG_DEFAULT
+    transfer_density: tuple | None = None  # (k, T_m(k, z=0))
+    transfer_vcb: tuple | None = None      # (k, T_vcb(k, z_dec) / c), same k
+
+    def _table(self, kt):
+        k = np.ascontiguousarray(kt[0], dtype=np.float64)
+        t = np.ascontiguousarray(kt[1], dtype=np.float64)
+        if k.ndim != 1 or k.shape != t.shape or k.size < 3:
+            raise ValueError("a transfer table is a pair of equally long 1-D arrays (k, T)")
+        tab = _abi.Table1DStruct()
+        tab.size = k.size
+        tab.x_values = k.ctypes.data_as(_abi.c_double_p)
+        tab.y_values = t.ctypes.data_as(_abi.c_double_p)
+        return tab, (k, t)
 
     @cached_property
     def cstruct(self):
         s = _abi.CosmoTablesStruct()
-        s.transfer_density = None
-        s.transfer_vcb = None
+        keep = []
+        for name in ("transfer_density", "transfer_vcb"):
+            kt = getattr(self, name)
+            if kt is None:
+                setattr(s, name, None)
+            else:
+                tab, arrays = self._table(kt)
+                keep.append((tab, arrays))
+                setattr(s, name, C.pointer(tab))
         s.ps_norm = self.ps_norm
         s.USE_SIGMA_8 = self.USE_SIGMA_8
         s.V_CB_AVG = self.V_CB_AVG
+        s._keep = keep  # the C side deep-copies the tables at broadcast (InputParameters.c:21-53)
         return s
 
 
@@ -354,13 +378,21 @@ class InputParameters:
     astro_params: AstroParams = field(default_factory=AstroParams)
     astro_options: AstroOptions = field(default_factory=AstroOptions)
     node_redshifts: tuple = ()
+    class_tables: CosmoTables | None = None  # POWER_SPECTRUM='CLASS': the tables classy would have made
 
     def __post_init__(self):
         if self.matter_options.power_spectrum == "CLASS":
-            raise NotImplementedError("POWER_SPECTRUM='CLASS' needs classy tables (out of scope)")
+            ct = self.class_tables
+            if ct is None or ct.transfer_density is None:
+                raise NotImplementedError("POWER_SPECTRUM='CLASS' needs classy, which is not part of this build: pass "
+                                          "class_tables=CosmoTables(transfer_density=(k, T), ...)")
+            if self.matter_options.V_CB_MODEL == "FLUCTS" and ct.transfer_vcb is None:
+                raise ValueError("V_CB_MODEL='FLUCTS' needs class_tables.transfer_vcb")
 
     @cached_property
     def cosmo_tables(self) -> CosmoTables:
+        if self.matter_options.power_spectrum == "CLASS":
+            return self.class_tables
         return CosmoTables(ps_norm=self.cosmo_params.SIGMA_8, USE_SIGMA_8=True)
 
     @property
