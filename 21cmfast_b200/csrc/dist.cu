@@ -17,7 +17,7 @@ struct BarrierArgs {
     DistControl *ctl[DIST_MAX_RANKS];
     int rank, world;
     unsigned long long target;
-    int mode; /* 0 barrier only, 1 gather 64-bit words, 2 combine {min key, max key} */
+    int mode; /* 0 barrier only, 1 gather 64-bit words, 2 combine {min key, max key}, 3 interleaved gather of 32-bit words */
     const unsigned long long *src[DIST_MAX_RANKS];
     unsigned long long *dst;
     int words;
@@ -40,12 +40,14 @@ DEV unsigned long long now_ns() {
 }
 DEV void spin_pause() { __nanosleep(64); }
 DEV unsigned long long peer_load(const unsigned long long *p) { return __ldcv(p); }
+DEV unsigned int peer_load32(const unsigned int *p) { return __ldcv(p); }
 #else
 inline void sys_signal(unsigned long long *p) { __atomic_fetch_add(p, 1ULL, __ATOMIC_SEQ_CST); }
 inline unsigned long long sys_load_acquire(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline unsigned long long now_ns() { return (unsigned long long)(omp_get_wtime() * 1e9); }
 inline void spin_pause() { sched_yield(); }
 inline unsigned long long peer_load(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline unsigned int peer_load32(const unsigned int *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 #endif
 
 /* one CTA: signal every rank (self included), wait until all `world` signals of this epoch have
@@ -65,6 +67,12 @@ __global__ void dist_barrier_kernel(BarrierArgs a) {
         for (int i = threadIdx.x; i < a.world * a.words; i += blockDim.x) {
             const int r = i / a.words, j = i - r * a.words;
             a.dst[i] = peer_load(a.src[r] + j);
+        }
+    } else if (a.mode == 3) {
+        unsigned int *dst = reinterpret_cast<unsigned int *>(a.dst);
+        for (int i = threadIdx.x; i < a.words; i += blockDim.x) {
+            const int r = i % a.world, j = i / a.world;
+            dst[i] = peer_load32(reinterpret_cast<const unsigned int *>(a.src[r]) + j);
         }
     } else if (a.mode == 2) {
         if (threadIdx.x == 0) {
@@ -116,6 +124,9 @@ static void launch_barrier(int mode, const unsigned long long *src_sym, unsigned
 void dist_barrier() { launch_barrier(0, nullptr, nullptr, 0); }
 void dist_barrier_gather(const unsigned long long *src_sym, unsigned long long *dst, int words) {
     launch_barrier(1, src_sym, dst, words);
+}
+void dist_barrier_gather_interleaved32(const unsigned int *src_sym, unsigned int *dst, int total_words) {
+    launch_barrier(3, reinterpret_cast<const unsigned long long *>(src_sym), reinterpret_cast<unsigned long long *>(dst), total_words);
 }
 void dist_barrier_minmax(const int *keys_sym, int *out) {
     launch_barrier(2, reinterpret_cast<const unsigned long long *>(keys_sym), reinterpret_cast<unsigned long long *>(out), 1);

@@ -58,6 +58,9 @@ void dist_barrier();
 /* barrier + gather of `words` 64-bit words per rank: dst[r * words + j] = (rank r's src)[j].
    src must live in the symmetric heap, dst is local memory. */
 void dist_barrier_gather(const unsigned long long *src_sym, unsigned long long *dst, int words);
+/* barrier + interleaved gather of 32-bit words: dst[i] = (rank i % world's src)[i / world] for i < total_words --
+   a table whose entries were computed round-robin over the ranks (the per-radius f_coll tables of the ladder) */
+void dist_barrier_gather_interleaved32(const unsigned int *src_sym, unsigned int *dst, int total_words);
 /* barrier + combine of {min key, max key} pairs (float_order_key integers): keys_sym (symmetric,
    int[2]) holds this rank's pair; out[0] = min over ranks, out[1] = max over ranks (local memory) */
 void dist_barrier_minmax(const int *keys_sym, int *out);

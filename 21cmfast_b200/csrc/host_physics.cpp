@@ -1083,7 +1083,7 @@ static double integrate_qag_cond_cached(double lo, double hi, const MFParams &p,
 }
 
 void build_nion_table(FcollTable *t, double redshift, double min_dens, double max_dens, double Mmin,
-                      double Mmax, const ScalingConstants *sc, int method, int n_threads) {
+                      double Mmax, const ScalingConstants *sc, int method, int n_threads, int part, int nparts) {
     /* initialise_Nion_Conditional_spline without mini-halos, interp_tables.c:291-408 */
     const double growthf = dicke(redshift);
     const double lnMmin = log(Mmin), lnMmax = log(Mmax), lnMcond = log(Mmax);
@@ -1107,7 +1107,7 @@ void build_nion_table(FcollTable *t, double redshift, double min_dens, double ma
     const double dcrit_lim = (float)0.99 * get_delta_crit(matter_options_global->HMF, sigma2, growthf);
     CondNodeCache qag_cache;
 #pragma omp parallel for num_threads(n_threads) schedule(dynamic, 1)
-    for (int i = 0; i < N_DENS_INTERP; i++) {
+    for (int i = part; i < N_DENS_INTERP; i += nparts) {
         try {
             const double dens = min_dens + (float)i / ((float)N_DENS_INTERP - 1.) * (max_dens - min_dens);
             double v;

@@ -101,9 +101,10 @@ struct FcollTable {
 };
 void build_fgtrm_table(FcollTable *t, double min_dens, double max_dens, double growthf,
                        double sigma_min, double sigma_max);
+/* part / nparts: only the entries i = part (mod nparts) are computed (one table built by several ranks) */
 void build_nion_table(FcollTable *t, double redshift, double min_dens, double max_dens,
                       double Mmin, double Mmax, const ScalingConstants *sc, int method,
-                      int n_threads);
+                      int n_threads, int part = 0, int nparts = 1);
 /* the same table for a condition mass that is not the upper limit (the Lagrangian cell of the halo
    boxes): initialise_Nion_Conditional_spline / initialise_SFRD_Conditional_table without mini-halos
    (interp_tables.c:291-408, :415-495); log_floor = -40 resp. -50 */

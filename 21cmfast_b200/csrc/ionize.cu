@@ -1453,9 +1453,13 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     /* slab mode: this rank's extrema keys and plane sums are published in the symmetric heap, one slot per radius */
     int *keys_sym = nullptr;
     double *plane_sym = nullptr;
+    float *tab_sym = nullptr; /* this rank's share of every radius' table */
+    const int tab_per = sl ? (N_DENS_INTERP + slab.P - 1) / slab.P : 0;
     if (sl) {
         keys_sym = (int *)dist_alloc(sizeof(int) * 2 * 64);
         plane_sym = (double *)dist_alloc(sizeof(double) * 64 * (size_t)nxl);
+        if (!(getenv("B200_SPLIT_TABLES") && getenv("B200_SPLIT_TABLES")[0] == '0'))
+            tab_sym = (float *)dist_alloc(sizeof(float) * 64 * (size_t)tab_per);
     }
     DevBuf<int> d_flag(1);
     dev_zero(d_flag, sizeof(int));
@@ -1639,10 +1643,15 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         const double min_density = (double)float_from_order_key(g_stage.h_keys[2 * k]) - 0.001;
         const double max_density = (double)float_from_order_key(g_stage.h_keys[2 * k + 1]) + 0.001;
 
-        /* setup_integration_tables (IonisationBox.c:702-768) on the host while the stream works */
+        /* setup_integration_tables (IonisationBox.c:702-768) on the host while the stream works.  On slabs every
+           rank sees the same extrema, so the ranks share the 400 quadratures of the table round-robin and
+           exchange their entries through the symmetric heap (at 8 GPUs the per-radius table, not the kernels,
+           bounded the ladder: 0.13-0.24 ms of host time against 0.2 ms of GPU time per radius) */
+        const bool split_table = sl && slab.P > 1 && c.mass_dep_zeta && tab_sym;
         if (c.mass_dep_zeta) {
             if (method == INTEG_GL) initialise_GL(c.lnMmin, rs.ln_M_max_R);
-            build_nion_table(&htab, c.redshift, min_density, max_density, c.M_min, rs.M_max_R, &c.sc, method, so->N_THREADS);
+            build_nion_table(&htab, c.redshift, min_density, max_density, c.M_min, rs.M_max_R, &c.sc, method, so->N_THREADS,
+                             split_table ? slab.rank : 0, split_table ? slab.P : 1);
         } else {
             build_fgtrm_table(&htab, min_density, max_density, c.growth_factor, c.sigma_minmass, rs.sigma_maxmass);
         }
@@ -1651,8 +1660,17 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         DevTable *st = &g_stage.h_tables[k];
         st->x_min = htab.x_min; st->x_width = htab.x_width; st->inv_width = 1.0 / htab.x_width;
         st->log_valued = htab.log_valued;
-        memcpy(st->y, htab.y, sizeof(st->y));
-        h2d_async(d_tables.p + k, st, sizeof(DevTable));
+        if (split_table) {
+            /* this rank's entries, packed, to its slot of the symmetric heap; the gather kernel assembles y[] */
+            for (int q = 0, i = slab.rank; i < N_DENS_INTERP; i += slab.P, q++) st->y[q] = htab.y[i];
+            h2d_async(tab_sym + (size_t)k * tab_per, st->y, tab_per * sizeof(float));
+            h2d_async(d_tables.p + k, st, offsetof(DevTable, y));
+            dist_barrier_gather_interleaved32(reinterpret_cast<const unsigned int *>(tab_sym + (size_t)k * tab_per),
+                                              reinterpret_cast<unsigned int *>(d_tables.p[k].y), N_DENS_INTERP);
+        } else {
+            memcpy(st->y, htab.y, sizeof(st->y));
+            h2d_async(d_tables.p + k, st, sizeof(DevTable));
+        }
 
         /* the reference leaves the last processed radius' f_coll in unnormalised_nion; every
            other radius only needs the grid sum and the ionised flags, so its f_coll grid is never

@@ -167,7 +167,7 @@ class SlabGroup:
     the library's kernels over NVLink.
     """
 
-    def __init__(self, *, inputs, backend, group=None, heap_bytes: int | None = None):
+    def __init__(self, *, inputs, backend, group=None, heap_bytes: int | None = None, ics: bool = False):
         import torch.distributed as dist
         self.backend, self.inputs, self.group = backend, inputs, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -183,6 +183,10 @@ class SlabGroup:
             pitch = ((hz // 2 + 1) + 7) // 8 * 8
             halo = min(self.nxl, 24)
             heap_bytes = (2 * 8 * self.nxl * hii * pitch + 8 * (self.nxl + 2 * halo) * hii * hz + (16 << 20))
+            if ics:  # slab ICs transform the hi-res box: two receive buffers and the two gathered Hermitian planes
+                dim, dz = so.dim, so.D_PARA
+                dpitch = ((dz // 2 + 1) + 7) // 8 * 8
+                heap_bytes = max(heap_bytes, 2 * 8 * (dim // self.world) * dim * dpitch + 16 * dim * dim + (16 << 20))
         lib = backend.lib
         lib.b200_dist_init.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
         lib.b200_dist_connect.argtypes = [C.c_void_p]
@@ -190,6 +194,7 @@ class SlabGroup:
             C.c_float, C.POINTER(_abi.InitialConditionsStruct), C.POINTER(_abi.PerturbedFieldStruct)]
         lib.b200_ComputeIonizedBox_slab.argtypes = [
             C.c_float, C.c_float, C.POINTER(_abi.PerturbedFieldStruct), C.POINTER(_abi.IonizedBoxStruct)]
+        lib.b200_ComputeInitialConditions_slab.argtypes = [C.c_ulonglong, C.POINTER(_abi.InitialConditionsStruct)]
         handle = C.create_string_buffer(64)
         st = lib.b200_dist_init(self.rank, self.world, C.c_ulonglong(heap_bytes), handle)
         _agree(st, "b200_dist_init", group)
@@ -221,6 +226,32 @@ class SlabGroup:
             return np.ascontiguousarray(a[idx])
         import torch
         return a[torch.as_tensor(idx, device=a.device)].contiguous()
+
+    def initial_conditions(self, *, device=None):
+        """The initial conditions of the box generated slab by slab (``b200_ComputeInitialConditions_slab``): the
+        hi-res box never exists on one GPU.  Returns this rank's x-slabs as tensors on ``device``:
+        ``hires_density`` (planes ``DIM / world * rank ...``) and the low-res density / velocity boxes
+        (planes ``x0 ... x0 + nxl``).  The group must have been built with ``ics=True`` (heap size)."""
+        import torch
+        be, inputs = self.backend, self.inputs
+        so, mo = inputs.simulation_options, inputs.matter_options
+        be.state.init(inputs, broadcast_inputs=True, ps=True)
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        lo = (self.nxl, so.HII_DIM, so.HII_D_PARA)
+        hi = (so.dim // self.world, so.dim, so.D_PARA)
+        names = ["lowres_density", "lowres_vx", "lowres_vy", "lowres_vz"]
+        if mo.PERTURB_ALGORITHM == "2LPT":
+            names += ["lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+        out = {k: torch.zeros(lo, dtype=torch.float32, device=dev) for k in names}
+        out["hires_density"] = torch.zeros(hi, dtype=torch.float32, device=dev)
+        s_ic = _abi.InitialConditionsStruct()
+        for k, t in out.items():
+            setattr(s_ic, k, _ptr(t))
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        st = be.lib.b200_ComputeInitialConditions_slab(C.c_ulonglong(inputs.random_seed), C.byref(s_ic))
+        _agree(st, "b200_ComputeInitialConditions_slab", self.group)
+        return out
 
     def perturb(self, *, redshift: float, ics_slab: dict):
         """ics_slab: device tensors of this rank's slabs (``hires_density`` from ``hires_slab``, the low-res

@@ -377,6 +377,13 @@ int b200_dist_barrier(void);
    sum).  ZELDOVICH / 2LPT on the low-res grid; ionisation without recombinations / spin temperature. */
 int b200_ComputePerturbedField_slab(float redshift, InitialConditions *d_boxes_slab, PerturbedField *d_pf_slab);
 int b200_ComputeIonizedBox_slab(float redshift, float prev_redshift, PerturbedField *d_pf_slab, IonizedBox *d_box_slab);
+/* ComputeInitialConditions (InitialConditions.c:547-772) with the hi-res box split into x-slabs, so that DIM is
+   bounded by the node's HBM instead of one GPU's: hires_density holds the DIM / world hi-res planes that start at
+   DIM / world * rank (no half-cell shift), the low-res density / velocity boxes the rank's HII_DIM / world
+   planes.  Bit-identical to the same planes of the single-GPU result, with the N_THREADS = 1 random stream of the
+   reference (every rank walks the one stream and keeps the modes of its k-space slab) or B200_IC_RNG=device.
+   Velocities on the low-res grid, integer DIM / HII_DIM, no relative velocities. */
+int b200_ComputeInitialConditions_slab(unsigned long long random_seed, InitialConditions *d_boxes_slab);
 
 /* Test hooks for the random stream of sample_ic_modes (InitialConditions.c:103-139; rng.c:31-90):
    n1 then n2 values of gsl_ran_ugaussian on gsl_rng_mt19937 seeded with mt_seed, produced by the

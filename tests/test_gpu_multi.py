@@ -74,7 +74,14 @@ for hii, dim, kw in {cases}:
     ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
     pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=be)
     whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=be)
-    grp = pkg.SlabGroup(inputs=inputs, backend=be)
+    grp = pkg.SlabGroup(inputs=inputs, backend=be, ics=True)
+    sics = grp.initial_conditions(device=dev)             # slab-decomposed ICs: bit-identical slabs
+    hn = inputs.simulation_options.dim // world
+    rk = dist.get_rank()
+    for k, t in sics.items():
+        full = getattr(ics, k)
+        want = full[rk * hn:(rk + 1) * hn] if k == "hires_density" else grp.lowres_slab(full)
+        assert np.array_equal(t.cpu().numpy(), want), (hii, k, float(np.abs(t.cpu().numpy() - want).max()))
     lo = ["lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
     slab = {{k: torch.from_numpy(np.ascontiguousarray(grp.lowres_slab(getattr(ics, k)))).to(dev) for k in lo
             if getattr(ics, k) is not None}}

@@ -110,7 +110,15 @@ for hii, dim, kw in {cases}:
     ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
     pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
     whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
-    grp = pkg.SlabGroup(inputs=inputs, backend=emu)
+    grp = pkg.SlabGroup(inputs=inputs, backend=emu, ics=True)
+    # slab-decomposed initial conditions (SURVEY 8e row 4): every rank walks the one Gaussian stream and keeps its
+    # y-slab of the modes, the Hermitian planes are fixed on gathered copies -- bit-identical slabs
+    sics = grp.initial_conditions()
+    hn = inputs.simulation_options.dim // world
+    for k, t in sics.items():
+        full = getattr(ics, k)
+        want = full[rank * hn:(rank + 1) * hn] if k == "hires_density" else grp.lowres_slab(full)
+        assert np.array_equal(t.numpy(), want), (hii, k, float(np.abs(t.numpy() - want).max()))
     lo = ["lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
     slab = {{k: torch.from_numpy(np.ascontiguousarray(grp.lowres_slab(getattr(ics, k)))) for k in lo
             if getattr(ics, k) is not None}}
