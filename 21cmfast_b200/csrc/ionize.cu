@@ -35,6 +35,7 @@
 
 #include <omp.h>
 #include <algorithm>
+#include <type_traits>
 #include <thread>
 #include <vector>
 
@@ -47,11 +48,18 @@ struct DevTable {
     float y[N_DENS_INTERP];
 };
 
+/* partial sums a CTA of the sum sweep writes per chunk: one per warp (256-thread CTAs), one in the host emulation */
+#ifndef B200_EMU
+#define SWEEP_PARTIALS 8
+#else
+#define SWEEP_PARTIALS 1
+#endif
+
 struct SweepArgs {
     int nx, ny, nz, nzc;
     const float *filtered;   /* padded real rows, already clipped to [-1, 1e6] */
     const DevTable *table;
-    double *partial;         /* [ceil(nx ny / chunk_rows)] sums of consecutive row chunks */
+    double *partial;         /* [ceil(nx ny / chunk_rows)][SWEEP_PARTIALS] sums of consecutive row chunks, per warp */
     float *fcoll;            /* unpadded f_coll grid of this radius, or null (sum only) */
     int chunk_rows;          /* rows per chunk: divides ny, so that chunks never straddle an x plane */
     /* speculative flags (fcoll_sum_kernel<LOG, true>), see SpecState */
@@ -201,11 +209,13 @@ DEV float2 exp_small_f2(float2 u) { /* Taylor series of exp, |u| <= 1/4, two lan
 }
 /* f_coll of two cells for the grid sum only: straight-line code; `steep` is raised when a lane's
    |t dy| leaves the range of the series and the caller must redo the chunk with fcoll_exact */
-template <bool LOG> DEV float2 fcoll_fast2(float2 d, const SweepTable *h, const SweepConstsF &k, bool &steep) {
+template <bool LOG> DEV float2 fcoll_fast2(float2 d, const float2 *rep_base, const SweepConstsF &k, bool &steep) {
+    /* rep_base is the kernel's own dynamic shared-memory array (not the generic pointer kept in SweepTable): the
+       lookups compile to LDS with 32-bit addresses instead of generic LD + 64-bit address arithmetic */
     int i0, i1;
     float2 t;
     table_coords_f2(d, k, i0, i1, t);
-    const float2 *rep = h->rep + sweep_rep_lane();
+    const float2 *rep = rep_base + sweep_rep_lane();
     const float2 e0 = rep[i0 * SWEEP_REP], e1 = rep[i1 * SWEEP_REP];
     const float2 u = f2_mul(t, make_float2(e0.y, e1.y));
     if (!LOG) return f2_add(make_float2(e0.x, e1.x), u);
@@ -301,18 +311,18 @@ DEV void for_each_chunk_blocked(const float *filtered, long long nrows, int nz, 
     const long long rstride = 2LL * pitch;
     const long long nchunks = (nrows + CH - 1) / CH;
 #ifndef B200_EMU
-    if (blockDim.x == 256 && q <= 256 && (256 % q) == 0 && (CH % (4 * (256 / q))) == 0) {
+    if (blockDim.x == 256 && q <= 256 && (256 % q) == 0 && (CH % (4 * (256 / q))) == 0 && (nrows % CH) == 0) {
+        /* the chunks tile the rows exactly: no row of an iteration lies outside the grid */
         const int rows_per_step = 256 / q;
         const int r = threadIdx.x / q, zc = threadIdx.x - r * q;
         const int step_rows = 4 * rows_per_step;
         const int ipc = CH / step_rows; /* iterations per chunk */
+        const float *const mine = filtered + (long long)r * rstride + 4 * zc; /* this thread's column of the first step */
+        const long long ustride = (long long)rows_per_step * rstride;
         auto issue = [&](long long row0, int slot) {
+            const float *p = mine + row0 * rstride;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                long long row = row0 + r + (long long)u * rows_per_step;
-                if (row >= nrows) row = nrows - 1; /* harmless duplicate, discarded below */
-                cp_async_16(&ring[(slot * 4 + u) * 256 + threadIdx.x], filtered + row * rstride + 4 * zc);
-            }
+            for (int u = 0; u < 4; u++) cp_async_16(&ring[(slot * 4 + u) * 256 + threadIdx.x], p + u * ustride);
             cp_async_commit();
         };
         long long chunk = blockIdx.x, next_chunk = blockIdx.x;
@@ -331,11 +341,7 @@ DEV void for_each_chunk_blocked(const float *filtered, long long nrows, int nz, 
             for (int u = 0; u < 4; u++) d4[u] = ring[((it & 1) * 4 + u) * 256 + threadIdx.x];
 #pragma unroll
             for (int u = 0; u < 4; u++) res[u] = fast(d4[u]);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const long long row = row0 + r + (long long)u * rows_per_step;
-                if (row < nrows) finish(res[u], d4[u], row, zc);
-            }
+            finish(res, d4, row0 + r, rows_per_step, zc, std::integral_constant<int, 4>()); /* rows row0 + r + u rows_per_step */
             const long long done = chunk;
             advance(chunk, it_in);
             if (it_in == 0) end_chunk(done);
@@ -352,8 +358,10 @@ DEV void for_each_chunk_blocked(const float *filtered, long long nrows, int nz, 
         for (long long id = threadIdx.x; id < nch; id += blockDim.x) {
             const long long row = r0 + id / q;
             const int zc = (int)(id - (row - r0) * q);
-            const float4 d = *reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc);
-            finish(fast(d), d, row, zc);
+            const float4 d1[4] = {*reinterpret_cast<const float4 *>(filtered + row * rstride + 4 * zc)};
+            R r1[4];
+            r1[0] = fast(d1[0]);
+            finish(r1, d1, row, 0, zc, std::integral_constant<int, 1>()); /* only entry 0 is live */
         }
         end_chunk(chunk);
     }
@@ -364,7 +372,6 @@ DEV void for_each_chunk_blocked(const float *filtered, long long nrows, int nz, 
    output) every cell takes the reference arithmetic and the float grid is written. */
 template <bool LOG, bool SPEC> __global__ void __launch_bounds__(256) fcoll_sum_kernel(SweepArgs a) {
     __shared__ SweepTable st;
-    __shared__ double red[8];
     __shared__ unsigned int q_n;
     DYN_SMEM(float2, rep);
     sweep_table_load(&st, a.table, rep, LOG);
@@ -448,23 +455,17 @@ template <bool LOG, bool SPEC> __global__ void __launch_bounds__(256) fcoll_sum_
     const float dens_floor = (float)(-1. + pc::FRACT_FLOAT_ERR);
     const SweepConstsF kf = sweep_consts(&st, dens_floor);
     double acc = 0.;
-    /* deterministic CTA reduction of the chunk's thread sums -> partial[chunk]: butterfly over the
-       lanes of each warp (every lane ends with the same bits), then the warp sums in warp order */
+    /* deterministic reduction of the chunk's thread sums: butterfly over the lanes of each warp (every lane ends
+       with the same bits) -> partial[chunk][warp]; plane_sum_kernel adds the warps' entries in order.  No CTA
+       barrier: the two __syncthreads per chunk of a CTA-wide reduction were 20 % of the sweep's stall cycles. */
     auto end_chunk = [&](long long chunk) {
 #ifndef B200_EMU
         double v = acc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
-            a.partial[chunk] = t;
-        }
-        __syncthreads();
+        if ((threadIdx.x & 31) == 0) a.partial[chunk * SWEEP_PARTIALS + (threadIdx.x >> 5)] = v;
 #else
-        a.partial[chunk] = acc;
+        a.partial[chunk * SWEEP_PARTIALS] = acc;
 #endif
         acc = 0.;
     };
@@ -476,22 +477,44 @@ template <bool LOG, bool SPEC> __global__ void __launch_bounds__(256) fcoll_sum_
                 SumRes r;
                 r.steep = false;
                 r.code = 0;
-                const float2 f = f2_add(fcoll_fast2<LOG>(make_float2(d.x, d.y), &st, kf, r.steep),
-                                        fcoll_fast2<LOG>(make_float2(d.z, d.w), &st, kf, r.steep));
+                const float2 f = f2_add(fcoll_fast2<LOG>(make_float2(d.x, d.y), rep, kf, r.steep),
+                                        fcoll_fast2<LOG>(make_float2(d.z, d.w), rep, kf, r.steep));
                 r.sum = f.x + f.y;
                 if (SPEC) r.code = classify4(d);
                 return r;
             },
-            [&](const SumRes &r, const float4 &d, long long row, int zc) {
-                if (r.steep) /* a steep bin somewhere in the chunk: reference arithmetic for its cells */
-                    acc += (fcoll_exact(fmaxf(d.x, dens_floor), &st) + fcoll_exact(fmaxf(d.y, dens_floor), &st)) +
-                           (fcoll_exact(fmaxf(d.z, dens_floor), &st) + fcoll_exact(fmaxf(d.w, dens_floor), &st));
-                else
-                    acc += (double)r.sum;
-                if (SPEC && r.code) {
-                    const unsigned int cell = (unsigned int)row * (unsigned int)a.nz + 4u * (unsigned int)zc; /* NL < 2^32 */
-                    if (r.code & 15u) set_sure(r.code & 15u, cell);
-                    if (r.code & 0xf0u) push_cells(r.code >> 4, cell, d);
+            [&](const SumRes (&r)[4], const float4 (&d)[4], long long row, int rows_per_step, int zc, auto live_c) {
+                constexpr int live = decltype(live_c)::value;
+                bool steep = false;
+                unsigned code = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (u < live) { steep = steep || r[u].steep; code |= r[u].code; }
+                if (!steep) { /* one conversion and one double add per 16 cells */
+                    float s4 = r[0].sum;
+#pragma unroll
+                    for (int u = 1; u < 4; u++)
+                        if (u < live) s4 += r[u].sum;
+                    acc += (double)s4;
+                } else { /* a steep bin somewhere: reference arithmetic for the cells of the steep groups */
+                    for (int u = 0; u < live; u++) {
+                        if (r[u].steep)
+                            acc += (fcoll_exact(fmaxf(d[u].x, dens_floor), &st) + fcoll_exact(fmaxf(d[u].y, dens_floor), &st)) +
+                                   (fcoll_exact(fmaxf(d[u].z, dens_floor), &st) + fcoll_exact(fmaxf(d[u].w, dens_floor), &st));
+                        else
+                            acc += (double)r[u].sum;
+                    }
+                }
+                if (SPEC && code) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (u < live && r[u].code) {
+                            const unsigned int cell = (unsigned int)(row + (long long)u * rows_per_step) * (unsigned int)a.nz +
+                                                      4u * (unsigned int)zc; /* NL < 2^32 */
+                            if (r[u].code & 15u) set_sure(r[u].code & 15u, cell);
+                            if (r[u].code & 0xf0u) push_cells(r[u].code >> 4, cell, d[u]);
+                        }
+                    }
                 }
             },
             end_chunk);
@@ -508,7 +531,7 @@ template <bool LOG, bool SPEC> __global__ void __launch_bounds__(256) fcoll_sum_
                         a.fcoll[row * a.nz + z] = (float)f;
                     } else {
                         bool steep = false;
-                        const float f = fcoll_fast2<LOG>(make_float2(src[z], src[z]), &st, kf, steep).x;
+                        const float f = fcoll_fast2<LOG>(make_float2(src[z], src[z]), rep, kf, steep).x;
                         acc += steep ? fcoll_exact(fmaxf(src[z], dens_floor), &st) : (double)f;
                     }
                 }
@@ -1448,7 +1471,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     const long long nchunks = (long long)nxl * chunks_per_plane;
     const int sum_blocks = sweep_grid(nchunks);
     const int sweep_blocks = grid_for((long long)nxl * ny, 1);
-    DevBuf<double> d_partial((size_t)nchunks);
+    DevBuf<double> d_partial((size_t)nchunks * SWEEP_PARTIALS);
     DevBuf<double> d_plane((size_t)nx);
     /* slab mode: this rank's extrema keys and plane sums are published in the symmetric heap, one slot per radius */
     int *keys_sym = nullptr;
@@ -1702,7 +1725,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             B200_LAUNCH_T(spec_j ? "fcoll_sum_classify_kernel" : "fcoll_sum_kernel", ks, sum_blocks, 256, SWEEP_REP_BYTES, sa);
         }
         {
-            PlaneSumArgs ps = {nxl, chunks_per_plane, d_partial, sl ? plane_sym + (size_t)k * nxl : d_plane.p};
+            PlaneSumArgs ps = {nxl, chunks_per_plane * SWEEP_PARTIALS, d_partial, sl ? plane_sym + (size_t)k * nxl : d_plane.p};
             B200_LAUNCH(plane_sum_kernel, (nxl + 31) / 32, 32, 0, ps);
             if (sl) dist_barrier_gather(reinterpret_cast<const unsigned long long *>(plane_sym + (size_t)k * nxl),
                                         reinterpret_cast<unsigned long long *>(d_plane.p), nxl);
