@@ -2007,8 +2007,15 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         if (ts && (!spin_temp || !spin_temp->xray_ionised_fraction || !spin_temp->kinetic_temp_neutral))
             b200_throw(B200_ValueError, "ComputeIonizedBox: USE_TS_FLUCT needs a computed TsBox");
 
-        DevBuf<float> d_density(N), d_xH(N), d_zre(N), d_prev, d_Tk, d_nion;
-        h2d(d_density, perturbed_field->density, N * sizeof(float));
+        DevBuf<float> d_density_own, d_xH(N), d_zre(N), d_prev, d_Tk, d_nion;
+        /* the perturbed density this box is computed from: the copy ComputePerturbedField left on the device
+           (opt-in residency, rt.h) or an upload of the caller's array */
+        const float *d_density = resident_get(perturbed_field->density, (size_t)N);
+        if (!d_density) {
+            d_density_own.alloc(N);
+            h2d(d_density_own, perturbed_field->density, N * sizeof(float));
+            d_density = d_density_own;
+        }
         /* neutral_fraction / kinetic_temperature / previous z_reion are first read at the last
            radius: their upload rides on the copy stream behind the radius ladder */
         const int slot = 60;
@@ -2088,6 +2095,10 @@ extern "C" int ComputeIonizedBox(float redshift, float prev_redshift, PerturbedF
         d2h(box->z_reion, d_zre, N * sizeof(float));
         if (want_Tk) d2h(box->kinetic_temperature, d_Tk, N * sizeof(float));
         if (d_nion.p && nion_written) d2h(box->unnormalised_nion, d_nion, N * sizeof(float));
+        if (resident_enabled()) { /* ComputeBrightnessTemp reads the neutral fraction next */
+            resident_put(box->neutral_fraction, d_xH.p, (size_t)N);
+            d_xH.p = nullptr; d_xH.n = 0;
+        }
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {
         try { copy_stream_sync(); } catch (B200Error &) {} /* no copy may outlive the buffers released above */

@@ -146,9 +146,12 @@ extern "C" int ComputeBrightnessTemp(float redshift, TsBox *spin_temp, IonizedBo
         const float const_factor =
             27 * (cp->OMb * cp->hlittle * cp->hlittle / 0.023) *
             sqrt((0.15 / (cp->OMm) / (cp->hlittle) / (cp->hlittle)) * (1. + redshift) / 10.0);
-        DevBuf<float> d_d(N), d_x(N), d_t(N);
-        h2d(d_d, perturb_field->density, N * sizeof(float));
-        h2d(d_x, ionized_box->neutral_fraction, N * sizeof(float));
+        DevBuf<float> d_d_own, d_x_own, d_t(N);
+        /* inputs: the copies the two producing calls left on the device (opt-in residency, rt.h), else uploads */
+        const float *d_d = resident_get(perturb_field->density, (size_t)N);
+        const float *d_x = resident_get(ionized_box->neutral_fraction, (size_t)N);
+        if (!d_d) { d_d_own.alloc(N); h2d(d_d_own, perturb_field->density, N * sizeof(float)); d_d = d_d_own; }
+        if (!d_x) { d_x_own.alloc(N); h2d(d_x_own, ionized_box->neutral_fraction, N * sizeof(float)); d_x = d_x_own; }
         DevBuf<float> d_ts, d_tau;
         DevBuf<int> d_flag(1);
         dev_zero(d_flag, sizeof(int));

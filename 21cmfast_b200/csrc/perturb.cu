@@ -967,6 +967,10 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
         d2h(pf->density, d_density, N * sizeof(float));
         for (int a = 0; a < 3; a++)
             if (host_v[a]) d2h(host_v[a], d_v[a], N * sizeof(float));
+        if (resident_enabled()) { /* ComputeIonizedBox / ComputeBrightnessTemp read this box next (rt.h) */
+            resident_put(pf->density, d_density.p, (size_t)N);
+            d_density.p = nullptr; d_density.n = 0;
+        }
         if (!use_cache) ics_cache_drop();
         g_stats.ms = timer.stop_ms();
     } catch (B200Error &e) {

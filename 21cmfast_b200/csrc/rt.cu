@@ -304,7 +304,44 @@ double DevTimer::stop_ms() { return (omp_get_wtime() - t0) * 1e3; }
 void ics_cache_drop();  /* perturb.cu */
 void fft_plans_drop();  /* fft.cu */
 
+/* ------------------------------------------------------------------ output residency (rt.h) */
+struct ResidentEntry { const void *host; float *dev; size_t n; unsigned long long stamp; };
+static ResidentEntry g_resident[RESIDENT_SLOTS];
+static unsigned long long g_resident_clock = 0;
+static bool g_resident_on = false;
+bool resident_enabled() { return g_resident_on; }
+void resident_clear() {
+    for (auto &e : g_resident) {
+        if (e.dev) dev_free(e.dev);
+        e = ResidentEntry{nullptr, nullptr, 0, 0};
+    }
+}
+void resident_put(const void *host, float *dev_owned, size_t n) {
+    if (!g_resident_on || !host) { dev_free(dev_owned); return; }
+    ResidentEntry *slot = nullptr;
+    for (auto &e : g_resident)
+        if (e.host == host) slot = &e; /* the same host array produced again: replace its copy */
+    if (!slot) {
+        slot = &g_resident[0];
+        for (auto &e : g_resident)
+            if (e.stamp < slot->stamp) slot = &e; /* empty slots have stamp 0: used first, then the oldest */
+    }
+    if (slot->dev) dev_free(slot->dev);
+    *slot = ResidentEntry{host, dev_owned, n, ++g_resident_clock};
+}
+const float *resident_get(const void *host, size_t n) {
+    if (!g_resident_on || !host) return nullptr;
+    for (auto &e : g_resident)
+        if (e.host == host && e.n == n && e.dev) { e.stamp = ++g_resident_clock; return e.dev; }
+    return nullptr;
+}
+extern "C" void b200_residency(int enable) {
+    g_resident_on = enable != 0;
+    if (!g_resident_on) resident_clear();
+}
+
 extern "C" void b200_release_device_cache(void) {
+    resident_clear();
     ics_cache_drop();
     fft_plans_drop();
     pool_drop();

@@ -267,6 +267,18 @@ template <typename T> struct DevBuf {
     operator T *() const { return p; }
 };
 
+/* Opt-in residency of OUTPUT boxes between the reference's own entry points: with
+   b200_residency(1) a call that produces a box the next call of the chain reads (perturbed density -> ionized
+   box -> brightness temperature) leaves its device copy behind under the HOST pointer the caller received it
+   in, and the consumer uses that copy instead of uploading the host array again.  The caller promises not to
+   modify or free those host arrays while residency is on (b200_residency(0) drops every copy); the last
+   RESIDENT_SLOTS boxes are kept.  Off by default: the reference reads the caller's arrays on every call. */
+#define RESIDENT_SLOTS 6
+bool resident_enabled();
+void resident_put(const void *host, float *dev_owned, size_t n); /* takes ownership of a dev_alloc'ed buffer */
+const float *resident_get(const void *host, size_t n);            /* device mirror of the host array, or null */
+void resident_clear();
+
 /* device timer (CUDA events on g_stream; wall clock in emulation) */
 struct DevTimer {
     void *a = nullptr, *b = nullptr;

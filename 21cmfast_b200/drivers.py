@@ -172,21 +172,27 @@ def run_coeval(*, out_redshifts=None, inputs: InputParameters, initial_condition
 
 class _resident_ics:
     """Keep the initial conditions in HBM for the duration of a driver loop that owns them (nothing
-    mutates ``ics`` inside the loop): one upload instead of one per redshift.  The cache is opt-in in
-    the library (``b200_ics_cache``); other backends (the compiled reference) have no such symbol."""
+    mutates ``ics`` inside the loop): one upload instead of one per redshift -- and hand the perturbed density
+    and the neutral fraction from one entry point to the next on the device (``b200_residency``: the loop
+    below never modifies a box after the call that made it, and keeps the boxes of the current redshift alive
+    while their copies are in use).  Both caches are opt-in in the library; other backends (the compiled
+    reference) have no such symbols."""
 
     def __init__(self, backend):
-        self.fn = getattr(backend.lib, "b200_ics_cache", None) if hasattr(backend.lib, "b200_ics_cache") else None
-        if self.fn is not None:
-            self.fn.argtypes, self.fn.restype = [C.c_int], None
+        self.fns = []
+        for name in ("b200_ics_cache", "b200_residency"):
+            if hasattr(backend.lib, name):
+                fn = getattr(backend.lib, name)
+                fn.argtypes, fn.restype = [C.c_int], None
+                self.fns.append(fn)
 
     def __enter__(self):
-        if self.fn is not None:
-            self.fn(1)
+        for fn in self.fns:
+            fn(1)
 
     def __exit__(self, *exc):
-        if self.fn is not None:
-            self.fn(0)
+        for fn in self.fns:
+            fn(0)
         return False
 
 

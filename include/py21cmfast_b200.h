@@ -323,6 +323,13 @@ void b200_release_device_cache(void);
    without calling b200_ics_cache_invalidate().  b200_ics_cache(0) switches it off and frees the copy. */
 void b200_ics_cache(int enable);
 void b200_ics_cache_invalidate(void);
+/* Opt-in residency of the boxes handed from one of the reference's entry points to the next
+   (drivers/coeval.py:835-853: PerturbedField -> IonizedBox -> BrightnessTemp): with enable != 0,
+   ComputePerturbedField leaves its density and ComputeIonizedBox its neutral fraction on the device under the host
+   pointer the caller received them in, and ComputeIonizedBox / ComputeBrightnessTemp use those copies instead of
+   uploading the arrays again.  The caller must not modify or free those host arrays while it is on;
+   enable = 0 drops every copy.  Off by default (the reference reads the caller's arrays on every call). */
+void b200_residency(int enable);
 /* Counters for the last Compute* call: kernels launched, H2D and D2H bytes, device milliseconds
    (CUDA events on the library's stream). Any pointer may be NULL. */
 void b200_last_call_stats(long long *kernel_launches, long long *h2d_bytes, long long *d2h_bytes,
