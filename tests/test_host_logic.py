@@ -233,15 +233,30 @@ def test_bench_reference_arm_line_contract():
     if common.ref_backend() is None:
         pytest.skip("needs oracle/_ref")
     root = Path(__file__).resolve().parent.parent
+    # a small grid here (the CPU tier has minutes, the default workload takes 44 s per step on 16 cores); the arm
+    # runs the workload it prints, so the label must carry these sizes -- and the defaults the benchmark's
     r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--ref-hii-dim", "32"], capture_output=True, text=True, timeout=900)
+                        "--hii-dim", "32", "--dim", "96", "--box-len", "48", "--r-bubble-max", "10"],
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("coeval cells/sec")
-    assert "HII_DIM=512 DIM=1536" in d["config"]["workload"] and "n_radii=40" in d["config"]["workload"]
+    assert "HII_DIM=32 DIM=96 BOX_LEN=48" in d["config"]["workload"]
+    assert "HII_DIM=32 DIM=96" in d["cpu_baseline"]["sample"]          # what ran is what the line says
+    assert abs(d["value"] - 32**3 / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod_ref", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    old_argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        dflt = bench.parse()
+    finally:
+        sys.argv = old_argv
+    assert bench.workload(dflt) == (512, 1536, 768.0) and bench.n_radii(512, 768.0, dflt.r_bubble_max) == 40
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
