@@ -48,6 +48,11 @@ void ics_cache_drop() {
    doing so): a hit is decided by the host pointers, the grid sizes and a signature of ~4096
    sampled words per array, which guards against a reused allocation, not against a sparse edit.
    A full-content hash would cost as much host time as the upload it saves (14.5 GB at DIM=1536). */
+/* b200_ics_share: the ranks of a connected group (b200_dist_connect) call ComputePerturbedField TOGETHER, each
+   with its own redshift but the SAME initial conditions in host memory (the redshifts of a coeval run or a
+   lightcone spread over the GPUs).  Off by default. */
+static bool g_ics_share = false;
+extern "C" void b200_ics_share(int enable) { g_ics_share = enable != 0; }
 static int g_ics_cache_on = -1; /* -1: follow the environment */
 extern "C" void b200_ics_cache(int enable) {
     g_ics_cache_on = enable ? 1 : 0;
@@ -928,6 +933,47 @@ extern "C" int ComputePerturbedField(float redshift, InitialConditions *boxes, P
         const int nuse = linear ? 1 : (lpt2 ? 7 : 4);
         for (int i = 0; i < nuse; i++)
             if (!hv[i]) b200_throw(B200_ValueError, "ComputePerturbedField: a required IC array is NULL");
+        /* opt-in, several GPUs working on the SAME initial conditions (one redshift each): every rank uploads
+           1 / world of every IC array over its own PCIe link and sends that share to the peers over NVLink */
+        if (g_ics_share && g_dist.ready && g_dist.world > 1) {
+            if (on_hires || linear) b200_throw(B200_ValueError, "shared IC upload: ZELDOVICH / 2LPT on the low-res grid only");
+            const int P = g_dist.world, me = g_dist.rank;
+            dist_reset();
+            float *sym[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            for (int i = 0; i < nuse; i++) sym[i] = (float *)dist_alloc(hn[i] * sizeof(float));
+            for (int i = 0; i < nuse; i++) {
+                const size_t lo = hn[i] * (size_t)me / P, hi = hn[i] * (size_t)(me + 1) / P;
+                h2d(sym[i] + lo, hv[i] + lo, (hi - lo) * sizeof(float));
+                for (int r = 1; r < P; r++) { /* staggered: at any time every rank writes to a different peer */
+                    const int peer = (me + r) % P;
+                    d2d(dist_peer(sym[i], peer) + lo, sym[i] + lo, (hi - lo) * sizeof(float));
+                }
+            }
+            dist_barrier(); /* every share of every array has landed everywhere */
+            DevBuf<float> d_density(N), d_v[3];
+            float *host_v[3] = {mo->KEEP_3D_VELOCITIES ? pf->velocity_x : nullptr,
+                                mo->KEEP_3D_VELOCITIES ? pf->velocity_y : nullptr, pf->velocity_z};
+            PerturbDeviceIO io;
+            memset(&io, 0, sizeof(io));
+            io.hires_density = sym[0]; io.lowres_density = sym[0];
+            for (int a = 0; a < 3; a++) {
+                io.v[a] = sym[1 + a]; io.v2[a] = lpt2 ? sym[4 + a] : nullptr;
+                if (host_v[a]) { d_v[a].alloc(N); io.vel[a] = d_v[a]; }
+            }
+            io.density = d_density;
+            perturb_core(redshift, io, nullptr);
+            dist_barrier(); /* no rank reuses the heap (next call's dist_reset) while a peer still reads its ICs */
+            d2h(pf->density, d_density, N * sizeof(float));
+            for (int a = 0; a < 3; a++)
+                if (host_v[a]) d2h(host_v[a], d_v[a], N * sizeof(float));
+            dist_check();
+            if (resident_enabled()) {
+                resident_put(pf->density, d_density.p, (size_t)N);
+                d_density.p = nullptr; d_density.n = 0;
+            }
+            g_stats.ms = timer.stop_ms();
+            return 0;
+        }
         /* opt-in: keep the initial conditions resident between calls (perturb_field is called once
            per redshift on the same ICs), see b200_ics_cache() above; default = upload every call */
         const bool use_cache = ics_cache_enabled();

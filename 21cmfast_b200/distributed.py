@@ -210,8 +210,24 @@ class SlabGroup:
 
     def close(self):
         if self.open:
+            self.share_ics(False)
             self.backend.lib.b200_dist_shutdown()
             self.open = False
+
+    def share_ics(self, enable: bool = True):
+        """Redshift-parallel runs on shared initial conditions (``b200_ics_share``): while enabled, the ranks call
+        ``perturb_field`` / ``ComputePerturbedField`` together, each with its own redshift but the same IC arrays in
+        host memory; every rank uploads 1 / world of them and the shares travel to the peers over NVLink.  The
+        group's heap must hold the ICs (``SlabGroup.ics_heap_bytes(inputs)``)."""
+        fn = self.backend.lib.b200_ics_share
+        fn.argtypes, fn.restype = [C.c_int], None
+        fn(1 if enable else 0)
+
+    @staticmethod
+    def ics_heap_bytes(inputs) -> int:
+        so = inputs.simulation_options
+        n_lo, n_hi = so.HII_DIM * so.HII_DIM * so.HII_D_PARA, so.dim * so.dim * so.D_PARA
+        return 4 * (n_hi + 6 * n_lo) + (64 << 20)
 
     # -- slab views of whole-box arrays (host-side helpers for tests / feeders) ------------------
     def lowres_slab(self, a):

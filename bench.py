@@ -65,6 +65,8 @@ def parse():
                          "halo pull (strong scaling); 'radius' = ONE box: deposit by x-slab + all-reduce(SUM) of the "
                          "accumulator, filter radii split over the GPUs + all-reduce(MAX) of the mask over NCCL")
     ap.add_argument("--no-strong", action="store_true", help="N > 1, partition boxes: skip the one-box strong legs")
+    ap.add_argument("--no-share-ics", action="store_true",
+                    help="N > 1, end-to-end leg: every rank uploads the whole initial conditions itself")
     ap.add_argument("--strong-steps", type=int, default=5)
     return ap.parse_args()
 
@@ -351,8 +353,9 @@ def main():
     hii, dim, box_len = workload(args)
     radius_mode = args.partition in ("radius", "slab") and world > 1  # ONE box over all ranks
     slab_mode = args.partition == "slab" and world > 1
-    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source,
-                                seed=1234 + (0 if radius_mode else rank),
+    # N > 1, partition boxes: the ranks work on ONE set of initial conditions, each on its own redshift (a coeval run
+    # or lightcone spread over the GPUs) -- what lets the end-to-end leg share the IC upload
+    inputs = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source, seed=1234,
                                 n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
     N, M = hii**3, dim**3
     nrad = n_radii(hii, box_len, args.r_bubble_max)
@@ -361,6 +364,7 @@ def main():
     ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
     be.state.init(inputs, broadcast_inputs=True, ps=True, sigma=True, heat=True)
     z = float(args.redshift)
+    z_own = z + (0.25 * rank if (world > 1 and not radius_mode) else 0.0)  # this rank's redshift in the weak legs
 
     d_ic_part = None
 
@@ -443,10 +447,10 @@ def main():
         d_ib["neutral_fraction"].fill_(1.0)
         d_ib["kinetic_temperature"].zero_()
         torch.cuda.synchronize()
-        st = lib.b200_ComputePerturbedField_device(C.c_float(z), C.byref(s_ic), C.byref(s_pf))
+        st = lib.b200_ComputePerturbedField_device(C.c_float(z_own), C.byref(s_ic), C.byref(s_pf))
         assert st == 0, st
         l1, _, _, ms1 = stats()
-        st = lib.b200_ComputeIonizedBox_device(C.c_float(z), C.c_float(-1.0), C.byref(s_pf), C.byref(s_ib))
+        st = lib.b200_ComputeIonizedBox_device(C.c_float(z_own), C.c_float(-1.0), C.byref(s_pf), C.byref(s_ib))
         assert st == 0, st
         l2, _, _, ms2 = stats()
         return ms1, ms2, l1 + l2
@@ -496,8 +500,8 @@ def main():
             t, a = pinned_like(torch, getattr(ics, k))
             keep.append(t)
             setattr(h_ics, k, a)
-        h_pf = pkg.PerturbedField(inputs, z)
-        h_ib = pkg.IonizedBox(inputs, z)
+        h_pf = pkg.PerturbedField(inputs, z_own)
+        h_ib = pkg.IonizedBox(inputs, z_own)
         h_prev = pkg.IonizedBox(inputs, -1.0)
         for obj, ks in ((h_pf, ("density", "velocity_z")),
                         (h_ib, ("neutral_fraction", "ionisation_rate_G12", "mean_free_path", "z_reion",
@@ -514,17 +518,23 @@ def main():
             h_ib.neutral_fraction[...] = 1.0
             h_ib.kinetic_temperature[...] = 0.0
             t0 = time.perf_counter()
-            st = lib.ComputePerturbedField(C.c_float(z), C.byref(h_ics.cstruct), C.byref(h_pf.cstruct))
+            st = lib.ComputePerturbedField(C.c_float(z_own), C.byref(h_ics.cstruct), C.byref(h_pf.cstruct))
             assert st == 0, st
             e2e_split.append(time.perf_counter() - t0)
             _, hb1, db1, _ = stats()
-            st = lib.ComputeIonizedBox(C.c_float(z), C.c_float(-1.0), C.byref(h_pf.cstruct), C.byref(ppf.cstruct),
+            st = lib.ComputeIonizedBox(C.c_float(z_own), C.c_float(-1.0), C.byref(h_pf.cstruct), C.byref(ppf.cstruct),
                                        C.byref(h_prev.cstruct), C.byref(ts.cstruct), C.byref(hb.cstruct),
                                        C.byref(h_ics.cstruct), C.byref(h_ib.cstruct))
             assert st == 0, st
             _, hb2, db2, _ = stats()
             return time.perf_counter() - t0, hb1 + hb2, db1 + db2
 
+        # N > 1: the ranks' boxes share their initial conditions, so each rank uploads 1 / N of them over its own
+        # PCIe link and the shares travel to the peers over NVLink (b200_ics_share); the C-ABI calls stay the same
+        share_grp = None
+        if world > 1 and not args.no_share_ics:
+            share_grp = pkg.SlabGroup(inputs=inputs, backend=be, heap_bytes=pkg.SlabGroup.ics_heap_bytes(inputs))
+            share_grp.share_ics(True)
         for _ in range(max(1, args.warmup - 1)):
             host_step()
         barrier()
@@ -534,6 +544,8 @@ def main():
             tt.append(t)
             h2d_b, d2h_b = hb_, db_
         barrier()
+        if share_grp is not None:
+            share_grp.close()
         e2e_s = float(np.mean(tt))
         xh_host = float(h_ib.neutral_fraction.mean())
         assert abs(xh_host - xh_dev) < 1e-6, (xh_host, xh_dev)
@@ -558,20 +570,11 @@ def main():
     if world > 1 and not radius_mode and not args.no_strong:
         strong = {}
         del d_ic_part
-        if rank != 0:  # every rank needs rank 0's box (seed 1234)
-            d_ic.clear()
-            torch.cuda.empty_cache()
-            cin = common.make_inputs(hii=hii, dim=dim, box_len=box_len, source=args.source, seed=1234,
-                                     n_threads=ncpu, R_BUBBLE_MAX=args.r_bubble_max)
-            cics = pkg.compute_initial_conditions(inputs=cin, backend=be)
-            d_c = {k: torch.from_numpy(getattr(cics, k)).to(dev) for k in names_ic if k != "lowres_density"}
-            del cics
-        else:
-            cin = inputs
-            d_c = {k: v for k, v in d_ic.items() if k != "lowres_density"}
+        cin = inputs  # every rank holds the same initial conditions (seed 1234)
+        d_c = {k: v for k, v in d_ic.items() if k != "lowres_density"}
         be.state.init(cin, broadcast_inputs=True, ps=True, sigma=True, heat=True)
         xh0 = torch.tensor([xh_dev], dtype=torch.float64, device=dev)
-        dist.broadcast(xh0, 0)  # the single-GPU answer for the same box
+        dist.broadcast(xh0, 0)  # the single-GPU answer for the same box at the same redshift (rank 0's)
         for name in ("slab", "radius"):
             try:
                 if name == "slab":
@@ -677,7 +680,8 @@ def main():
                                        f"stores over NVLink), slab deposit + halo pull") if slab_mode else
                                       (f"one box over {world} GPUs: x-slab deposit + all-reduce(SUM), radii split + "
                                        f"all-reduce(MAX) of the mask") if radius_mode else
-                                      f"{world} independent coeval boxes (one per GPU)",
+                                      (f"{world} coeval boxes at {world} redshifts (z + 0.25 rank) on shared initial "
+                                       f"conditions, one per GPU" if world > 1 else "1 coeval box"),
                        "l2": f"inputs larger than L2 (every pass streams a {4 * N / 1e6:.0f} MB box; L2 is 126 MB)",
                        "ms_perturb": ms_perturb, "ms_ionize": ms_ionize, "global_xH": xh_dev,
                        "wall_ms_per_step": 1e3 * t_wall / args.steps},
@@ -696,6 +700,9 @@ def main():
             out["e2e"] = {"value": world * N / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(e2e[1]),
                           "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": 1e3 * e2e_s,
                           "ms_perturb_call": 1e3 * e2e[3], "ms_ionize_call": 1e3 * (e2e_s - e2e[3]),
+                          "ics_upload": ("shared: h2d bytes are this rank's 1/N share of the initial conditions, the "
+                                         "rest arrives from the peers over NVLink" if (world > 1 and not args.no_share_ics)
+                                         else "whole initial conditions per call"),
                           "pinned_copy_yardstick": e2e[4]}
         print(json.dumps(out))
     if world > 1:

@@ -376,6 +376,12 @@ int b200_dist_shutdown(void);
 int b200_dist_rank(void);
 int b200_dist_world(void);
 int b200_dist_barrier(void);
+/* Redshift-parallel runs on shared initial conditions: with enable != 0 the ranks of a
+   connected group call ComputePerturbedField TOGETHER, each with its own redshift and output arrays but the same
+   IC arrays in host memory; every rank then uploads 1 / world of each IC array over its own PCIe link and sends
+   that share to the peers' heaps over NVLink (the heap must hold the ICs: 4 (DIM^3 + 6 HII_DIM^3) bytes).  On a
+   node whose host-to-device rate is shared by the GPUs this divides the upload time by the number of ranks. */
+void b200_ics_share(int enable);
 /* Slab entry points: the structs hold DEVICE pointers to this rank's x-slab of every array, planes
    [rank, rank + 1) * HII_DIM / world: low-res boxes [HII_DIM / world][HII_DIM][HII_D_PARA]; hires_density
    the F * HII_DIM / world hi-res planes that start at global plane F * x0 - F / 2 (periodic), F = DIM /

@@ -156,3 +156,53 @@ def test_gloo_slab_decomposed_box(tmp_path, nproc):
                        capture_output=True, text=True, timeout=1200, env=env)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert r.stdout.count("OK slab") == len(cases)
+
+
+WORKER_SHARE = r'''
+import os, sys
+sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
+import numpy as np, torch, torch.distributed as dist
+import common
+pkg = common.pkg
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+emu = common.emu_backend()
+inputs = common.make_inputs(hii=16, dim=48, seed=99)          # the SAME initial conditions on every rank
+ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+z = 7.0 + rank                                                 # one redshift per rank
+want = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=emu)
+grp = pkg.SlabGroup(inputs=inputs, backend=emu, heap_bytes=pkg.SlabGroup.ics_heap_bytes(inputs))
+grp.share_ics(True)
+import ctypes as C
+for rep in range(2):                                           # twice: the heap is carved anew by every call
+    got = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=emu)
+    a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_double()
+    emu.lib.b200_last_call_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    for k, v in want.arrays().items():
+        assert np.array_equal(v, got.arrays()[k]), (rank, k)
+    n_ic = 4 * (48**3 + 6 * 16**3)
+    assert abs(b.value - n_ic / world) <= 64, (b.value, n_ic / world)   # this rank uploaded its share only
+grp.share_ics(False)
+plain = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=emu)
+assert np.array_equal(plain.density, want.density)
+grp.close()
+if rank == 0: print("OK shared ics", world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_gloo_shared_initial_conditions(tmp_path, nproc):
+    """Redshift-parallel ranks on shared ICs (SURVEY 8e row 5): every rank uploads 1 / world of the IC arrays and
+    receives the rest from its peers' heaps; the perturbed field of each rank's redshift is bit-identical to the
+    plain call, and the rank's host-to-device bytes are its share only."""
+    if not (ROOT / "tests" / "_emu" / "libb200_emu.so").exists():
+        pytest.skip("tests/_emu not built")
+    script = tmp_path / "worker_share.py"
+    script.write_text(WORKER_SHARE.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29571 + nproc), str(script)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert "OK shared ics" in r.stdout
