@@ -94,3 +94,23 @@ def test_lagrangian_sources_vs_reference_emulated(name):
 @pytest.mark.parametrize("name", list(CASES))
 def test_lagrangian_sources_vs_reference_gpu(name):
     print(name, _check(common.gpu_backend(), name))
+
+
+def test_run_coeval_builds_the_halo_boxes_for_lagrangian_sources():
+    """run_coeval with SOURCE_MODEL='L-INTEGRAL' computes a HaloBox per redshift (coeval.py:783-800) and hands it to
+    the ionisation step; same boxes as the explicit chain."""
+    be = common.emu_backend()
+    if be is None:
+        pytest.skip("tests/_emu not built")
+    inputs, _ = _inputs("exp_filter")
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    got = pkg.run_coeval(out_redshifts=(8.0, 7.0), inputs=inputs, initial_conditions=ics, backend=be)
+    assert [g["redshift"] for g in got] == [8.0, 7.0]
+    for g in got:
+        z = g["redshift"]
+        pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=be)
+        hb = pkg.compute_halobox(redshift=z, initial_conditions=ics, backend=be)
+        ib = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, halobox=hb, backend=be)
+        assert np.array_equal(ib.neutral_fraction, g["ionized_box"].neutral_fraction)
+        assert np.isfinite(g["brightness_temp"].brightness_temp).all()
+    assert got[1]["ionized_box"].global_xH < got[0]["ionized_box"].global_xH
