@@ -1004,6 +1004,83 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
     }
 }
 
+/* Last radius of the plain ladder and the finalisation in ONE pass (ionise_kernel + finalize_kernel read and wrote
+   the mask, x_HI and T_k twice: 3.0 ms of the step at 512^3, a fifth of the HBM rate each, one cell per thread
+   and iteration).  Four cells per thread, every array touched once; the same per-cell arithmetic in the same
+   order, so the outputs are bit-identical to the two-kernel sequence (B200_FUSED_LAST=0 keeps that one). */
+struct LastArgs {
+    CritArgs c;
+    FinalArgs f;
+};
+DEV void last_cell(const LastArgs &a, double mean_fix, float fcoll, unsigned char m, float dens, float pz, float xh_in,
+                   float tk_in, float &xh_out, float &zre_out, float &tk_out, bool &bad) {
+    double curr_fcoll = mean_fix * (double)fcoll;
+    if (a.c.mass_dep_zeta && curr_fcoll < a.c.f_limit) curr_fcoll = a.c.f_limit;
+    float xh = xh_in, tk = tk_in;
+    bool ion = m != 0;
+    if (curr_fcoll * a.c.ion_eff_factor > 1.0) {
+        ion = true;
+    } else if (a.c.R_index == 0 && !ion && (xh_in > pc::TINY)) { /* ionise_cell's partial ionisation */
+        double res_xH = 1. - curr_fcoll * a.c.ion_eff_factor;
+        const float T_HI = (float)(a.c.TK_nofluct * (1 + a.c.adia_TK_term * dens));
+        tk = partially_ionized_temperature(T_HI, (float)res_xH, (float)a.c.T_re);
+        if (res_xH < 0) res_xH = 0;
+        else if (res_xH > 1) res_xH = 1;
+        xh = (float)res_xH;
+    }
+    float zre = -1.0f;
+    if (ion) { /* finalize_kernel */
+        zre = (pz < 0) ? (float)a.f.redshift : pz;
+        xh = 0.f;
+        if (zre > 0) {
+            tk = fully_ionized_temperature(zre, (float)a.f.stored_redshift, dens, a.f.c_Tre17, a.f.c_z17);
+            const float thistk = (float)(a.f.TK_nofluct * (1 + a.f.adia_TK_term * dens));
+            if (tk < thistk) tk = thistk;
+        }
+    }
+    if (!isfinite(tk)) bad = true;
+    xh_out = xh; zre_out = zre; tk_out = tk;
+}
+__global__ void __launch_bounds__(256) ionise_last_fused_kernel(LastArgs a) {
+    __shared__ double red[256];
+    double acc = 0.;
+    for (int i = threadIdx.x; i < a.c.n_partial; i += blockDim.x) acc += a.c.partial[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    double grid_mean = red[0] / a.c.n_cells;
+    if (a.c.mass_dep_zeta) {
+        if (grid_mean <= a.c.f_limit) grid_mean = a.c.f_limit;
+    } else {
+        if (grid_mean <= pc::FRACT_FLOAT_ERR) grid_mean = pc::FRACT_FLOAT_ERR;
+    }
+    const double mean_fix = a.c.mean_f_coll / grid_mean;
+    bool bad = false;
+    const long long n4 = a.c.n >> 2;
+    const float4 *f4 = reinterpret_cast<const float4 *>(a.c.fcoll), *d4 = reinterpret_cast<const float4 *>(a.c.density);
+    const float4 *p4 = reinterpret_cast<const float4 *>(a.c.prev_zre);
+    const uchar4 *m4 = reinterpret_cast<const uchar4 *>(a.c.mask);
+    float4 *x4 = reinterpret_cast<float4 *>(a.c.xH), *z4 = reinterpret_cast<float4 *>(a.c.z_reion), *t4 = reinterpret_cast<float4 *>(a.c.Tk);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 fc = f4[i], dn = d4[i], xin = x4[i];
+        const uchar4 mk = m4[i];
+        const float4 pz = p4 ? p4[i] : make_float4(-1.f, -1.f, -1.f, -1.f);
+        const float4 tin = t4 ? t4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xo, zo, to;
+        last_cell(a, mean_fix, fc.x, mk.x, dn.x, pz.x, xin.x, tin.x, xo.x, zo.x, to.x, bad);
+        last_cell(a, mean_fix, fc.y, mk.y, dn.y, pz.y, xin.y, tin.y, xo.y, zo.y, to.y, bad);
+        last_cell(a, mean_fix, fc.z, mk.z, dn.z, pz.z, xin.z, tin.z, xo.z, zo.z, to.z, bad);
+        last_cell(a, mean_fix, fc.w, mk.w, dn.w, pz.w, xin.w, tin.w, xo.w, zo.w, to.w, bad);
+        x4[i] = xo;
+        z4[i] = zo;
+        if (t4) t4[i] = to;
+    }
+    if (bad && a.c.Tk) *a.f.nonfinite = 1;
+}
+
 /* set_recombination_rates, inhomogeneous model (IonisationBox.c:1277-1341): per cell, the
    PDF-integrated rate at the cell's effective redshift (1 + z) (1 + delta)^(1/3) - 1 and its own
    Gamma12, evaluated from the host-built table (host_recomb.cpp): index-sampled in redshift, natural
@@ -1636,6 +1713,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     DevBuf<unsigned int> d_qcounts(use_spec ? sum_blocks : 0);
 
     FcollTable htab;
+    bool fused_last = false; /* the last radius' kernel also finalised the box */
     double t_wait = 0, t_table = 0, t_launch = 0;
     const bool verbose = getenv("B200_TIMING") != nullptr;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -1773,7 +1851,20 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             const bool dilate_last = sphere && rs.R_index != 0; /* at R_index 0 the sphere is the centre cell itself */
             if (sphere) ca.paint = d_paint;
             if (dilate_last) { dev_zero(d_centre, (size_t)N); ca.mask = d_centre; }
-            B200_LAUNCH(ionise_kernel, grid_for(NL, 1024), 256, 0, ca);
+            /* plain ladder: the last radius and the finalisation are one pass (ionise_last_fused_kernel) */
+            fused_last = last && !general && !sphere && pt.phase < 0 && (NL & 3) == 0 &&
+                         !(getenv("B200_FUSED_LAST") && getenv("B200_FUSED_LAST")[0] == '0');
+            if (fused_last) {
+                const float zf = (float)c.stored_redshift, Tref = (float)c.T_re;
+                LastArgs la;
+                la.c = ca;
+                la.f = FinalArgs{NL, d_mask, io.density, io.prev_zre, io.xH, io.z_reion, io.Tk, d_flag,
+                                 c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
+                                 pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), nullptr, nullptr};
+                B200_LAUNCH(ionise_last_fused_kernel, grid_for(NL, 1024), 256, 0, la);
+            } else {
+                B200_LAUNCH(ionise_kernel, grid_for(NL, 1024), 256, 0, ca);
+            }
             if (dilate_last) paint_spheres(rs.R);
         }
     }
@@ -1794,7 +1885,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
                         c.redshift, c.stored_redshift, c.T_re, c.TK_nofluct, c.adia_TK_term,
                         pow((double)Tref, 1.7), pow(1e4 * ((1. + zf) / 4.), 1.7), ts ? io.Tk_neutral : nullptr,
                         sphere ? d_paint.p : nullptr};
-        B200_LAUNCH(finalize_kernel, grid_for(NL, 1024), 256, 0, fa);
+        if (!fused_last) B200_LAUNCH(finalize_kernel, grid_for(NL, 1024), 256, 0, fa);
         if (sl) dist_barrier(); /* no rank leaves (and reuses the symmetric heap) before every rank is done */
         int flag = 0;
         d2h(&flag, d_flag, sizeof(int)); /* also drains the stream before the work boxes are released */

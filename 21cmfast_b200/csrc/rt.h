@@ -125,6 +125,7 @@ struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct uint2 { unsigned int x, y; };
+struct uchar4 { unsigned char x, y, z, w; };
 static inline uint2 make_uint2(unsigned int a, unsigned int b) { uint2 r = {a, b}; return r; }
 static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r; }
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r = {a, b, c, d}; return r; }

@@ -15,7 +15,7 @@ pkg = common.pkg
 
 
 def _ladder(be, pf, ics, **env):
-    keys = ("B200_SPEC", "B200_SPEC_QCAP", "B200_SPEC_EPS")
+    keys = ("B200_SPEC", "B200_SPEC_QCAP", "B200_SPEC_EPS", "B200_FUSED_LAST")
     old = {k: os.environ.pop(k, None) for k in keys}
     os.environ.update({k: str(v) for k, v in env.items()})
     try:
@@ -42,6 +42,8 @@ def _check(be, ics_be, source, hii, z):
     _identical(_ladder(be, pf, ics), two_sweeps)
     _identical(_ladder(be, pf, ics, B200_SPEC_QCAP=2), two_sweeps)      # every segment overflows
     _identical(_ladder(be, pf, ics, B200_SPEC_EPS=1e-7), two_sweeps)    # the prediction must fail: re-run
+    # the last radius and the finalisation as one pass (default) or as two kernels
+    _identical(_ladder(be, pf, ics, B200_SPEC=0, B200_FUSED_LAST=0), two_sweeps)
     return two_sweeps
 
 
