@@ -126,6 +126,11 @@ class GlobalState:
             self.inputs = inputs
         i = self.inputs
         if (broadcast_inputs or ps or sigma or heat or recomb) and not self.inputs_are_broadcast:
+            if hasattr(lib, "b200_set_device"):
+                # another binding of the same shared object (cffi, a second Backend) may have left its copy of the
+                # cosmo tables behind: the C side copies them only once per Free_cosmo_tables_global
+                # (InputParameters.c:9-53); the library's own free is a no-op when nothing is allocated
+                lib.Free_cosmo_tables_global()
             # keep the structs alive: the C side stores *pointers* (InputParameters.c:11-20)
             self._keep = (i.simulation_options.cstruct, i.matter_options.cstruct,
                           i.cosmo_params.cstruct, i.astro_params.cstruct,

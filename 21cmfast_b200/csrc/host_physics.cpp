@@ -309,6 +309,14 @@ static void class_init() {
     g_class.ready = true;
 }
 static double tf_class(double k, int dv) {
+    if (!g_class.ready || (dv == 1 && !g_class.has_vcb)) {
+        /* tables were never broadcast / splined (Broadcast_struct_global_all copies them once, init_ps splines
+           them): a number, not a crash, for the scalar entry points of the C surface */
+        static bool said = false;
+        if (!said) fprintf(stderr, "[21cmfast_b200] POWER_SPECTRUM=CLASS: the transfer tables are not initialised (Free_cosmo_tables_global, Broadcast_struct_global_all, init_ps)\n");
+        said = true;
+        return std::nan("");
+    }
     const size_t n = g_class.k.size();
     if (k > g_class.k[n - 1]) {
         if (dv == 0) return g_class.eh_ratio_at_kmax * tf_EH(k) * k * k;
@@ -465,6 +473,7 @@ void ps_export_consts(PsConsts *o) {
     o->ck = o->cTm = o->cCm = o->cTv = o->cCv = nullptr;
     o->eh_ratio_at_kmax = 0.;
     if (MO->POWER_SPECTRUM == 5) {
+        if (!g_class.ready) b200_throw(B200_ValueError, "POWER_SPECTRUM=CLASS: the transfer tables are not initialised");
         const size_t n = g_class.k.size();
         if (!g_class.d_nodes) {
             std::vector<double> h(5 * n, 0.0);

@@ -89,6 +89,7 @@ def test_cffi_dlopen_host_entry_points(cffi_lib):
     assert lib.matter_options_global.SOURCE_MODEL == inputs.matter_options.cdict["SOURCE_MODEL"]
     lib.freeSigmaMInterpTable()
     lib.free_ps()
+    lib.Free_cosmo_tables_global()  # _global_initialization.py:77-87 frees the C-side copy with the structs
     del keep
     print("cdef from", origin)
 
@@ -134,4 +135,5 @@ def test_cffi_dlopen_compute_calls_reproduce_golden(cffi_lib):
     lib.destruct_heat()
     lib.freeSigmaMInterpTable()
     lib.free_ps()
+    lib.Free_cosmo_tables_global()
     del keep

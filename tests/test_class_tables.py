@@ -80,3 +80,20 @@ def test_class_tables_and_relative_velocities_emulated(flucts, sigma8):
 @pytest.mark.parametrize("flucts,sigma8", [(True, True), (False, True), (True, False)])
 def test_class_tables_and_relative_velocities_gpu(flucts, sigma8):
     print(_check(common.gpu_backend(), flucts, sigma8))
+
+
+def test_class_tables_after_another_binding_left_its_cosmo_tables_behind():
+    """The C side copies the cosmo tables once per Free_cosmo_tables_global (InputParameters.c:9-53).  A second binding
+    of the same shared object (cffi route B, another Backend) that broadcast analytic-spectrum inputs and never freed
+    them must not leave a later CLASS run without its tables (this crashed the GPU tier once: the scalar entry points
+    now also return NaN instead of dereferencing missing tables)."""
+    path = common.ROOT / "tests" / "_emu" / "libb200_emu.so"
+    if not path.exists() or common.ref_backend() is None:
+        pytest.skip("tests/_emu / oracle/_ref not built")
+    first = pkg.Backend(path)
+    first.state.init(common.make_inputs(hii=16, dim=32), broadcast_inputs=True, ps=True)   # EH tables stay allocated
+    second = pkg.Backend(path)
+    inputs = _inputs(flucts=True, sigma8=True)
+    got, want = _scalars(second, inputs), _scalars(common.ref_backend(), inputs)
+    for k in want:
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-9, err_msg=k)
