@@ -7,7 +7,6 @@ TAG=${1:-r02_final}
 O=gpurun_out/$TAG
 mkdir -p "$O"
 nvidia-smi --query-gpu=name,memory.total --format=csv > "$O/gpu.txt"; nproc >> "$O/gpu.txt"
-( time timeout 1500 python -m pytest tests -m gpu -q -x --durations=12 ) > "$O/pytest_gpu.log" 2>&1; tail -18 "$O/pytest_gpu.log"
 python __graft_entry__.py smoke > "$O/smoke.log" 2>&1; tail -1 "$O/smoke.log"
 python bench.py --steps 10 --warmup 3 > "$O/bench.json" 2> "$O/bench.err"; tail -2 "$O/bench.err" | cut -c1-300; cut -c1-600 "$O/bench.json"
 B200_SPEC=0 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-yardstick > "$O/bench_two_sweeps.json" 2>> "$O/bench.err"
@@ -25,9 +24,17 @@ done
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 --csv --log-file "$O/launches.csv" \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-yardstick > "$O/ncu_launches.log" 2>&1
 python tools/launch_summary.py "$O/launches.csv" > "$O/launches.md" 2>/dev/null; head -24 "$O/launches.md"
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:'fft_strided_pow2_kernel|fft_c2r_z_pow2_kernel|fcoll_sum_kernel|spec_resolve_kernel|move_cic_grouped' \
-    -s 0 -c 44 -o "$O/prof_hot" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-yardstick > "$O/ncu_full.log" 2>&1
-tail -2 "$O/ncu_full.log" | cut -c1-200
+# two small full captures (the reports are too large to travel: keep the raw page and a summary, drop the .ncu-rep)
+timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k regex:'move_cic_grouped|ionise_last_fused' -s 0 -c 2 \
+    -o "$O/prof_a" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-yardstick > "$O/ncu_a.log" 2>&1
+timeout 900 ncu --set full --clock-control none --kernel-name-base demangled \
+    -k regex:'fft_strided_pow2_kernel|fft_c2r_z_pow2_kernel|fcoll_sum_kernel|spec_resolve_kernel' -s 22 -c 14 \
+    -o "$O/prof_b" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-yardstick > "$O/ncu_b.log" 2>&1
+tail -1 "$O/ncu_a.log" | cut -c1-200; tail -1 "$O/ncu_b.log" | cut -c1-200
+for r in a b; do
+  ncu -i "$O/prof_$r.ncu-rep" --page raw --csv > "$O/ncu_full_raw_$r.csv" 2>/dev/null
+  python tools/ncu_summary.py "$O/prof_$r.ncu-rep" "$O/ncu_full_$r" --hii 512 > "$O/ncu_full_$r.md" 2>&1; cat "$O/ncu_full_$r.md"
+  rm -f "$O/prof_$r.ncu-rep"
+done
 ( time python bench.py --impl reference --steps 20 --warmup 5 ) > "$O/bench_ref.json" 2> "$O/bench_ref.err"; tail -3 "$O/bench_ref.err"; cut -c1-500 "$O/bench_ref.json"
 ls -la "$O"
