@@ -15,8 +15,9 @@
  * carries 29 more bits), and a second kernel rounds the two accumulators to the float outputs
  * (whalo_sfr = n_ion / (t_h t_star) with recombinations, map_mass.c:326-331).
  *
- * In scope: no mini-halos, no spin temperature (halo_xray), no extra fields, HMF in {PS, ST, DELOS}
- * (the others need the mean fix of get_uhmf_averages) -- anything else returns ValueError.
+ * In scope: no mini-halos, no spin temperature (halo_xray), no extra fields -- anything else returns ValueError.
+ * For the mass functions without a conditional form (WATSON, WATSON-Z, REED07, YUNG24) the grids are rescaled to the
+ * unconditional expectation (mean_fix_grids, HaloBox.c:209-243).
  */
 #include "rt.h"
 #include "host_physics.h"
@@ -26,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 extern "C" double dicke(double z);
 extern "C" double minimum_source_mass(double redshift, bool xray);
@@ -140,6 +142,35 @@ __global__ void dens_range_kernel(DensRangeArgs a) {
     atomic_max_i32(&a.keys[1], float_order_key(float_as_int_bits(hi)));
 }
 
+/* box mean of a float grid (deterministic block sums, added in order on the host) and its rescaling */
+struct GridSumArgs {
+    long long n;
+    const float *grid;
+    double *partial; /* [gridDim.x] */
+};
+__global__ void __launch_bounds__(256) grid_sum_kernel(GridSumArgs a) {
+    __shared__ double red[256];
+    double acc = 0.;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
+        acc += (double)a.grid[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
+}
+struct GridScaleArgs {
+    long long n;
+    float *grid;
+    double ratio;
+};
+__global__ void grid_scale_kernel(GridScaleArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
+        a.grid[i] = (float)((double)a.grid[i] * a.ratio);
+}
+
 static int grid_of(long long n) {
     long long want = (n + 255) / 256, cap = (long long)dev_num_sms() * 8;
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
@@ -160,8 +191,6 @@ extern "C" int ComputeHaloBox(double redshift, InitialConditions *ini_boxes, Hal
             ao->USE_UPPER_STELLAR_TURNOVER || ao->PHOTON_CONS_TYPE != 0)
             b200_throw(B200_ValueError, "ComputeHaloBox: mini-halos, spin temperature, extra fields, median scaling relations, "
                                         "the upper stellar turnover and photon conservation are not built");
-        if (mo->HMF != HMF_PS && mo->HMF != HMF_ST && mo->HMF != HMF_DELOS)
-            b200_throw(B200_ValueError, "ComputeHaloBox: HMF=%d needs the mean fix of the fixed grids, which is not built", mo->HMF);
         if (mo->USE_INTERPOLATION_TABLES != 2)
             b200_throw(B200_ValueError, "this build needs USE_INTERPOLATION_TABLES='hmf-interpolation'");
         if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR)
@@ -257,6 +286,35 @@ extern "C" int ComputeHaloBox(double redshift, InitialConditions *ini_boxes, Hal
         }
         GalpropsOutArgs oa = {N, acc_nion, acc_sfr, d_nion, d_sfr, recomb ? d_wsfr.p : nullptr, 1. / sc.t_h / sc.t_star};
         B200_LAUNCH(galprops_out_kernel, grid_of(N), 256, 0, oa);
+        /* mean_fix_grids (HaloBox.c:209-243; set_scaling_constants sets fix_mean for the mass functions that have no
+           conditional form, scaling_relations.c:40-42): every grid is rescaled so that its box mean equals the
+           unconditional integral (get_uhmf_averages, :105-163) */
+        const bool fix_mean = mo->HMF == HMF_WATSON || mo->HMF == HMF_WATSON_Z || mo->HMF == HMF_REED07 || mo->HMF == HMF_YUNG24;
+        if (fix_mean && M_min < M_max) {
+            const double lnMmin = log(M_min), lnMmax = log(M_max);
+            const double Mturn_a = pow(10., grids->log10_Mcrit_ACG_ave);
+            const ScalingConstants sc_sfrd = evolve_scaling_constants_sfr(&sc);
+            const double pref_stars = rho_crit() * cosmo_params_global->OMb * sc.fstar_10;
+            const double pref_sfr = pref_stars / sc.t_star / sc.t_h;
+            const double i_fesc = Nion_General(redshift, lnMmin, lnMmax, Mturn_a, &sc);
+            const double i_stars = Nion_General(redshift, lnMmin, lnMmax, Mturn_a, &sc_sfrd);
+            const double want[3] = {i_fesc * pref_stars * sc.fesc_10 * sc.pop2_ion, i_stars * pref_sfr,
+                                    i_fesc * pref_sfr * sc.fesc_10 * sc.pop2_ion};
+            float *grid[3] = {d_nion.p, d_sfr.p, recomb ? d_wsfr.p : nullptr};
+            const int nb = grid_of(N);
+            DevBuf<double> d_part((size_t)nb);
+            std::vector<double> hp((size_t)nb);
+            for (int g = 0; g < 3; g++) {
+                if (!grid[g]) continue;
+                GridSumArgs sa = {N, grid[g], d_part};
+                B200_LAUNCH(grid_sum_kernel, nb, 256, 0, sa);
+                d2h(hp.data(), d_part, hp.size() * sizeof(double));
+                double sum = 0.;
+                for (int i = 0; i < nb; i++) sum += hp[i];
+                GridScaleArgs ga2 = {N, grid[g], want[g] / (sum / (double)N)};
+                B200_LAUNCH(grid_scale_kernel, nb, 256, 0, ga2);
+            }
+        }
         d2h(grids->n_ion, d_nion, N * sizeof(float));
         d2h(grids->halo_sfr, d_sfr, N * sizeof(float));
         if (recomb) d2h(grids->whalo_sfr, d_wsfr, N * sizeof(float));

@@ -808,8 +808,10 @@ double Fcoll_General(double z, double lnMmin, double lnMmax) { /* hmf.c:945-953 
     });
 }
 double Nion_General(double z, double lnMmin, double lnMmax, double Mturn, const ScalingConstants *sc) {
-    const double args[4] = {z, lnMmin, lnMmax, Mturn}; /* sc derives from astro params (in the key) */
-    return memoised(3, true, args, 4, [&] {
+    /* the scaling constants are part of the key: callers also pass modified copies (evolve_scaling_constants_sfr) */
+    const double args[10] = {z, lnMmin, lnMmax, Mturn, sc->fstar_10, sc->alpha_star, sc->Mlim_Fstar,
+                             sc->fesc_10, sc->alpha_esc, sc->Mlim_Fesc};
+    return memoised(3, true, args, 10, [&] {
         MFParams p = mf_params(dicke(z), Mturn, sc); /* hmf.c:955-971 */
         p.redshift = z;
         return integrate_qag(lnMmin, lnMmax, p, 1);

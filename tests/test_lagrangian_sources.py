@@ -18,14 +18,17 @@ CASES = {
     "recomb_cell": (24, 48, 6.5, dict(USE_EXP_FILTER=True, RECOMB_MODEL="inhomogeneous", CELL_RECOMB=True), False),
     "recomb_filtered": (24, 48, 7.5, dict(USE_EXP_FILTER=False, RECOMB_MODEL="inhomogeneous", CELL_RECOMB=False), False),
     "hires_zeldovich": (24, 48, 7.0, dict(USE_EXP_FILTER=True, CELL_RECOMB=True), True),
+    # a mass function without a conditional form: the fixed grids are rescaled to the unconditional mean
+    "watson_mean_fix": (24, 48, 7.0, dict(USE_EXP_FILTER=False, RECOMB_MODEL="inhomogeneous", CELL_RECOMB=True), False),
 }
+HMF_OF = {"watson_mean_fix": "WATSON"}
 
 
 def _inputs(name):
     hii, dim, z, ao_over, hires = CASES[name]
     inp = common.make_inputs(hii=hii, dim=dim, seed=11, source="L-INTEGRAL", perturb="ZELDOVICH" if hires else "2LPT")
     ao = dataclasses.replace(inp.astro_options, **ao_over)
-    mo = dataclasses.replace(inp.matter_options, PERTURB_ON_HIGH_RES=hires)
+    mo = dataclasses.replace(inp.matter_options, PERTURB_ON_HIGH_RES=hires, HMF=HMF_OF.get(name, "ST"))
     return dataclasses.replace(inp, astro_options=ao, matter_options=mo), z
 
 
