@@ -1979,13 +1979,27 @@ static void ionize_core_lagrangian(float redshift_f, float prev_redshift_f, cons
     }
     const double dk0 = 2.0 * M_PI / so->BOX_LEN, dkz = 2.0 * M_PI / (so->BOX_LEN * so->NON_CUBIC_FACTOR);
     const int filter_hf = ao->USE_EXP_FILTER ? 3 : c.hii_filter;
+    /* top-hat / gaussian windows over |n|^2 as in the Eulerian ladder (cubic boxes): one table per radius, shared by
+       every grid that is filtered with HII_FILTER; the exponential filter keeps the per-mode double evaluation */
+    const bool cubic = nx == ny && ny == nz && so->NON_CUBIC_FACTOR == 1.0f;
+    const bool use_wtab = cubic && (c.hii_filter == 0 || c.hii_filter == 2);
+    const int wtab_n = use_wtab ? window_table_size(plan) : 0;
+    const size_t wtab3_n = use_wtab ? window_table3_size(plan) : 0;
+    const bool use_wtab3 = use_wtab && (nx & (nx - 1)) == 0 && nx >= 16 && wtab3_n * sizeof(float) <= ((size_t)1 << 30);
+    DevBuf<float> d_wtab((size_t)wtab_n), d_wtab3(use_wtab3 ? wtab3_n : 0);
     for (int k = 0; k < n_todo; k++) {
         const RadiusSpec &rs = radii[todo[k]];
         KMul km, kh; /* density / N_rec window, halo-field window */
         if (rs.R_index > 0) {
             km.kind = KMUL_FILTER; km.filter_type = c.hii_filter; km.R = (float)rs.R;
             km.dk[0] = dk0; km.dk[1] = dk0; km.dk[2] = dkz;
-            kh = km;
+            kh = km; /* the exact window unless it is the density's own */
+            if (use_wtab) { /* stream-ordered reuse of the one slot: the passes of the previous radius are enqueued before */
+                window_table_build(plan, c.hii_filter, km.R, dk0, d_wtab);
+                km.fast = 1; km.wtab = d_wtab; km.wtab_n = wtab_n;
+                if (use_wtab3) { window_table_expand(plan, d_wtab, d_wtab3); km.wtab3 = d_wtab3; }
+                if (filter_hf == c.hii_filter) kh = km;
+            }
             kh.filter_type = filter_hf;
             if (filter_hf == 3) { /* filter_box(.., 3, R, mfp, 0.) with float arguments (filtering.c:308,330) */
                 kh.R_param = (double)(float)c.mfp_meandens;
