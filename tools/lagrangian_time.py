@@ -31,7 +31,10 @@ def ms():
     return d.value
 
 
+be.lib.b200_profile_report.argtypes = [C.c_char_p, C.c_int]
 for rep in range(3):
+    if rep == 2:
+        be.lib.b200_profile_enable(1)
     t0 = time.perf_counter()
     hb = pkg.compute_halobox(redshift=7.0, initial_conditions=ics, backend=be)
     t1 = time.perf_counter()
@@ -39,3 +42,6 @@ for rep in range(3):
     t2 = time.perf_counter()
     print(f"HII_DIM={hii} {'exp-mfp' if exp_filter else 'top-hat'} filter: halobox {1e3 * (t1 - t0):.1f} ms wall, "
           f"ionize {1e3 * (t2 - t1):.1f} ms wall ({ms():.1f} ms device incl. copies), xH={ib.global_xH:.4f}")
+buf = C.create_string_buffer(1 << 16)
+be.lib.b200_profile_report(buf, len(buf))
+print(buf.value.decode())
