@@ -85,7 +85,7 @@ struct SweepArgs {
    true mean fix lies inside the bracket and decides the queued cells with the reference arithmetic.  If the
    prediction ever fails, flags may already be wrong: the kernel raises `failed` and the host re-runs the
    ladder of this call without speculation (never observed; the check is what makes the shortcut exact).
-   A queue that overflows only costs that radius a full flag sweep (spec_fallback). */
+   A queue segment that overflows (it holds a sixteenth of the CTA's cells; ~1.3 % are queued) does the same. */
 #define SPEC_EPS 0.02
 #define SPEC_MAX_RADII 64
 struct SpecState {
@@ -552,20 +552,27 @@ struct PlaneSumArgs {
     double *plane;
 };
 __global__ void plane_sum_kernel(PlaneSumArgs a) {
+#ifndef B200_EMU
+    /* one warp per plane: lane l adds the entries l, l + 32, ... in order, then a butterfly over the lanes -- a fixed
+       tree of the plane's entries, the same on every grid size and slab split */
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int x = warp; x < a.nx; x += nwarps) {
+        const double *p = a.partial + (long long)x * a.chunks_per_plane;
+        double acc = 0.;
+        for (int c = lane; c < a.chunks_per_plane; c += 32) acc += p[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) a.plane[x] = acc;
+    }
+#else
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.nx; x += gridDim.x * blockDim.x) {
         const double *p = a.partial + (long long)x * a.chunks_per_plane;
         double acc = 0.;
-        int c = 0;
-        for (; c + 8 <= a.chunks_per_plane; c += 8) { /* eight loads in flight, added in order */
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = p[c + u];
-#pragma unroll
-            for (int u = 0; u < 8; u++) acc += v[u];
-        }
-        for (; c < a.chunks_per_plane; c++) acc += p[c];
+        for (int c = 0; c < a.chunks_per_plane; c++) acc += p[c];
         a.plane[x] = acc;
     }
+#endif
 }
 
 struct CritArgs {
@@ -928,7 +935,7 @@ __global__ void __launch_bounds__(256) spec_resolve_kernel(CritDeltaArgs a) {
         unsigned int n = a.qcounts[sg];
         if (threadIdx.x == 0) {
             atomic_fetch_add_u32(&a.spec->qcount[a.j], n);
-            if (n > a.qcap) a.spec->overflow[a.j] = 1;
+            if (n > a.qcap) { a.spec->overflow[a.j] = 1; a.spec->failed = 1; } /* cells were dropped: the host re-runs the ladder */
         }
         if (n > a.qcap) n = a.qcap;
         const uint2 *seg = a.queue + (size_t)sg * a.qcap;
@@ -1729,7 +1736,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         if (pt.phase <= 0) dev_zero(d_mask, (size_t)NL);
         KeyInitArgs ka = {n_todo, sl ? keys_sym : d_keys.p};
         B200_LAUNCH(minmax_key_init_kernel, 1, 64, 0, ka);
-        if (verbose) fprintf(stderr, "[21cmfast_b200] ionize: mean-fix prediction left its bracket, ladder re-run without speculation\n");
+        if (verbose) fprintf(stderr, "[21cmfast_b200] ionize: mean-fix prediction left its bracket (or a queue segment overflowed), ladder re-run without speculation\n");
     }
     int next_enq = 0;
     if (n_mine > 0) enqueue_transform(next_enq++);
@@ -1804,7 +1811,7 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
         }
         {
             PlaneSumArgs ps = {nxl, chunks_per_plane * SWEEP_PARTIALS, d_partial, sl ? plane_sym + (size_t)k * nxl : d_plane.p};
-            B200_LAUNCH(plane_sum_kernel, (nxl + 31) / 32, 32, 0, ps);
+            B200_LAUNCH(plane_sum_kernel, (nxl + 7) / 8, 256, 0, ps); /* a warp per plane (a thread per plane in the emulation) */
             if (sl) dist_barrier_gather(reinterpret_cast<const unsigned long long *>(plane_sym + (size_t)k * nxl),
                                         reinterpret_cast<unsigned long long *>(d_plane.p), nxl);
         }
@@ -1819,12 +1826,14 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
             cd.n_cells = (double)N; cd.mean_f_coll = box->mean_f_coll; cd.f_limit = f_limit;
             cd.ion_eff_factor = c.ion_eff_factor; cd.mass_dep_zeta = c.mass_dep_zeta ? 1 : 0;
             if (use_spec) { cd.spec = d_spec.p; cd.j = j; cd.queue = d_queue.p; cd.qcounts = d_qcounts.p; cd.qcap = qcap; cd.n_seg = sum_blocks; }
-            if (spec_j) { /* queued cells, then (only if the queue overflowed) the full flag sweep */
+            if (spec_j) { /* the queued cells; an overflowing segment raises `failed` like a missed bracket (an empty
+                             fallback launch per radius cost 0.7 ms per step for a case that has not been observed) */
                 B200_LAUNCH(spec_resolve_kernel, dev_num_sms() * 2, 256, SWEEP_REP_BYTES, cd);
-                cd.only_if_overflow = 1;
+            } else if (htab.log_valued) {
+                B200_LAUNCH(ionise_delta_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
+            } else {
+                B200_LAUNCH(ionise_delta_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
             }
-            if (htab.log_valued) B200_LAUNCH(ionise_delta_kernel<true>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
-            else B200_LAUNCH(ionise_delta_kernel<false>, sweep_blocks, 256, SWEEP_REP_BYTES, cd);
             if (sphere) paint_spheres(rs.R);
         } else {
             if (io.wait_slot >= 0) main_wait_copy_event(io.wait_slot);
