@@ -288,6 +288,12 @@ static void class_free() {
     g_class.d_nodes = nullptr;
     g_class.ready = false;
 }
+/* called when the device-side caches are released (b200_release_device_cache, also on a device switch): the spline
+   nodes are uploaded again by the next ps_export_consts */
+void ps_device_tables_drop() {
+    if (g_class.d_nodes) dev_free(g_class.d_nodes);
+    g_class.d_nodes = nullptr;
+}
 static void class_init() {
     const Table1D *td = cosmo_tables_global->transfer_density;
     if (!td || td->size < 3 || !td->x_values || !td->y_values)

@@ -303,6 +303,7 @@ double DevTimer::stop_ms() { return (omp_get_wtime() - t0) * 1e3; }
 
 void ics_cache_drop();  /* perturb.cu */
 void fft_plans_drop();  /* fft.cu */
+void ps_device_tables_drop(); /* host_physics.cpp: device copy of the CLASS spline nodes */
 
 /* ------------------------------------------------------------------ output residency (rt.h) */
 struct ResidentEntry { const void *host; float *dev; size_t n; unsigned long long stamp; };
@@ -342,6 +343,7 @@ extern "C" void b200_residency(int enable) {
 
 extern "C" void b200_release_device_cache(void) {
     resident_clear();
+    ps_device_tables_drop();
     ics_cache_drop();
     fft_plans_drop();
     pool_drop();
