@@ -269,6 +269,24 @@ class SlabGroup:
         _agree(st, "b200_ComputeInitialConditions_slab", self.group)
         return out
 
+    def shift_hires(self, hires_natural):
+        """The hi-res planes ``perturb`` reads start half a low-res cell below the rank's slab (``hires_slab``); the
+        slab-decomposed ICs deliver the planes ``F x0 ... F (x0 + nxl)``.  Fetches the last ``F // 2`` planes of the
+        previous rank (periodic) with one small all-gather and returns the shifted slab."""
+        import torch
+        import torch.distributed as dist
+        h = self.F // 2
+        if h == 0:
+            return hires_natural
+        tail = hires_natural[-h:].contiguous()
+        if self.world > 1:
+            tails = [torch.empty_like(tail) for _ in range(self.world)]
+            dist.all_gather(tails, tail, group=self.group)
+            prev = tails[(self.rank - 1) % self.world]
+        else:
+            prev = tail
+        return torch.cat([prev, hires_natural[:-h]]).contiguous()
+
     def perturb(self, *, redshift: float, ics_slab: dict):
         """ics_slab: device tensors of this rank's slabs (``hires_density`` from ``hires_slab``, the low-res
         velocity boxes from ``lowres_slab``).  Returns ``dict(density, velocity_z)`` slabs."""

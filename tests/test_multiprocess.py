@@ -120,9 +120,11 @@ for hii, dim, kw in {cases}:
         want = full[rank * hn:(rank + 1) * hn] if k == "hires_density" else grp.lowres_slab(full)
         assert np.array_equal(t.numpy(), want), (hii, k, float(np.abs(t.numpy() - want).max()))
     lo = ["lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
-    slab = {{k: torch.from_numpy(np.ascontiguousarray(grp.lowres_slab(getattr(ics, k)))) for k in lo
-            if getattr(ics, k) is not None}}
-    slab["hires_density"] = torch.from_numpy(grp.hires_slab(ics.hires_density))
+    # the whole pipeline on slabs: the ICs made slab by slab feed the slab perturb (half-cell shift of the hi-res planes
+    # through one small all-gather), which feeds the slab ionize -- no whole box anywhere
+    slab = {{k: sics[k] for k in lo if k in sics}}
+    slab["hires_density"] = grp.shift_hires(sics["hires_density"])
+    assert np.array_equal(slab["hires_density"].numpy(), grp.hires_slab(ics.hires_density))
     ppf = grp.perturb(redshift=8.0, ics_slab=slab)
     for k in ("density", "velocity_z"):                  # slab deposit + halo pull + slab FFTs: bit-identical
         a, b = ppf[k].numpy(), grp.lowres_slab(getattr(pf, k))
