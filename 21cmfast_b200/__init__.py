@@ -9,7 +9,7 @@ wrapper/driver layer for that path.  The directory name starts with a digit, so 
 """
 from .drivers import (brightness_temperature, compute_halobox, compute_initial_conditions,  # noqa: F401
                       compute_ionization_field, get_logspaced_redshifts, perturb_field,
-                      run_coeval)
+                      run_coeval, run_coeval_parallel)
 from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  # noqa: F401
                      MatterOptions, SimulationOptions)
 from .outputs import (BrightnessTemp, HaloBox, InitialConditions, IonizedBox,  # noqa: F401

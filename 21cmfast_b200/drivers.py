@@ -223,3 +223,48 @@ def _run_coeval(outs, inputs, ics, backend):
         if z in nodes:
             prev_pf, prev_ib = pf, ib
     return out
+
+
+def run_coeval_parallel(*, out_redshifts, inputs: InputParameters, initial_conditions: InitialConditions,
+                        backend: Backend | None = None, group=None):
+    """The redshifts of a coeval run (or the snapshots of a lightcone) spread over the GPUs of a node, one process per
+    GPU (``drivers/coeval.py:782-853`` loops over them on one device).  Every rank holds
+    the same ``initial_conditions`` in host memory and takes the redshifts ``rank, rank + world, ...`` of the sorted
+    list; the ranks call ``perturb_field`` in lockstep so that the upload of the initial conditions is shared
+    (``SlabGroup.share_ics``: 1 / world of the arrays per PCIe link, the rest over NVLink).  Returns this rank's
+    results, highest redshift first, as ``run_coeval`` does.  Needs options without evolution across redshifts."""
+    import torch.distributed as dist
+
+    from .distributed import SlabGroup
+    if inputs.evolution_required:
+        raise ValueError("redshifts are independent only without USE_TS_FLUCT, recombinations and mini-halos")
+    be = backend or get_backend()
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    zs = sorted((float(z) for z in out_redshifts), reverse=True)
+    rounds = (len(zs) + world - 1) // world
+    lagrangian = inputs.matter_options.lagrangian_source_grid
+    grp = SlabGroup(inputs=inputs, backend=be, group=group, heap_bytes=SlabGroup.ics_heap_bytes(inputs))
+    residency = getattr(be.lib, "b200_residency", None) if hasattr(be.lib, "b200_residency") else None
+    out = []
+    try:
+        grp.share_ics(world > 1)
+        if residency is not None:  # density / neutral fraction stay on the device between the three calls of a redshift
+            residency.argtypes, residency.restype = [C.c_int], None
+            residency(1)
+        for r in range(rounds):
+            i = r * world + rank
+            mine = i < len(zs)
+            z = zs[i] if mine else zs[-1]  # a rank without work in the last round still takes part in the shared upload
+            pf = perturb_field(redshift=z, initial_conditions=initial_conditions, backend=be)
+            if not mine:
+                continue
+            hb = compute_halobox(redshift=z, initial_conditions=initial_conditions, backend=be) if lagrangian else None
+            ib = compute_ionization_field(perturbed_field=pf, initial_conditions=initial_conditions, halobox=hb, backend=be)
+            bt = brightness_temperature(ionized_box=ib, perturbed_field=pf, backend=be)
+            out.append({"redshift": z, "perturbed_field": pf, "ionized_box": ib, "brightness_temp": bt})
+    finally:
+        if residency is not None:
+            residency(0)
+        grp.close()
+    return out

@@ -208,3 +208,46 @@ def test_gloo_shared_initial_conditions(tmp_path, nproc):
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert "OK shared ics" in r.stdout
+
+
+WORKER_COEVAL = r'''
+import os, sys
+sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
+import numpy as np, torch, torch.distributed as dist
+import common
+pkg = common.pkg
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+emu = common.emu_backend()
+inputs = common.make_inputs(hii=16, dim=32, seed=7)
+ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+zs = (9.0, 8.0, 7.0)                                    # three redshifts on two ranks: the last round has an idle rank
+mine = pkg.run_coeval_parallel(out_redshifts=zs, inputs=inputs, initial_conditions=ics, backend=emu)
+serial = {{r["redshift"]: r for r in pkg.run_coeval(out_redshifts=zs, inputs=inputs, initial_conditions=ics, backend=emu)}}
+want = sorted(zs, reverse=True)[rank::world]
+assert [r["redshift"] for r in mine] == want, (rank, [r["redshift"] for r in mine], want)
+for r in mine:
+    s = serial[r["redshift"]]
+    for key in ("perturbed_field", "ionized_box", "brightness_temp"):
+        for k, v in s[key].arrays().items():
+            assert np.array_equal(v, r[key].arrays()[k]), (rank, r["redshift"], key, k)
+n = torch.tensor([float(len(mine))]); dist.all_reduce(n)
+assert n.item() == len(zs)
+if rank == 0: print("OK coeval parallel", world, want)
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_redshift_parallel_coeval(tmp_path):
+    """run_coeval_parallel: the redshifts of a run round-robin over two ranks on shared initial conditions, every box
+    identical to the serial run_coeval's."""
+    if not (ROOT / "tests" / "_emu" / "libb200_emu.so").exists():
+        pytest.skip("tests/_emu not built")
+    script = tmp_path / "worker_coeval.py"
+    script.write_text(WORKER_COEVAL.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert "OK coeval parallel" in r.stdout
