@@ -77,7 +77,7 @@ struct SweepArgs {
    the reference (and ionise_delta_kernel) walk the filtered grid a second time.  The mean fix, however,
    drifts by well under a per cent from one radius of the ladder to the next.  The sum sweep therefore
    classifies every cell against a BRACKET of the mean fix predicted from the two previous radii
-   (geometric extrapolation, +- SPEC_EPS): cells that are ionised for every mean fix inside the bracket
+   (geometric extrapolation, +- SPEC_EPS or 0.3 SPEC_EPS, see spec_bracket): cells that are ionised for every mean fix inside the bracket
    are flagged at once, cells that are neutral for every mean fix inside it are skipped, and the few cells
    in between are queued (4-byte cell indices; every CTA fills a private segment of the queue behind a
    shared-memory counter -- one global counter serialised the sweep: 0.95 ms per radius against 0.19).  Once
@@ -99,13 +99,23 @@ struct SpecBracket {
     double gain_lo, gain_hi; /* mean_fix zeta at the ends of the bracket */
 };
 DEV SpecBracket spec_bracket(const SpecState *sp, int j, double ion_eff_factor) {
+    /* geometric extrapolation of the mean fix from the previous radii: first order (ratio of the last two) for the
+       third radius of a call, second order (the ratio's own ratio) from the fourth on -- the mean fix is a smooth
+       function of the radius, and the second-order prediction misses it by 0.08-0.14 % where the first-order one
+       misses by 0.55 % (512^3 and 32^3 ladders, both source models), so its bracket is 0.3 eps wide and the queue
+       a third as long */
     const double p1 = sp->mean_fix[j - 1], p2 = sp->mean_fix[j - 2];
-    double ratio = p1 / p2;
+    double ratio = p1 / p2, half = sp->eps;
     if (!(ratio > 0.5 && ratio < 2.0)) ratio = 1.0;
+    if (j >= 3) {
+        const double r2 = p2 / sp->mean_fix[j - 3];
+        const double accel = ratio / r2;
+        if (r2 > 0.5 && r2 < 2.0 && accel > 0.9 && accel < 1.1) { ratio *= accel; half *= 0.3; }
+    }
     const double pred = p1 * ratio;
     SpecBracket b;
-    b.gain_lo = pred * (1.0 - sp->eps) * ion_eff_factor;
-    b.gain_hi = pred * (1.0 + sp->eps) * ion_eff_factor;
+    b.gain_lo = pred * (1.0 - half) * ion_eff_factor;
+    b.gain_hi = pred * (1.0 + half) * ion_eff_factor;
     return b;
 }
 
@@ -1366,7 +1376,13 @@ static int sweep_chunk_rows(int ny, int nz) {
 }
 /* CTAs of the sum sweep: the largest divisor of the chunk count that is resident at once (no tail) */
 static int sweep_grid(long long nchunks) {
-    const long long cap = (long long)dev_num_sms() * 8;
+    static int mult = 0; /* resident 256-thread CTAs per SM the sweeps are sized for (B200_SWEEP_CTAS overrides) */
+    if (mult == 0) {
+        const char *e = getenv("B200_SWEEP_CTAS");
+        mult = e ? atoi(e) : 8;
+        if (mult < 1 || mult > 16) mult = 8;
+    }
+    const long long cap = (long long)dev_num_sms() * mult;
     if (nchunks <= cap) return (int)(nchunks > 0 ? nchunks : 1);
     for (long long g = cap; g >= cap / 2; g--)
         if (nchunks % g == 0) return (int)g;
