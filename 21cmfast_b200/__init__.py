@@ -7,7 +7,8 @@ is the C-ABI shared library ``csrc/lib21cmfast_b200.so`` (hand-written CUDA + C 
 wrapper/driver layer for that path.  The directory name starts with a digit, so import it with
 ``importlib.import_module("21cmfast_b200")``.
 """
-from .drivers import (brightness_temperature, compute_halobox, compute_initial_conditions,  # noqa: F401
+from .drivers import (brightness_temperature, compute_halo_grid, compute_halobox,  # noqa: F401
+                      compute_initial_conditions,
                       compute_ionization_field, get_logspaced_redshifts, perturb_field,
                       run_coeval, run_coeval_parallel)
 from .inputs import (AstroOptions, AstroParams, CosmoParams, InputParameters,  # noqa: F401

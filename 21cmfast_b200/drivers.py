@@ -79,6 +79,19 @@ def compute_halobox(*, redshift: float, initial_conditions: InitialConditions,
     return hb
 
 
+def compute_halo_grid(*, redshift: float, initial_conditions: InitialConditions, inputs: InputParameters | None = None,
+                      halo_catalog=None, previous_spin_temp: TsBox | None = None,
+                      previous_ionize_box: IonizedBox | None = None, backend: Backend | None = None) -> HaloBox:
+    """The reference's name and keywords for ``compute_halobox`` (``drivers/single_field.py:297-380``).  A sampled
+    ``halo_catalog`` is outside the scoped path: only the integrated grids of ``SOURCE_MODEL='L-INTEGRAL'`` are built."""
+    if halo_catalog is not None:
+        raise NotImplementedError("sampled halo catalogues are outside the scoped path (SURVEY.md section 8)")
+    if inputs is not None and inputs != initial_conditions.inputs:
+        raise ValueError("inputs differ from the ones the initial conditions were made with")
+    return compute_halobox(redshift=redshift, initial_conditions=initial_conditions, previous_spin_temp=previous_spin_temp,
+                           previous_ionize_box=previous_ionize_box, backend=backend)
+
+
 def compute_ionization_field(*, perturbed_field: PerturbedField,
                              initial_conditions: InitialConditions,
                              previous_perturbed_field: PerturbedField | None = None,

@@ -117,3 +117,21 @@ def test_run_coeval_builds_the_halo_boxes_for_lagrangian_sources():
         assert np.array_equal(ib.neutral_fraction, g["ionized_box"].neutral_fraction)
         assert np.isfinite(g["brightness_temp"].brightness_temp).all()
     assert got[1]["ionized_box"].global_xH < got[0]["ionized_box"].global_xH
+
+
+def test_compute_halo_grid_is_the_reference_named_entry():
+    """``compute_halo_grid`` (the reference driver's name and keywords) is ``compute_halobox``; a sampled catalogue or a
+    source model that needs one is refused loudly."""
+    be = common.emu_backend()
+    if be is None:
+        pytest.skip("tests/_emu not built")
+    inputs, z = _inputs("plain")
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    a = pkg.compute_halo_grid(redshift=z, initial_conditions=ics, inputs=inputs, backend=be)
+    b = pkg.compute_halobox(redshift=z, initial_conditions=ics, backend=be)
+    assert np.array_equal(a.n_ion, b.n_ion) and np.array_equal(a.halo_sfr, b.halo_sfr)
+    with pytest.raises(NotImplementedError):
+        pkg.compute_halo_grid(redshift=z, initial_conditions=ics, halo_catalog=object(), backend=be)
+    eul = common.make_inputs(hii=16, dim=32, source="E-INTEGRAL")
+    with pytest.raises(NotImplementedError):
+        pkg.compute_halobox(redshift=z, initial_conditions=pkg.compute_initial_conditions(inputs=eul, backend=be), backend=be)
