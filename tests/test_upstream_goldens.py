@@ -6,6 +6,8 @@ This is the reference's ``tests/test_integration_features.py`` restated for the 
 reference asserts (``test_integration_features.py:306-309``: atol 5e-3, rtol 1e-3).  The reference only *prints* the
 coeval differences at rtol 1e-4 (``:69-80``); here they are asserted at the rtol its lightcone test uses for the same
 fields (1e-3 for most, ``:120-131``), with the bins that are numerically empty in the golden compared absolutely.
+The global signals (mean x_HI and T_b at every node redshift, up to 18 chained snapshots with recombinations) are
+asserted at rtol 1e-3 as the reference does (``:166-168``).
 
 The goldens were produced upstream, with the real GSL / FFTW / OpenMP: they pin the oracle (oracle/_ref, the compiled
 reference over this repo's GSL / FFTW shims, N_THREADS=2 generator set included) *and* the product, independently of
@@ -18,7 +20,8 @@ import common
 import powerspec
 
 pkg = common.pkg
-GOLD = np.load(common.GOLDEN / "upstream_goldens.npz")
+with np.load(common.GOLDEN / "upstream_goldens.npz") as _z:
+    GOLD = {k: _z[k] for k in _z.files}
 
 # produce_integration_test_data.py:46-63
 SEED = 12345
@@ -43,11 +46,14 @@ OPTIONS_COEVAL = {
 }
 
 
-def _inputs(redshift, **kwargs):
-    """get_all_options_struct + get_node_z (produce_integration_test_data.py:292-344) without USE_TS_FLUCT."""
+def _inputs(redshift, lc=False, **kwargs):
+    """get_all_options_struct + get_node_z (produce_integration_test_data.py:292-344) without USE_TS_FLUCT: nodes
+    up to z + 2, or up to Z_HEAT_MAX when the boxes evolve."""
     node = None
-    if kwargs.get("RECOMB_MODEL", "none") != "none":
-        node = pkg.get_logspaced_redshifts(min_redshift=redshift, max_redshift=redshift + 2,
+    evolves = kwargs.get("RECOMB_MODEL", "none") != "none"
+    if lc or evolves:
+        zmax = pkg.SimulationOptions().Z_HEAT_MAX if evolves else redshift + 2
+        node = pkg.get_logspaced_redshifts(min_redshift=redshift, max_redshift=zmax,
                                            z_step_factor=DEFAULTS["ZPRIME_STEP_FACTOR"])
     # USE_LYA_HEATING only acts inside the spin-temperature calculation; off, so that the heating table (not part
     # of the scoped path's data) need not exist
@@ -90,10 +96,18 @@ COEVAL_RTOL = {"neutral_fraction": 5e-3, "brightness_temp": 5e-3, "z_reion": 5e-
 
 def _check_coeval(be, name):
     redshift, kwargs = OPTIONS_COEVAL[name]
-    inputs = _inputs(redshift, **kwargs)
+    inputs = _inputs(redshift, lc=True, **kwargs)
     ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
-    out = pkg.run_coeval(out_redshifts=redshift, inputs=inputs, initial_conditions=ics, backend=be)[-1]
-    assert out["redshift"] == redshift
+    # the node redshifts of the reference's lightcone run; its coeval run is the last of them
+    outs = pkg.run_coeval(inputs=inputs, initial_conditions=ics, backend=be)
+    assert [o["redshift"] for o in outs] == [float(z) for z in inputs.node_redshifts]
+    # test_integration_features.py:166-168: the global signal of every node, asserted at rtol 1e-3
+    for key, field in (("neutral_fraction", lambda o: o["ionized_box"].neutral_fraction),
+                       ("brightness_temp", lambda o: o["brightness_temp"].brightness_temp)):
+        got = [float(np.mean(field(o), dtype=np.float64)) for o in outs]
+        np.testing.assert_allclose(got, GOLD[f"lightcone/{name}/global_{key}"], atol=0, rtol=1e-3, err_msg=key)
+    out = outs[-1]
+    assert abs(out["redshift"] - redshift) < 1e-9
     pt, ib, bt = out["perturbed_field"], out["ionized_box"], out["brightness_temp"]
     assert np.all(np.isfinite(bt.brightness_temp))
     fields = {
