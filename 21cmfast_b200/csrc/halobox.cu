@@ -193,13 +193,12 @@ extern "C" int ComputeHaloBox(double redshift, InitialConditions *ini_boxes, Hal
                                         "the upper stellar turnover and photon conservation are not built");
         if (mo->USE_INTERPOLATION_TABLES != 2)
             b200_throw(B200_ValueError, "this build needs USE_INTERPOLATION_TABLES='hmf-interpolation'");
-        if (mo->PERTURB_ALGORITHM == PERTURB_LINEAR)
-            b200_throw(B200_ValueError, "ComputeHaloBox: the Lagrangian grids need PERTURB_ALGORITHM = ZELDOVICH or 2LPT");
         if (!ini_boxes || !grids || !grids->n_ion || !grids->halo_sfr)
             b200_throw(B200_ValueError, "ComputeHaloBox: NULL struct/array");
         const bool recomb = ao->RECOMB_MODEL != 0;
         if (recomb && !grids->whalo_sfr) b200_throw(B200_ValueError, "ComputeHaloBox: RECOMB_MODEL != none needs whalo_sfr");
         const bool hires = mo->PERTURB_ON_HIGH_RES;
+        /* PERTURB_ALGORITHM = LINEAR moves the sources by the first-order velocities, like ZELDOVICH (map_mass.c:269-283) */
         const bool lpt2 = mo->PERTURB_ALGORITHM == PERTURB_2LPT;
         const int on[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
         const int dn[3] = {hires ? so->DIM : so->HII_DIM, hires ? so->DIM : so->HII_DIM, hires ? d_para() : hii_d_para()};

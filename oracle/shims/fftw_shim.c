@@ -245,8 +245,56 @@ fftwf_plan fftwf_plan_dft_c2r_3d(int n0, int n1, int n2, fftwf_complex *in, floa
     if ((void *)in != (void *)out) { fprintf(stderr, "oracle fftw shim: in-place only\n"); abort(); }
     return mkplan(n0, n1, n2, in, 1);
 }
+/* The reference feeds c2r planes that are NOT Hermitian: multiplying by i k at the Nyquist index gives
+ * F(N/2, j, 0) and F(N/2, -j, 0) the same factor instead of conjugate ones (InitialConditions.c velocity
+ * modes, PerturbedField.c:344-345).  FFTW's answer for such input is fixed by its algorithm -- complex
+ * transforms over axes 0 and 1 of the stored half, then the real transform along axis 2, which drops the
+ * imaginary parts of the self-conjugate bins -- and `own` is that algorithm.  MKL agrees for every cubic and
+ * near-cubic shape, but picks another order for some small, strongly non-cubic ones (12x12x15, 10x10x12,
+ * 8x8x30 ...: measured, tests/test_oracle_shims.py), where its answer differs at the 1e-3 level.  Shapes up to
+ * 2^18 cells are therefore probed once with arbitrary complex input; a shape on which MKL is not FFTW-like
+ * runs its c2r on `own`.  Larger shapes (the cubic production grids) are not probed. */
+#define PROBE_MAX_CELLS (1L << 18)
+static struct { int n0, n1, n2, fftw_like; } probe_cache[64];
+static int probe_count = 0;
+
+static int mkl_c2r_is_fftw_like(int n0, int n1, int n2) {
+    for (int i = 0; i < probe_count; i++)
+        if (probe_cache[i].n0 == n0 && probe_cache[i].n1 == n1 && probe_cache[i].n2 == n2) return probe_cache[i].fftw_like;
+    const size_t nc = (size_t)(n2 / 2 + 1), count = (size_t)n0 * n1 * nc;
+    cpx *a = (cpx *)fftwf_malloc(sizeof(cpx) * count), *b = (cpx *)fftwf_malloc(sizeof(cpx) * count);
+    unsigned int lcg = 12345u;
+    for (size_t i = 0; i < count; i++) {
+        lcg = lcg * 1664525u + 1013904223u; const float re = (float)(lcg >> 8) / 8388608.0f - 1.0f;
+        lcg = lcg * 1664525u + 1013904223u; const float im = (float)(lcg >> 8) / 8388608.0f - 1.0f;
+        a[i] = b[i] = re + im * _Complex_I;
+    }
+    struct oracle_fftwf_plan_s pa = {n0, n1, n2, 1, a}, pb = {n0, n1, n2, 1, b};
+    int like = 0;
+    if (mkl_execute(&pa) == 0) {
+        own_execute(&pb);
+        float worst = 0.0f, scale = 0.0f;
+        for (int i = 0; i < n0 * n1; i++)
+            for (int k = 0; k < n2; k++) {
+                const float x = ((float *)a)[(size_t)i * 2 * nc + k], y = ((float *)b)[(size_t)i * 2 * nc + k];
+                if (fabsf(x - y) > worst) worst = fabsf(x - y);
+                if (fabsf(y) > scale) scale = fabsf(y);
+            }
+        like = worst <= 1e-3f * scale;
+    }
+    fftwf_free(a); fftwf_free(b);
+    if (probe_count < 64) {
+        probe_cache[probe_count].n0 = n0; probe_cache[probe_count].n1 = n1; probe_cache[probe_count].n2 = n2;
+        probe_cache[probe_count++].fftw_like = like;
+    }
+    return like;
+}
+
 void fftwf_execute(const fftwf_plan p) {
-    if (mkl_load() && mkl_execute(p) == 0) return;
+    if (mkl_load()) {
+        const int probe = p->inverse && (long)p->n0 * p->n1 * p->n2 <= PROBE_MAX_CELLS;
+        if ((!probe || mkl_c2r_is_fftw_like(p->n0, p->n1, p->n2)) && mkl_execute(p) == 0) return;
+    }
     own_execute(p);
 }
 void fftwf_destroy_plan(fftwf_plan p) { free(p); }

@@ -20,13 +20,16 @@ CASES = {
     "hires_zeldovich": (24, 48, 7.0, dict(USE_EXP_FILTER=True, CELL_RECOMB=True), True),
     # a mass function without a conditional form: the fixed grids are rescaled to the unconditional mean
     "watson_mean_fix": (24, 48, 7.0, dict(USE_EXP_FILTER=False, RECOMB_MODEL="inhomogeneous", CELL_RECOMB=True), False),
+    # PERTURB_ALGORITHM = LINEAR: the sources still move, by the first-order velocities (map_mass.c:269-283)
+    "linear_perturb": (24, 48, 7.0, dict(USE_EXP_FILTER=False), False),
 }
 HMF_OF = {"watson_mean_fix": "WATSON"}
+PERTURB_OF = {"hires_zeldovich": "ZELDOVICH", "linear_perturb": "LINEAR"}
 
 
 def _inputs(name):
     hii, dim, z, ao_over, hires = CASES[name]
-    inp = common.make_inputs(hii=hii, dim=dim, seed=11, source="L-INTEGRAL", perturb="ZELDOVICH" if hires else "2LPT")
+    inp = common.make_inputs(hii=hii, dim=dim, seed=11, source="L-INTEGRAL", perturb=PERTURB_OF.get(name, "2LPT"))
     ao = dataclasses.replace(inp.astro_options, **ao_over)
     mo = dataclasses.replace(inp.matter_options, PERTURB_ON_HIGH_RES=hires, HMF=HMF_OF.get(name, "ST"))
     return dataclasses.replace(inp, astro_options=ao, matter_options=mo), z
@@ -74,6 +77,16 @@ def _check(be, name):
         out["crossing_mismatch"] = int((~crossing).sum())
         assert out["crossing_mismatch"] <= max(2, common.TOL_MASK_FRACTION * mask_r.size), out
         same &= crossing
+    # the partial ionisations divide the source grid by (1 + delta) (IonisationBox.c:1054-1066): in the nearly empty
+    # cells a linearly evolved density allows (delta -> -1), float rounding of either side is amplified by
+    # 1 / (1 + delta); those cells are compared with the bar scaled accordingly
+    cond = np.maximum(1.0 + pf[z].density.astype(np.float64), 1e-3)
+    thin = cond < 0.1
+    if thin.any():
+        d = np.abs(ib.neutral_fraction.astype(np.float64) - r_ib.neutral_fraction)[same & thin]
+        assert np.all(d <= common.TOL_FIELD / cond[same & thin]), float(d.max())
+        out["thin_cells"] = int(thin.sum())
+        same &= ~thin
     for k, rv in r_ib.arrays().items():
         tv = ib.arrays()[k]
         e = common.rel_err(tv[same], rv[same])

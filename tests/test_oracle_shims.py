@@ -199,3 +199,36 @@ print('mkl' if lib.oracle_fft_backend_is_mkl() else 'own')
     assert r.returncode == 0, r.stderr[-2000:]
     if backend == "own":
         assert r.stdout.strip() == "own"
+
+
+@pytest.mark.parametrize("backend", ["own", "mkl"])
+def test_fftw_shim_c2r_of_non_hermitian_input_follows_fftw(backend):
+    """The reference hands c2r planes that are not Hermitian (i k at the Nyquist index: InitialConditions.c
+    velocity modes, PerturbedField.c:344-345).  FFTW's answer is fixed by its algorithm: complex transforms over
+    axes 0 and 1 of the stored half, then the real transform along axis 2 (imaginary parts of the self-conjugate
+    bins dropped) -- numpy's ifft2 + irfft below.  MKL alone differs on small non-cubic shapes (0.1 relative on
+    12x12x15); the shim probes such shapes once and runs them on its own FFT."""
+    code = f"""
+import ctypes as C, numpy as np, os
+os.environ['ORACLE_FFT'] = '{backend}'
+if '{backend}' == 'mkl':
+    import torch
+    os.environ['ORACLE_TORCH_LIB'] = os.path.join(os.path.dirname(torch.__file__), 'lib', 'libtorch_cpu.so')
+lib = C.CDLL('{SHIM}')
+lib.fftwf_plan_dft_c2r_3d.restype = C.c_void_p
+lib.fftwf_plan_dft_c2r_3d.argtypes = [C.c_int]*3 + [C.c_void_p, C.c_void_p, C.c_uint]
+lib.fftwf_execute.argtypes = [C.c_void_p]
+for n0, n1, n2 in [(12, 12, 15), (10, 10, 12), (8, 8, 30), (8, 8, 7), (16, 16, 16), (12, 12, 18), (24, 24, 36), (50, 50, 50)]:
+    nc = n2 // 2 + 1
+    rng = np.random.default_rng(3)
+    g = (rng.normal(size=(n0, n1, nc)) + 1j * rng.normal(size=(n0, n1, nc))).astype(np.complex64)
+    buf = np.zeros((n0, n1, 2 * nc), np.float32)
+    buf.view(np.complex64).reshape(n0, n1, nc)[...] = g
+    p = lib.fftwf_plan_dft_c2r_3d(n0, n1, n2, buf.ctypes.data, buf.ctypes.data, 64)
+    lib.fftwf_execute(p)
+    exp = np.fft.irfft(np.fft.ifft2(g.astype(np.complex128), axes=(0, 1)), n=n2, axis=2) * (n0 * n1 * n2)
+    err = np.abs(buf[:, :, :n2] - exp).max() / np.abs(exp).max()
+    assert err < 2e-6, ((n0, n1, n2), err)
+"""
+    r = subprocess.run(["python", "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
