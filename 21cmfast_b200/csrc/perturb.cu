@@ -782,8 +782,9 @@ static void perturb_core_slab(float redshift_f, const PerturbDeviceIO &io) {
     const SimulationOptions *so = simulation_options_global;
     const MatterOptions *mo = matter_options_global;
     dist_require();
-    if (mo->PERTURB_ON_HIGH_RES || mo->PERTURB_ALGORITHM == PERTURB_LINEAR)
-        b200_throw(B200_ValueError, "the slab-decomposed perturbed field needs PERTURB_ALGORITHM = ZELDOVICH or 2LPT on the low-res grid");
+    if (mo->PERTURB_ON_HIGH_RES)
+        b200_throw(B200_ValueError, "the slab-decomposed perturbed field works on the low-res grid (PERTURB_ON_HIGH_RES = False)");
+    const bool linear = mo->PERTURB_ALGORITHM == PERTURB_LINEAR;
     const double redshift = redshift_f;
     const int hn[3] = {so->HII_DIM, so->HII_DIM, hii_d_para()};
     const int dn[3] = {so->DIM, so->DIM, d_para()};
@@ -801,68 +802,78 @@ static void perturb_core_slab(float redshift_f, const PerturbDeviceIO &io) {
     float *padded = reinterpret_cast<float *>(work.p);
 
     const double growth = dicke(redshift);
-    MoveArgs a;
-    memset(&a, 0, sizeof(a));
-    const double boxlen = so->BOX_LEN, boxlen_z = boxlen * so->NON_CUBIC_FACTOR;
-    const double box_size[3] = {boxlen, boxlen, boxlen_z};
-    const double init_growth = dicke(so->INITIAL_REDSHIFT);
-    const double d2 = -(3.0 / 7.0) * growth * growth, d2i = -(3.0 / 7.0) * init_growth * init_growth;
-    for (int ax = 0; ax < 3; ax++) {
-        a.dn[ax] = dn[ax]; a.vn[ax] = hn[ax]; a.on[ax] = hn[ax];
-        a.v[ax] = io.v[ax];
-        a.v2[ax] = (mo->PERTURB_ALGORITHM == PERTURB_2LPT) ? io.v2[ax] : nullptr;
-        a.vdf[ax] = (growth - init_growth) / box_size[ax] * dn[ax];
-        a.vdf2[ax] = (d2 - d2i) / box_size[ax] * dn[ax];
-    }
-    a.vn[0] = nxl; /* local velocity planes */
-    a.dens = io.hires_density;
-    a.ratio_vel = (double)hn[0] / (double)dn[0];
-    a.ratio_out = (double)hn[0] / (double)dn[0];
-    a.init_growth = init_growth;
-
-    /* halo width from the largest x displacement of the whole box */
-    int *keys_sym = (int *)dist_alloc(2 * sizeof(int));
-    DevBuf<int> d_keys(2), d_over(1);
+    DevBuf<int> d_over(1);
     dev_zero(d_over, sizeof(int));
-    {
-        const int init[2] = {2147483647, -2147483647 - 1};
-        h2d(keys_sym, init, sizeof(init));
-        g_stats.h2d -= (long long)sizeof(init);
-        MaxDispArgs ma = {(long long)nxl * plane, a.v[0], a.v2[0], a.vdf[0], a.vdf2[0], a.ratio_out, keys_sym};
-        B200_LAUNCH(max_disp_kernel, dev_num_sms() * 4, 256, 0, ma);
-        dist_barrier_minmax(keys_sym, d_keys);
-    }
-    int hkeys[2];
-    d2h(hkeys, d_keys, sizeof(hkeys));
-    g_stats.d2h -= (long long)sizeof(hkeys);
-    const double max_disp = (double)float_from_order_key(hkeys[1]);
-    int halo = (int)ceil(max_disp) + 2;
-    if (const char *e = getenv("B200_SLAB_HALO")) halo = atoi(e);
-    if (halo < 1) halo = 1;
-    if (halo > nxl)
-        b200_throw(B200_ValueError, "slab deposit: displacements of %.1f cells exceed the slab thickness %d (use fewer ranks)", max_disp, nxl);
-
-    a.vel_x0 = x0;
-    a.dens_x0 = F * x0 - F / 2;
-    a.out_x0 = x0 - halo;
-    a.out_nxl = nxl + 2 * halo;
-    a.overflow = d_over;
-    const size_t acc_n = (size_t)a.out_nxl * plane;
-    unsigned long long *acc = (unsigned long long *)dist_alloc(acc_n * sizeof(unsigned long long));
-    dev_zero(acc, acc_n * sizeof(unsigned long long));
-    a.acc = acc;
-    const long long ngroups = (long long)nxl * plane;
-    if (F == 1) launch_grouped<1>(a, 0, ngroups);
-    else if (F == 2) launch_grouped<2>(a, 0, ngroups);
-    else if (F == 3) launch_grouped<3>(a, 0, ngroups);
-    else launch_grouped<4>(a, 0, ngroups);
-    dist_barrier(); /* every rank's deposit has landed before the halos are pulled */
-    {
+    int halo = 0;
+    if (linear) { /* PerturbedField.c:66-82: the linear field of the rank's own planes, nothing moves */
+        if (!io.lowres_density) b200_throw(B200_ValueError, "slab perturb (LINEAR): lowres_density slab is NULL");
         const int row_blocks = (int)((long long)nxl * hn[1] < 4096 ? (long long)nxl * hn[1] : 4096);
-        AccSlabArgs ca = {nxl, halo, plane, hn[1], hn[2], plan->pitch, acc,
-                          dist_peer(acc, (slab.rank + P - 1) % P), dist_peer(acc, (slab.rank + 1) % P), padded,
-                          (double)N / (double)M};
-        B200_LAUNCH(acc_to_delta_slab_kernel, row_blocks, 256, 0, ca);
+        LinearArgs la = {(long long)nxl * hn[1], hn[2], plan->pitch, io.lowres_density, padded, growth};
+        B200_LAUNCH(linear_density_kernel, row_blocks, 256, 0, la);
+    } else {
+        MoveArgs a;
+        memset(&a, 0, sizeof(a));
+        const double boxlen = so->BOX_LEN, boxlen_z = boxlen * so->NON_CUBIC_FACTOR;
+        const double box_size[3] = {boxlen, boxlen, boxlen_z};
+        const double init_growth = dicke(so->INITIAL_REDSHIFT);
+        const double d2 = -(3.0 / 7.0) * growth * growth, d2i = -(3.0 / 7.0) * init_growth * init_growth;
+        for (int ax = 0; ax < 3; ax++) {
+            a.dn[ax] = dn[ax]; a.vn[ax] = hn[ax]; a.on[ax] = hn[ax];
+            a.v[ax] = io.v[ax];
+            a.v2[ax] = (mo->PERTURB_ALGORITHM == PERTURB_2LPT) ? io.v2[ax] : nullptr;
+            a.vdf[ax] = (growth - init_growth) / box_size[ax] * dn[ax];
+            a.vdf2[ax] = (d2 - d2i) / box_size[ax] * dn[ax];
+        }
+        a.vn[0] = nxl; /* local velocity planes */
+        a.dens = io.hires_density;
+        a.ratio_vel = (double)hn[0] / (double)dn[0];
+        a.ratio_out = (double)hn[0] / (double)dn[0];
+        a.init_growth = init_growth;
+
+        /* halo width from the largest x displacement of the whole box */
+        int *keys_sym = (int *)dist_alloc(2 * sizeof(int));
+        DevBuf<int> d_keys(2);
+        {
+            const int init[2] = {2147483647, -2147483647 - 1};
+            h2d(keys_sym, init, sizeof(init));
+            g_stats.h2d -= (long long)sizeof(init);
+            MaxDispArgs ma = {(long long)nxl * plane, a.v[0], a.v2[0], a.vdf[0], a.vdf2[0], a.ratio_out, keys_sym};
+            B200_LAUNCH(max_disp_kernel, dev_num_sms() * 4, 256, 0, ma);
+            dist_barrier_minmax(keys_sym, d_keys);
+        }
+        int hkeys[2];
+        d2h(hkeys, d_keys, sizeof(hkeys));
+        g_stats.d2h -= (long long)sizeof(hkeys);
+        const double max_disp = (double)float_from_order_key(hkeys[1]);
+        halo = (int)ceil(max_disp) + 2;
+        if (const char *e = getenv("B200_SLAB_HALO")) halo = atoi(e);
+        if (halo < 1) halo = 1;
+        if (halo > nxl)
+            b200_throw(B200_ValueError, "slab deposit: displacements of %.1f cells exceed the slab thickness %d (use fewer ranks)", max_disp, nxl);
+
+        a.vel_x0 = x0;
+        a.dens_x0 = F * x0 - F / 2;
+        a.out_x0 = x0 - halo;
+        a.out_nxl = nxl + 2 * halo;
+        a.overflow = d_over;
+        const size_t acc_n = (size_t)a.out_nxl * plane;
+        unsigned long long *acc = (unsigned long long *)dist_alloc(acc_n * sizeof(unsigned long long));
+        dev_zero(acc, acc_n * sizeof(unsigned long long));
+        a.acc = acc;
+        const long long ngroups = (long long)nxl * plane;
+        if (F == 1) launch_grouped<1>(a, 0, ngroups);
+        else if (F == 2) launch_grouped<2>(a, 0, ngroups);
+        else if (F == 3) launch_grouped<3>(a, 0, ngroups);
+        else launch_grouped<4>(a, 0, ngroups);
+        dist_barrier(); /* every rank's deposit has landed before the halos are pulled */
+        {
+            const int row_blocks = (int)((long long)nxl * hn[1] < 4096 ? (long long)nxl * hn[1] : 4096);
+            AccSlabArgs ca = {nxl, halo, plane, hn[1], hn[2], plan->pitch, acc,
+                              dist_peer(acc, (slab.rank + P - 1) % P), dist_peer(acc, (slab.rank + 1) % P), padded,
+                              (double)N / (double)M};
+            B200_LAUNCH(acc_to_delta_slab_kernel, row_blocks, 256, 0, ca);
+        }
+
     }
 
     /* smooth_and_clip_density, PerturbedField.c:212-282 */

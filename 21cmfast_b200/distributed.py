@@ -289,7 +289,8 @@ class SlabGroup:
 
     def perturb(self, *, redshift: float, ics_slab: dict):
         """ics_slab: device tensors of this rank's slabs (``hires_density`` from ``hires_slab``, the low-res
-        velocity boxes from ``lowres_slab``).  Returns ``dict(density, velocity_z)`` slabs."""
+        velocity boxes from ``lowres_slab``; ``PERTURB_ALGORITHM='LINEAR'`` reads ``lowres_density`` instead).
+        Returns ``dict(density, velocity_z)`` slabs."""
         import torch
         be = self.backend
         be.state.init(self.inputs, broadcast_inputs=True)

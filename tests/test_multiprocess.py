@@ -119,7 +119,7 @@ for hii, dim, kw in {cases}:
         full = getattr(ics, k)
         want = full[rank * hn:(rank + 1) * hn] if k == "hires_density" else grp.lowres_slab(full)
         assert np.array_equal(t.numpy(), want), (hii, k, float(np.abs(t.numpy() - want).max()))
-    lo = ["lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+    lo = ["lowres_density", "lowres_vx", "lowres_vy", "lowres_vz", "lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
     # the whole pipeline on slabs: the ICs made slab by slab feed the slab perturb (half-cell shift of the hi-res planes
     # through one small all-gather), which feeds the slab ionize -- no whole box anywhere
     slab = {{k: sics[k] for k in lo if k in sics}}
@@ -146,10 +146,11 @@ def test_gloo_slab_decomposed_box(tmp_path, nproc):
     """One box on x-slabs over 1 / 2 / 4 ranks: slab deposit with halo pull, slab-decomposed FFTs whose
     transposes are stores into the peers' (shared-memory) heaps, per-radius extrema / plane sums through
     the barrier kernel -- every output slab bit-identical to the single-rank box.  Power-of-two and
-    mixed-radix grids, 2LPT and Zel'dovich, top-hat (window rows) and sharp-k."""
+    mixed-radix grids, 2LPT, Zel'dovich and the linear field, top-hat (window rows), sharp-k and Gaussian."""
     if not (ROOT / "tests" / "_emu" / "libb200_emu.so").exists():
         pytest.skip("tests/_emu not built")
-    cases = [(32, 64, {}), (24, 72, dict(perturb="ZELDOVICH", hii_filter="sharp-k", source="CONST-ION-EFF"))]
+    cases = [(32, 64, {}), (24, 72, dict(perturb="ZELDOVICH", hii_filter="sharp-k", source="CONST-ION-EFF")),
+             (16, 32, dict(perturb="LINEAR", hii_filter="gaussian"))]  # LINEAR: the rank's planes of lowres_density
     script = tmp_path / "worker_slab.py"
     script.write_text(WORKER_SLAB.format(root=ROOT, cases=repr(cases)))
     env = dict(os.environ, OMP_NUM_THREADS="2")

@@ -1,0 +1,113 @@
+"""Random grids and options: the slab-decomposed box against the single-rank box, bit for bit (TEST INFRASTRUCTURE).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
+        tools/fuzz_slab.py [--seed S] [--cases N] [--backend emu|gpu]
+
+Every rank draws the same cases.  Per case: whole-box ICs -> perturb -> ionize on this rank (the single-GPU path),
+then the same box on x-slabs over the ranks (slab ICs, slab perturb with halo pull, slab ionize with the slab FFTs and
+the barrier-kernel reductions); every output slab must equal the matching planes of the whole box exactly.  A case
+the slab entry points refuse (status 3 on every rank) is reported as refused, not as a failure.  The fixed cases of
+tests/test_multiprocess.py cover two grids; this covers shapes (non-cubic, mixed radix, one plane per rank) and
+option combinations.
+"""
+import argparse
+import random
+import sys
+import traceback
+from pathlib import Path
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import common  # noqa: E402
+
+pkg = common.pkg
+
+
+def draw(rng, world):
+    hii = world * rng.choice([1, 2, 3, 4, 5, 6, 8])
+    while hii < 8:
+        hii *= 2
+    sim = dict(HII_DIM=hii, DIM=hii * rng.choice([2, 3, 4]), BOX_LEN=rng.choice([1.0, 1.5, 2.0]) * hii, N_THREADS=1,
+               NON_CUBIC_FACTOR=rng.choice([1.0, 1.0, 1.25, 1.5]))
+    matter = dict(SOURCE_MODEL=rng.choice(["E-INTEGRAL", "CONST-ION-EFF"]),
+                  PERTURB_ALGORITHM=rng.choice(["2LPT", "2LPT", "ZELDOVICH", "LINEAR"]),
+                  SMOOTH_EVOLVED_DENSITY_FIELD=rng.choice([False, False, True]))
+    aopt = dict(USE_EXP_FILTER=False, CELL_RECOMB=False, USE_LYA_HEATING=False, USE_UPPER_STELLAR_TURNOVER=False,
+                HII_FILTER=rng.choice(["spherical-tophat", "spherical-tophat", "gaussian", "sharp-k"]))
+    astro = dict(R_BUBBLE_MAX=rng.choice([8.0, 15.0, 30.0]), HII_EFF_FACTOR=rng.choice([20.0, 30.0, 50.0]))
+    return dict(sim=sim, matter=matter, aopt=aopt, astro=astro, z=rng.choice([6.0, 7.0, 8.0, 9.5, 12.0]),
+                seed=rng.randrange(1, 10**6))
+
+
+def run_case(be, c, rank, world):
+    inputs = pkg.InputParameters(
+        random_seed=c["seed"], simulation_options=pkg.SimulationOptions(**c["sim"]),
+        matter_options=pkg.MatterOptions(**c["matter"]), astro_params=pkg.AstroParams(**c["astro"]),
+        astro_options=pkg.AstroOptions(**c["aopt"]))
+    z = c["z"]
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=be)
+    whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=be)
+    grp = pkg.SlabGroup(inputs=inputs, backend=be, ics=True)
+    try:
+        sics = grp.initial_conditions()
+        hn = inputs.simulation_options.dim // world
+        for k, t in sics.items():
+            full = getattr(ics, k)
+            want = full[rank * hn:(rank + 1) * hn] if k == "hires_density" else grp.lowres_slab(full)
+            assert np.array_equal(t.cpu().numpy(), want), f"slab ICs: {k}"
+        slab = {k: v for k, v in sics.items() if k.startswith("lowres_")}  # LINEAR reads lowres_density
+        slab["hires_density"] = grp.shift_hires(sics["hires_density"])
+        ppf = grp.perturb(redshift=z, ics_slab=slab)
+        for k in ("density", "velocity_z"):
+            assert np.array_equal(ppf[k].cpu().numpy(), grp.lowres_slab(getattr(pf, k))), f"slab perturb: {k}"
+        part = grp.ionize(redshift=z, density_slab=ppf["density"])
+        for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion"):
+            want = grp.lowres_slab(getattr(whole, k).reshape(pf.density.shape))
+            assert np.array_equal(part[k].cpu().numpy(), want), f"slab ionize: {k}"
+        assert part["mean_f_coll"] == whole.mean_f_coll, "mean_f_coll"
+    finally:
+        grp.close()
+    return whole.global_xH
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cases", type=int, default=20)
+    ap.add_argument("--backend", choices=["emu", "gpu"], default="emu")
+    args = ap.parse_args()
+    dist.init_process_group("gloo" if args.backend == "emu" else "nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    be = common.emu_backend() if args.backend == "emu" else common.gpu_backend()
+    rng = random.Random(args.seed)
+    bad = ran = 0
+    for it in range(args.cases):
+        c = draw(rng, world)
+        try:
+            xh = run_case(be, c, rank, world)
+            ran += 1
+            if rank == 0:
+                print(f"{it:3d} ok   xH={xh:.3f}  {c['sim']['HII_DIM']}/{c['sim']['DIM']} x{c['sim']['NON_CUBIC_FACTOR']}", flush=True)
+        except AssertionError as e:
+            bad += 1
+            print(f"{it:3d} rank {rank} SLAB != WHOLE: {e}\n      {c}", flush=True)
+        except (ValueError, pkg.BackendError) as e:
+            if rank == 0:
+                print(f"{it:3d} refused: {e}\n      {c}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            bad += 1
+            print(f"{it:3d} rank {rank} ERROR {e!r}\n      {c}", flush=True)
+            traceback.print_exc()
+    if rank == 0:
+        print(f"{ran} cases compared on {world} ranks, {bad} failures on rank 0")
+    dist.destroy_process_group()
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
