@@ -91,7 +91,10 @@ def run_case(be, ref, c, spec):
     r_hb = None
     if lagrangian:
         r_hb = pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=ref)
-        common.compare_struct(pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=be), r_hb, tol=5e-6)
+        # QAG stops at a relative tolerance of 1e-3 (hmf.c:596): a last-bit difference in the integrand can change
+        # where it stops subdividing, so that is the bar for its tables (seen once, with the PEEBLES spectrum: 2e-4)
+        hb_tol = 1e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else 5e-6
+        common.compare_struct(pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=be), r_hb, tol=hb_tol)
     kw = dict(perturbed_field=r_pf, initial_conditions=r_ics, halobox=r_hb)
     if inputs.evolution_required:  # the snapshot above (made by the reference) is the previous box of both sides
         zp = z + 1.0
@@ -124,6 +127,9 @@ def run_case(be, ref, c, spec):
             continue
         e = common.rel_err(tv[same], rv[same]) if same.any() else 0.0
         assert e <= common.TOL_FIELD, f"{k}: rel err {e:.3e}"
+    # brightness temperature of the reference's boxes (BrightnessTemperatureBox.c:22-105)
+    common.compare_struct(pkg.brightness_temperature(ionized_box=r_ib, perturbed_field=r_pf, backend=be),
+                          pkg.brightness_temperature(ionized_box=r_ib, perturbed_field=r_pf, backend=ref))
     # Eulerian: the analytic mean; Lagrangian: a float grid mean (IonisationBox.c:1623-1628)
     bar = 2e-6 if lagrangian else 1e-9
     assert abs(ib.mean_f_coll - r_ib.mean_f_coll) <= bar * abs(r_ib.mean_f_coll), "mean_f_coll"
@@ -136,15 +142,19 @@ def main():
     ap.add_argument("--cases", type=int, default=30)
     ap.add_argument("--backend", choices=["emu", "gpu"], default="emu")
     ap.add_argument("--spec", action="store_true")
+    ap.add_argument("--start", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--carry", type=int, nargs=2, default=(0, 0), help=argparse.SUPPRESS)
     args = ap.parse_args()
     ref = common.ref_backend()
     be = common.emu_backend() if args.backend == "emu" else common.gpu_backend()
     if ref is None or be is None:
         sys.exit("needs oracle/_ref and the chosen product library")
     rng = random.Random(args.seed)
-    bad = ran = 0
+    ran, bad = args.carry
     for it in range(args.cases):
         c = draw(rng)
+        if it < args.start:
+            continue
         t = time.time()
         try:
             mism, xh = run_case(be, ref, c, args.spec)
@@ -153,8 +163,17 @@ def main():
         except AssertionError as e:
             bad += 1
             print(f"{it:3d} PARITY FAIL: {e}\n      {c}", flush=True)
-        except (ValueError, pkg.BackendError) as e:
+        except ValueError as e:
             print(f"{it:3d} refused: {e}\n      {c}", flush=True)
+        except pkg.BackendError as e:
+            print(f"{it:3d} refused: {e}\n      {c}", flush=True)
+            if e.code != 3:
+                # the reference leaves an exception by longjmp out of an OpenMP region (a GSL error inside a table
+                # build): its state is undefined afterwards, so the remaining cases run in a fresh process
+                sys.stdout.flush()
+                os.execv(sys.executable, [sys.executable, __file__, "--seed", str(args.seed), "--cases", str(args.cases),
+                                          "--backend", args.backend, "--start", str(it + 1), "--carry", str(ran), str(bad)]
+                         + (["--spec"] if args.spec else []))
         except Exception as e:  # noqa: BLE001
             bad += 1
             print(f"{it:3d} ERROR {e!r}\n      {c}", flush=True)
