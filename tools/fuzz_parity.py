@@ -60,6 +60,10 @@ def draw(rng):
         aopt["INTEGRATION_METHOD_ATOMIC"] = "GAUSS-LEGENDRE"
     if rng.random() < 0.3 and not aopt["USE_EXP_FILTER"]:  # two chained snapshots with recombinations
         aopt["RECOMB_MODEL"] = rng.choice(["homogeneous", "inhomogeneous"])
+        if aopt["RECOMB_MODEL"] == "homogeneous":
+            aopt["CELL_RECOMB"] = True  # the reference refuses the homogeneous model with filtered recombinations
+    if rng.random() < 0.2 and matter["SOURCE_MODEL"] != "L-INTEGRAL":
+        aopt["USE_TS_FLUCT"] = True  # x_e filtering, T_k / T_s from a synthetic TsBox (the same on both sides)
     return dict(sim=sim, matter=matter, aopt=aopt, astro=astro, cosmo=cosmo,
                 z=rng.choice([5.5, 6.5, 7.0, 8.0, 9.5, 12.0, 25.0]), seed=rng.randrange(1, 10**6))
 
@@ -74,6 +78,21 @@ def ladder(be, spec, **kw):
         os.environ.pop("B200_SPEC", None)
         if old is not None:
             os.environ["B200_SPEC"] = old
+
+
+def synthetic_ts(inputs, pf):
+    """tests/test_recombinations.py::_synthetic_ts: x_e of a few per cent following the density with excursions
+    beyond [0, 1], adiabatic-like T_k, T_s between it and the CMB (the spin-temperature calculation is out of scope)."""
+    ts = pkg.TsBox.new(inputs, pf.redshift)
+    rng = np.random.default_rng(int(pf.redshift * 100))
+    d = pf.density.astype(np.float64)
+    xe = 0.03 * (1 + d) + 0.02 * rng.standard_normal(d.shape)
+    xe[rng.random(d.shape) < 1e-3] = 1.2
+    ts.xray_ionised_fraction[...] = xe
+    tk = 40.0 * np.cbrt(np.clip(1 + d, 1e-3, None)) ** 2 * (1 + 0.1 * rng.random(d.shape))
+    ts.kinetic_temp_neutral[...] = tk
+    ts.spin_temperature[...] = 0.5 * (tk + 2.7255 * (1 + pf.redshift)) + 1.0
+    return ts
 
 
 def run_case(be, ref, c, spec):
@@ -96,12 +115,16 @@ def run_case(be, ref, c, spec):
         hb_tol = 1e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else 5e-6
         common.compare_struct(pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=be), r_hb, tol=hb_tol)
     kw = dict(perturbed_field=r_pf, initial_conditions=r_ics, halobox=r_hb)
+    ts_on = inputs.astro_options.USE_TS_FLUCT
+    if ts_on:
+        kw["spin_temp"] = synthetic_ts(inputs, r_pf)
     if inputs.evolution_required:  # the snapshot above (made by the reference) is the previous box of both sides
         zp = z + 1.0
         p_pf = pkg.perturb_field(redshift=zp, initial_conditions=r_ics, backend=ref)
         p_hb = pkg.compute_halobox(redshift=zp, initial_conditions=r_ics, backend=ref) if lagrangian else None
         p_ib = pkg.compute_ionization_field(
             perturbed_field=p_pf, initial_conditions=r_ics, halobox=p_hb, backend=ref,
+            spin_temp=synthetic_ts(inputs, p_pf) if ts_on else None,
             previous_ionized_box=pkg.IonizedBox.initial(inputs), previous_perturbed_field=pkg.PerturbedField.initial(inputs))
         kw.update(previous_ionized_box=p_ib, previous_perturbed_field=p_pf)
     r_ib = pkg.compute_ionization_field(backend=ref, **kw)
@@ -128,8 +151,8 @@ def run_case(be, ref, c, spec):
         e = common.rel_err(tv[same], rv[same]) if same.any() else 0.0
         assert e <= common.TOL_FIELD, f"{k}: rel err {e:.3e}"
     # brightness temperature of the reference's boxes (BrightnessTemperatureBox.c:22-105)
-    common.compare_struct(pkg.brightness_temperature(ionized_box=r_ib, perturbed_field=r_pf, backend=be),
-                          pkg.brightness_temperature(ionized_box=r_ib, perturbed_field=r_pf, backend=ref))
+    tb = dict(ionized_box=r_ib, perturbed_field=r_pf, spin_temp=kw.get("spin_temp"))
+    common.compare_struct(pkg.brightness_temperature(backend=be, **tb), pkg.brightness_temperature(backend=ref, **tb))
     # Eulerian: the analytic mean; Lagrangian: a float grid mean (IonisationBox.c:1623-1628)
     bar = 2e-6 if lagrangian else 1e-9
     assert abs(ib.mean_f_coll - r_ib.mean_f_coll) <= bar * abs(r_ib.mean_f_coll), "mean_f_coll"
