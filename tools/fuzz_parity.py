@@ -54,6 +54,12 @@ def draw(rng):
         astro.update(F_STAR10=rng.choice([-1.5, -1.3, -1.0]), ALPHA_STAR=rng.choice([0.3, 0.5]),
                      F_ESC10=rng.choice([-1.2, -1.0, -0.7]), ALPHA_ESC=rng.choice([-0.5, -0.2, 0.0]),
                      M_TURN=rng.choice([8.0, 8.7, 9.3]), t_STAR=rng.choice([0.3, 0.5]))
+    if rng.random() < 0.12:  # tabulated transfer functions (synthetic: classy is not in the image) and v_cb fluctuations
+        matter["POWER_SPECTRUM"] = "CLASS"
+        matter["V_CB_MODEL"] = rng.choice(["NONE", "FLUCTS"])
+        # sigma_8-normalised: with the A_s normalisation the synthetic tables give |delta| ~ 1e-4, where the float
+        # rounding of (1 + delta) - 1 is all that is left to compare (tests/test_class_tables.py covers A_s on the ICs)
+        cosmo["_class_sigma8"] = True
     if matter.get("POWER_SPECTRUM") in ("PEEBLES", "WHITE") and aopt["INTEGRATION_METHOD_ATOMIC"] == "GAMMA-APPROX":
         # the triple power law of sigma(M) behind the approximation does not hold for these spectra: with positive
         # exponents the sum of incomplete gamma functions cancels to noise on both sides (QAG gives ~0 there)
@@ -96,8 +102,17 @@ def synthetic_ts(inputs, pf):
 
 
 def run_case(be, ref, c, spec):
+    cosmo = dict(c["cosmo"])
+    class_sigma8 = cosmo.pop("_class_sigma8", None)
+    class_tables = None
+    if c["matter"].get("POWER_SPECTRUM") == "CLASS":
+        import test_class_tables as tct
+        td, tv = tct._tables()
+        class_tables = tct.CosmoTables(ps_norm=cosmo.get("SIGMA_8", 0.8102) if class_sigma8 else 2.1e-9,
+                                       USE_SIGMA_8=bool(class_sigma8), transfer_density=td,
+                                       transfer_vcb=tv if c["matter"].get("V_CB_MODEL") == "FLUCTS" else None)
     inputs = pkg.InputParameters(
-        random_seed=c["seed"], cosmo_params=pkg.CosmoParams(**c["cosmo"]),
+        random_seed=c["seed"], cosmo_params=pkg.CosmoParams(**cosmo), class_tables=class_tables,
         simulation_options=pkg.SimulationOptions(**c["sim"]),
         matter_options=pkg.MatterOptions(**c["matter"]), astro_params=pkg.AstroParams(**c["astro"]),
         astro_options=pkg.AstroOptions(**c["aopt"]))
