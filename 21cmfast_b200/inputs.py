@@ -234,6 +234,8 @@ class AstroOptions(_InputStruct):
             raise ValueError("USE_EXP_FILTER can only be used with a real-space tophat HII_FILTER==0")
         if self.USE_EXP_FILTER and not self.CELL_RECOMB:
             raise ValueError("USE_EXP_FILTER is True but CELL_RECOMB is False")
+        if not self.CELL_RECOMB and self.RECOMB_MODEL == "homogeneous":  # wrapper/inputs.py:1384-1387
+            raise ValueError("CELL_RECOMB cannot be False when RECOMB_MODEL is 'homogeneous'!")
         if self.USE_MINI_HALOS and (self.RECOMB_MODEL == "none" or not self.USE_TS_FLUCT):
             raise ValueError("USE_MINI_HALOS needs RECOMB_MODEL != 'none' and USE_TS_FLUCT")
 

@@ -109,7 +109,10 @@ def _unsupported_cases(be):
         ao = dataclasses.replace(base.astro_options, **kw)
         return dataclasses.replace(base, astro_options=ao)
 
-    for kw in (dict(USE_TS_FLUCT=True), dict(RECOMB_MODEL="homogeneous"), dict(PHOTON_CONS_TYPE="z-photoncons")):
+    # the reference's own input validation (wrapper/inputs.py:1384-1387) refuses this one before any C call
+    with pytest.raises(ValueError):
+        with_opts(RECOMB_MODEL="homogeneous")   # CELL_RECOMB is False in these inputs
+    for kw in (dict(USE_TS_FLUCT=True), dict(PHOTON_CONS_TYPE="z-photoncons")):  # no TsBox arrays / not built
         inp = with_opts(**kw)
         be.state.init(inp, broadcast_inputs=True, ps=True, sigma=True, heat=True)
         box = pkg.IonizedBox.new(inp, 8.0)

@@ -101,6 +101,27 @@ def synthetic_ts(inputs, pf):
     return ts
 
 
+class ReferenceRefused(Exception):
+    """The reference itself returned an error status for this draw: nothing to compare."""
+
+
+class _Ref:
+    """The reference backend's calls, with its error statuses set apart from the product's."""
+
+    def __init__(self, be):
+        self.be = be
+
+    def __getattr__(self, name):
+        fn = getattr(pkg, name)
+
+        def call(**kw):
+            try:
+                return fn(backend=self.be, **kw)
+            except pkg.BackendError as e:
+                raise ReferenceRefused(str(e), e.code) from e
+        return call
+
+
 def run_case(be, ref, c, spec):
     cosmo = dict(c["cosmo"])
     class_sigma8 = cosmo.pop("_class_sigma8", None)
@@ -117,14 +138,15 @@ def run_case(be, ref, c, spec):
         matter_options=pkg.MatterOptions(**c["matter"]), astro_params=pkg.AstroParams(**c["astro"]),
         astro_options=pkg.AstroOptions(**c["aopt"]))
     z, lagrangian = c["z"], c["matter"]["SOURCE_MODEL"] == "L-INTEGRAL"
-    r_ics = pkg.compute_initial_conditions(inputs=inputs, backend=ref)
+    R = _Ref(ref)
+    r_ics = R.compute_initial_conditions(inputs=inputs)
     common.compare_struct(pkg.compute_initial_conditions(inputs=inputs, backend=be), r_ics)
-    r_pf = pkg.perturb_field(redshift=z, initial_conditions=r_ics, backend=ref)
+    r_pf = R.perturb_field(redshift=z, initial_conditions=r_ics)
     pf = pkg.perturb_field(redshift=z, initial_conditions=r_ics, backend=be)
     common.compare_struct(pf, r_pf, tols={k: common.TOL_VELOCITY for k in ("velocity_x", "velocity_y", "velocity_z")})
     r_hb = None
     if lagrangian:
-        r_hb = pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=ref)
+        r_hb = R.compute_halobox(redshift=z, initial_conditions=r_ics)
         # QAG stops at a relative tolerance of 1e-3 (hmf.c:596): a last-bit difference in the integrand can change
         # where it stops subdividing, so that is the bar for its tables (seen once, with the PEEBLES spectrum: 2e-4)
         hb_tol = 1e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else 5e-6
@@ -135,21 +157,25 @@ def run_case(be, ref, c, spec):
         kw["spin_temp"] = synthetic_ts(inputs, r_pf)
     if inputs.evolution_required:  # the snapshot above (made by the reference) is the previous box of both sides
         zp = z + 1.0
-        p_pf = pkg.perturb_field(redshift=zp, initial_conditions=r_ics, backend=ref)
-        p_hb = pkg.compute_halobox(redshift=zp, initial_conditions=r_ics, backend=ref) if lagrangian else None
-        p_ib = pkg.compute_ionization_field(
-            perturbed_field=p_pf, initial_conditions=r_ics, halobox=p_hb, backend=ref,
+        p_pf = R.perturb_field(redshift=zp, initial_conditions=r_ics)
+        p_hb = R.compute_halobox(redshift=zp, initial_conditions=r_ics) if lagrangian else None
+        p_ib = R.compute_ionization_field(
+            perturbed_field=p_pf, initial_conditions=r_ics, halobox=p_hb,
             spin_temp=synthetic_ts(inputs, p_pf) if ts_on else None,
             previous_ionized_box=pkg.IonizedBox.initial(inputs), previous_perturbed_field=pkg.PerturbedField.initial(inputs))
         kw.update(previous_ionized_box=p_ib, previous_perturbed_field=p_pf)
-    r_ib = pkg.compute_ionization_field(backend=ref, **kw)
+    r_ib = R.compute_ionization_field(**kw)
     ib = ladder(be, True, **kw)
     if spec and not lagrangian and not inputs.evolution_required:
         two = ladder(be, False, **kw)
         for k, v in two.arrays().items():
             assert np.array_equal(v, ib.arrays()[k]), f"single-sweep ladder differs from two sweeps in {k}"
     mask_t, mask_r = ib.neutral_fraction == 0, r_ib.neutral_fraction == 0
-    mism = int((mask_t != mask_r).sum())
+    # Lagrangian sources: the collapsed fraction is the source grid over (1 + delta) (IonisationBox.c:1054-1066); in
+    # nearly empty cells (a linearly evolved density is clipped at -1 + 1e-7) that division amplifies float rounding
+    # by up to 1e7, flags included -- those cells are left out (tests/test_lagrangian_sources.py scales the bar)
+    well = (1.0 + r_pf.density) > 0.1 if lagrangian else np.ones(mask_r.shape, bool)
+    mism = int(((mask_t != mask_r) & well).sum())
     assert mism <= common.TOL_MASK_FRACTION * mask_r.size, f"mask differs in {mism} cells"
     same = mask_t == mask_r
     if "mean_free_path" in r_ib.arrays() and inputs.evolution_required:
@@ -157,8 +183,7 @@ def run_case(be, ref, c, spec):
         crossing = ib.mean_free_path == r_ib.mean_free_path
         assert (~crossing).sum() <= max(2, common.TOL_MASK_FRACTION * mask_r.size), "first-crossing radius differs"
         same &= crossing
-    if lagrangian:  # the partial ionisations divide by (1 + delta): see tests/test_lagrangian_sources.py
-        same &= (1.0 + r_pf.density) > 0.1
+    same &= well
     for k, rv in r_ib.arrays().items():
         tv = ib.arrays()[k]
         if rv.shape != same.shape:
@@ -167,7 +192,7 @@ def run_case(be, ref, c, spec):
         assert e <= common.TOL_FIELD, f"{k}: rel err {e:.3e}"
     # brightness temperature of the reference's boxes (BrightnessTemperatureBox.c:22-105)
     tb = dict(ionized_box=r_ib, perturbed_field=r_pf, spin_temp=kw.get("spin_temp"))
-    common.compare_struct(pkg.brightness_temperature(backend=be, **tb), pkg.brightness_temperature(backend=ref, **tb))
+    common.compare_struct(pkg.brightness_temperature(backend=be, **tb), R.brightness_temperature(**tb))
     # Eulerian: the analytic mean; Lagrangian: a float grid mean (IonisationBox.c:1623-1628)
     bar = 2e-6 if lagrangian else 1e-9
     assert abs(ib.mean_f_coll - r_ib.mean_f_coll) <= bar * abs(r_ib.mean_f_coll), "mean_f_coll"
@@ -201,11 +226,14 @@ def main():
         except AssertionError as e:
             bad += 1
             print(f"{it:3d} PARITY FAIL: {e}\n      {c}", flush=True)
-        except ValueError as e:
-            print(f"{it:3d} refused: {e}\n      {c}", flush=True)
-        except pkg.BackendError as e:
-            print(f"{it:3d} refused: {e}\n      {c}", flush=True)
-            if e.code != 3:
+        except ValueError as e:  # the input validation both sides share
+            print(f"{it:3d} invalid inputs: {e}", flush=True)
+        except pkg.BackendError as e:  # the reference computed it, the product returned an error status
+            bad += 1
+            print(f"{it:3d} PRODUCT REFUSED what the reference computes: {e}\n      {c}", flush=True)
+        except ReferenceRefused as e:
+            print(f"{it:3d} reference refused: {e.args[0]}\n      {c}", flush=True)
+            if e.args[1] != 3:
                 # the reference leaves an exception by longjmp out of an OpenMP region (a GSL error inside a table
                 # build): its state is undefined afterwards, so the remaining cases run in a fresh process
                 sys.stdout.flush()
