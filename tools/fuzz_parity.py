@@ -149,7 +149,7 @@ def run_case(be, ref, c, spec):
         r_hb = R.compute_halobox(redshift=z, initial_conditions=r_ics)
         # QAG stops at a relative tolerance of 1e-3 (hmf.c:596): a last-bit difference in the integrand can change
         # where it stops subdividing, so that is the bar for its tables (seen once, with the PEEBLES spectrum: 2e-4)
-        hb_tol = 1e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else 5e-6
+        hb_tol = 1e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else common.TOL_FIELD
         common.compare_struct(pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=be), r_hb, tol=hb_tol)
     kw = dict(perturbed_field=r_pf, initial_conditions=r_ics, halobox=r_hb)
     ts_on = inputs.astro_options.USE_TS_FLUCT
@@ -188,7 +188,11 @@ def run_case(be, ref, c, spec):
         tv = ib.arrays()[k]
         if rv.shape != same.shape:
             continue
-        e = common.rel_err(tv[same], rv[same]) if same.any() else 0.0
+        if lagrangian and k == "neutral_fraction":  # partial ionisations: the bar follows the conditioning 1 / (1 + delta)
+            d = np.abs(tv.astype(np.float64) - rv)[same] * np.minimum(1.0, 1.0 + r_pf.density[same])
+            e = float(d.max()) if d.size else 0.0
+        else:
+            e = common.rel_err(tv[same], rv[same]) if same.any() else 0.0
         assert e <= common.TOL_FIELD, f"{k}: rel err {e:.3e}"
     # brightness temperature of the reference's boxes (BrightnessTemperatureBox.c:22-105)
     tb = dict(ionized_box=r_ib, perturbed_field=r_pf, spin_temp=kw.get("spin_temp"))
