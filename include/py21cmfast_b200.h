@@ -387,7 +387,7 @@ void b200_ics_share(int enable);
    the F * HII_DIM / world hi-res planes that start at global plane F * x0 - F / 2 (periodic), F = DIM /
    HII_DIM integer <= 4.  Outputs are the rank's slab of the result, bit-identical to the same planes of the
    single-GPU box (same per-line FFT arithmetic, integer deposit sums, fixed reduction tree of the grid
-   sum).  ZELDOVICH / 2LPT on the low-res grid; ionisation without recombinations / spin temperature. */
+   sum).  LINEAR / ZELDOVICH / 2LPT on the low-res grid (LINEAR reads the lowres_density slab); ionisation without recombinations / spin temperature. */
 int b200_ComputePerturbedField_slab(float redshift, InitialConditions *d_boxes_slab, PerturbedField *d_pf_slab);
 int b200_ComputeIonizedBox_slab(float redshift, float prev_redshift, PerturbedField *d_pf_slab, IonizedBox *d_box_slab);
 /* ComputeInitialConditions (InitialConditions.c:547-772) with the hi-res box split into x-slabs, so that DIM is
