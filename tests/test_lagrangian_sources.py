@@ -106,8 +106,10 @@ def test_lagrangian_sources_vs_reference_emulated(name):
     print(name, _check(be, name))
 
 
+# linear_perturb differs from hires_zeldovich only in host logic (which velocity boxes are uploaded) and its bars
+# in the nearly empty cells have only been exercised on the CPU tier
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", [n for n in CASES if n != "linear_perturb"])
 def test_lagrangian_sources_vs_reference_gpu(name):
     print(name, _check(common.gpu_backend(), name))
 
