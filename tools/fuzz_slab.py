@@ -43,7 +43,7 @@ def draw(rng, world):
                 seed=rng.randrange(1, 10**6))
 
 
-def run_case(be, c, rank, world):
+def run_case(be, c, rank, world, device=None):
     inputs = pkg.InputParameters(
         random_seed=c["seed"], simulation_options=pkg.SimulationOptions(**c["sim"]),
         matter_options=pkg.MatterOptions(**c["matter"]), astro_params=pkg.AstroParams(**c["astro"]),
@@ -54,7 +54,7 @@ def run_case(be, c, rank, world):
     whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=be)
     grp = pkg.SlabGroup(inputs=inputs, backend=be, ics=True)
     try:
-        sics = grp.initial_conditions()
+        sics = grp.initial_conditions(device=device)
         hn = inputs.simulation_options.dim // world
         for k, t in sics.items():
             full = getattr(ics, k)
@@ -81,15 +81,25 @@ def main():
     ap.add_argument("--cases", type=int, default=20)
     ap.add_argument("--backend", choices=["emu", "gpu"], default="emu")
     args = ap.parse_args()
+    device = None
+    if args.backend == "gpu":  # one process per GPU
+        import os
+
+        import torch
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        device = f"cuda:{local}"
     dist.init_process_group("gloo" if args.backend == "emu" else "nccl")
     rank, world = dist.get_rank(), dist.get_world_size()
     be = common.emu_backend() if args.backend == "emu" else common.gpu_backend()
+    if device:
+        assert be.lib.b200_set_device(int(device.split(":")[1])) == 0
     rng = random.Random(args.seed)
     bad = ran = 0
     for it in range(args.cases):
         c = draw(rng, world)
         try:
-            xh = run_case(be, c, rank, world)
+            xh = run_case(be, c, rank, world, device)
             ran += 1
             if rank == 0:
                 print(f"{it:3d} ok   xH={xh:.3f}  {c['sim']['HII_DIM']}/{c['sim']['DIM']} x{c['sim']['NON_CUBIC_FACTOR']}", flush=True)
