@@ -1577,13 +1577,16 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     int *keys_sym = nullptr;
     double *plane_sym = nullptr;
     float *tab_sym = nullptr; /* this rank's share of every radius' table */
+    unsigned long long *fail_sym = nullptr; /* this rank's SpecState::failed, so that the ranks re-run the ladder together */
     const int tab_per = sl ? (N_DENS_INTERP + slab.P - 1) / slab.P : 0;
     if (sl) {
         keys_sym = (int *)dist_alloc(sizeof(int) * 2 * 64);
         plane_sym = (double *)dist_alloc(sizeof(double) * 64 * (size_t)nxl);
         if (!(getenv("B200_SPLIT_TABLES") && getenv("B200_SPLIT_TABLES")[0] == '0'))
             tab_sym = (float *)dist_alloc(sizeof(float) * 64 * (size_t)tab_per);
+        fail_sym = (unsigned long long *)dist_alloc(sizeof(unsigned long long));
     }
+    DevBuf<unsigned long long> d_fail_all(sl ? (size_t)slab.P : 0);
     DevBuf<int> d_flag(1);
     dev_zero(d_flag, sizeof(int));
     DevBuf<unsigned char> own_mask;
@@ -1813,6 +1816,17 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
                 fprintf(stderr, "[21cmfast_b200] ionize speculation: mean fix / queued cells per radius:");
                 for (int q = 0; q < j; q++) fprintf(stderr, " %.6f/%u", hs.mean_fix[q], hs.qcount[q]);
                 fprintf(stderr, " (queue: %d segments of %u)\n", sum_blocks, qcap);
+            }
+            if (sl) {
+                /* a queue segment can overflow on one rank only: the ranks must leave the ladder together, or their
+                   barrier sequences part ways */
+                dev_zero(fail_sym, sizeof(unsigned long long));
+                d2d(fail_sym, reinterpret_cast<const char *>(d_spec.p) + offsetof(SpecState, failed), sizeof(int));
+                dist_barrier_gather(fail_sym, d_fail_all.p, 1);
+                unsigned long long all[DIST_MAX_RANKS];
+                d2h(all, d_fail_all.p, sizeof(unsigned long long) * (size_t)slab.P);
+                g_stats.d2h -= (long long)(sizeof(unsigned long long) * (size_t)slab.P);
+                for (int r = 0; r < slab.P; r++) hs.failed |= (all[r] != 0);
             }
             if (hs.failed) { restart = true; break; }
         }

@@ -161,6 +161,50 @@ def test_gloo_slab_decomposed_box(tmp_path, nproc):
     assert r.stdout.count("OK slab") == len(cases)
 
 
+WORKER_ASYM = r'''
+import os, sys
+sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
+import numpy as np, torch, torch.distributed as dist
+import common
+pkg = common.pkg
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+emu = common.emu_backend()
+inputs = common.make_inputs(hii=32, dim=64, seed=4242)
+ics = pkg.compute_initial_conditions(inputs=inputs, backend=emu)
+pf = pkg.perturb_field(redshift=8.0, initial_conditions=ics, backend=emu)
+whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=emu)
+grp = pkg.SlabGroup(inputs=inputs, backend=emu)
+dens = torch.from_numpy(np.ascontiguousarray(grp.lowres_slab(pf.density)))
+if rank == 1:
+    os.environ["B200_SPEC_QCAP"] = "3"      # only this rank's queue segments overflow
+part = grp.ionize(redshift=8.0, density_slab=dens)
+for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion"):
+    assert np.array_equal(part[k].numpy(), grp.lowres_slab(getattr(whole, k).reshape(pf.density.shape))), k
+grp.close()
+print("OK asym", rank)
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_slab_ranks_leave_the_speculative_ladder_together(tmp_path):
+    """Single-sweep ladder on slabs: a queue segment that overflows on ONE rank only (forced here through that
+    rank's B200_SPEC_QCAP) must send every rank into the two-sweep re-run -- the failed flag is gathered over the
+    ranks before the decision (a local decision left the ranks in different barrier sequences: deadlock).
+    Outputs stay bit-identical to the single-rank box."""
+    if not (ROOT / "tests" / "_emu" / "libb200_emu.so").exists():
+        pytest.skip("tests/_emu not built")
+    script = tmp_path / "worker_asym.py"
+    script.write_text(WORKER_ASYM.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env.pop("B200_SPEC_QCAP", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29561", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert r.stdout.count("OK asym") == 2
+
+
 WORKER_SHARE = r'''
 import os, sys
 sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
