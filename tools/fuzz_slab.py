@@ -43,6 +43,32 @@ def draw(rng, world):
                 seed=rng.randrange(1, 10**6))
 
 
+def run_case_radius(be, c, rank, world, device=None):
+    """the other one-box partition: deposit by x-slab + all_reduce(SUM), radii split over the ranks + all_reduce(MAX)"""
+    import torch
+    inputs = pkg.InputParameters(
+        random_seed=c["seed"], simulation_options=pkg.SimulationOptions(**c["sim"]),
+        matter_options=pkg.MatterOptions(**c["matter"]), astro_params=pkg.AstroParams(**c["astro"]),
+        astro_options=pkg.AstroOptions(**c["aopt"]))
+    z = c["z"]
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    pf = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=be)
+    whole = pkg.compute_ionization_field(perturbed_field=pf, initial_conditions=ics, backend=be)
+    names = ["hires_density", "lowres_vx", "lowres_vy", "lowres_vz"]
+    if c["matter"]["PERTURB_ALGORITHM"] == "2LPT":
+        names += ["lowres_vx_2LPT", "lowres_vy_2LPT", "lowres_vz_2LPT"]
+    dev = device or "cpu"
+    ppf = pkg.perturb_slab_parallel(redshift=z, ics={k: torch.from_numpy(getattr(ics, k)).to(dev) for k in names},
+                                    inputs=inputs, backend=be)
+    for k in ("density", "velocity_z"):
+        assert np.array_equal(ppf[k].cpu().numpy(), getattr(pf, k)), f"partitioned perturb: {k}"
+    part = pkg.ionize_radius_parallel(redshift=z, density=ppf["density"], inputs=inputs, backend=be)
+    for k in ("neutral_fraction", "z_reion", "kinetic_temperature", "unnormalised_nion"):
+        assert np.array_equal(part[k].cpu().numpy(), getattr(whole, k).reshape(part[k].shape)), f"radius-parallel ionize: {k}"
+    assert part["mean_f_coll"] == whole.mean_f_coll, "mean_f_coll"
+    return whole.global_xH
+
+
 def run_case(be, c, rank, world, device=None):
     inputs = pkg.InputParameters(
         random_seed=c["seed"], simulation_options=pkg.SimulationOptions(**c["sim"]),
@@ -80,6 +106,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cases", type=int, default=20)
     ap.add_argument("--backend", choices=["emu", "gpu"], default="emu")
+    ap.add_argument("--mode", choices=["slab", "radius"], default="slab")
     args = ap.parse_args()
     device = None
     if args.backend == "gpu":  # one process per GPU
@@ -99,7 +126,7 @@ def main():
     for it in range(args.cases):
         c = draw(rng, world)
         try:
-            xh = run_case(be, c, rank, world, device)
+            xh = (run_case if args.mode == "slab" else run_case_radius)(be, c, rank, world, device)
             ran += 1
             if rank == 0:
                 print(f"{it:3d} ok   xH={xh:.3f}  {c['sim']['HII_DIM']}/{c['sim']['DIM']} x{c['sim']['NON_CUBIC_FACTOR']}", flush=True)
