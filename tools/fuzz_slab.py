@@ -1,14 +1,15 @@
 """Random grids and options: the slab-decomposed box against the single-rank box, bit for bit (TEST INFRASTRUCTURE).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
-        tools/fuzz_slab.py [--seed S] [--cases N] [--backend emu|gpu]
+        tools/fuzz_slab.py [--seed S] [--cases N] [--backend emu|gpu] [--mode slab|radius|share]
 
 Every rank draws the same cases.  Per case: whole-box ICs -> perturb -> ionize on this rank (the single-GPU path),
 then the same box on x-slabs over the ranks (slab ICs, slab perturb with halo pull, slab ionize with the slab FFTs and
 the barrier-kernel reductions); every output slab must equal the matching planes of the whole box exactly.  A case
 the slab entry points refuse (status 3 on every rank) is reported as refused, not as a failure.  The fixed cases of
 tests/test_multiprocess.py cover two grids; this covers shapes (non-cubic, mixed radix, one plane per rank) and
-option combinations.
+option combinations.  --mode radius: the other one-box partition (deposit by x-slab + all-reduce, radii split over
+the ranks); --mode share: redshift-parallel ranks on a shared upload of the initial conditions.
 """
 import argparse
 import random
@@ -69,6 +70,31 @@ def run_case_radius(be, c, rank, world, device=None):
     return whole.global_xH
 
 
+def run_case_share(be, c, rank, world, device=None):
+    """redshift-parallel ranks on shared initial conditions (b200_ics_share): each rank uploads 1 / world of the IC
+    arrays, the rest arrives from the peers' heaps; the perturbed field of the rank's own redshift must not change"""
+    inputs = pkg.InputParameters(
+        random_seed=c["seed"], simulation_options=pkg.SimulationOptions(**c["sim"]),
+        matter_options=pkg.MatterOptions(**c["matter"]), astro_params=pkg.AstroParams(**c["astro"]),
+        astro_options=pkg.AstroOptions(**c["aopt"]))
+    z = c["z"] + 0.5 * rank
+    ics = pkg.compute_initial_conditions(inputs=inputs, backend=be)
+    want = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=be)
+    grp = pkg.SlabGroup(inputs=inputs, backend=be, heap_bytes=pkg.SlabGroup.ics_heap_bytes(inputs))
+    try:
+        grp.share_ics(True)
+        for _ in range(2):
+            got = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=be)
+            for k, v in want.arrays().items():
+                assert np.array_equal(v, got.arrays()[k]), f"shared upload: {k}"
+        grp.share_ics(False)
+        plain = pkg.perturb_field(redshift=z, initial_conditions=ics, backend=be)
+        assert np.array_equal(plain.density, want.density), "after sharing"
+    finally:
+        grp.close()
+    return float(want.density.std())
+
+
 def run_case(be, c, rank, world, device=None):
     inputs = pkg.InputParameters(
         random_seed=c["seed"], simulation_options=pkg.SimulationOptions(**c["sim"]),
@@ -106,7 +132,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cases", type=int, default=20)
     ap.add_argument("--backend", choices=["emu", "gpu"], default="emu")
-    ap.add_argument("--mode", choices=["slab", "radius"], default="slab")
+    ap.add_argument("--mode", choices=["slab", "radius", "share"], default="slab")
     args = ap.parse_args()
     device = None
     if args.backend == "gpu":  # one process per GPU
@@ -126,7 +152,7 @@ def main():
     for it in range(args.cases):
         c = draw(rng, world)
         try:
-            xh = (run_case if args.mode == "slab" else run_case_radius)(be, c, rank, world, device)
+            xh = {"slab": run_case, "radius": run_case_radius, "share": run_case_share}[args.mode](be, c, rank, world, device)
             ran += 1
             if rank == 0:
                 print(f"{it:3d} ok   xH={xh:.3f}  {c['sim']['HII_DIM']}/{c['sim']['DIM']} x{c['sim']['NON_CUBIC_FACTOR']}", flush=True)
