@@ -167,6 +167,35 @@ DEV void stockham_stage_any(int R, const float2 *src, float2 *dst, int n, int Ns
     }
 }
 
+/* any larger prime radix: the direct sum straight out of shared memory (no local array), O(R^2) per butterfly.
+   FFTW takes every length, so the reference does too; these sizes are rare and slow there as well. */
+DEV void stockham_stage_big(int R, const float2 *src, float2 *dst, int n, int Ns, int T, int Tp,
+                            const float2 *__restrict__ tw, int sign) {
+    const int nb = n / R;
+    const int tws = n / (Ns * R);
+    const int rstep = n / R;
+    for (int w = threadIdx.x; w < nb * T; w += blockDim.x) {
+        const int c = w % T, j = w / T;
+        const int k = j % Ns;
+        const int j0 = (j - k) * R + k;
+        for (int p = 0; p < R; p++) {
+            float2 acc = src[j * Tp + c];
+            for (int q = 1; q < R; q++) {
+                float2 a = src[(j + q * nb) * Tp + c];
+                if (Ns > 1) {
+                    float2 t = ldg(&tw[q * k * tws]);
+                    if (sign > 0) t.y = -t.y;
+                    a = cmul(a, t);
+                }
+                float2 t = ldg(&tw[(int)(((long long)p * q) % R) * rstep]);
+                if (sign > 0) t.y = -t.y;
+                acc = cadd(acc, cmul(a, t));
+            }
+            dst[(j0 + p * Ns) * Tp + c] = acc;
+        }
+    }
+}
+
 /* all stages; returns the buffer holding the result */
 DEV float2 *fft_tile(float2 *A, float2 *B, int n, int T, int Tp, const FftFactors &f,
                      const float2 *__restrict__ tw, int sign) {
@@ -181,7 +210,10 @@ DEV float2 *fft_tile(float2 *A, float2 *B, int n, int T, int Tp, const FftFactor
             case 3: stockham_stage<3>(src, dst, n, Ns, T, Tp, tw, sign); break;
             case 5: stockham_stage<5>(src, dst, n, Ns, T, Tp, tw, sign); break;
             case 7: stockham_stage<7>(src, dst, n, Ns, T, Tp, tw, sign); break;
-            default: stockham_stage_any(R, src, dst, n, Ns, T, Tp, tw, sign); break;
+            default:
+                if (R <= 31) stockham_stage_any(R, src, dst, n, Ns, T, Tp, tw, sign);
+                else stockham_stage_big(R, src, dst, n, Ns, T, Tp, tw, sign);
+                break;
         }
         __syncthreads();
         Ns *= R;
@@ -426,13 +458,17 @@ static bool factorize(int n, FftFactors &f) {
     for (int i = 0; i < n8; i++) f.r[f.nf++] = 8;
     for (int i = 0; i < n4; i++) f.r[f.nf++] = 4;
     for (int i = 0; i < n2; i++) f.r[f.nf++] = 2;
-    for (int p = 3; p <= 31; p += 2)
+    for (int p = 3; (long long)p * p <= n; p += 2)
         while (n % p == 0) {
             if (f.nf >= FFT_MAX_FACTORS) return false;
             f.r[f.nf++] = p;
             n /= p;
         }
-    return n == 1;
+    if (n > 1) { /* what is left is one prime (of any size: stockham_stage_big) */
+        if (f.nf >= FFT_MAX_FACTORS) return false;
+        f.r[f.nf++] = n;
+    }
+    return true;
 }
 
 static std::map<int, Fft1D> g_plans1d;
@@ -444,7 +480,7 @@ static Fft1D &plan1d(int n) {
     Fft1D p;
     p.n = n;
     if (!factorize(n, p.f))
-        b200_throw(B200_ValueError, "FFT length %d has a prime factor > 31 (unsupported)", n);
+        b200_throw(B200_ValueError, "FFT length %d has more than %d prime factors", n, FFT_MAX_FACTORS);
     std::vector<float2> tw(n);
     for (int k = 0; k < n; k++) {
         double ph = -2.0 * M_PI * (double)k / (double)n;

@@ -8,7 +8,7 @@
  * for alignment.  Transforms are unnormalised in both directions, like FFTW.
  *
  * Algorithm: three passes of batched 1-D Stockham autosort FFTs held entirely in shared memory
- * (mixed radix 8/4/2/3/5/7 + generic small primes), one pass per axis:
+ * (mixed radix 8/4/2/3/5/7, unrolled primes up to 31, a direct-sum stage for larger primes), one pass per axis:
  *   x, y axes : strided lines; a CTA owns a tile of T adjacent lines so that every global
  *               row access is T*8 contiguous bytes
  *   z axis    : contiguous lines; the real<->complex conversion, scaling, clipping and the
