@@ -87,7 +87,8 @@ struct SweepArgs {
    ladder of this call without speculation (never observed; the check is what makes the shortcut exact).
    A queue segment that overflows (it holds a sixteenth of the CTA's cells; ~1.3 % are queued) does the same. */
 #define SPEC_EPS 0.02
-#define SPEC_MAX_RADII 64
+#define MAX_RADII 256 /* filter radii of one ladder: DELTA_R_HII_FACTOR = 1.03 between 0.62 and 50 Mpc gives 149 */
+#define SPEC_MAX_RADII MAX_RADII
 struct SpecState {
     double eps;                      /* half width of the bracket (SPEC_EPS; B200_SPEC_EPS overrides it for tests) */
     double mean_fix[SPEC_MAX_RADII]; /* true mean fix of every radius processed so far in this call */
@@ -1324,17 +1325,18 @@ struct IonStaging {
     int cap = 0;
     int *h_keys = nullptr;       /* [cap][2] */
     DevTable *h_tables = nullptr; /* [cap] */
-    void *events[64];
+    void *events[MAX_RADII];
     ~IonStaging() {}
     void ensure(int n) {
         if (n <= cap) return;
-        if (n > 64) b200_throw(B200_ValueError, "more than 64 filter radii");
+        if (n > MAX_RADII) b200_throw(B200_ValueError, "more than %d filter radii", MAX_RADII);
         host_pinned_free(h_keys);
         host_pinned_free(h_tables);
-        h_keys = (int *)host_pinned_alloc(sizeof(int) * 2 * 64);
-        h_tables = (DevTable *)host_pinned_alloc(sizeof(DevTable) * 64);
-        for (int i = cap; i < 64; i++) events[i] = dev_event_create();
-        cap = 64;
+        const int want = n <= 64 ? 64 : MAX_RADII; /* the usual ladders stay on the small staging buffers */
+        h_keys = (int *)host_pinned_alloc(sizeof(int) * 2 * want);
+        h_tables = (DevTable *)host_pinned_alloc(sizeof(DevTable) * want);
+        for (int i = cap; i < want; i++) events[i] = dev_event_create();
+        cap = want;
     }
 };
 static IonStaging g_stage;
@@ -1580,10 +1582,10 @@ static void ionize_core(float redshift_f, float prev_redshift_f, const IonDevice
     unsigned long long *fail_sym = nullptr; /* this rank's SpecState::failed, so that the ranks re-run the ladder together */
     const int tab_per = sl ? (N_DENS_INTERP + slab.P - 1) / slab.P : 0;
     if (sl) {
-        keys_sym = (int *)dist_alloc(sizeof(int) * 2 * 64);
-        plane_sym = (double *)dist_alloc(sizeof(double) * 64 * (size_t)nxl);
+        keys_sym = (int *)dist_alloc(sizeof(int) * 2 * MAX_RADII);
+        plane_sym = (double *)dist_alloc(sizeof(double) * MAX_RADII * (size_t)nxl);
         if (!(getenv("B200_SPLIT_TABLES") && getenv("B200_SPLIT_TABLES")[0] == '0'))
-            tab_sym = (float *)dist_alloc(sizeof(float) * 64 * (size_t)tab_per);
+            tab_sym = (float *)dist_alloc(sizeof(float) * MAX_RADII * (size_t)tab_per);
         fail_sym = (unsigned long long *)dist_alloc(sizeof(unsigned long long));
     }
     DevBuf<unsigned long long> d_fail_all(sl ? (size_t)slab.P : 0);

@@ -38,6 +38,8 @@ CASES = {
     "barely_ionised_z18": dict(z=18.0),
     # FFTW takes every length: a grid whose sides have a prime factor above 31 (37, 2 x 37) runs the direct-sum stage
     "prime_grid_37": dict(sim=dict(HII_DIM=37, DIM=74, BOX_LEN=55.5)),
+    # DELTA_R_HII_FACTOR = 1.03: 94 filter radii (the staging of the ladder held 64 before)
+    "fine_radius_steps": dict(astro=dict(DELTA_R_HII_FACTOR=1.03)),
 }
 
 
@@ -79,8 +81,9 @@ def test_option_matrix_emulated_vs_reference(name):
     _run_case(emu, ref, name)
 
 
-# prime_grid_37: added after the round's last GPU session; the stage it exercises has only run in the host emulation
-GPU_CASES = [c for c in CASES if c != "prime_grid_37"]
+# added after the round's last GPU session: what they exercise has only run in the host emulation
+CPU_TIER_ONLY = ("prime_grid_37", "fine_radius_steps")
+GPU_CASES = [c for c in CASES if c not in CPU_TIER_ONLY]
 
 
 @pytest.mark.gpu

@@ -45,7 +45,8 @@ def draw(rng):
                 INTEGRATION_METHOD_ATOMIC=rng.choice(["GSL-QAG", "GAUSS-LEGENDRE", "GAUSS-LEGENDRE", "GAMMA-APPROX"]))
     if matter["SOURCE_MODEL"] == "L-INTEGRAL" and aopt["HII_FILTER"] == "spherical-tophat" and rng.random() < 0.5:
         aopt.update(USE_EXP_FILTER=True, CELL_RECOMB=True)
-    astro = dict(R_BUBBLE_MAX=rng.choice([10.0, 15.0, 30.0]), HII_EFF_FACTOR=rng.choice([20.0, 30.0, 50.0]))
+    astro = dict(R_BUBBLE_MAX=rng.choice([10.0, 15.0, 30.0]), HII_EFF_FACTOR=rng.choice([20.0, 30.0, 50.0]),
+                 DELTA_R_HII_FACTOR=rng.choice([1.1, 1.1, 1.1, 1.1, 1.05, 1.03]))  # the finer steps pass 64 radii
     cosmo = {}
     if rng.random() < 0.5:  # another cosmology / transfer function / star-formation scaling
         cosmo = dict(SIGMA_8=rng.choice([0.75, 0.8102, 0.9]), hlittle=rng.choice([0.6766, 0.7]),

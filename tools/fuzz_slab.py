@@ -39,7 +39,8 @@ def draw(rng, world):
                   SMOOTH_EVOLVED_DENSITY_FIELD=rng.choice([False, False, True]))
     aopt = dict(USE_EXP_FILTER=False, CELL_RECOMB=False, USE_LYA_HEATING=False, USE_UPPER_STELLAR_TURNOVER=False,
                 HII_FILTER=rng.choice(["spherical-tophat", "spherical-tophat", "gaussian", "sharp-k"]))
-    astro = dict(R_BUBBLE_MAX=rng.choice([8.0, 15.0, 30.0]), HII_EFF_FACTOR=rng.choice([20.0, 30.0, 50.0]))
+    astro = dict(R_BUBBLE_MAX=rng.choice([8.0, 15.0, 30.0]), HII_EFF_FACTOR=rng.choice([20.0, 30.0, 50.0]),
+                 DELTA_R_HII_FACTOR=rng.choice([1.1, 1.1, 1.1, 1.04, 1.02]))  # up to ~200 radii
     return dict(sim=sim, matter=matter, aopt=aopt, astro=astro, z=rng.choice([6.0, 7.0, 8.0, 9.5, 12.0]),
                 seed=rng.randrange(1, 10**6))
 
