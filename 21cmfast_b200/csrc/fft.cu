@@ -196,7 +196,9 @@ DEV void stockham_stage_big(int R, const float2 *src, float2 *dst, int n, int Ns
     }
 }
 
-/* all stages; returns the buffer holding the result */
+/* all stages; returns the buffer holding the result.  BIG: the length has a prime factor above 31 -- a separate
+   instantiation of the kernels, so that the code generated for every other length is what it was without it */
+template <bool BIG>
 DEV float2 *fft_tile(float2 *A, float2 *B, int n, int T, int Tp, const FftFactors &f,
                      const float2 *__restrict__ tw, int sign) {
     float2 *src = A, *dst = B;
@@ -211,8 +213,8 @@ DEV float2 *fft_tile(float2 *A, float2 *B, int n, int T, int Tp, const FftFactor
             case 5: stockham_stage<5>(src, dst, n, Ns, T, Tp, tw, sign); break;
             case 7: stockham_stage<7>(src, dst, n, Ns, T, Tp, tw, sign); break;
             default:
-                if (R <= 31) stockham_stage_any(R, src, dst, n, Ns, T, Tp, tw, sign);
-                else stockham_stage_big(R, src, dst, n, Ns, T, Tp, tw, sign);
+                if (BIG && R > 31) stockham_stage_big(R, src, dst, n, Ns, T, Tp, tw, sign);
+                else stockham_stage_any(R, src, dst, n, Ns, T, Tp, tw, sign);
                 break;
         }
         __syncthreads();
@@ -314,6 +316,7 @@ DEV float2 apply_kmul(float2 v, int i, int col, const StridedArgs &a) {
     return v;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restrict__ src,
                                                           float2 *__restrict__ dst,
                                                           StridedArgs a) {
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(256) fft_strided_kernel(const float2 *__restri
         A[i * a.Tp + c] = v;
     }
     __syncthreads();
-    const float2 *res = fft_tile(A, B, a.n, a.T, a.Tp, a.f, a.tw, a.sign);
+    const float2 *res = fft_tile<BIG>(A, B, a.n, a.T, a.Tp, a.f, a.tw, a.sign);
     for (int w = threadIdx.x; w < a.n * a.T; w += blockDim.x) {
         const int c = w % a.T, i = w / a.T;
         const int col = col0 + c;
@@ -359,6 +362,7 @@ struct ZArgs {
 };
 
 /* complex rows -> real rows (inverse).  Builds the full Hermitian line in shared memory. */
+template <bool BIG>
 __global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict__ src,
                                                         float *__restrict__ dst, ZArgs a) {
     DYN_SMEM(float2, smem);
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict
         if (k > 0 && 2 * k < n) A[(n - k) * a.Tp + l] = make_float2(v.x, -v.y);
     }
     __syncthreads();
-    const float2 *res = fft_tile(A, B, n, a.L, a.Tp, a.f, a.tw, +1);
+    const float2 *res = fft_tile<BIG>(A, B, n, a.L, a.Tp, a.f, a.tw, +1);
     float lmin = 3.0e38f, lmax = -3.0e38f;
     for (int w = threadIdx.x; w < a.L * n; w += blockDim.x) {
         const int z = w % n, l = w / n;
@@ -412,6 +416,7 @@ __global__ void __launch_bounds__(256) fft_c2r_z_kernel(const float2 *__restrict
 }
 
 /* real rows -> complex rows (forward) */
+template <bool BIG>
 __global__ void __launch_bounds__(256) fft_r2c_z_kernel(const float *__restrict__ src,
                                                         float2 *__restrict__ dst, ZArgs a) {
     DYN_SMEM(float2, smem);
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(256) fft_r2c_z_kernel(const float *__restrict_
         A[z * a.Tp + l] = make_float2(val, 0.f);
     }
     __syncthreads();
-    const float2 *res = fft_tile(A, B, n, a.L, a.Tp, a.f, a.tw, -1);
+    const float2 *res = fft_tile<BIG>(A, B, n, a.L, a.Tp, a.f, a.tw, -1);
     for (int w = threadIdx.x; w < a.L * nzc; w += blockDim.x) {
         const int k = w % nzc, l = w / nzc;
         const long long row = row0 + l;
@@ -447,6 +452,11 @@ __global__ void __launch_bounds__(256) fft_r2c_z_kernel(const float *__restrict_
 }
 
 /* ------------------------------------------------------------------ plans */
+static bool has_big_prime(const FftFactors &f) {
+    for (int i = 0; i < f.nf; i++)
+        if (f.r[i] > 31) return true;
+    return false;
+}
 static bool factorize(int n, FftFactors &f) {
     f.nf = 0;
     int e = 0;
@@ -583,9 +593,14 @@ static void run_strided(const Fft1D &p1, const float2 *src, float2 *dst, long lo
     }
     if (pow2_strided(src, dst, a, ngroups)) return;
     size_t smem = tile_smem(a.n, a.T);
-    allow_smem(fft_strided_kernel, smem);
     dim3 grid((ncols + a.T - 1) / a.T, ngroups, 1);
-    B200_LAUNCH(fft_strided_kernel, grid, 256, smem, src, dst, a);
+    if (has_big_prime(a.f)) {
+        allow_smem(fft_strided_kernel<true>, smem);
+        B200_LAUNCH_T("fft_strided_kernel", fft_strided_kernel<true>, grid, 256, smem, src, dst, a);
+    } else {
+        allow_smem(fft_strided_kernel<false>, smem);
+        B200_LAUNCH_T("fft_strided_kernel", fft_strided_kernel<false>, grid, 256, smem, src, dst, a);
+    }
 }
 
 /* x-planes per (y pass, z pass) chunk of fft_c2r: the y pass leaves its output dirty in L2 and the z
@@ -631,8 +646,13 @@ void fft_c2r(Fft3D *p, const float2 *src, float2 *work, const KMul &km, const ZE
         if (pow2_c2r_z(w, d, a)) continue;
         const int nblocks = (a.nrows + a.L - 1) / a.L;
         size_t smem = tile_smem(a.n, a.L);
-        allow_smem(fft_c2r_z_kernel, smem);
-        B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, w, d, a);
+        if (has_big_prime(a.f)) {
+            allow_smem(fft_c2r_z_kernel<true>, smem);
+            B200_LAUNCH_T("fft_c2r_z_kernel", fft_c2r_z_kernel<true>, dim3(nblocks), 256, smem, w, d, a);
+        } else {
+            allow_smem(fft_c2r_z_kernel<false>, smem);
+            B200_LAUNCH_T("fft_c2r_z_kernel", fft_c2r_z_kernel<false>, dim3(nblocks), 256, smem, w, d, a);
+        }
     }
 }
 
@@ -650,8 +670,13 @@ void fft_r2c(Fft3D *p, float2 *box, const ZPrologue &pro) {
     if (!pow2_r2c_z(src, box, a)) {
         const int nblocks = (a.nrows + a.L - 1) / a.L;
         size_t smem = tile_smem(a.n, a.L);
-        allow_smem(fft_r2c_z_kernel, smem);
-        B200_LAUNCH(fft_r2c_z_kernel, dim3(nblocks), 256, smem, src, box, a);
+        if (has_big_prime(a.f)) {
+            allow_smem(fft_r2c_z_kernel<true>, smem);
+            B200_LAUNCH_T("fft_r2c_z_kernel", fft_r2c_z_kernel<true>, dim3(nblocks), 256, smem, src, box, a);
+        } else {
+            allow_smem(fft_r2c_z_kernel<false>, smem);
+            B200_LAUNCH_T("fft_r2c_z_kernel", fft_r2c_z_kernel<false>, dim3(nblocks), 256, smem, src, box, a);
+        }
     }
     run_strided(p->py, box, box, pitch, pitch, (long long)ny * pitch, nx, -1, 1.f, nullptr, p);
     run_strided(p->px, box, box, (long long)ny * pitch, ny * pitch, 0, 1, -1, pro.post_scale, nullptr, p);
@@ -696,8 +721,13 @@ void fft_r2c_slab(FftSlab *s, float2 *kT, float2 *tmp, const ZPrologue &pro) {
     if (!pow2_r2c_z(src, tmp, a)) {
         const int nblocks = (a.nrows + a.L - 1) / a.L;
         size_t smem = tile_smem(a.n, a.L);
-        allow_smem(fft_r2c_z_kernel, smem);
-        B200_LAUNCH(fft_r2c_z_kernel, dim3(nblocks), 256, smem, src, tmp, a);
+        if (has_big_prime(a.f)) {
+            allow_smem(fft_r2c_z_kernel<true>, smem);
+            B200_LAUNCH_T("fft_r2c_z_kernel", fft_r2c_z_kernel<true>, dim3(nblocks), 256, smem, src, tmp, a);
+        } else {
+            allow_smem(fft_r2c_z_kernel<false>, smem);
+            B200_LAUNCH_T("fft_r2c_z_kernel", fft_r2c_z_kernel<false>, dim3(nblocks), 256, smem, src, tmp, a);
+        }
     }
     /* y: lines over kz per local x plane; point y goes to rank y / nyl at [x0 + xl][y % nyl][kz] */
     float2 *recv = s->recv[g_dist.transforms & 1];
@@ -738,8 +768,13 @@ void fft_c2r_slab(FftSlab *s, const float2 *kT, float2 *work, const KMul &km, co
     if (pow2_c2r_z(work, dst, a)) return;
     const int nblocks = (a.nrows + a.L - 1) / a.L;
     size_t smem = tile_smem(a.n, a.L);
-    allow_smem(fft_c2r_z_kernel, smem);
-    B200_LAUNCH(fft_c2r_z_kernel, dim3(nblocks), 256, smem, work, dst, a);
+    if (has_big_prime(a.f)) {
+        allow_smem(fft_c2r_z_kernel<true>, smem);
+        B200_LAUNCH_T("fft_c2r_z_kernel", fft_c2r_z_kernel<true>, dim3(nblocks), 256, smem, work, dst, a);
+    } else {
+        allow_smem(fft_c2r_z_kernel<false>, smem);
+        B200_LAUNCH_T("fft_c2r_z_kernel", fft_c2r_z_kernel<false>, dim3(nblocks), 256, smem, work, dst, a);
+    }
 }
 
 /* ------------------------------------------------------------------ in-place k-space window */
