@@ -36,10 +36,10 @@ CASES = {
     "neutral_box_z25": dict(z=25.0),
     "noncubic_neutral_z25": dict(sim=dict(NON_CUBIC_FACTOR=1.5), z=25.0),
     "barely_ionised_z18": dict(z=18.0),
-    # FFTW takes every length: a grid whose sides have a prime factor above 31 (37, 2 x 37) runs the direct-sum stage
-    "prime_grid_37": dict(sim=dict(HII_DIM=37, DIM=74, BOX_LEN=55.5)),
-    # DELTA_R_HII_FACTOR = 1.03: 94 filter radii (the staging of the ladder held 64 before)
-    "fine_radius_steps": dict(astro=dict(DELTA_R_HII_FACTOR=1.03)),
+    # FFTW takes every length: a grid whose sides have a prime factor above 31 runs the direct-sum stage
+    "prime_grid_37": dict(sim=dict(HII_DIM=37, DIM=37, BOX_LEN=55.5)),
+    # DELTA_R_HII_FACTOR = 1.04: 81 filter radii (the staging of the ladder held 64 before)
+    "fine_radius_steps": dict(astro=dict(DELTA_R_HII_FACTOR=1.04, R_BUBBLE_MAX=30.0)),
 }
 
 
