@@ -187,10 +187,12 @@ extern "C" int ComputeHaloBox(double redshift, InitialConditions *ini_boxes, Hal
         const AstroOptions *ao = astro_options_global;
         if (mo->SOURCE_MODEL != SRC_L_INTEGRAL)
             b200_throw(B200_ValueError, "ComputeHaloBox: only SOURCE_MODEL = L-INTEGRAL is built (the halo samplers are out of scope)");
+        /* USE_UPPER_STELLAR_TURNOVER (the reference's default) is accepted: it acts on sampled halos (get_halo_stellarmass,
+           scaling_relations.c:326-370) and on L_X / SFR (:314-324, spin temperature), not on the fixed grids' integrals */
         if (ao->USE_MINI_HALOS || ao->USE_TS_FLUCT || config_settings.EXTRA_HALOBOX_FIELDS || ao->HALO_SCALING_RELATIONS_MEDIAN ||
-            ao->USE_UPPER_STELLAR_TURNOVER || ao->PHOTON_CONS_TYPE != 0)
-            b200_throw(B200_ValueError, "ComputeHaloBox: mini-halos, spin temperature, extra fields, median scaling relations, "
-                                        "the upper stellar turnover and photon conservation are not built");
+            ao->PHOTON_CONS_TYPE != 0)
+            b200_throw(B200_ValueError, "ComputeHaloBox: mini-halos, spin temperature, extra fields, median scaling relations "
+                                        "and photon conservation are not built");
         if (mo->USE_INTERPOLATION_TABLES != 2)
             b200_throw(B200_ValueError, "this build needs USE_INTERPOLATION_TABLES='hmf-interpolation'");
         if (!ini_boxes || !grids || !grids->n_ion || !grids->halo_sfr)

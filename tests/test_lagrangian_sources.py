@@ -150,3 +150,29 @@ def test_compute_halo_grid_is_the_reference_named_entry():
     eul = common.make_inputs(hii=16, dim=32, source="E-INTEGRAL")
     with pytest.raises(NotImplementedError):
         pkg.compute_halobox(redshift=z, initial_conditions=pkg.compute_initial_conditions(inputs=eul, backend=be), backend=be)
+
+
+def test_reference_default_options_run_for_every_in_scope_source_model():
+    """The reference's default switches (USE_EXP_FILTER, CELL_RECOMB, USE_UPPER_STELLAR_TURNOVER, USE_LYA_HEATING ... all
+    True) with each source model of the scoped path: a user who only picks SOURCE_MODEL gets boxes, not a ValueError.
+    USE_UPPER_STELLAR_TURNOVER acts on sampled halos and on L_X / SFR only (scaling_relations.c:314-370): the fixed
+    grids must not depend on it."""
+    be = common.emu_backend()
+    if be is None:
+        pytest.skip("tests/_emu not built")
+    sim = pkg.SimulationOptions(HII_DIM=16, DIM=32, BOX_LEN=24.0)
+    xh = {}
+    for src in ("L-INTEGRAL", "E-INTEGRAL", "CONST-ION-EFF"):
+        inp = pkg.InputParameters(random_seed=3, simulation_options=sim, matter_options=pkg.MatterOptions(SOURCE_MODEL=src))
+        assert inp.astro_options.USE_UPPER_STELLAR_TURNOVER and inp.astro_options.USE_EXP_FILTER
+        out = pkg.run_coeval(out_redshifts=7.0, inputs=inp, backend=be)[-1]
+        xh[src] = out["ionized_box"].global_xH
+        assert np.isfinite(out["brightness_temp"].brightness_temp).all()
+    assert 0.05 < xh["L-INTEGRAL"] < 0.95 and 0.05 < xh["E-INTEGRAL"] < 0.95
+    inp = pkg.InputParameters(random_seed=3, simulation_options=sim, matter_options=pkg.MatterOptions(SOURCE_MODEL="L-INTEGRAL"))
+    ics = pkg.compute_initial_conditions(inputs=inp, backend=be)
+    off = dataclasses.replace(inp, astro_options=dataclasses.replace(inp.astro_options, USE_UPPER_STELLAR_TURNOVER=False))
+    a = pkg.compute_halobox(redshift=7.0, initial_conditions=ics, backend=be)
+    ics_off = pkg.compute_initial_conditions(inputs=off, backend=be)
+    b = pkg.compute_halobox(redshift=7.0, initial_conditions=ics_off, backend=be)
+    assert np.array_equal(a.n_ion, b.n_ion) and np.array_equal(a.halo_sfr, b.halo_sfr)
