@@ -29,7 +29,8 @@ pkg = common.pkg
 
 
 def draw(rng):
-    hii = rng.choice([12, 16, 20, 24, 28, 32])
+    hii = rng.choice([int(v) for v in os.environ["FUZZ_HII"].split(",")] if os.environ.get("FUZZ_HII")
+                     else [12, 16, 20, 24, 28, 32])  # FUZZ_HII=40,48,64: larger grids (slow in the emulation)
     sim = dict(HII_DIM=hii, DIM=hii * rng.choice([2, 3]), BOX_LEN=rng.choice([1.0, 1.5, 2.0, 3.0]) * hii,
                N_THREADS=rng.choice([1, 1, 2, 3]), NON_CUBIC_FACTOR=rng.choice([1.0, 1.0, 1.0, 1.25, 1.5]))
     matter = dict(SOURCE_MODEL=rng.choice(["E-INTEGRAL", "CONST-ION-EFF", "L-INTEGRAL"]),
